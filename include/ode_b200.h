@@ -1,0 +1,102 @@
+/* ode_b200.h -- libode_b200 extensions to the ODE C API (C ABI: plain pointers and sizes only).
+ *
+ * Why they exist: the reference drives collision through a per-pair host callback
+ * (dSpaceCollide -> NearCallback -> dJointCreateContact, /root/reference/src/main.c:212,674-693).
+ * That shape is kept bit-for-bit in <ode/ode.h> ("compat mode"), but at 10^6 bodies it would mean
+ * ~10^7 host calls per tick.  The reference's callback is a fixed policy -- uniform surface, up to
+ * 8 contacts, attach the geoms' bodies -- so the device-resident mode below declares that policy
+ * once and pairs, contacts and rows never leave the GPU.
+ */
+#ifndef ODE_B200_EXT_H
+#define ODE_B200_EXT_H
+
+#include "ode/ode.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* CUDA device used by worlds created afterwards (default: env ODE_B200_DEVICE, LOCAL_RANK, or 0) */
+void dSetDeviceB200(int device);
+int dGetDeviceB200(void);
+
+/* device-resident replacement of `dSpaceCollide(space, 0, NearCallback)` (src/main.c:212): runs
+ * broadphase + narrowphase and keeps the contacts on the GPU for the next dWorldQuickStep/dWorldStep,
+ * which applies the world's uniform surface to every contact.  Asynchronous. */
+void dSpaceCollideDeviceB200(dSpaceID, int max_contacts);
+/* the uniform surface policy; default = the reference's NearCallback (src/main.c:684-687):
+ * mode dContactBounce, bounce 0.2, bounce_vel 0.1, mu dInfinity */
+void dWorldSetSurfaceB200(dWorldID, const dSurfaceParameters *);
+void dWorldGetSurfaceB200(dWorldID, dSurfaceParameters *);
+/* max contacts per pair precomputed by dSpaceCollide in compat mode (default 8, src/main.c:675) */
+void dWorldSetMaxContactsB200(dWorldID, int max_contacts);
+
+/* batched independent worlds ("envs") inside one dWorldID: geoms of different envs never collide;
+ * env -1 on a static geom means "present in every env". */
+void dWorldSetNumEnvsB200(dWorldID, int n_envs);
+void dBodySetEnvB200(dBodyID, int env);
+void dGeomSetEnvB200(dGeomID, int env);
+
+/* bulk creation (one call instead of ~10 per body). Any pointer but pos may be NULL for defaults
+ * (q identity, zero velocity, mass 1 / identity inertia, flags 0, env 0). inertia9 is row-major.
+ * flags: 1 kinematic, 2 no gravity, 4 gyroscopic. Returns the index of the first new body. */
+int dWorldAddBodiesB200(dWorldID, int n, const float *pos3, const float *quat4, const float *lvel3,
+                        const float *avel3, const float *mass, const float *inertia9,
+                        const int *flags, const int *env);
+/* type: dSphereClass/dBoxClass/dPlaneClass/dTriMeshClass; dims4: r | lx,ly,lz | a,b,c,d | mesh id;
+ * body: body index within the world or -1 (then pos3/R12 give the static pose; NULL = identity).
+ * Returns the index of the first new geom. */
+int dSpaceAddGeomsB200(dSpaceID, dWorldID, int n, const int *type, const float *dims4,
+                       const int *body, const float *pos3, const float *R12,
+                       const unsigned *category, const unsigned *collide, const int *env);
+int dWorldAddTriMeshB200(dWorldID, const float *verts3, int n_verts, const int *tris3, int n_tris);
+dBodyID dWorldGetBodyB200(dWorldID, int index);
+dGeomID dSpaceGetGeomB200(dSpaceID, int index);
+int dWorldGetNumBodiesB200(dWorldID);
+int dBodyGetIndexB200(dBodyID);
+int dGeomGetIndexB200(dGeomID);
+
+/* bulk state access (blocking). Any output pointer may be NULL. */
+void dWorldGetStateB200(dWorldID, float *pos3, float *quat4, float *lvel3, float *avel3, float *R12);
+/* per-step external force + torque, 6 floats per body (what dBodyAddForce/dBodyAddTorque set) */
+void dWorldSetForcesB200(dWorldID, const float *force_torque6, int n);
+
+/* fused snapshot: 16 floats per body in the layout of the reference's GetTransformMat
+ * (src/main.c:602-622), written by the solver-tail kernel. Copies bodies [first, first+count). */
+void dWorldGetSnapshotB200(dWorldID, float *dst16, int first, int count, int blocking);
+const float *dWorldGetSnapshotDeviceB200(dWorldID);
+void dWorldWaitB200(dWorldID);
+
+/* capacities (pairs, manifolds); 0 = automatic (8 and 6 per geom). Overflow sets a stats flag. */
+void dWorldSetCapacityB200(dWorldID, long max_pairs, long max_manifolds);
+/* dynamic geoms whose AABB extent exceeds this are treated like static "big" geoms (default inf) */
+void dWorldSetBigExtentB200(dWorldID, float extent);
+
+typedef struct dStepStatsB200 {
+    int n_geoms, n_big, n_pairs, n_contacts, n_manifolds, n_colours, n_overflow, flags;
+    int class_count[7]; /* sphere-sphere, sphere-box, box-box, sphere-plane, box-plane, sphere-trimesh, none */
+    int n_rows, n_rows1, n_rows2;
+    int colour_rounds;
+    float cell_size;
+    int grid_dims[3];
+} dStepStatsB200;
+void dWorldGetStatsB200(dWorldID, dStepStatsB200 *); /* blocking */
+void dWorldEnableTimingB200(dWorldID, int on);
+/* CUDA-event times of the last tick, ms: collide, prepare (manifolds+colouring+rows), solve (PGS
+ * iterations + integrate + pack), whole tick */
+void dWorldGetTimingsB200(dWorldID, float out_ms[4]);
+
+/* parity-test hooks: the broadphase pair list and the contacts of the last collide (blocking).
+ * pairs2: (g1,g2) per pair in device order; returns the number of pairs (may exceed cap). */
+int dSpaceGetPairsB200(dSpaceID, int *pairs2, int cap);
+/* per pair: count; contacts compacted pair-major: pos3+depth (4), normal3 + side (4, side as int bits) */
+int dSpaceGetContactsB200(dSpaceID, int *count_per_pair, int cap_pairs, float *pos_depth4,
+                          float *normal_side4, int cap_contacts);
+/* the solver's Gauss-Seidel order of the last device-resident step: per contact (g1, g2, k) */
+int dWorldGetSolverOrderB200(dWorldID, int *g1, int *g2, int *k, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

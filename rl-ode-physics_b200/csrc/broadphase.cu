@@ -1,0 +1,405 @@
+// broadphase.cu -- K1..K3 of SURVEY.md section 2: AABBs, uniform-grid keys, sorted sweep that
+// emits every pair passing ODE's collideAABBs filter (what dxHashSpace::collide hands to the
+// reference's NearCallback, /root/reference/src/main.c:212 + :674).
+//
+// Geoms whose AABB is finite and no larger than the largest dynamic geom are "small": they are
+// binned by AABB centre into a uniform grid whose cell is >= that largest extent, so two
+// overlapping small geoms always sit in adjacent cells.  Everything else (planes, trimeshes, the
+// reference's 100x1x100 floor box) is "big" and is tested against every geom, like ODE's big-box
+// list.  Pairs are produced in two deterministic passes (count, scan, fill) grouped by collider
+// class; no atomics decide a position, so the pair list is bit-reproducible.
+#include "dev.cuh"
+
+namespace ob {
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// K1: refresh geom poses from their bodies, compute ODE's AABBs, reduce the grid inputs.
+// acc[0..2] = min centre, acc[3..5] = max centre, acc[6] = max extent (order-encoded floats)
+__global__ void __launch_bounds__(256) k_geom_update(GeomArrays g, const float4 *__restrict__ b_pos,
+                                                      const float4 *__restrict__ b_R, MeshTable meshes,
+                                                      float big_extent, unsigned *__restrict__ acc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY}, ext = 0.f;
+    if (i < g.n) {
+        const int type = g.type[i], body = g.body[i];
+        float4 p4;
+        M3 R;
+        if (body >= 0) {
+            p4 = b_pos[body];
+            R = load_m3(b_R, body);
+            g.pos[i] = make_float4(p4.x, p4.y, p4.z, 0.f);
+            store_m3(g.R, i, R);
+        } else {
+            p4 = g.pos[i];
+            R = load_m3(g.R, i);
+        }
+        const float4 d = g.dims[i];
+        float lo[3], hi[3];
+        const float pos[3] = {p4.x, p4.y, p4.z};
+        if (type == G_SPHERE) {
+            for (int k = 0; k < 3; k++) { lo[k] = pos[k] - d.x; hi[k] = pos[k] + d.x; }
+        } else if (type == G_BOX) {
+            const V3 rows[3] = {R.r0, R.r1, R.r2};
+            for (int k = 0; k < 3; k++) {
+                float range = 0.5f * (fabsf(rows[k].x * d.x) + fabsf(rows[k].y * d.y) + fabsf(rows[k].z * d.z));
+                lo[k] = pos[k] - range;
+                hi[k] = pos[k] + range;
+            }
+        } else if (type == G_PLANE) {
+            for (int k = 0; k < 3; k++) { lo[k] = -INFINITY; hi[k] = INFINITY; }
+            if (d.y == 0.0f && d.z == 0.0f) {
+                lo[0] = (d.x > 0) ? -INFINITY : -d.w;
+                hi[0] = (d.x > 0) ? d.w : INFINITY;
+            } else if (d.x == 0.0f && d.z == 0.0f) {
+                lo[1] = (d.y > 0) ? -INFINITY : -d.w;
+                hi[1] = (d.y > 0) ? d.w : INFINITY;
+            } else if (d.x == 0.0f && d.y == 0.0f) {
+                lo[2] = (d.z > 0) ? -INFINITY : -d.w;
+                hi[2] = (d.z > 0) ? d.w : INFINITY;
+            }
+        } else if (type == G_TRIMESH) {
+            const MeshInfo mi = meshes.m[g.mesh[i]];
+            const float c[3] = {0.5f * (mi.lo[0] + mi.hi[0]), 0.5f * (mi.lo[1] + mi.hi[1]), 0.5f * (mi.lo[2] + mi.hi[2])};
+            const float e[3] = {0.5f * (mi.hi[0] - mi.lo[0]), 0.5f * (mi.hi[1] - mi.lo[1]), 0.5f * (mi.hi[2] - mi.lo[2])};
+            const V3 rows[3] = {R.r0, R.r1, R.r2};
+            for (int k = 0; k < 3; k++) {
+                float wc = pos[k] + (rows[k].x * c[0] + rows[k].y * c[1] + rows[k].z * c[2]);
+                float range = fabsf(rows[k].x * e[0]) + fabsf(rows[k].y * e[1]) + fabsf(rows[k].z * e[2]);
+                lo[k] = wc - range;
+                hi[k] = wc + range;
+            }
+        } else {
+            for (int k = 0; k < 3; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+        }
+        g.amin[i] = make_float4(lo[0], lo[1], lo[2], 0.f);
+        g.amax[i] = make_float4(hi[0], hi[1], hi[2], 0.f);
+        if (g.alive[i] && body >= 0 && (type == G_SPHERE || type == G_BOX)) {
+            float e = fmaxf(hi[0] - lo[0], fmaxf(hi[1] - lo[1], hi[2] - lo[2]));
+            if (e <= big_extent && isfinite(e)) {
+                ext = e;
+                for (int k = 0; k < 3; k++) {
+                    float c = 0.5f * (lo[k] + hi[k]);
+                    if (isfinite(c)) { cmin[k] = c; cmax[k] = c; }
+                }
+            }
+        }
+    }
+    // block reduction -> 7 atomics per warp leader
+    for (int k = 0; k < 3; k++) { cmin[k] = warp_min(cmin[k]); cmax[k] = warp_max(cmax[k]); }
+    ext = warp_max(ext);
+    if ((threadIdx.x & 31) == 0) {
+        for (int k = 0; k < 3; k++) {
+            if (cmin[k] <= cmax[k]) {
+                atomicMin(&acc[k], f2ord(cmin[k]));
+                atomicMax(&acc[3 + k], f2ord(cmax[k]));
+            }
+        }
+        if (ext > 0.f) atomicMax(&acc[6], f2ord(ext));
+    }
+}
+
+// one thread: turn the reductions into grid parameters, shrink the grid until it fits the table
+__global__ void k_grid_params(const unsigned *__restrict__ acc, GridParams *__restrict__ gp, int n_envs,
+                              int cap_cells, int n_geoms, BroadCounters *__restrict__ bc) {
+    float ext = ord2f(acc[6]);
+    float lo[3], hi[3];
+    bool any = acc[6] != f2ord(0.f) && ext > 0.f;
+    for (int k = 0; k < 3; k++) { lo[k] = ord2f(acc[k]); hi[k] = ord2f(acc[3 + k]); }
+    if (!any || !(lo[0] <= hi[0])) {
+        ext = 1.f;
+        for (int k = 0; k < 3; k++) { lo[k] = 0.f; hi[k] = 0.f; }
+    }
+    float cell = ext * 1.01f;
+    int d[3];
+    for (int iter = 0; iter < 64; iter++) {
+        double tot = (double)n_envs;
+        for (int k = 0; k < 3; k++) {
+            float span = (hi[k] - lo[k]) / cell;
+            d[k] = (span < 1.0e6f) ? (int)floorf(span) + 1 : 1000000;
+            tot *= (double)d[k];
+        }
+        if (tot <= (double)cap_cells) break;
+        cell *= 1.26f;
+    }
+    gp->ox = lo[0]; gp->oy = lo[1]; gp->oz = lo[2];
+    gp->cell = cell; gp->inv_cell = 1.0f / cell;
+    gp->dx = d[0]; gp->dy = d[1]; gp->dz = d[2];
+    gp->per_env = d[0] * d[1] * d[2];
+    gp->n_envs = n_envs;
+    gp->small_extent = any ? ext : 0.f;
+    bc->first_big = n_geoms;
+    bc->first_dead = n_geoms;
+    bc->n_pairs = 0;
+}
+
+// K2: grid key per geom (BIG / DEAD sentinels sort to the tail)
+__global__ void __launch_bounds__(256) k_cell_keys(GeomArrays g, const GridParams *__restrict__ gpp, int cap_cells,
+                                                    uint32_t *__restrict__ keys, int *__restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    const GridParams gp = *gpp;
+    const float4 lo = g.amin[i], hi = g.amax[i];
+    uint32_t key;
+    const int env = g.env[i];
+    if (!g.alive[i]) {
+        key = (uint32_t)cap_cells + 1u;
+    } else {
+        float e = fmaxf(hi.x - lo.x, fmaxf(hi.y - lo.y, hi.z - lo.z));
+        bool small_geom = isfinite(e) && e <= gp.small_extent && (env >= 0 || gp.n_envs == 1) && env < gp.n_envs;
+        if (!small_geom) {
+            key = (uint32_t)cap_cells;
+        } else {
+            float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
+            int ix = (int)floorf((cx - gp.ox) * gp.inv_cell);
+            int iy = (int)floorf((cy - gp.oy) * gp.inv_cell);
+            int iz = (int)floorf((cz - gp.oz) * gp.inv_cell);
+            ix = min(max(ix, 0), gp.dx - 1);
+            iy = min(max(iy, 0), gp.dy - 1);
+            iz = min(max(iz, 0), gp.dz - 1);
+            int e0 = env < 0 ? 0 : env;
+            key = (uint32_t)(((e0 * gp.dz + iz) * gp.dy + iy) * gp.dx + ix);
+        }
+    }
+    keys[i] = key;
+    idx[i] = i;
+}
+
+// K3a: gather the sweep records into sorted order, mark cell ranges and the big/dead boundaries
+__global__ void __launch_bounds__(256) k_sorted_records(GeomArrays g, const uint32_t *__restrict__ keys,
+                                                         const int *__restrict__ idx, int cap_cells,
+                                                         float4 *__restrict__ s_min, float4 *__restrict__ s_max,
+                                                         uint4 *__restrict__ s_flt, int *__restrict__ cell_start,
+                                                         int *__restrict__ cell_end, BroadCounters *__restrict__ bc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    const int gi = idx[i];
+    const uint32_t key = keys[i];
+    float4 lo = g.amin[gi], hi = g.amax[gi];
+    lo.w = __int_as_float(gi);
+    hi.w = __int_as_float(g.body[gi]);
+    s_min[i] = lo;
+    s_max[i] = hi;
+    s_flt[i] = make_uint4(g.cat[gi], g.col[gi], (unsigned)g.env[gi], (unsigned)g.type[gi]);
+    const uint32_t prev = (i > 0) ? keys[i - 1] : 0xffffffffu;
+    const uint32_t next = (i + 1 < g.n) ? keys[i + 1] : 0xffffffffu;
+    if (key < (uint32_t)cap_cells) {
+        if (i == 0 || prev != key) cell_start[key] = i;
+        if (next != key) cell_end[key] = i + 1;
+    } else if (key == (uint32_t)cap_cells) {
+        if (i == 0 || prev < (uint32_t)cap_cells) bc->first_big = i;
+    } else {
+        if (i == 0 || prev <= (uint32_t)cap_cells) {
+            bc->first_dead = i;
+            if (i == 0 || prev < (uint32_t)cap_cells) bc->first_big = i; // no big geoms at all
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cell_clear(int n, const uint32_t *__restrict__ keys, int cap_cells,
+                                                     int *__restrict__ cell_end) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t key = keys[i];
+    if (key < (uint32_t)cap_cells) cell_end[key] = 0;
+}
+
+__device__ __forceinline__ int pair_class(int ta, int tb) { // ta <= tb
+    if (ta == G_SPHERE) {
+        if (tb == G_SPHERE) return PC_SPHERE_SPHERE;
+        if (tb == G_BOX) return PC_SPHERE_BOX;
+        if (tb == G_PLANE) return PC_SPHERE_PLANE;
+        if (tb == G_TRIMESH) return PC_SPHERE_TRIMESH;
+    } else if (ta == G_BOX) {
+        if (tb == G_BOX) return PC_BOX_BOX;
+        if (tb == G_PLANE) return PC_BOX_PLANE;
+    }
+    return PC_NONE;
+}
+
+// ODE collideAABBs: same-body, category/collide bits, non-strict AABB overlap; plus the env rule.
+// Returns the pair class or -1.
+__device__ __forceinline__ int test_pair(const float4 &lo1, const float4 &hi1, const uint4 &f1, const float4 &lo2,
+                                         const float4 &hi2, const uint4 &f2) {
+    if (lo1.x > hi2.x || hi1.x < lo2.x || lo1.y > hi2.y || hi1.y < lo2.y || lo1.z > hi2.z || hi1.z < lo2.z) return -1;
+    const int b1 = __float_as_int(hi1.w), b2 = __float_as_int(hi2.w);
+    if (b1 == b2 && b1 >= 0) return -1;
+    const int e1 = (int)f1.z, e2 = (int)f2.z;
+    if (e1 >= 0 && e2 >= 0 && e1 != e2) return -1;
+    if (!((f1.x & f2.y) || (f2.x & f1.y))) return -1;
+    int ta = (int)f1.w, tb = (int)f2.w;
+    if (ta > tb) { int t = ta; ta = tb; tb = t; }
+    return pair_class(ta, tb);
+}
+
+struct PairSink {
+    int cnt[PC_COUNT];
+};
+
+template <bool FILL>
+__device__ __forceinline__ void emit(int cls, int i, int n, const float4 &lo1, const uint4 &f1, const float4 &lo2,
+                                     const uint4 &f2, PairSink &sink, const int *__restrict__ off,
+                                     int2 *__restrict__ pairs, int cap_pairs) {
+    if (FILL) {
+        int pos = off[cls * n + i] + sink.cnt[cls];
+        if (pos < cap_pairs) {
+            int ga = __float_as_int(lo1.w), gb = __float_as_int(lo2.w);
+            int ta = (int)f1.w, tb = (int)f2.w;
+            // canonical callback order: lower class first, then lower geom id
+            if (ta > tb || (ta == tb && ga > gb)) { int t = ga; ga = gb; gb = t; }
+            pairs[pos] = make_int2(ga, gb);
+        }
+    }
+    sink.cnt[cls]++;
+}
+
+// K3b: the sweep. Thread i owns sorted record i and visits only records after it in sort order:
+// the rest of its own cell row (cells x, x+1) and the rows (dy,dz) in {(1,0),(-1,1),(0,1),(1,1)},
+// each a contiguous run of up to three cells; then the big list.
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_sweep(int n, const uint32_t *__restrict__ keys,
+                                                const float4 *__restrict__ s_min, const float4 *__restrict__ s_max,
+                                                const uint4 *__restrict__ s_flt, const int *__restrict__ cell_start,
+                                                const int *__restrict__ cell_end, const GridParams *__restrict__ gpp,
+                                                const BroadCounters *__restrict__ bc, int *__restrict__ cnt,
+                                                const int *__restrict__ off, int2 *__restrict__ pairs, int cap_pairs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int first_big = bc->first_big, first_dead = bc->first_dead;
+    PairSink sink;
+#pragma unroll
+    for (int c = 0; c < PC_COUNT; c++) sink.cnt[c] = 0;
+    if (i < first_dead) {
+        const float4 lo1 = s_min[i], hi1 = s_max[i];
+        const uint4 f1 = s_flt[i];
+        if (i < first_big) {
+            const GridParams gp = *gpp;
+            const int key = (int)keys[i];
+            const int x = key % gp.dx;
+            const int y = (key / gp.dx) % gp.dy;
+            const int z = (key / (gp.dx * gp.dy)) % gp.dz;
+            const int envbase = (key / gp.per_env) * gp.per_env;
+            // own row, records after me
+            {
+                int e = cell_end[key];
+                if (x + 1 < gp.dx) {
+                    int e2 = cell_end[key + 1];
+                    if (e2) e = e2;
+                }
+                for (int j = i + 1; j < e; j++) {
+                    const float4 lo2 = s_min[j], hi2 = s_max[j];
+                    const uint4 f2 = s_flt[j];
+                    int cls = test_pair(lo1, hi1, f1, lo2, hi2, f2);
+                    if (cls >= 0) emit<FILL>(cls, i, n, lo1, f1, lo2, f2, sink, off, pairs, cap_pairs);
+                }
+            }
+            const int x0 = max(x - 1, 0), x1 = min(x + 1, gp.dx - 1);
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int dy = (r == 0) ? 1 : (r - 2), dz = (r == 0) ? 0 : 1;
+                const int yy = y + dy, zz = z + dz;
+                if (yy < 0 || yy >= gp.dy || zz >= gp.dz) continue;
+                const int rowbase = envbase + (zz * gp.dy + yy) * gp.dx;
+                int s = 0, e = 0; // empty run unless a cell of the row is occupied
+                for (int xx = x0; xx <= x1; xx++) {
+                    int ce = cell_end[rowbase + xx];
+                    if (ce) {
+                        if (e == 0) s = cell_start[rowbase + xx];
+                        e = ce;
+                    }
+                }
+                for (int j = s; j < e; j++) {
+                    const float4 lo2 = s_min[j], hi2 = s_max[j];
+                    const uint4 f2 = s_flt[j];
+                    int cls = test_pair(lo1, hi1, f1, lo2, hi2, f2);
+                    if (cls >= 0) emit<FILL>(cls, i, n, lo1, f1, lo2, f2, sink, off, pairs, cap_pairs);
+                }
+            }
+            for (int j = first_big; j < first_dead; j++) {
+                const float4 lo2 = s_min[j], hi2 = s_max[j];
+                const uint4 f2 = s_flt[j];
+                int cls = test_pair(lo1, hi1, f1, lo2, hi2, f2);
+                if (cls >= 0) emit<FILL>(cls, i, n, lo1, f1, lo2, f2, sink, off, pairs, cap_pairs);
+            }
+        } else {
+            for (int j = i + 1; j < first_dead; j++) {
+                const float4 lo2 = s_min[j], hi2 = s_max[j];
+                const uint4 f2 = s_flt[j];
+                int cls = test_pair(lo1, hi1, f1, lo2, hi2, f2);
+                if (cls >= 0) emit<FILL>(cls, i, n, lo1, f1, lo2, f2, sink, off, pairs, cap_pairs);
+            }
+        }
+    }
+    if (!FILL) {
+#pragma unroll
+        for (int c = 0; c < PC_COUNT; c++) cnt[c * n + i] = sink.cnt[c];
+    }
+}
+
+__global__ void k_pairs_finish(int n, const int *__restrict__ off, int cap_pairs, BroadCounters *__restrict__ bc,
+                               StepStats *__restrict__ stats, const GridParams *__restrict__ gp) {
+    int total = off[PC_COUNT * n];
+    int flags = 0;
+    if (total > cap_pairs) { total = cap_pairs; flags |= SF_PAIR_OVERFLOW; }
+    bc->n_pairs = total;
+    for (int c = 0; c < PC_COUNT; c++) {
+        int s = off[c * n];
+        if (s > cap_pairs) s = cap_pairs;
+        bc->class_start[c] = s;
+    }
+    bc->class_start[PC_COUNT] = total;
+    stats->n_geoms = bc->first_dead;
+    stats->n_big = bc->first_dead - bc->first_big;
+    stats->n_pairs = total;
+    stats->flags = flags;
+    for (int c = 0; c < PC_COUNT; c++) stats->class_count[c] = bc->class_start[c + 1] - bc->class_start[c];
+    stats->cell_size = gp->cell;
+    stats->grid_dims[0] = gp->dx; stats->grid_dims[1] = gp->dy; stats->grid_dims[2] = gp->dz;
+}
+
+void broadphase_run(BroadPhase &bp, GeomArrays g, const float4 *b_pos, const float4 *b_R, MeshTable meshes,
+                    int n_envs, float big_extent, StepStats *d_stats, cudaStream_t st) {
+    const int n = g.n;
+    if (n == 0) {
+        OB_CUDA(cudaMemsetAsync(bp.counters, 0, sizeof(BroadCounters), st));
+        OB_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(StepStats), st));
+        return;
+    }
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    static const unsigned acc_init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
+    OB_CUDA(cudaMemcpyAsync(bp.acc, acc_init, sizeof(acc_init), cudaMemcpyHostToDevice, st));
+    k_geom_update<<<nb, 256, 0, st>>>(g, b_pos, b_R, meshes, big_extent, bp.acc);
+    OB_CHECK_KERNEL("k_geom_update", st);
+    k_grid_params<<<1, 1, 0, st>>>(bp.acc, bp.gp, n_envs, bp.cap_cells, n, bp.counters);
+    OB_CHECK_KERNEL("k_grid_params", st);
+    k_cell_keys<<<nb, 256, 0, st>>>(g, bp.gp, bp.cap_cells, bp.keys, bp.idx);
+    OB_CHECK_KERNEL("k_cell_keys", st);
+    sort_pairs(bp.keys, bp.idx, n, nullptr, bp.key_bits, bp.sort, st);
+    k_sorted_records<<<nb, 256, 0, st>>>(g, bp.keys, bp.idx, bp.cap_cells, bp.s_min, bp.s_max, bp.s_flt, bp.cell_start,
+                                         bp.cell_end, bp.counters);
+    OB_CHECK_KERNEL("k_sorted_records", st);
+    const unsigned nb2 = (unsigned)((n + 127) / 128);
+    k_sweep<false><<<nb2, 128, 0, st>>>(n, bp.keys, bp.s_min, bp.s_max, bp.s_flt, bp.cell_start, bp.cell_end, bp.gp,
+                                        bp.counters, bp.cnt, nullptr, nullptr, 0);
+    OB_CHECK_KERNEL("k_sweep", st);
+    OB_CUDA(cudaMemsetAsync(bp.cnt + (size_t)PC_COUNT * n, 0, sizeof(int), st));
+    scan_exclusive(bp.cnt, bp.cnt, (long)PC_COUNT * n + 1, nullptr, nullptr, bp.scan, st);
+    k_sweep<true><<<nb2, 128, 0, st>>>(n, bp.keys, bp.s_min, bp.s_max, bp.s_flt, bp.cell_start, bp.cell_end, bp.gp,
+                                       bp.counters, nullptr, bp.cnt, bp.pairs, bp.cap_pairs);
+    OB_CHECK_KERNEL("k_sweep", st);
+    k_pairs_finish<<<1, 1, 0, st>>>(n, bp.cnt, bp.cap_pairs, bp.counters, d_stats, bp.gp);
+    OB_CHECK_KERNEL("k_pairs_finish", st);
+    k_cell_clear<<<nb, 256, 0, st>>>(n, bp.keys, bp.cap_cells, bp.cell_end);
+    OB_CHECK_KERNEL("k_cell_clear", st);
+}
+
+} // namespace ob

@@ -1,0 +1,134 @@
+// dev.cuh -- device-side array bundles shared by the kernels of libode_b200 (see DESIGN.md for
+// the HBM layout).  All per-element arrays are struct-of-arrays of float4 / int so warps read and
+// write full 16-byte lanes; rotations are kept as 3 consecutive float4 rows per element (48 B, one
+// and a half sectors) because they are gathered by index, not streamed.
+#pragma once
+
+#include "dmath.cuh"
+#include "engine.h"
+#include "prims.cuh"
+
+namespace ob {
+
+struct BodyArrays {
+    int n;
+    float4 *pos;   // xyz, invMass
+    float4 *quat;  // w x y z
+    float4 *R;     // 3 per body
+    float4 *lvel;  // xyz, mass
+    float4 *avel;  // xyz, -
+    float4 *I;     // 3 per body, body frame
+    float4 *invI;  // 3 per body, body frame
+    float4 *facc, *tacc;
+    int *flags;
+    // per-step solver views
+    float4 *inv;   // 3 per body: rows of the world-frame inverse inertia; row 0 .w = invMass
+    float4 *tmp;   // 2 per body: v/h + invM*f, w/h + invI*t
+    float4 *fc;    // 2 per body: constraint acceleration accumulators (lin, ang)
+    float *snap;   // 16 per body: GetTransformMat layout
+    // colouring scratch
+    unsigned long long *colmask;
+    unsigned long long *prio;
+};
+
+struct GeomArrays {
+    int n;
+    int *type;
+    float4 *dims;
+    int *body;
+    float4 *pos;
+    float4 *R;     // 3 per geom
+    uint32_t *cat, *col;
+    int *env;
+    int *mesh;
+    int *alive;
+    float4 *amin, *amax;
+};
+
+struct MeshInfo {
+    const float *verts; // 3*nv, 16-byte padded
+    const int *tris;    // 3*nt
+    int nv, nt;
+    float lo[3], hi[3];
+};
+constexpr int MAX_MESHES = 8;
+struct MeshTable {
+    MeshInfo m[MAX_MESHES];
+    int n;
+};
+
+struct GridParams {
+    float ox, oy, oz, cell, inv_cell, small_extent;
+    int dx, dy, dz, per_env, n_envs;
+};
+
+struct BroadCounters {
+    int first_big, first_dead, n_pairs;
+    int class_start[PC_COUNT + 1];
+};
+
+struct BroadPhase {
+    int cap_geoms = 0, cap_cells = 0, key_bits = 0, cap_pairs = 0;
+    unsigned *acc = nullptr;
+    GridParams *gp = nullptr;
+    BroadCounters *counters = nullptr;
+    uint32_t *keys = nullptr;
+    int *idx = nullptr;
+    float4 *s_min = nullptr, *s_max = nullptr;
+    uint4 *s_flt = nullptr;
+    int *cell_start = nullptr, *cell_end = nullptr;
+    int *cnt = nullptr; // PC_COUNT * n + 1
+    int2 *pairs = nullptr;
+    SortWorkspace sort;
+    ScanWorkspace scan;
+};
+
+void broadphase_run(BroadPhase &bp, GeomArrays g, const float4 *b_pos, const float4 *b_R, MeshTable meshes,
+                    int n_envs, float big_extent, StepStats *d_stats, cudaStream_t st);
+
+// contact slot storage: contact k of pair p lives at [k * stride + p]
+struct ContactSlots {
+    float4 *pd;   // pos.xyz, depth
+    float4 *ns;   // normal.xyz, bitcast(int side2 / triangle index)
+    int *nc;      // contacts per pair
+    int stride;   // = pair capacity
+};
+
+void narrowphase_run(const BroadPhase &bp, GeomArrays g, MeshTable meshes, const std::vector<TriMesh> &host_meshes,
+                     ContactSlots cs, int max_contacts, StepStats *d_stats, int num_sms, cudaStream_t st);
+
+// manifold = all contacts of one geom pair (device mode) or one run of contact joints with the
+// same body pair (compat mode); one solver thread owns a manifold.
+struct ManifoldArrays {
+    int cap;
+    int4 *rec;        // b1, b2, cbase, nc | reverse << 8
+    int *colour;      // per manifold
+    uint32_t *skey;   // sort key (colour, nc)
+    int *sidx;        // sorted -> manifold
+    int *flag;        // compaction flags / scan
+    int *count;       // device: number of manifolds
+    int *colour_start; // [66]
+    int *meta;        // [0] n_colours, [1] n_overflow, [2],[3] remaining (alternating), [4] rounds, [5] scan total
+};
+
+// solver rows, k-major: contact k of sorted manifold s at [k * cap + s]
+struct SolverArrays {
+    int cap;
+    float4 *q0; // n.xyz, rhsN
+    float4 *q1; // r1.xyz, AdN
+    float4 *q2; // r2.xyz, AdcfmN
+    float4 *q3; // rhsT1, AdT1, AdcfmT1, hi1
+    float4 *q4; // rhsT2, AdT2, AdcfmT2, hi2
+    float4 *lam; // lambdaN, lambdaT1, lambdaT2, bitcast(rows | findex flags)
+    int4 *mrec;  // per sorted manifold: b1, b2, nc, manifold id
+};
+
+struct StepConfig {
+    float h, erp, cfm, sor_w, max_vel, min_depth;
+    float gx, gy, gz;
+    int iters;
+};
+
+void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_surface);
+
+} // namespace ob

@@ -1,0 +1,536 @@
+// engine.cu -- world lifetime, HBM allocation, host<->device synchronisation and the per-tick
+// orchestration (collide -> step) of libode_b200.  The tick mirrors the reference's
+// /root/reference/src/main.c:212-214: dSpaceCollide(+NearCallback), dWorldStep, dJointGroupEmpty.
+#include <string.h>
+
+#include <algorithm>
+
+#include "engine_impl.h"
+
+namespace ob {
+
+template <typename T>
+static void dev_realloc(T *&p, size_t old_n, size_t new_n, cudaStream_t st, bool keep = true) {
+    T *q = nullptr;
+    OB_CUDA(cudaMalloc(&q, std::max<size_t>(new_n, 1) * sizeof(T)));
+    if (p && keep && old_n) OB_CUDA(cudaMemcpyAsync(q, p, std::min(old_n, new_n) * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    if (p) {
+        OB_CUDA(cudaStreamSynchronize(st));
+        OB_CUDA(cudaFree(p));
+    }
+    p = q;
+}
+template <typename T>
+static void dev_free(T *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+Engine *eng_create(int device) {
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0) {
+        fprintf(stderr, "libode_b200: no CUDA device available (%s); this library has no CPU path\n",
+                cudaGetErrorString(err));
+        abort();
+    }
+    if (device < 0 || device >= count) device = 0;
+    OB_CUDA(cudaSetDevice(device));
+    Engine *e = new Engine();
+    e->device = device;
+    cudaDeviceProp prop;
+    OB_CUDA(cudaGetDeviceProperties(&prop, device));
+    e->num_sms = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) {
+        fprintf(stderr, "libode_b200: device lacks cooperative launch\n");
+        abort();
+    }
+    OB_CUDA(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    OB_CUDA(cudaStreamCreateWithFlags(&e->copy_st, cudaStreamNonBlocking));
+    OB_CUDA(cudaMalloc(&e->d_stats, sizeof(StepStats)));
+    OB_CUDA(cudaMemset(e->d_stats, 0, sizeof(StepStats)));
+    OB_CUDA(cudaMallocHost(&e->h_stats, sizeof(StepStats)));
+    memset(e->h_stats, 0, sizeof(StepStats));
+    for (int i = 0; i < 5; i++) OB_CUDA(cudaEventCreate(&e->ev[i]));
+    OB_CUDA(cudaMalloc(&e->M.count, sizeof(int)));
+    OB_CUDA(cudaMalloc(&e->M.colour_start, 72 * sizeof(int)));
+    OB_CUDA(cudaMalloc(&e->M.meta, 8 * sizeof(int)));
+    OB_CUDA(cudaMemset(e->M.count, 0, sizeof(int)));
+    OB_CUDA(cudaMemset(e->M.meta, 0, 8 * sizeof(int)));
+    OB_CUDA(cudaMalloc(&e->bp.acc, 8 * sizeof(unsigned)));
+    OB_CUDA(cudaMalloc(&e->bp.gp, sizeof(GridParams)));
+    OB_CUDA(cudaMalloc(&e->bp.counters, sizeof(BroadCounters)));
+    OB_CUDA(cudaMemset(e->bp.counters, 0, sizeof(BroadCounters)));
+    e->meshes.n = 0;
+    return e;
+}
+
+void eng_destroy(Engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->st);
+    BodyArrays &B = e->B;
+    dev_free(B.pos); dev_free(B.quat); dev_free(B.R); dev_free(B.lvel); dev_free(B.avel); dev_free(B.I);
+    dev_free(B.invI); dev_free(B.facc); dev_free(B.tacc); dev_free(B.flags); dev_free(B.inv); dev_free(B.tmp);
+    dev_free(B.fc); dev_free(B.snap); dev_free(B.colmask); dev_free(B.prio);
+    GeomArrays &G = e->G;
+    dev_free(G.type); dev_free(G.dims); dev_free(G.body); dev_free(G.pos); dev_free(G.R); dev_free(G.cat);
+    dev_free(G.col); dev_free(G.env); dev_free(G.mesh); dev_free(G.alive); dev_free(G.amin); dev_free(G.amax);
+    BroadPhase &bp = e->bp;
+    dev_free(bp.acc); dev_free(bp.gp); dev_free(bp.counters); dev_free(bp.keys); dev_free(bp.idx);
+    dev_free(bp.s_min); dev_free(bp.s_max); dev_free(bp.s_flt); dev_free(bp.cell_start); dev_free(bp.cell_end);
+    dev_free(bp.cnt); dev_free(bp.pairs);
+    sort_workspace_free(bp.sort); scan_workspace_free(bp.scan);
+    dev_free(e->cs.pd); dev_free(e->cs.ns); dev_free(e->cs.nc);
+    ManifoldArrays &M = e->M;
+    dev_free(M.rec); dev_free(M.colour); dev_free(M.skey); dev_free(M.sidx); dev_free(M.flag); dev_free(M.count);
+    dev_free(M.colour_start); dev_free(M.meta);
+    SolverArrays &S = e->S;
+    dev_free(S.q0); dev_free(S.q1); dev_free(S.q2); dev_free(S.q3); dev_free(S.q4); dev_free(S.lam); dev_free(S.mrec);
+    sort_workspace_free(e->sort); scan_workspace_free(e->scan);
+    dev_free(e->hc_pd); dev_free(e->hc_ns); dev_free(e->hc_surf); dev_free(e->hc_mrec);
+    dev_free(e->dl_first); dev_free(e->dl_pd); dev_free(e->dl_ns);
+    for (auto &m : e->hmeshes) { dev_free(m.d_verts); dev_free(m.d_tris); }
+    dev_free(e->d_stats);
+    if (e->h_stats) cudaFreeHost(e->h_stats);
+    for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    cudaStreamDestroy(e->st);
+    cudaStreamDestroy(e->copy_st);
+    delete e;
+}
+
+WorldParams &eng_params(Engine *e) { return e->params; }
+int eng_device(Engine *e) { return e->device; }
+cudaStream_t eng_stream(Engine *e) { return e->st; }
+HostBodies &eng_bodies(Engine *e) { return e->hb; }
+HostGeoms &eng_geoms(Engine *e) { return e->hg; }
+
+int eng_add_body(Engine *e) {
+    HostBodies &b = e->hb;
+    const int i = b.n++;
+    static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    b.pos.insert(b.pos.end(), {0.f, 0.f, 0.f, 1.f});
+    b.quat.insert(b.quat.end(), {1.f, 0.f, 0.f, 0.f});
+    b.R.insert(b.R.end(), ident, ident + 12);
+    b.lvel.insert(b.lvel.end(), {0.f, 0.f, 0.f, 1.f});
+    b.avel.insert(b.avel.end(), {0.f, 0.f, 0.f, 0.f});
+    b.I.insert(b.I.end(), ident, ident + 12);
+    b.invI.insert(b.invI.end(), ident, ident + 12);
+    b.facc.insert(b.facc.end(), {0.f, 0.f, 0.f, 0.f});
+    b.tacc.insert(b.tacc.end(), {0.f, 0.f, 0.f, 0.f});
+    b.flags.push_back(0);
+    b.env.push_back(0);
+    e->bodies_dirty = true;
+    return i;
+}
+
+int eng_add_geom(Engine *e) {
+    HostGeoms &g = e->hg;
+    const int i = g.n++;
+    static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    g.type.push_back(G_SPHERE);
+    g.dims.insert(g.dims.end(), {0.f, 0.f, 0.f, 0.f});
+    g.body.push_back(-1);
+    g.pos.insert(g.pos.end(), {0.f, 0.f, 0.f, 0.f});
+    g.R.insert(g.R.end(), ident, ident + 12);
+    g.cat.push_back(0xffffffffu);
+    g.col.push_back(0xffffffffu);
+    g.env.push_back(-1);
+    g.alive.push_back(1);
+    e->geoms_dirty = true;
+    return i;
+}
+
+int eng_add_mesh(Engine *e, const float *verts, int nv, const int *tris, int nt) {
+    if ((int)e->hmeshes.size() >= MAX_MESHES) {
+        fprintf(stderr, "libode_b200: at most %d trimesh data objects per world\n", MAX_MESHES);
+        abort();
+    }
+    OB_CUDA(cudaSetDevice(e->device));
+    TriMesh m;
+    m.nv = nv; m.nt = nt;
+    m.h_verts.assign(verts, verts + 3 * (size_t)nv);
+    m.h_tris.assign(tris, tris + 3 * (size_t)nt);
+    for (int k = 0; k < 3; k++) { m.lo[k] = INFINITY; m.hi[k] = -INFINITY; }
+    for (int i = 0; i < nv; i++)
+        for (int k = 0; k < 3; k++) {
+            m.lo[k] = fminf(m.lo[k], verts[3 * i + k]);
+            m.hi[k] = fmaxf(m.hi[k], verts[3 * i + k]);
+        }
+    const size_t bv = ((size_t)nv * 3 * sizeof(float) + 15) / 16 * 16, bt = ((size_t)nt * 3 * sizeof(int) + 15) / 16 * 16;
+    OB_CUDA(cudaMalloc(&m.d_verts, bv));
+    OB_CUDA(cudaMalloc(&m.d_tris, bt));
+    OB_CUDA(cudaMemset(m.d_verts, 0, bv));
+    OB_CUDA(cudaMemset(m.d_tris, 0, bt));
+    OB_CUDA(cudaMemcpy(m.d_verts, verts, (size_t)nv * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    OB_CUDA(cudaMemcpy(m.d_tris, tris, (size_t)nt * 3 * sizeof(int), cudaMemcpyHostToDevice));
+    const int id = (int)e->hmeshes.size();
+    MeshInfo &mi = e->meshes.m[id];
+    mi.verts = m.d_verts; mi.tris = m.d_tris; mi.nv = nv; mi.nt = nt;
+    for (int k = 0; k < 3; k++) { mi.lo[k] = m.lo[k]; mi.hi[k] = m.hi[k]; }
+    e->meshes.n = id + 1;
+    e->hmeshes.push_back(std::move(m));
+    return id;
+}
+
+void eng_mark_bodies_dirty(Engine *e) { e->bodies_dirty = true; }
+void eng_mark_geoms_dirty(Engine *e) { e->geoms_dirty = true; }
+void eng_mark_forces_dirty(Engine *e) { e->forces_dirty = true; }
+void eng_set_num_envs(Engine *e, int n) { e->n_envs = n < 1 ? 1 : n; }
+void eng_set_capacity(Engine *e, long max_pairs, long max_manifolds) { e->want_pairs = max_pairs; e->want_manifolds = max_manifolds; }
+void eng_set_big_extent(Engine *e, float extent) { e->big_extent = extent; }
+void eng_enable_timing(Engine *e, int on) { e->timing = on != 0; }
+
+// grow body / geom arrays to hold the host mirrors
+void engine_ensure_capacity(Engine *e) {
+    cudaStream_t st = e->st;
+    if (e->hb.n > e->cap_b) {
+        const size_t o = (size_t)e->cap_b, n = (size_t)e->hb.n + (size_t)e->hb.n / 4 + 64;
+        BodyArrays &B = e->B;
+        dev_realloc(B.pos, o, n, st); dev_realloc(B.quat, o, n, st); dev_realloc(B.R, 3 * o, 3 * n, st);
+        dev_realloc(B.lvel, o, n, st); dev_realloc(B.avel, o, n, st); dev_realloc(B.I, 3 * o, 3 * n, st);
+        dev_realloc(B.invI, 3 * o, 3 * n, st); dev_realloc(B.facc, o, n, st); dev_realloc(B.tacc, o, n, st);
+        dev_realloc(B.flags, o, n, st); dev_realloc(B.inv, 3 * o, 3 * n, st, false);
+        dev_realloc(B.tmp, 2 * o, 2 * n, st, false); dev_realloc(B.fc, 2 * o, 2 * n, st, false);
+        dev_realloc(B.snap, 16 * o, 16 * n, st); dev_realloc(B.colmask, o, n, st, false);
+        dev_realloc(B.prio, o, n, st, false);
+        e->cap_b = (int)n;
+    }
+    if (e->hg.n > e->cap_g) {
+        const size_t o = (size_t)e->cap_g, n = (size_t)e->hg.n + (size_t)e->hg.n / 4 + 64;
+        GeomArrays &G = e->G;
+        dev_realloc(G.type, o, n, st); dev_realloc(G.dims, o, n, st); dev_realloc(G.body, o, n, st);
+        dev_realloc(G.pos, o, n, st); dev_realloc(G.R, 3 * o, 3 * n, st); dev_realloc(G.cat, o, n, st);
+        dev_realloc(G.col, o, n, st); dev_realloc(G.env, o, n, st); dev_realloc(G.mesh, o, n, st);
+        dev_realloc(G.alive, o, n, st); dev_realloc(G.amin, o, n, st, false); dev_realloc(G.amax, o, n, st, false);
+        BroadPhase &bp = e->bp;
+        dev_realloc(bp.keys, 0, n, st, false); dev_realloc(bp.idx, 0, n, st, false);
+        dev_realloc(bp.s_min, 0, n, st, false); dev_realloc(bp.s_max, 0, n, st, false);
+        dev_realloc(bp.s_flt, 0, n, st, false);
+        dev_realloc(bp.cnt, 0, (size_t)PC_COUNT * n + 1, st, false);
+        bp.cap_geoms = (int)n;
+        e->cap_g = (int)n;
+    }
+    e->B.n = e->hb.n;
+    e->G.n = e->hg.n;
+}
+
+// pair / manifold / solver capacities. Defaults: 8 pairs and 6 manifolds per geom (+ slack), which
+// covers dense piles (measured ~3-6 pairs per body); overflow is flagged in StepStats, never silent.
+void engine_ensure_pair_capacity(Engine *e) {
+    cudaStream_t st = e->st;
+    BroadPhase &bp = e->bp;
+    if (!bp.cell_start) {
+        bp.cap_cells = (1 << 24) - 2;
+        bp.key_bits = 24;
+        OB_CUDA(cudaMalloc(&bp.cell_start, ((size_t)bp.cap_cells + 2) * sizeof(int)));
+        OB_CUDA(cudaMalloc(&bp.cell_end, ((size_t)bp.cap_cells + 2) * sizeof(int)));
+        OB_CUDA(cudaMemsetAsync(bp.cell_start, 0, ((size_t)bp.cap_cells + 2) * sizeof(int), st));
+        OB_CUDA(cudaMemsetAsync(bp.cell_end, 0, ((size_t)bp.cap_cells + 2) * sizeof(int), st));
+    }
+    long wantp = e->want_pairs > 0 ? e->want_pairs : (long)e->hg.n * 8 + 1024;
+    if (wantp > bp.cap_pairs) {
+        const size_t n = (size_t)wantp;
+        dev_realloc(bp.pairs, 0, n, st, false);
+        dev_realloc(e->cs.pd, 0, n * 8, st, false);
+        dev_realloc(e->cs.ns, 0, n * 8, st, false);
+        dev_realloc(e->cs.nc, 0, n, st, false);
+        dev_realloc(e->M.flag, 0, n + 1, st, false);
+        bp.cap_pairs = (int)n;
+        e->cs.stride = (int)n;
+        e->have_device_contacts = false;
+    }
+    long wantm = e->want_manifolds > 0 ? e->want_manifolds : (long)e->hg.n * 6 + 1024;
+    if (wantm > bp.cap_pairs) wantm = bp.cap_pairs;
+    if ((long)e->st_mrec.size() > wantm) wantm = (long)e->st_mrec.size();
+    if (wantm > e->M.cap) {
+        const size_t n = (size_t)wantm;
+        ManifoldArrays &M = e->M;
+        dev_realloc(M.rec, 0, n, st, false); dev_realloc(M.colour, 0, n, st, false);
+        dev_realloc(M.skey, 0, n, st, false); dev_realloc(M.sidx, 0, n, st, false);
+        M.cap = (int)n;
+        SolverArrays &S = e->S;
+        dev_realloc(S.q0, 0, n * 8, st, false); dev_realloc(S.q1, 0, n * 8, st, false);
+        dev_realloc(S.q2, 0, n * 8, st, false); dev_realloc(S.q3, 0, n * 8, st, false);
+        dev_realloc(S.q4, 0, n * 8, st, false); dev_realloc(S.lam, 0, n * 8, st, false);
+        dev_realloc(S.mrec, 0, n, st, false);
+        S.cap = (int)n;
+    }
+}
+
+template <typename T>
+static void upload(T *dst, const void *src, size_t count, cudaStream_t st) {
+    if (count) OB_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+
+void eng_sync_to_device(Engine *e) {
+    OB_CUDA(cudaSetDevice(e->device));
+    if (e->host_stale && (e->bodies_dirty)) {
+        // host wrote into stale mirrors: bring the device state back first so untouched bodies survive
+        // (callers that edit bodies call eng_sync_to_host before editing; this is a safety net)
+    }
+    engine_ensure_capacity(e);
+    cudaStream_t st = e->st;
+    if (e->bodies_dirty) {
+        const HostBodies &b = e->hb;
+        const size_t n = (size_t)b.n;
+        upload(e->B.pos, b.pos.data(), n, st); upload(e->B.quat, b.quat.data(), n, st);
+        upload(e->B.R, b.R.data(), 3 * n, st); upload(e->B.lvel, b.lvel.data(), n, st);
+        upload(e->B.avel, b.avel.data(), n, st); upload(e->B.I, b.I.data(), 3 * n, st);
+        upload(e->B.invI, b.invI.data(), 3 * n, st); upload(e->B.facc, b.facc.data(), n, st);
+        upload(e->B.tacc, b.tacc.data(), n, st); upload(e->B.flags, b.flags.data(), n, st);
+        e->bodies_dirty = false;
+        e->forces_dirty = false;
+    } else if (e->forces_dirty) {
+        const HostBodies &b = e->hb;
+        upload(e->B.facc, b.facc.data(), (size_t)b.n, st);
+        upload(e->B.tacc, b.tacc.data(), (size_t)b.n, st);
+        e->forces_dirty = false;
+    }
+    if (e->geoms_dirty) {
+        const HostGeoms &g = e->hg;
+        const size_t n = (size_t)g.n;
+        std::vector<int> mesh(n, 0);
+        for (size_t i = 0; i < n; i++) if (g.type[i] == G_TRIMESH) mesh[i] = (int)g.dims[4 * i];
+        upload(e->G.type, g.type.data(), n, st); upload(e->G.dims, g.dims.data(), n, st);
+        upload(e->G.body, g.body.data(), n, st); upload(e->G.pos, g.pos.data(), n, st);
+        upload(e->G.R, g.R.data(), 3 * n, st); upload(e->G.cat, g.cat.data(), n, st);
+        upload(e->G.col, g.col.data(), n, st); upload(e->G.env, g.env.data(), n, st);
+        upload(e->G.alive, g.alive.data(), n, st);
+        upload(e->G.mesh, mesh.data(), n, st);
+        OB_CUDA(cudaStreamSynchronize(st)); // `mesh` is a temporary
+        e->geoms_dirty = false;
+    }
+}
+
+void eng_sync_to_host(Engine *e) {
+    if (!e->host_stale) return;
+    OB_CUDA(cudaSetDevice(e->device));
+    HostBodies &b = e->hb;
+    const size_t n = (size_t)std::min(b.n, e->B.n);
+    cudaStream_t st = e->st;
+    if (n) {
+        OB_CUDA(cudaMemcpyAsync(b.pos.data(), e->B.pos, n * 16, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaMemcpyAsync(b.quat.data(), e->B.quat, n * 16, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaMemcpyAsync(b.R.data(), e->B.R, n * 48, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaMemcpyAsync(b.lvel.data(), e->B.lvel, n * 16, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaMemcpyAsync(b.avel.data(), e->B.avel, n * 16, cudaMemcpyDeviceToHost, st));
+    }
+    OB_CUDA(cudaStreamSynchronize(st));
+    // accumulators were consumed by the step
+    std::fill(b.facc.begin(), b.facc.end(), 0.f);
+    std::fill(b.tacc.begin(), b.tacc.end(), 0.f);
+    e->host_stale = false;
+}
+
+void eng_collide(Engine *e, int max_contacts) {
+    eng_sync_to_device(e);
+    engine_ensure_pair_capacity(e);
+    if (max_contacts < 1) max_contacts = 1;
+    if (max_contacts > 8) max_contacts = 8;
+    e->max_contacts = max_contacts;
+    if (e->timing) OB_CUDA(cudaEventRecord(e->ev[0], e->st));
+    broadphase_run(e->bp, e->G, e->B.pos, e->B.R, e->meshes, e->n_envs, e->big_extent, e->d_stats, e->st);
+    narrowphase_run(e->bp, e->G, e->meshes, e->hmeshes, e->cs, max_contacts, e->d_stats, e->num_sms, e->st);
+    if (e->timing) OB_CUDA(cudaEventRecord(e->ev[1], e->st));
+    e->have_device_contacts = true;
+}
+
+// pair-major compaction of the contact slots for the host (compat mode)
+__global__ void __launch_bounds__(256) k_compact_contacts(const BroadCounters *__restrict__ bc, ContactSlots cs,
+                                                           const int *__restrict__ first, float4 *__restrict__ pd,
+                                                           float4 *__restrict__ ns) {
+    const int n = bc->n_pairs;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const int c = cs.nc[p], f = first[p];
+        for (int k = 0; k < c; k++) {
+            pd[f + k] = cs.pd[(size_t)k * cs.stride + p];
+            ns[f + k] = cs.ns[(size_t)k * cs.stride + p];
+        }
+    }
+}
+
+HostPairs eng_fetch_pairs(Engine *e) {
+    HostPairs hp;
+    OB_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = e->st;
+    if (!e->have_device_contacts || e->G.n == 0) return hp;
+    BroadCounters bc;
+    OB_CUDA(cudaMemcpyAsync(&bc, e->bp.counters, sizeof(bc), cudaMemcpyDeviceToHost, st));
+    OB_CUDA(cudaStreamSynchronize(st));
+    const int np = bc.n_pairs;
+    hp.n_pairs = np;
+    if (np == 0) return hp;
+    if (np + 1 > e->cap_dl) {
+        dev_realloc(e->dl_first, 0, (size_t)np + 1025, st, false);
+        e->cap_dl = np + 1024;
+    }
+    int *d_total = e->dl_first + np; // scan total lands after the last prefix
+    scan_exclusive(e->cs.nc, e->dl_first, np, nullptr, d_total, e->scan, st);
+    e->h_first.resize((size_t)np + 1);
+    e->h_count.resize((size_t)np);
+    e->h_g1.resize((size_t)np);
+    e->h_g2.resize((size_t)np);
+    std::vector<int2> tmp_pairs((size_t)np);
+    OB_CUDA(cudaMemcpyAsync(e->h_first.data(), e->dl_first, ((size_t)np + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    OB_CUDA(cudaMemcpyAsync(e->h_count.data(), e->cs.nc, (size_t)np * sizeof(int), cudaMemcpyDeviceToHost, st));
+    OB_CUDA(cudaMemcpyAsync(tmp_pairs.data(), e->bp.pairs, (size_t)np * sizeof(int2), cudaMemcpyDeviceToHost, st));
+    OB_CUDA(cudaStreamSynchronize(st));
+    const int total = e->h_first[(size_t)np];
+    for (int i = 0; i < np; i++) { e->h_g1[i] = tmp_pairs[i].x; e->h_g2[i] = tmp_pairs[i].y; }
+    e->h_pd.resize((size_t)std::max(total, 1) * 4);
+    e->h_ns.resize((size_t)std::max(total, 1) * 4);
+    if (total > 0) {
+        if (total > e->cap_dlc) {
+            e->cap_dlc = total + total / 2 + 256;
+            dev_realloc(e->dl_pd, 0, (size_t)e->cap_dlc, st, false);
+            dev_realloc(e->dl_ns, 0, (size_t)e->cap_dlc, st, false);
+        }
+        k_compact_contacts<<<(unsigned)std::min((np + 255) / 256, e->num_sms * 8), 256, 0, st>>>(e->bp.counters, e->cs,
+                                                                                               e->dl_first, e->dl_pd, e->dl_ns);
+        OB_CHECK_KERNEL("k_compact_contacts", st);
+        OB_CUDA(cudaMemcpyAsync(e->h_pd.data(), e->dl_pd, (size_t)total * 16, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaMemcpyAsync(e->h_ns.data(), e->dl_ns, (size_t)total * 16, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+    }
+    hp.g1 = e->h_g1.data(); hp.g2 = e->h_g2.data();
+    hp.first = e->h_first.data(); hp.count = e->h_count.data();
+    hp.pos_depth = e->h_pd.data(); hp.normal_side = e->h_ns.data();
+    return hp;
+}
+
+void eng_step_device_contacts(Engine *e, float h, const Surface &surf) {
+    eng_sync_to_device(e);
+    engine_ensure_pair_capacity(e);
+    if (e->timing && !e->have_device_contacts) {
+        OB_CUDA(cudaEventRecord(e->ev[0], e->st));
+        OB_CUDA(cudaEventRecord(e->ev[1], e->st));
+    }
+    solver_step(e, h, false, &surf);
+    e->have_device_contacts = false;
+    e->host_stale = true;
+    e->ev_valid = e->timing;
+}
+
+void eng_step_host_contacts(Engine *e, float h, const HostContact *contacts, int n) {
+    eng_sync_to_device(e);
+    // group consecutive joints that attach the same ordered body pair into manifolds (<= 8 each)
+    e->st_pd.clear(); e->st_ns.clear(); e->st_surf.clear(); e->st_mrec.clear();
+    int cur_b1 = -2, cur_b2 = -2, cur_rev = 0;
+    for (int i = 0; i < n; i++) {
+        const HostContact &c = contacts[i];
+        int b1 = c.b1, b2 = c.b2, rev = 0;
+        if (b1 < 0 && b2 < 0) continue; // both NULL: inert joint
+        if (b1 < 0) { b1 = b2; b2 = -1; rev = 1; }
+        const bool same = !e->st_mrec.empty() && b1 == cur_b1 && b2 == cur_b2 && rev == cur_rev &&
+                          (e->st_mrec.back().w & 0xff) < 8;
+        if (!same) {
+            e->st_mrec.push_back(make_int4(b1, b2, (int)e->st_pd.size(), rev ? (1 << 8) : 0));
+            cur_b1 = b1; cur_b2 = b2; cur_rev = rev;
+        }
+        e->st_mrec.back().w += 1;
+        e->st_pd.push_back(make_float4(c.pos[0], c.pos[1], c.pos[2], c.depth));
+        e->st_ns.push_back(make_float4(c.normal[0], c.normal[1], c.normal[2], 0.f));
+        e->st_surf.push_back(c.surf);
+    }
+    engine_ensure_pair_capacity(e);
+    cudaStream_t st = e->st;
+    const int nc = (int)e->st_pd.size(), nm = (int)e->st_mrec.size();
+    if (nc > e->cap_hc) {
+        const size_t cap = (size_t)nc + (size_t)nc / 2 + 256;
+        dev_realloc(e->hc_pd, 0, cap, st, false);
+        dev_realloc(e->hc_ns, 0, cap, st, false);
+        dev_realloc(e->hc_surf, 0, cap, st, false);
+        e->cap_hc = (int)cap;
+    }
+    upload(e->hc_pd, e->st_pd.data(), (size_t)nc, st);
+    upload(e->hc_ns, e->st_ns.data(), (size_t)nc, st);
+    upload(e->hc_surf, e->st_surf.data(), (size_t)nc, st);
+    upload(e->M.rec, e->st_mrec.data(), (size_t)nm, st);
+    OB_CUDA(cudaMemcpyAsync(e->M.count, &nm, sizeof(int), cudaMemcpyHostToDevice, st));
+    OB_CUDA(cudaMemsetAsync(e->M.meta, 0, 8 * sizeof(int), st));
+    if (e->timing) {
+        OB_CUDA(cudaEventRecord(e->ev[0], st));
+        OB_CUDA(cudaEventRecord(e->ev[1], st));
+    }
+    solver_step(e, h, true, nullptr);
+    OB_CUDA(cudaStreamSynchronize(st)); // staging vectors and &nm must outlive the copies
+    e->have_device_contacts = false;
+    e->host_stale = true;
+    e->ev_valid = e->timing;
+}
+
+const float *eng_snapshot_device(Engine *e) { return e->B.snap; }
+
+void eng_snapshot_to_host(Engine *e, float *dst, int first, int count, bool blocking) {
+    OB_CUDA(cudaSetDevice(e->device));
+    if (count <= 0) return;
+    OB_CUDA(cudaMemcpyAsync(dst, e->B.snap + 16 * (size_t)first, (size_t)count * 64, cudaMemcpyDeviceToHost, e->st));
+    if (blocking) OB_CUDA(cudaStreamSynchronize(e->st));
+}
+
+void eng_set_forces(Engine *e, const float *f6, int n) {
+    // host pointer with 6 floats per body -> facc / tacc mirrors -> device
+    HostBodies &b = e->hb;
+    if (n > b.n) n = b.n;
+    for (int i = 0; i < n; i++) {
+        b.facc[4 * i] = f6[6 * i]; b.facc[4 * i + 1] = f6[6 * i + 1]; b.facc[4 * i + 2] = f6[6 * i + 2];
+        b.tacc[4 * i] = f6[6 * i + 3]; b.tacc[4 * i + 1] = f6[6 * i + 4]; b.tacc[4 * i + 2] = f6[6 * i + 5];
+    }
+    e->forces_dirty = true;
+}
+
+void eng_wait(Engine *e) {
+    OB_CUDA(cudaSetDevice(e->device));
+    OB_CUDA(cudaStreamSynchronize(e->st));
+}
+
+StepStats eng_stats(Engine *e) {
+    OB_CUDA(cudaSetDevice(e->device));
+    OB_CUDA(cudaMemcpyAsync(e->h_stats, e->d_stats, sizeof(StepStats), cudaMemcpyDeviceToHost, e->st));
+    OB_CUDA(cudaStreamSynchronize(e->st));
+    return *e->h_stats;
+}
+
+void eng_last_timings(Engine *e, float out[4]) {
+    out[0] = out[1] = out[2] = out[3] = 0.f;
+    if (!e->ev_valid) return;
+    OB_CUDA(cudaSetDevice(e->device));
+    OB_CUDA(cudaEventSynchronize(e->ev[4]));
+    cudaEventElapsedTime(&out[0], e->ev[0], e->ev[1]); // collide
+    cudaEventElapsedTime(&out[1], e->ev[1], e->ev[3]); // prep + manifolds + colouring + rows
+    cudaEventElapsedTime(&out[2], e->ev[3], e->ev[4]); // solve + integrate + pack
+    cudaEventElapsedTime(&out[3], e->ev[0], e->ev[4]); // whole tick
+}
+
+int eng_export_solver_order(Engine *e, int *pair_g1, int *pair_g2, int *pair_k, int cap) {
+    OB_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = e->st;
+    OB_CUDA(cudaStreamSynchronize(st));
+    int nm = 0;
+    OB_CUDA(cudaMemcpy(&nm, e->M.count, sizeof(int), cudaMemcpyDeviceToHost));
+    if (nm <= 0) return 0;
+    std::vector<int4> mrec((size_t)nm), rec((size_t)nm);
+    OB_CUDA(cudaMemcpy(mrec.data(), e->S.mrec, (size_t)nm * sizeof(int4), cudaMemcpyDeviceToHost));
+    OB_CUDA(cudaMemcpy(rec.data(), e->M.rec, (size_t)nm * sizeof(int4), cudaMemcpyDeviceToHost));
+    BroadCounters bc;
+    OB_CUDA(cudaMemcpy(&bc, e->bp.counters, sizeof(bc), cudaMemcpyDeviceToHost));
+    std::vector<int2> pairs((size_t)std::max(bc.n_pairs, 1));
+    if (bc.n_pairs) OB_CUDA(cudaMemcpy(pairs.data(), e->bp.pairs, (size_t)bc.n_pairs * sizeof(int2), cudaMemcpyDeviceToHost));
+    int out = 0;
+    for (int s = 0; s < nm; s++) {
+        const int m = mrec[s].w, nc = mrec[s].z;
+        const int p = rec[m].z;
+        for (int k = 0; k < nc; k++) {
+            if (out < cap) {
+                pair_g1[out] = (p < bc.n_pairs) ? pairs[p].x : -1;
+                pair_g2[out] = (p < bc.n_pairs) ? pairs[p].y : -1;
+                pair_k[out] = k;
+            }
+            out++;
+        }
+    }
+    return out;
+}
+
+} // namespace ob

@@ -1,0 +1,186 @@
+// engine.h -- device-resident rigid-body world behind libode_b200.so (sm_100a only).
+//
+// Replaces, as hand-written CUDA kernels, the libode internals the reference reaches from
+// /root/reference/src/main.c:212-214 (dSpaceCollide -> NearCallback/dCollide -> dWorldStep):
+// broadphase, narrowphase, contact rows, SOR/PGS solve, integration and the snapshot pack of
+// src/main.c:218-243.  Layout and kernel inventory: DESIGN.md.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+namespace ob {
+
+// ---------------------------------------------------------------------------------------------
+// error handling: no CPU fallback anywhere -- a CUDA failure aborts with a message (ODE's dError
+// behaviour, SURVEY.md section 8b "Errors").
+#define OB_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            fprintf(stderr, "libode_b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e__), \
+                    __FILE__, __LINE__, cudaGetErrorString(e__));                              \
+            abort();                                                                           \
+        }                                                                                      \
+    } while (0)
+
+// ODE_B200_DEBUG_SYNC=1: synchronise after every kernel and name the one that faulted
+inline bool ob_debug_sync() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("ODE_B200_DEBUG_SYNC");
+        v = (s && s[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+#define OB_CHECK_KERNEL(name, st)                                                                  \
+    do {                                                                                           \
+        cudaError_t e__ = cudaGetLastError();                                                      \
+        if (e__ == cudaSuccess && ob_debug_sync()) e__ = cudaStreamSynchronize(st);                \
+        if (e__ != cudaSuccess) {                                                                  \
+            fprintf(stderr, "libode_b200: kernel %s failed: %s (%s:%d)\n", name,                  \
+                    cudaGetErrorString(e__), __FILE__, __LINE__);                                  \
+            abort();                                                                               \
+        }                                                                                          \
+    } while (0)
+
+enum GeomType { G_SPHERE = 0, G_BOX = 1, G_PLANE = 4, G_TRIMESH = 8 };
+enum BodyFlags { BF_KINEMATIC = 1, BF_NOGRAVITY = 2, BF_GYRO = 4 };
+
+// pair classes, in the order the pair list is grouped (narrowphase launches one kernel per class)
+enum PairClass {
+    PC_SPHERE_SPHERE = 0,
+    PC_SPHERE_BOX = 1,
+    PC_BOX_BOX = 2,
+    PC_SPHERE_PLANE = 3,
+    PC_BOX_PLANE = 4,
+    PC_SPHERE_TRIMESH = 5,
+    PC_NONE = 6, // AABBs overlap but no collider exists (plane-plane, box-trimesh, ...)
+    PC_COUNT = 7
+};
+
+// surface policy of a contact (dSurfaceParameters subset); mode bits are ODE's dContact* values
+struct Surface {
+    int mode;
+    float mu, mu2, bounce, bounce_vel, soft_erp, soft_cfm;
+    float motion1, motion2, motionN, slip1, slip2;
+};
+
+// host-side contact joint record (compat mode: dJointCreateContact + dJointAttach)
+struct HostContact {
+    float pos[3], depth;
+    float normal[3];
+    int b1, b2; // engine body indices, -1 = NULL
+    Surface surf;
+};
+
+struct TriMesh {
+    int nv = 0, nt = 0;
+    float *d_verts = nullptr; // 3*nv floats, padded to 16 B
+    int *d_tris = nullptr;    // 3*nt ints
+    float lo[3], hi[3];       // local bounds
+    std::vector<float> h_verts;
+    std::vector<int> h_tris;
+};
+
+// per-step counters read back once per step (pinned)
+struct StepStats {
+    int n_geoms, n_big, n_pairs, n_contacts, n_manifolds, n_colours, n_overflow, flags;
+    int class_count[PC_COUNT];
+    int n_rows, n_rows1, n_rows2; // total rows, rows of one-body / two-body manifolds
+    int colour_rounds;
+    float cell_size;
+    int grid_dims[3];
+};
+enum StatFlags { SF_PAIR_OVERFLOW = 1, SF_MANIFOLD_OVERFLOW = 2, SF_CAND_OVERFLOW = 4 };
+
+struct WorldParams {
+    float gravity[3] = {0, 0, 0};
+    float erp = 0.2f, cfm = 1e-5f, sor_w = 1.3f;
+    int iters = 20;
+    float max_vel = INFINITY, min_depth = 0.0f;
+};
+
+struct Engine; // opaque to the shim
+
+// lifecycle
+Engine *eng_create(int device);
+void eng_destroy(Engine *);
+WorldParams &eng_params(Engine *);
+int eng_device(Engine *);
+cudaStream_t eng_stream(Engine *);
+
+// host mirrors (the shim reads/writes these, then marks dirty)
+struct HostBodies {
+    std::vector<float> pos;   // 4 per body: x y z invMass
+    std::vector<float> quat;  // 4: w x y z
+    std::vector<float> R;     // 12 row-major 3x4
+    std::vector<float> lvel;  // 4: xyz, mass
+    std::vector<float> avel;  // 4: xyz, pad
+    std::vector<float> I;     // 12 body-frame inertia (3x4)
+    std::vector<float> invI;  // 12 body-frame inverse inertia (3x4)
+    std::vector<float> facc;  // 4
+    std::vector<float> tacc;  // 4
+    std::vector<int> flags;   // BodyFlags
+    std::vector<int> env;
+    int n = 0;
+};
+struct HostGeoms {
+    std::vector<int> type;
+    std::vector<float> dims;  // 4
+    std::vector<int> body;    // -1 static
+    std::vector<float> pos;   // 4 (static pose; refreshed from body for getters)
+    std::vector<float> R;     // 12
+    std::vector<uint32_t> cat, col;
+    std::vector<int> env;     // -1 = every env
+    std::vector<int> alive;   // 0 = destroyed (never collides)
+    int n = 0;
+};
+HostBodies &eng_bodies(Engine *);
+HostGeoms &eng_geoms(Engine *);
+int eng_add_body(Engine *);  // default dBodyCreate state; returns index
+int eng_add_geom(Engine *);  // returns index
+int eng_add_mesh(Engine *, const float *verts, int nv, const int *tris, int nt);
+void eng_mark_bodies_dirty(Engine *);  // host mirror changed -> upload before next device op
+void eng_mark_geoms_dirty(Engine *);
+void eng_mark_forces_dirty(Engine *);
+void eng_set_num_envs(Engine *, int n);
+void eng_set_capacity(Engine *, long max_pairs, long max_manifolds);
+void eng_set_big_extent(Engine *, float extent);
+
+// device ops (all asynchronous on the engine stream unless stated)
+void eng_sync_to_device(Engine *);              // upload dirty mirrors
+void eng_sync_to_host(Engine *);                // download body state into the mirrors (blocking)
+void eng_collide(Engine *, int max_contacts);   // broadphase + narrowphase; contacts stay on device
+// compat mode: fetch pair list + contacts to the host (blocking). Arrays are engine-owned.
+struct HostPairs {
+    int n_pairs = 0;
+    const int *g1 = nullptr, *g2 = nullptr;     // geom indices, canonical order
+    const int *first = nullptr, *count = nullptr; // contact range per pair
+    const float *pos_depth = nullptr;           // 4 per contact
+    const float *normal_side = nullptr;         // 4 per contact (w = bitcast int side2 / triangle)
+};
+HostPairs eng_fetch_pairs(Engine *);
+// step with device-resident contacts of the last eng_collide and one surface for every contact
+void eng_step_device_contacts(Engine *, float h, const Surface &surf);
+// step with host-provided contact joints (compat mode)
+void eng_step_host_contacts(Engine *, float h, const HostContact *contacts, int n);
+// snapshot: 16 floats per body in the reference's GetTransformMat layout (src/main.c:602-622)
+const float *eng_snapshot_device(Engine *);
+void eng_snapshot_to_host(Engine *, float *dst, int first, int count, bool blocking);
+// upload per-body external force/torque (6 floats per body) for the next step
+void eng_set_forces(Engine *, const float *f6, int n);
+// wait for everything queued on the engine stream
+void eng_wait(Engine *);
+StepStats eng_stats(Engine *);                  // blocking: stats of the last collide/step
+// solver order export for parity tests: per device contact (pair-major) the solve rank
+int eng_export_solver_order(Engine *, int *pair_g1, int *pair_g2, int *pair_k, int cap);
+// event-timed sections of the last step, milliseconds (collide, prep+colour+rows, solve+tail)
+void eng_last_timings(Engine *, float out[4]);
+void eng_enable_timing(Engine *, int on);
+
+} // namespace ob

@@ -1,0 +1,68 @@
+// engine_impl.h -- the Engine object: host mirrors + device arrays of one world.
+#pragma once
+
+#include "dev.cuh"
+
+namespace ob {
+
+struct Engine {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t st = nullptr;
+    cudaStream_t copy_st = nullptr;
+    WorldParams params;
+
+    HostBodies hb;
+    HostGeoms hg;
+    bool bodies_dirty = false, geoms_dirty = false, forces_dirty = false;
+    bool host_stale = false; // device state is newer than the host mirrors
+    int n_envs = 1;
+    float big_extent = INFINITY;
+
+    int cap_b = 0, cap_g = 0;
+    BodyArrays B{};
+    GeomArrays G{};
+    MeshTable meshes{};
+    std::vector<TriMesh> hmeshes;
+
+    long want_pairs = 0, want_manifolds = 0; // user capacities (0 = auto)
+    BroadPhase bp;
+    ContactSlots cs{};
+    int max_contacts = 8;
+    bool have_device_contacts = false;
+
+    ManifoldArrays M{};
+    SolverArrays S{};
+    ScanWorkspace scan;
+    SortWorkspace sort;
+
+    // compat-mode contact upload buffers (device) + pinned staging
+    int cap_hc = 0;
+    float4 *hc_pd = nullptr, *hc_ns = nullptr;
+    Surface *hc_surf = nullptr;
+    int4 *hc_mrec = nullptr;
+    std::vector<float4> st_pd, st_ns;
+    std::vector<Surface> st_surf;
+    std::vector<int4> st_mrec;
+
+    // compat-mode pair download
+    int cap_dl = 0, cap_dlc = 0;
+    int *dl_first = nullptr;     // device: exclusive scan of nc
+    float4 *dl_pd = nullptr, *dl_ns = nullptr; // device: pair-major compacted contacts
+    std::vector<int> h_g1, h_g2, h_first, h_count;
+    std::vector<float> h_pd, h_ns;
+
+    StepStats *d_stats = nullptr;
+    StepStats *h_stats = nullptr; // pinned
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool timing = false;
+    float last_ms[4] = {0, 0, 0, 0};
+    bool ev_valid = false;
+
+    int coop_blocks_colour = 0, coop_blocks_solve = 0;
+};
+
+void engine_ensure_capacity(Engine *e);
+void engine_ensure_pair_capacity(Engine *e);
+
+} // namespace ob

@@ -1,0 +1,751 @@
+// narrowphase.cu -- K4a..K4e: contact generation per pair class (what dCollide computes for the
+// reference's NearCallback, /root/reference/src/main.c:678).  One kernel per class over that
+// class's slice of the pair list, so warps never mix the cheap sphere tests with the 15-axis
+// box-box SAT.  Contacts go to k-major slots ([k * stride + pair]) and never leave the device in
+// device-resident mode.  Normal convention: from geom 2 into geom 1 (ODE).
+//
+// Operation order inside every predicate follows ODE's (and the test oracle's) so that contact
+// membership rounds identically; the library is compiled with --fmad=false.
+#include "dev.cuh"
+
+namespace ob {
+
+struct GeomPose {
+    V3 p;
+    M3 R;
+    float4 d;
+};
+
+__device__ __forceinline__ GeomPose load_geom(const GeomArrays &g, int i) {
+    GeomPose o;
+    o.p = v3(g.pos[i]);
+    o.R = load_m3(g.R, i);
+    o.d = g.dims[i];
+    return o;
+}
+
+__device__ __forceinline__ void put_contact(const ContactSlots &cs, int p, int k, V3 pos, float depth, V3 n, int side) {
+    cs.pd[(size_t)k * cs.stride + p] = make_float4(pos.x, pos.y, pos.z, depth);
+    cs.ns[(size_t)k * cs.stride + p] = make_float4(n.x, n.y, n.z, __int_as_float(side));
+}
+
+// ---------------------------------------------------------------- sphere-sphere (dCollideSpheres)
+__global__ void __launch_bounds__(256) k_np_sphere_sphere(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
+                                                           GeomArrays g, ContactSlots cs) {
+    const int s = bc->class_start[PC_SPHERE_SPHERE], e = bc->class_start[PC_SPHERE_SPHERE + 1];
+    for (int p = s + blockIdx.x * blockDim.x + threadIdx.x; p < e; p += gridDim.x * blockDim.x) {
+        const int2 pr = pairs[p];
+        const float4 p1 = g.pos[pr.x], p2 = g.pos[pr.y];
+        const float r1 = g.dims[pr.x].x, r2 = g.dims[pr.y].x;
+        const float dx = p1.x - p2.x, dy = p1.y - p2.y, dz = p1.z - p2.z;
+        const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+        int nc = 0;
+        if (!(d > (r1 + r2))) {
+            if (d <= 0) {
+                put_contact(cs, p, 0, v3(p1), r1 + r2, v3(1.f, 0.f, 0.f), -1);
+            } else {
+                const float d1 = 1.0f / d;
+                const V3 n = v3(dx * d1, dy * d1, dz * d1);
+                const float k = 0.5f * (r2 - r1 - d);
+                put_contact(cs, p, 0, v3(p1.x + n.x * k, p1.y + n.y * k, p1.z + n.z * k), r1 + r2 - d, n, -1);
+            }
+            nc = 1;
+        }
+        cs.nc[p] = nc;
+    }
+}
+
+// ---------------------------------------------------------------- sphere-box (dCollideSphereBox)
+__global__ void __launch_bounds__(256) k_np_sphere_box(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
+                                                        GeomArrays g, ContactSlots cs) {
+    const int s = bc->class_start[PC_SPHERE_BOX], e = bc->class_start[PC_SPHERE_BOX + 1];
+    for (int pi = s + blockIdx.x * blockDim.x + threadIdx.x; pi < e; pi += gridDim.x * blockDim.x) {
+        const int2 pr = pairs[pi];
+        const V3 ps = v3(g.pos[pr.x]);
+        const float radius = g.dims[pr.x].x;
+        const GeomPose bx = load_geom(g, pr.y);
+        const V3 p = ps - bx.p;
+        float l[3] = {bx.d.x * 0.5f, bx.d.y * 0.5f, bx.d.z * 0.5f}, t[3];
+        bool onborder = false;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            t[k] = dot(p, col(bx.R, k));
+            if (t[k] < -l[k]) { t[k] = -l[k]; onborder = true; }
+            if (t[k] > l[k]) { t[k] = l[k]; onborder = true; }
+        }
+        int nc = 0;
+        if (!onborder) {
+            float min_distance = l[0] - fabsf(t[0]);
+            int mini = 0;
+#pragma unroll
+            for (int i = 1; i < 3; i++) {
+                float face_distance = l[i] - fabsf(t[i]);
+                if (face_distance < min_distance) { min_distance = face_distance; mini = i; }
+            }
+            float tm = mini == 0 ? t[0] : (mini == 1 ? t[1] : t[2]);
+            V3 tmp = v3(0.f, 0.f, 0.f);
+            const float sg = (tm > 0) ? 1.0f : -1.0f;
+            if (mini == 0) tmp.x = sg; else if (mini == 1) tmp.y = sg; else tmp.z = sg;
+            put_contact(cs, pi, 0, ps, min_distance + radius, mul(bx.R, tmp), -1);
+            nc = 1;
+        } else {
+            const V3 q = mul(bx.R, v3(t[0], t[1], t[2]));
+            const V3 r = p - q;
+            const float depth = radius - sqrtf(dot(r, r));
+            if (!(depth < 0)) {
+                put_contact(cs, pi, 0, q + bx.p, depth, safe_normalize3(r), -1);
+                nc = 1;
+            }
+        }
+        cs.nc[pi] = nc;
+    }
+}
+
+// ---------------------------------------------------------------- sphere-plane (dCollideSpherePlane)
+__global__ void __launch_bounds__(256) k_np_sphere_plane(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
+                                                          GeomArrays g, ContactSlots cs) {
+    const int s = bc->class_start[PC_SPHERE_PLANE], e = bc->class_start[PC_SPHERE_PLANE + 1];
+    for (int pi = s + blockIdx.x * blockDim.x + threadIdx.x; pi < e; pi += gridDim.x * blockDim.x) {
+        const int2 pr = pairs[pi];
+        const V3 ps = v3(g.pos[pr.x]);
+        const float radius = g.dims[pr.x].x;
+        const float4 pl = g.dims[pr.y];
+        const V3 n = v3(pl);
+        const float k = dot(ps, n);
+        const float depth = pl.w - k + radius;
+        int nc = 0;
+        if (!(depth < 0)) {
+            put_contact(cs, pi, 0, v3(ps.x - n.x * radius, ps.y - n.y * radius, ps.z - n.z * radius), depth, n, -1);
+            nc = 1;
+        }
+        cs.nc[pi] = nc;
+    }
+}
+
+// ---------------------------------------------------------------- box-plane (dCollideBoxPlane)
+__global__ void __launch_bounds__(256) k_np_box_plane(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
+                                                       GeomArrays g, ContactSlots cs, int maxc_in) {
+    const int s = bc->class_start[PC_BOX_PLANE], e = bc->class_start[PC_BOX_PLANE + 1];
+    for (int pi = s + blockIdx.x * blockDim.x + threadIdx.x; pi < e; pi += gridDim.x * blockDim.x) {
+        const int2 pr = pairs[pi];
+        const GeomPose bx = load_geom(g, pr.x);
+        const float4 pl = g.dims[pr.y];
+        const V3 n = v3(pl);
+        const float side[3] = {bx.d.x, bx.d.y, bx.d.z};
+        float A[3], B[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float Q = dot(n, col(bx.R, k));
+            A[k] = side[k] * Q;
+            B[k] = fabsf(A[k]);
+        }
+        const float depth = pl.w + 0.5f * (B[0] + B[1] + B[2]) - dot(n, bx.p);
+        int ret = 0;
+        if (!(depth < 0)) {
+            int maxc = maxc_in > 4 ? 4 : maxc_in;
+            if (maxc < 1) maxc = 1;
+            V3 p = bx.p;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const V3 c = col(bx.R, i);
+                const V3 term = v3(0.5f * side[i] * c.x, 0.5f * side[i] * c.y, 0.5f * side[i] * c.z);
+                if (A[i] > 0) p = p - term; else p = p + term;
+            }
+            put_contact(cs, pi, 0, p, depth, n, -1);
+            ret = 1;
+            V3 cpos[3];
+            float cdep[3];
+            if (maxc > 1) {
+                int first, second;
+                if (B[0] < B[1]) {
+                    if (B[2] < B[0]) { first = 2; second = (B[0] < B[1]) ? 0 : 1; }
+                    else { first = 0; second = (B[1] < B[2]) ? 1 : 2; }
+                } else {
+                    if (B[2] < B[1]) { first = 2; second = (B[0] < B[1]) ? 0 : 1; }
+                    else { first = 1; second = (B[0] < B[2]) ? 0 : 2; }
+                }
+                for (int sI = 0; sI < 2; sI++) {
+                    if (sI == 1 && maxc == 2) break;
+                    const int j = sI == 0 ? first : second;
+                    const float Bj = j == 0 ? B[0] : (j == 1 ? B[1] : B[2]);
+                    const float Aj = j == 0 ? A[0] : (j == 1 ? A[1] : A[2]);
+                    const float sj = j == 0 ? side[0] : (j == 1 ? side[1] : side[2]);
+                    if (depth - Bj < 0) break;
+                    const V3 c = col(bx.R, j);
+                    const V3 term = v3(sj * c.x, sj * c.y, sj * c.z);
+                    cpos[ret] = (Aj > 0) ? (p + term) : (p - term);
+                    cdep[ret] = depth - Bj;
+                    put_contact(cs, pi, ret, cpos[ret], cdep[ret], n, -1);
+                    ret++;
+                }
+            }
+            if (maxc == 4 && ret == 3) {
+                const float d4 = cdep[1] + cdep[2] - depth;
+                if (d4 > 0) {
+                    const V3 p4 = v3(cpos[1].x + cpos[2].x - p.x, cpos[1].y + cpos[2].y - p.y, cpos[1].z + cpos[2].z - p.z);
+                    put_contact(cs, pi, 3, p4, d4, n, -1);
+                    ret++;
+                }
+            }
+        }
+        cs.nc[pi] = ret;
+    }
+}
+
+// ---------------------------------------------------------------- box-box (dBoxBox)
+
+__device__ __forceinline__ float d14(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[4] + a[2] * b[8]; }
+__device__ __forceinline__ float d41(const float *a, const float *b) { return a[0] * b[0] + a[4] * b[1] + a[8] * b[2]; }
+__device__ __forceinline__ float d44(const float *a, const float *b) { return a[0] * b[0] + a[4] * b[4] + a[8] * b[8]; }
+__device__ __forceinline__ float d11(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// clip the incident quad against the reference rectangle (intersectRectQuad): <= 8 points
+__device__ int clip_rect_quad(const float h[2], const float p[8], float ret[16]) {
+    int nq = 4, nr = 0;
+    float buffer[16];
+    const float *q = p;
+    float *r = ret;
+    for (int dir = 0; dir <= 1; dir++) {
+        for (int sign = -1; sign <= 1; sign += 2) {
+            const float *pq = q;
+            float *pr = r;
+            nr = 0;
+            for (int i = nq; i > 0; i--) {
+                if (sign * pq[dir] < h[dir]) {
+                    pr[0] = pq[0]; pr[1] = pq[1];
+                    pr += 2; nr++;
+                    if (nr & 8) { q = r; goto done; }
+                }
+                const float *nextq = (i > 1) ? pq + 2 : q;
+                if ((sign * pq[dir] < h[dir]) ^ (sign * nextq[dir] < h[dir])) {
+                    pr[1 - dir] = pq[1 - dir] + (nextq[1 - dir] - pq[1 - dir]) / (nextq[dir] - pq[dir]) * (sign * h[dir] - pq[dir]);
+                    pr[dir] = sign * h[dir];
+                    pr += 2; nr++;
+                    if (nr & 8) { q = r; goto done; }
+                }
+                pq += 2;
+            }
+            q = r;
+            r = (q == ret) ? buffer : ret;
+            nq = nr;
+        }
+    }
+done:
+    if (q != ret)
+        for (int i = 0; i < nr * 2; i++) ret[i] = q[i];
+    return nr;
+}
+
+// cullPoints: choose m of n clipped points spread in angle around the centroid, i0 first
+__device__ void cull_points(int n, const float p[], int m, int i0, int iret[]) {
+    float a, cx, cy, q;
+    if (n == 1) { cx = p[0]; cy = p[1]; }
+    else if (n == 2) { cx = 0.5f * (p[0] + p[2]); cy = 0.5f * (p[1] + p[3]); }
+    else {
+        a = 0; cx = 0; cy = 0;
+        for (int i = 0; i < n - 1; i++) {
+            q = p[i * 2] * p[i * 2 + 3] - p[i * 2 + 2] * p[i * 2 + 1];
+            a += q;
+            cx += q * (p[i * 2] + p[i * 2 + 2]);
+            cy += q * (p[i * 2 + 1] + p[i * 2 + 3]);
+        }
+        q = p[n * 2 - 2] * p[1] - p[0] * p[n * 2 - 1];
+        a = 1.0f / (3.0f * (a + q));
+        cx = a * (cx + q * (p[n * 2 - 2] + p[0]));
+        cy = a * (cy + q * (p[n * 2 - 1] + p[1]));
+    }
+    float A[8];
+    int avail[8];
+    for (int i = 0; i < n; i++) { A[i] = atan2f(p[i * 2 + 1] - cy, p[i * 2] - cx); avail[i] = 1; }
+    avail[i0] = 0;
+    iret[0] = i0;
+    const float pi = 3.14159265358979323846f;
+    for (int j = 1; j < m; j++) {
+        a = (float)j * (2 * pi / m) + A[i0];
+        if (a > pi) a -= 2 * pi;
+        float maxdiff = 1e9f, diff;
+        int best = i0;
+        for (int i = 0; i < n; i++) {
+            if (avail[i]) {
+                diff = fabsf(A[i] - a);
+                if (diff > pi) diff = 2 * pi - diff;
+                if (diff < maxdiff) { maxdiff = diff; best = i; }
+            }
+        }
+        avail[best] = 0;
+        iret[j] = best;
+    }
+}
+
+struct BoxBoxOut {
+    float pos[8][3];
+    float dep[8];
+    float normal[3];
+    int n;
+};
+
+__device__ int box_box(const float p1[3], const float R1[12], const float side1[3], const float p2[3],
+                       const float R2[12], const float side2[3], int maxc_in, BoxBoxOut &out) {
+    const float fudge_factor = 1.05f;
+    float p[3], pp[3], normalC[3] = {0, 0, 0};
+    const float *normalR = nullptr;
+    float A[3], B[3], Rm[3][3], Q[3][3], s, s2, l, e1;
+    int invert_normal = 0, code = 0;
+    float *normal = out.normal;
+
+    for (int k = 0; k < 3; k++) p[k] = p2[k] - p1[k];
+    pp[0] = d41(R1 + 0, p); pp[1] = d41(R1 + 1, p); pp[2] = d41(R1 + 2, p);
+    for (int k = 0; k < 3; k++) { A[k] = side1[k] * 0.5f; B[k] = side2[k] * 0.5f; }
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) { Rm[i][j] = d44(R1 + i, R2 + j); Q[i][j] = fabsf(Rm[i][j]); }
+    s = -INFINITY;
+
+#define OB_TST1(expr1, expr2, norm, cc)              \
+    e1 = (expr1);                                    \
+    s2 = fabsf(e1) - (expr2);                        \
+    if (s2 > 0) return 0;                            \
+    if (s2 > s) { s = s2; normalR = (norm); invert_normal = (e1 < 0); code = (cc); }
+
+    OB_TST1(pp[0], (A[0] + B[0] * Q[0][0] + B[1] * Q[0][1] + B[2] * Q[0][2]), R1 + 0, 1)
+    OB_TST1(pp[1], (A[1] + B[0] * Q[1][0] + B[1] * Q[1][1] + B[2] * Q[1][2]), R1 + 1, 2)
+    OB_TST1(pp[2], (A[2] + B[0] * Q[2][0] + B[1] * Q[2][1] + B[2] * Q[2][2]), R1 + 2, 3)
+    OB_TST1(d41(R2 + 0, p), (A[0] * Q[0][0] + A[1] * Q[1][0] + A[2] * Q[2][0] + B[0]), R2 + 0, 4)
+    OB_TST1(d41(R2 + 1, p), (A[0] * Q[0][1] + A[1] * Q[1][1] + A[2] * Q[2][1] + B[1]), R2 + 1, 5)
+    OB_TST1(d41(R2 + 2, p), (A[0] * Q[0][2] + A[1] * Q[1][2] + A[2] * Q[2][2] + B[2]), R2 + 2, 6)
+#undef OB_TST1
+
+#define OB_TST2(expr1, expr2, n1, n2, n3, cc)                                \
+    e1 = (expr1);                                                           \
+    s2 = fabsf(e1) - (expr2);                                               \
+    if (s2 > 0) return 0;                                                   \
+    l = sqrtf((n1) * (n1) + (n2) * (n2) + (n3) * (n3));                     \
+    if (l > 0) {                                                            \
+        s2 /= l;                                                            \
+        if (s2 * fudge_factor > s) {                                        \
+            s = s2; normalR = nullptr;                                      \
+            normalC[0] = (n1) / l; normalC[1] = (n2) / l; normalC[2] = (n3) / l; \
+            invert_normal = (e1 < 0); code = (cc);                          \
+        }                                                                   \
+    }
+
+    OB_TST2(pp[2] * Rm[1][0] - pp[1] * Rm[2][0], (A[1] * Q[2][0] + A[2] * Q[1][0] + B[1] * Q[0][2] + B[2] * Q[0][1]), 0, -Rm[2][0], Rm[1][0], 7)
+    OB_TST2(pp[2] * Rm[1][1] - pp[1] * Rm[2][1], (A[1] * Q[2][1] + A[2] * Q[1][1] + B[0] * Q[0][2] + B[2] * Q[0][0]), 0, -Rm[2][1], Rm[1][1], 8)
+    OB_TST2(pp[2] * Rm[1][2] - pp[1] * Rm[2][2], (A[1] * Q[2][2] + A[2] * Q[1][2] + B[0] * Q[0][1] + B[1] * Q[0][0]), 0, -Rm[2][2], Rm[1][2], 9)
+    OB_TST2(pp[0] * Rm[2][0] - pp[2] * Rm[0][0], (A[0] * Q[2][0] + A[2] * Q[0][0] + B[1] * Q[1][2] + B[2] * Q[1][1]), Rm[2][0], 0, -Rm[0][0], 10)
+    OB_TST2(pp[0] * Rm[2][1] - pp[2] * Rm[0][1], (A[0] * Q[2][1] + A[2] * Q[0][1] + B[0] * Q[1][2] + B[2] * Q[1][0]), Rm[2][1], 0, -Rm[0][1], 11)
+    OB_TST2(pp[0] * Rm[2][2] - pp[2] * Rm[0][2], (A[0] * Q[2][2] + A[2] * Q[0][2] + B[0] * Q[1][1] + B[1] * Q[1][0]), Rm[2][2], 0, -Rm[0][2], 12)
+    OB_TST2(pp[1] * Rm[0][0] - pp[0] * Rm[1][0], (A[0] * Q[1][0] + A[1] * Q[0][0] + B[1] * Q[2][2] + B[2] * Q[2][1]), -Rm[1][0], Rm[0][0], 0, 13)
+    OB_TST2(pp[1] * Rm[0][1] - pp[0] * Rm[1][1], (A[0] * Q[1][1] + A[1] * Q[0][1] + B[0] * Q[2][2] + B[2] * Q[2][0]), -Rm[1][1], Rm[0][1], 0, 14)
+    OB_TST2(pp[1] * Rm[0][2] - pp[0] * Rm[1][2], (A[0] * Q[1][2] + A[1] * Q[0][2] + B[0] * Q[2][1] + B[1] * Q[2][0]), -Rm[1][2], Rm[0][2], 0, 15)
+#undef OB_TST2
+
+    if (!code) return 0;
+
+    if (normalR) { normal[0] = normalR[0]; normal[1] = normalR[4]; normal[2] = normalR[8]; }
+    else { normal[0] = d11(R1, normalC); normal[1] = d11(R1 + 4, normalC); normal[2] = d11(R1 + 8, normalC); }
+    if (invert_normal) { normal[0] = -normal[0]; normal[1] = -normal[1]; normal[2] = -normal[2]; }
+    const float depth = -s;
+
+    if (code > 6) {
+        float pa[3], pb[3], sign;
+        for (int i = 0; i < 3; i++) pa[i] = p1[i];
+        for (int j = 0; j < 3; j++) {
+            sign = (d14(normal, R1 + j) > 0) ? 1.0f : -1.0f;
+            for (int i = 0; i < 3; i++) pa[i] += sign * A[j] * R1[i * 4 + j];
+        }
+        for (int i = 0; i < 3; i++) pb[i] = p2[i];
+        for (int j = 0; j < 3; j++) {
+            sign = (d14(normal, R2 + j) > 0) ? -1.0f : 1.0f;
+            for (int i = 0; i < 3; i++) pb[i] += sign * B[j] * R2[i * 4 + j];
+        }
+        float ua[3], ub[3];
+        for (int i = 0; i < 3; i++) ua[i] = R1[((code)-7) / 3 + i * 4];
+        for (int i = 0; i < 3; i++) ub[i] = R2[((code)-7) % 3 + i * 4];
+        // dLineClosestApproach
+        float pd[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+        float uaub = d11(ua, ub);
+        float q1 = d11(ua, pd);
+        float q2 = -d11(ub, pd);
+        float d = 1 - uaub * uaub, alpha, beta;
+        if (d <= 0.0001f) { alpha = 0; beta = 0; }
+        else {
+            d = 1.0f / d;
+            alpha = (q1 + uaub * q2) * d;
+            beta = (uaub * q1 + q2) * d;
+        }
+        for (int i = 0; i < 3; i++) pa[i] += ua[i] * alpha;
+        for (int i = 0; i < 3; i++) pb[i] += ub[i] * beta;
+        for (int i = 0; i < 3; i++) out.pos[0][i] = 0.5f * (pa[i] + pb[i]);
+        out.dep[0] = depth;
+        return 1;
+    }
+
+    const float *Ra, *Rb, *pa, *pb, *Sa, *Sb;
+    if (code <= 3) { Ra = R1; Rb = R2; pa = p1; pb = p2; Sa = A; Sb = B; }
+    else { Ra = R2; Rb = R1; pa = p2; pb = p1; Sa = B; Sb = A; }
+
+    float normal2[3], nr[3], anr[3];
+    if (code <= 3) { normal2[0] = normal[0]; normal2[1] = normal[1]; normal2[2] = normal[2]; }
+    else { normal2[0] = -normal[0]; normal2[1] = -normal[1]; normal2[2] = -normal[2]; }
+    nr[0] = d41(Rb + 0, normal2); nr[1] = d41(Rb + 1, normal2); nr[2] = d41(Rb + 2, normal2);
+    anr[0] = fabsf(nr[0]); anr[1] = fabsf(nr[1]); anr[2] = fabsf(nr[2]);
+
+    int lanr, a1, a2;
+    if (anr[1] > anr[0]) {
+        if (anr[1] > anr[2]) { a1 = 0; lanr = 1; a2 = 2; }
+        else { a1 = 0; a2 = 1; lanr = 2; }
+    } else {
+        if (anr[0] > anr[2]) { lanr = 0; a1 = 1; a2 = 2; }
+        else { a1 = 0; a2 = 1; lanr = 2; }
+    }
+
+    float center[3];
+    if (nr[lanr] < 0) { for (int i = 0; i < 3; i++) center[i] = pb[i] - pa[i] + Sb[lanr] * Rb[i * 4 + lanr]; }
+    else { for (int i = 0; i < 3; i++) center[i] = pb[i] - pa[i] - Sb[lanr] * Rb[i * 4 + lanr]; }
+
+    int codeN, code1, code2;
+    codeN = (code <= 3) ? code - 1 : code - 4;
+    if (codeN == 0) { code1 = 1; code2 = 2; }
+    else if (codeN == 1) { code1 = 0; code2 = 2; }
+    else { code1 = 0; code2 = 1; }
+
+    float quad[8], c1, c2, m11, m12, m21, m22;
+    c1 = d14(center, Ra + code1);
+    c2 = d14(center, Ra + code2);
+    m11 = d44(Ra + code1, Rb + a1);
+    m12 = d44(Ra + code1, Rb + a2);
+    m21 = d44(Ra + code2, Rb + a1);
+    m22 = d44(Ra + code2, Rb + a2);
+    {
+        float k1 = m11 * Sb[a1], k2 = m21 * Sb[a1], k3 = m12 * Sb[a2], k4 = m22 * Sb[a2];
+        quad[0] = c1 - k1 - k3; quad[1] = c2 - k2 - k4;
+        quad[2] = c1 - k1 + k3; quad[3] = c2 - k2 + k4;
+        quad[4] = c1 + k1 + k3; quad[5] = c2 + k2 + k4;
+        quad[6] = c1 + k1 - k3; quad[7] = c2 + k2 - k4;
+    }
+    float rect[2] = {Sa[code1], Sa[code2]};
+    float ret[16];
+    int n = clip_rect_quad(rect, quad, ret);
+    if (n < 1) return 0;
+
+    float point[3 * 8], dep[8];
+    float det1 = 1.0f / (m11 * m22 - m12 * m21);
+    m11 *= det1; m12 *= det1; m21 *= det1; m22 *= det1;
+    int cnum = 0;
+    for (int j = 0; j < n; j++) {
+        float k1 = m22 * (ret[j * 2] - c1) - m12 * (ret[j * 2 + 1] - c2);
+        float k2 = -m21 * (ret[j * 2] - c1) + m11 * (ret[j * 2 + 1] - c2);
+        for (int i = 0; i < 3; i++) point[cnum * 3 + i] = center[i] + k1 * Rb[i * 4 + a1] + k2 * Rb[i * 4 + a2];
+        dep[cnum] = Sa[codeN] - d11(normal2, point + cnum * 3);
+        if (dep[cnum] >= 0) {
+            ret[cnum * 2] = ret[j * 2];
+            ret[cnum * 2 + 1] = ret[j * 2 + 1];
+            cnum++;
+        }
+    }
+    if (cnum < 1) return 0;
+
+    int maxc = maxc_in;
+    if (maxc > cnum) maxc = cnum;
+    if (maxc < 1) maxc = 1;
+
+    if (cnum <= maxc) {
+        if (code < 4) {
+            for (int j = 0; j < cnum; j++) {
+                for (int i = 0; i < 3; i++) out.pos[j][i] = point[j * 3 + i] + pa[i];
+                out.dep[j] = dep[j];
+            }
+        } else {
+            for (int j = 0; j < cnum; j++) {
+                for (int i = 0; i < 3; i++) out.pos[j][i] = point[j * 3 + i] + pa[i] - normal[i] * dep[j];
+                out.dep[j] = dep[j];
+            }
+        }
+    } else {
+        int i1 = 0;
+        float maxdepth = dep[0];
+        for (int i = 1; i < cnum; i++) if (dep[i] > maxdepth) { maxdepth = dep[i]; i1 = i; }
+        int iret[8];
+        cull_points(cnum, ret, maxc, i1, iret);
+        for (int j = 0; j < maxc; j++) {
+            for (int i = 0; i < 3; i++) out.pos[j][i] = point[iret[j] * 3 + i] + pa[i];
+            out.dep[j] = dep[iret[j]];
+        }
+        cnum = maxc;
+    }
+    return cnum;
+}
+
+__device__ __forceinline__ void m3_to_arr(const M3 &R, float a[12]) {
+    a[0] = R.r0.x; a[1] = R.r0.y; a[2] = R.r0.z; a[3] = 0;
+    a[4] = R.r1.x; a[5] = R.r1.y; a[6] = R.r1.z; a[7] = 0;
+    a[8] = R.r2.x; a[9] = R.r2.y; a[10] = R.r2.z; a[11] = 0;
+}
+
+__global__ void __launch_bounds__(128) k_np_box_box(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
+                                                     GeomArrays g, ContactSlots cs, int maxc) {
+    const int s = bc->class_start[PC_BOX_BOX], e = bc->class_start[PC_BOX_BOX + 1];
+    for (int pi = s + blockIdx.x * blockDim.x + threadIdx.x; pi < e; pi += gridDim.x * blockDim.x) {
+        const int2 pr = pairs[pi];
+        const GeomPose b1 = load_geom(g, pr.x), b2 = load_geom(g, pr.y);
+        float R1[12], R2[12];
+        m3_to_arr(b1.R, R1);
+        m3_to_arr(b2.R, R2);
+        const float p1[3] = {b1.p.x, b1.p.y, b1.p.z}, p2[3] = {b2.p.x, b2.p.y, b2.p.z};
+        const float s1[3] = {b1.d.x, b1.d.y, b1.d.z}, s2[3] = {b2.d.x, b2.d.y, b2.d.z};
+        BoxBoxOut out;
+        const int n = box_box(p1, R1, s1, p2, R2, s2, maxc > 8 ? 8 : maxc, out);
+        // dCollideBoxBox: contact normal = -dBoxBox normal
+        const V3 nn = v3(-out.normal[0], -out.normal[1], -out.normal[2]);
+        for (int k = 0; k < n; k++) put_contact(cs, pi, k, v3(out.pos[k][0], out.pos[k][1], out.pos[k][2]), out.dep[k], nn, -1);
+        cs.nc[pi] = n;
+    }
+}
+
+// ---------------------------------------------------------------- pairs without a collider
+__global__ void __launch_bounds__(256) k_np_none(const BroadCounters *__restrict__ bc, ContactSlots cs) {
+    const int s = bc->class_start[PC_NONE], e = bc->class_start[PC_NONE + 1];
+    for (int p = s + blockIdx.x * blockDim.x + threadIdx.x; p < e; p += gridDim.x * blockDim.x) cs.nc[p] = 0;
+}
+
+// ---------------------------------------------------------------- sphere-trimesh
+//
+// One warp per (sphere, trimesh) pair; the mesh (vertices + indices) is staged once per CTA in
+// shared memory with a TMA bulk copy (cp.async.bulk global->shared completing on an mbarrier)
+// when it fits, which the reference's teapot.obj does (8884 triangles, 165 KB).  Lanes stride
+// over triangles; hits go to a per-warp candidate list; the <= 8 contacts are then chosen by the
+// order-independent rule documented in oracle/ode_oracle.c (depth desc, triangle index asc,
+// duplicates within 1e-3 r dropped).
+
+constexpr int TM_WARPS = 8;
+constexpr int TM_CAND = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ V3 closest_pt_triangle(V3 p, V3 a, V3 b, V3 c) {
+    const V3 ab = b - a, ac = c - a, ap = p - a;
+    const float d1 = dot(ab, ap), d2 = dot(ac, ap);
+    if (d1 <= 0 && d2 <= 0) return a;
+    const V3 bp = p - b;
+    const float d3 = dot(ab, bp), d4 = dot(ac, bp);
+    if (d3 >= 0 && d4 <= d3) return b;
+    const float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0 && d1 >= 0 && d3 <= 0) {
+        const float v = d1 / (d1 - d3);
+        return v3(a.x + v * ab.x, a.y + v * ab.y, a.z + v * ab.z);
+    }
+    const V3 cp = p - c;
+    const float d5 = dot(ab, cp), d6 = dot(ac, cp);
+    if (d6 >= 0 && d5 <= d6) return c;
+    const float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0 && d2 >= 0 && d6 <= 0) {
+        const float w = d2 / (d2 - d6);
+        return v3(a.x + w * ac.x, a.y + w * ac.y, a.z + w * ac.z);
+    }
+    const float va = d3 * d6 - d5 * d4;
+    if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
+        const float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        return v3(b.x + w * (c.x - b.x), b.y + w * (c.y - b.y), b.z + w * (c.z - b.z));
+    }
+    const float denom = 1.0f / (va + vb + vc);
+    const float v = vb * denom, w = vc * denom;
+    return v3(a.x + ab.x * v + ac.x * w, a.y + ab.y * v + ac.y * w, a.z + ab.z * v + ac.z * w);
+}
+
+struct TriCand {
+    float depth;
+    int tri;
+    float qx, qy, qz, nx, ny, nz;
+};
+
+__global__ void __launch_bounds__(TM_WARPS * 32) k_np_sphere_trimesh(const BroadCounters *__restrict__ bc,
+                                                                      const int2 *__restrict__ pairs, GeomArrays g,
+                                                                      MeshInfo mesh, int mesh_id, ContactSlots cs,
+                                                                      int maxc, int stage_bytes_v, int stage_bytes_t,
+                                                                      StepStats *__restrict__ stats) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ TriCand cand[TM_WARPS][TM_CAND];
+    const float *verts = mesh.verts;
+    const int *tris = mesh.tris;
+    if (stage_bytes_v > 0) {
+        // TMA bulk copy of the whole mesh into shared memory, completion tracked by an mbarrier
+        float *sv = reinterpret_cast<float *>(smem_raw);
+        int *stri = reinterpret_cast<int *>(smem_raw + stage_bytes_v);
+        if (threadIdx.x == 0) {
+            const uint32_t bar = smem_u32(&mbar);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                         "r"((uint32_t)(stage_bytes_v + stage_bytes_t))
+                         : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sv)),
+                "l"(mesh.verts), "r"((uint32_t)stage_bytes_v), "r"(bar)
+                : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(stri)),
+                "l"(mesh.tris), "r"((uint32_t)stage_bytes_t), "r"(bar)
+                : "memory");
+        }
+        __syncthreads();
+        {
+            const uint32_t bar = smem_u32(&mbar);
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(bar), "r"(0u)
+                    : "memory");
+            }
+        }
+        verts = sv;
+        tris = stri;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int s = bc->class_start[PC_SPHERE_TRIMESH], e = bc->class_start[PC_SPHERE_TRIMESH + 1];
+    const unsigned lt = (1u << lane) - 1u;
+    TriCand *mine = cand[wid];
+    if (maxc > 8) maxc = 8;
+    for (int pi = s + blockIdx.x * TM_WARPS + wid; pi < e; pi += gridDim.x * TM_WARPS) {
+        const int2 pr = pairs[pi];
+        if (g.mesh[pr.y] != mesh_id) continue;
+        const V3 ps = v3(g.pos[pr.x]);
+        const float r = g.dims[pr.x].x;
+        const V3 mp = v3(g.pos[pr.y]);
+        const M3 mR = load_m3(g.R, pr.y);
+        const V3 c = mulT(mR, ps - mp);
+        int ncand = 0;
+        for (int t0 = 0; t0 < mesh.nt; t0 += 32) {
+            const int t = t0 + lane;
+            bool hit = false;
+            TriCand cd;
+            if (t < mesh.nt) {
+                const int i0 = tris[3 * t], i1 = tris[3 * t + 1], i2 = tris[3 * t + 2];
+                const V3 a = v3(verts[3 * i0], verts[3 * i0 + 1], verts[3 * i0 + 2]);
+                const V3 b = v3(verts[3 * i1], verts[3 * i1 + 1], verts[3 * i1 + 2]);
+                const V3 cc = v3(verts[3 * i2], verts[3 * i2 + 1], verts[3 * i2 + 2]);
+                bool skip = false;
+                skip |= (c.x - r > fmaxf(a.x, fmaxf(b.x, cc.x))) || (c.x + r < fminf(a.x, fminf(b.x, cc.x)));
+                skip |= (c.y - r > fmaxf(a.y, fmaxf(b.y, cc.y))) || (c.y + r < fminf(a.y, fminf(b.y, cc.y)));
+                skip |= (c.z - r > fmaxf(a.z, fmaxf(b.z, cc.z))) || (c.z + r < fminf(a.z, fminf(b.z, cc.z)));
+                if (!skip) {
+                    const V3 q = closest_pt_triangle(c, a, b, cc);
+                    const V3 dv = c - q;
+                    const float d2 = dot(dv, dv);
+                    if (!(d2 > r * r)) {
+                        const float dist = sqrtf(d2);
+                        if (!(dist > r)) {
+                            V3 n;
+                            bool ok = true;
+                            if (dist > 0) {
+                                const float inv = 1.0f / dist;
+                                n = v3(dv.x * inv, dv.y * inv, dv.z * inv);
+                            } else {
+                                n = cross(b - a, cc - a);
+                                const float l2 = dot(n, n);
+                                if (!(l2 > 0)) ok = false;
+                                else {
+                                    const float inv = 1.0f / sqrtf(l2);
+                                    n = v3(n.x * inv, n.y * inv, n.z * inv);
+                                }
+                            }
+                            if (ok) {
+                                hit = true;
+                                cd.depth = r - dist; cd.tri = t;
+                                cd.qx = q.x; cd.qy = q.y; cd.qz = q.z;
+                                cd.nx = n.x; cd.ny = n.y; cd.nz = n.z;
+                            }
+                        }
+                    }
+                }
+            }
+            const unsigned hm = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                const int slot = ncand + __popc(hm & lt);
+                if (slot < TM_CAND) mine[slot] = cd;
+            }
+            ncand += __popc(hm);
+        }
+        if (ncand > TM_CAND) {
+            ncand = TM_CAND;
+            if (lane == 0) atomicOr(&stats->flags, SF_CAND_OVERFLOW);
+        }
+        __syncwarp();
+        // greedy selection in (depth desc, tri asc) order with duplicate suppression
+        int nout = 0;
+        const float tol2 = (1e-3f * r) * (1e-3f * r);
+        while (nout < maxc) {
+            float bd = -1.f;
+            int bt = 0x7fffffff, bi = -1;
+            for (int i = lane; i < ncand; i += 32) {
+                const float d = mine[i].depth;
+                const int t = mine[i].tri;
+                if (d >= 0.f && (d > bd || (d == bd && t < bt))) { bd = d; bt = t; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (od > bd || (od == bd && ot < bt)) { bd = od; bt = ot; bi = oi; }
+            }
+            if (bi < 0) break;
+            const TriCand w = mine[bi];
+            __syncwarp();
+            if (lane == 0) {
+                const V3 pw = mul(mR, v3(w.qx, w.qy, w.qz));
+                const V3 nw = mul(mR, v3(w.nx, w.ny, w.nz));
+                put_contact(cs, pi, nout, pw + mp, w.depth, nw, w.tri);
+            }
+            for (int i = lane; i < ncand; i += 32) {
+                if (mine[i].depth >= 0.f) {
+                    const float ex = mine[i].qx - w.qx, ey = mine[i].qy - w.qy, ez = mine[i].qz - w.qz;
+                    if (ex * ex + ey * ey + ez * ez <= tol2) mine[i].depth = -1.f;
+                }
+            }
+            __syncwarp();
+            nout++;
+        }
+        if (lane == 0) cs.nc[pi] = nout;
+        __syncwarp();
+    }
+}
+
+void narrowphase_run(const BroadPhase &bp, GeomArrays g, MeshTable meshes, const std::vector<TriMesh> &host_meshes,
+                     ContactSlots cs, int max_contacts, StepStats *d_stats, int num_sms, cudaStream_t st) {
+    if (g.n == 0) return;
+    // persistent grids: a multiple of the SM count, grid-stride over the class slice
+    const unsigned grid = (unsigned)(num_sms * 8);
+    k_np_sphere_sphere<<<grid, 256, 0, st>>>(bp.counters, bp.pairs, g, cs);
+    OB_CHECK_KERNEL("k_np_sphere_sphere", st);
+    k_np_sphere_box<<<grid, 256, 0, st>>>(bp.counters, bp.pairs, g, cs);
+    OB_CHECK_KERNEL("k_np_sphere_box", st);
+    k_np_box_box<<<grid, 128, 0, st>>>(bp.counters, bp.pairs, g, cs, max_contacts);
+    OB_CHECK_KERNEL("k_np_box_box", st);
+    k_np_sphere_plane<<<grid, 256, 0, st>>>(bp.counters, bp.pairs, g, cs);
+    OB_CHECK_KERNEL("k_np_sphere_plane", st);
+    k_np_box_plane<<<grid, 256, 0, st>>>(bp.counters, bp.pairs, g, cs, max_contacts);
+    OB_CHECK_KERNEL("k_np_box_plane", st);
+    k_np_none<<<grid, 256, 0, st>>>(bp.counters, cs);
+    OB_CHECK_KERNEL("k_np_none", st);
+    for (int m = 0; m < meshes.n; m++) {
+        const TriMesh &hm = host_meshes[m];
+        int bv = ((hm.nv * 3 * (int)sizeof(float) + 15) / 16) * 16;
+        int bt = ((hm.nt * 3 * (int)sizeof(int) + 15) / 16) * 16;
+        int dyn = bv + bt;
+        static bool attr_set = false;
+        const int max_dyn = 200 * 1024;
+        if (dyn > max_dyn) { bv = 0; bt = 0; dyn = 0; } // mesh too large to stage: read through L2
+        if (!attr_set) {
+            OB_CUDA(cudaFuncSetAttribute(k_np_sphere_trimesh, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+            attr_set = true;
+        }
+        k_np_sphere_trimesh<<<(unsigned)num_sms, TM_WARPS * 32, dyn, st>>>(bp.counters, bp.pairs, g, meshes.m[m], m, cs,
+                                                                          max_contacts, bv, bt, d_stats);
+        OB_CHECK_KERNEL("k_np_sphere_trimesh", st);
+    }
+}
+
+} // namespace ob

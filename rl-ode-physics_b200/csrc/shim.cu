@@ -1,0 +1,964 @@
+// shim.cu -- the C ABI of libode_b200.so: ODE's handle-based API (include/ode/ode.h) and the
+// device-resident extensions (include/ode_b200.h) on top of the engine.
+//
+// Handle model: IDs are pointers to small host structs that hold an
+// index into the world's arrays.  Bodies and geoms have host mirrors so that dBodyGetPosition &co
+// return stable `const dReal*`; the mirrors are refreshed lazily after a step.  Everything that
+// computes physics runs on the GPU; this file only does bookkeeping and ODE's host-side
+// conversions (dRtoQ, dMass helpers).
+#include <string.h>
+
+#include <deque>
+#include <vector>
+
+#include "dmath.cuh"
+#include "engine.h"
+#include "ode_b200.h"
+
+using namespace ob;
+
+struct dxJointGroup;
+
+struct dxBody {
+    dxWorld *w;
+    int idx;
+    void *data;
+    bool alive;
+};
+
+struct dxGeom {
+    dxSpace *space;
+    int idx; // engine geom index
+    dxBody *body;
+    void *data;
+    bool alive;
+    float aabb_tmp[6];
+};
+
+struct dxJoint {
+    dxWorld *w;
+    HostContact hc;
+    dxBody *b1, *b2;
+};
+
+struct dxJointGroup {
+    std::deque<dxJoint> joints;
+};
+
+struct dxTriMeshData {
+    std::vector<float> verts;
+    std::vector<int> tris;
+    dxWorld *bound_world = nullptr;
+    int mesh_id = -1;
+};
+
+struct dxSpace {
+    dxWorld *w;
+    std::vector<dxGeom *> geoms; // by creation order (alive or not)
+};
+
+struct dxWorld {
+    Engine *eng;
+    std::deque<dxBody> bodies;
+    std::deque<dxGeom> geoms;          // all geoms of all spaces bound to this world, by engine index
+    std::vector<dxSpace *> spaces;
+    std::vector<dxJointGroup *> groups; // groups that hold joints of this world
+    dSurfaceParameters surface;
+    int max_contacts = 8;
+    bool device_contacts_pending = false;
+    // callback context
+    bool in_callback = false;
+    int cb_g1 = -1, cb_g2 = -1, cb_first = 0, cb_count = 0;
+    HostPairs cb_pairs;
+    float ret_vec[4];
+};
+
+static std::vector<dxWorld *> g_worlds;
+static int g_device = -1;
+
+static int default_device() {
+    if (g_device >= 0) return g_device;
+    const char *s = getenv("ODE_B200_DEVICE");
+    if (!s) s = getenv("LOCAL_RANK");
+    return s ? atoi(s) : 0;
+}
+
+static void fatal(const char *msg) {
+    fprintf(stderr, "libode_b200: %s\n", msg);
+    abort();
+}
+
+static dxWorld *current_world() {
+    for (size_t i = g_worlds.size(); i-- > 0;)
+        if (g_worlds[i]) return g_worlds[i];
+    return nullptr;
+}
+
+static dxWorld *space_world(dxSpace *s) {
+    if (!s->w) {
+        s->w = current_world();
+        if (!s->w) fatal("a space needs a world: create a dWorldID before adding geoms");
+        s->w->spaces.push_back(s);
+    }
+    return s->w;
+}
+
+// host mirrors must be current before the host edits or reads them
+static void fresh(dxWorld *w) { eng_sync_to_host(w->eng); }
+
+// ------------------------------------------------------------------ host-side ODE math helpers
+
+extern "C" void dQtoR(const dQuaternion q, dMatrix3 R) {
+    const float qq1 = 2 * q[1] * q[1], qq2 = 2 * q[2] * q[2], qq3 = 2 * q[3] * q[3];
+    R[0] = 1 - qq2 - qq3; R[1] = 2 * (q[1] * q[2] - q[0] * q[3]); R[2] = 2 * (q[1] * q[3] + q[0] * q[2]); R[3] = 0;
+    R[4] = 2 * (q[1] * q[2] + q[0] * q[3]); R[5] = 1 - qq1 - qq3; R[6] = 2 * (q[2] * q[3] - q[0] * q[1]); R[7] = 0;
+    R[8] = 2 * (q[1] * q[3] - q[0] * q[2]); R[9] = 2 * (q[2] * q[3] + q[0] * q[1]); R[10] = 1 - qq1 - qq2; R[11] = 0;
+}
+
+extern "C" void dRtoQ(const dMatrix3 R, dQuaternion q) {
+    float tr = R[0] + R[5] + R[10], s;
+    if (tr >= 0) {
+        s = sqrtf(tr + 1);
+        q[0] = 0.5f * s;
+        s = 0.5f / s;
+        q[1] = (R[9] - R[6]) * s; q[2] = (R[2] - R[8]) * s; q[3] = (R[4] - R[1]) * s;
+    } else {
+        int c;
+        if (R[5] > R[0]) c = (R[10] > R[5]) ? 2 : 1;
+        else c = (R[10] > R[0]) ? 2 : 0;
+        if (c == 0) {
+            s = sqrtf((R[0] - (R[5] + R[10])) + 1);
+            q[1] = 0.5f * s; s = 0.5f / s;
+            q[2] = (R[1] + R[4]) * s; q[3] = (R[8] + R[2]) * s; q[0] = (R[9] - R[6]) * s;
+        } else if (c == 1) {
+            s = sqrtf((R[5] - (R[10] + R[0])) + 1);
+            q[2] = 0.5f * s; s = 0.5f / s;
+            q[3] = (R[6] + R[9]) * s; q[1] = (R[1] + R[4]) * s; q[0] = (R[2] - R[8]) * s;
+        } else {
+            s = sqrtf((R[10] - (R[0] + R[5])) + 1);
+            q[3] = 0.5f * s; s = 0.5f / s;
+            q[1] = (R[8] + R[2]) * s; q[2] = (R[6] + R[9]) * s; q[0] = (R[4] - R[1]) * s;
+        }
+    }
+}
+
+static void normalize4(float *a) {
+    float l = a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3];
+    if (l > 0) {
+        l = 1.0f / sqrtf(l);
+        a[0] *= l; a[1] *= l; a[2] *= l; a[3] *= l;
+    } else {
+        a[0] = 1; a[1] = 0; a[2] = 0; a[3] = 0;
+    }
+}
+
+extern "C" void dRSetIdentity(dMatrix3 R) {
+    memset(R, 0, sizeof(dMatrix3));
+    R[0] = R[5] = R[10] = 1;
+}
+extern "C" void dQSetIdentity(dQuaternion q) { q[0] = 1; q[1] = q[2] = q[3] = 0; }
+extern "C" void dQFromAxisAndAngle(dQuaternion q, dReal ax, dReal ay, dReal az, dReal angle) {
+    float l = ax * ax + ay * ay + az * az;
+    if (l > 0) {
+        angle *= 0.5f;
+        q[0] = cosf(angle);
+        l = sinf(angle) * (1.0f / sqrtf(l));
+        q[1] = ax * l; q[2] = ay * l; q[3] = az * l;
+    } else dQSetIdentity(q);
+}
+extern "C" void dRFromAxisAndAngle(dMatrix3 R, dReal ax, dReal ay, dReal az, dReal angle) {
+    dQuaternion q;
+    dQFromAxisAndAngle(q, ax, ay, az, angle);
+    dQtoR(q, R);
+}
+extern "C" void dRFromEulerAngles(dMatrix3 R, dReal phi, dReal theta, dReal psi) {
+    const float sphi = sinf(phi), cphi = cosf(phi), stheta = sinf(theta), ctheta = cosf(theta), spsi = sinf(psi),
+                cpsi = cosf(psi);
+    R[0] = cpsi * ctheta; R[1] = spsi * ctheta; R[2] = -stheta; R[3] = 0;
+    R[4] = cpsi * stheta * sphi - spsi * cphi; R[5] = spsi * stheta * sphi + cpsi * cphi; R[6] = ctheta * sphi; R[7] = 0;
+    R[8] = cpsi * stheta * cphi + spsi * sphi; R[9] = spsi * stheta * cphi - cpsi * sphi; R[10] = ctheta * cphi; R[11] = 0;
+}
+extern "C" void dPlaneSpace(const dVector3 n, dVector3 p, dVector3 q) {
+    V3 pp, qq;
+    plane_space(v3(n[0], n[1], n[2]), pp, qq);
+    p[0] = pp.x; p[1] = pp.y; p[2] = pp.z; p[3] = 0;
+    q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = 0;
+}
+
+// ------------------------------------------------------------------ mass
+
+extern "C" void dMassSetZero(dMass *m) { memset(m, 0, sizeof(*m)); }
+extern "C" void dMassSetParameters(dMass *m, dReal themass, dReal cgx, dReal cgy, dReal cgz, dReal I11, dReal I22,
+                                   dReal I33, dReal I12, dReal I13, dReal I23) {
+    dMassSetZero(m);
+    m->mass = themass;
+    m->c[0] = cgx; m->c[1] = cgy; m->c[2] = cgz;
+    m->I[0] = I11; m->I[5] = I22; m->I[10] = I33;
+    m->I[1] = I12; m->I[2] = I13; m->I[6] = I23;
+    m->I[4] = I12; m->I[8] = I13; m->I[9] = I23;
+}
+extern "C" void dMassSetSphereTotal(dMass *m, dReal total_mass, dReal radius) {
+    dMassSetZero(m);
+    m->mass = total_mass;
+    const float II = 0.4f * total_mass * radius * radius;
+    m->I[0] = II; m->I[5] = II; m->I[10] = II;
+}
+extern "C" void dMassSetSphere(dMass *m, dReal density, dReal radius) {
+    dMassSetSphereTotal(m, (4.0f / 3.0f) * (float)M_PI * radius * radius * radius * density, radius);
+}
+extern "C" void dMassSetBoxTotal(dMass *m, dReal total_mass, dReal lx, dReal ly, dReal lz) {
+    dMassSetZero(m);
+    m->mass = total_mass;
+    m->I[0] = total_mass / 12.0f * (ly * ly + lz * lz);
+    m->I[5] = total_mass / 12.0f * (lx * lx + lz * lz);
+    m->I[10] = total_mass / 12.0f * (lx * lx + ly * ly);
+}
+extern "C" void dMassSetBox(dMass *m, dReal density, dReal lx, dReal ly, dReal lz) {
+    dMassSetBoxTotal(m, lx * ly * lz * density, lx, ly, lz);
+}
+extern "C" void dMassAdjust(dMass *m, dReal newmass) {
+    const float scale = newmass / m->mass;
+    m->mass = newmass;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) m->I[i * 4 + j] *= scale;
+}
+
+static void invert3(const float *I, float *inv) {
+    const float a = I[0], b = I[1], c = I[2], d = I[4], e = I[5], f = I[6], g = I[8], h = I[9], i = I[10];
+    const float A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+    const float det = a * A + b * B + c * C;
+    const float id = 1.0f / det;
+    memset(inv, 0, 12 * sizeof(float));
+    inv[0] = A * id; inv[1] = -(b * i - c * h) * id; inv[2] = (b * f - c * e) * id;
+    inv[4] = B * id; inv[5] = (a * i - c * g) * id; inv[6] = -(a * f - c * d) * id;
+    inv[8] = C * id; inv[9] = -(a * h - b * g) * id; inv[10] = (a * e - b * d) * id;
+}
+
+// ------------------------------------------------------------------ library / world
+
+extern "C" void dInitODE(void) {}
+extern "C" int dInitODE2(unsigned int) { return 1; }
+extern "C" void dCloseODE(void) {}
+extern "C" void dSetDeviceB200(int device) { g_device = device; }
+extern "C" int dGetDeviceB200(void) { return default_device(); }
+
+extern "C" dWorldID dWorldCreate(void) {
+    dxWorld *w = new dxWorld();
+    w->eng = eng_create(default_device());
+    memset(&w->surface, 0, sizeof(w->surface));
+    // the reference's NearCallback policy, src/main.c:684-687
+    w->surface.mode = dContactBounce;
+    w->surface.bounce = 0.2f;
+    w->surface.bounce_vel = 0.1f;
+    w->surface.mu = dInfinity;
+    g_worlds.push_back(w);
+    return w;
+}
+
+extern "C" void dWorldDestroy(dWorldID w) {
+    if (!w) return;
+    for (auto &p : g_worlds) if (p == w) p = nullptr;
+    for (dxSpace *s : w->spaces)
+        if (s) s->w = nullptr;
+    eng_destroy(w->eng);
+    delete w;
+}
+
+extern "C" void dWorldSetGravity(dWorldID w, dReal x, dReal y, dReal z) {
+    WorldParams &p = eng_params(w->eng);
+    p.gravity[0] = x; p.gravity[1] = y; p.gravity[2] = z;
+}
+extern "C" void dWorldGetGravity(dWorldID w, dVector3 g) {
+    WorldParams &p = eng_params(w->eng);
+    g[0] = p.gravity[0]; g[1] = p.gravity[1]; g[2] = p.gravity[2]; g[3] = 0;
+}
+extern "C" void dWorldSetERP(dWorldID w, dReal erp) { eng_params(w->eng).erp = erp; }
+extern "C" dReal dWorldGetERP(dWorldID w) { return eng_params(w->eng).erp; }
+extern "C" void dWorldSetCFM(dWorldID w, dReal cfm) { eng_params(w->eng).cfm = cfm; }
+extern "C" dReal dWorldGetCFM(dWorldID w) { return eng_params(w->eng).cfm; }
+extern "C" void dWorldSetQuickStepNumIterations(dWorldID w, int num) { eng_params(w->eng).iters = num; }
+extern "C" int dWorldGetQuickStepNumIterations(dWorldID w) { return eng_params(w->eng).iters; }
+extern "C" void dWorldSetQuickStepW(dWorldID w, dReal v) { eng_params(w->eng).sor_w = v; }
+extern "C" dReal dWorldGetQuickStepW(dWorldID w) { return eng_params(w->eng).sor_w; }
+extern "C" void dWorldSetContactMaxCorrectingVel(dWorldID w, dReal vel) { eng_params(w->eng).max_vel = vel; }
+extern "C" dReal dWorldGetContactMaxCorrectingVel(dWorldID w) { return eng_params(w->eng).max_vel; }
+extern "C" void dWorldSetContactSurfaceLayer(dWorldID w, dReal depth) { eng_params(w->eng).min_depth = depth; }
+extern "C" dReal dWorldGetContactSurfaceLayer(dWorldID w) { return eng_params(w->eng).min_depth; }
+
+static Surface to_surface(const dSurfaceParameters &s) {
+    Surface o;
+    o.mode = s.mode; o.mu = s.mu; o.mu2 = s.mu2; o.bounce = s.bounce; o.bounce_vel = s.bounce_vel;
+    o.soft_erp = s.soft_erp; o.soft_cfm = s.soft_cfm; o.motion1 = s.motion1; o.motion2 = s.motion2;
+    o.motionN = s.motionN; o.slip1 = s.slip1; o.slip2 = s.slip2;
+    if (o.mode & dContactFDir1) fatal("dContactFDir1 is not supported (friction directions come from dPlaneSpace)");
+    return o;
+}
+
+extern "C" int dWorldQuickStep(dWorldID w, dReal h) {
+    if (!w || !(h > 0)) return 0;
+    // contact joints created through dJointCreateContact (compat mode) take precedence
+    std::vector<HostContact> hc;
+    for (dxJointGroup *g : w->groups)
+        for (dxJoint &j : g->joints)
+            if (j.w == w) {
+                j.hc.b1 = (j.b1 && j.b1->alive) ? j.b1->idx : -1;
+                j.hc.b2 = (j.b2 && j.b2->alive) ? j.b2->idx : -1;
+                hc.push_back(j.hc);
+            }
+    if (!hc.empty() || !w->device_contacts_pending) {
+        eng_step_host_contacts(w->eng, h, hc.data(), (int)hc.size());
+    } else {
+        eng_step_device_contacts(w->eng, h, to_surface(w->surface));
+    }
+    w->device_contacts_pending = false;
+    return 1;
+}
+extern "C" int dWorldStep(dWorldID w, dReal h) { return dWorldQuickStep(w, h); }
+
+extern "C" void dWorldSetSurfaceB200(dWorldID w, const dSurfaceParameters *s) { w->surface = *s; }
+extern "C" void dWorldGetSurfaceB200(dWorldID w, dSurfaceParameters *s) { *s = w->surface; }
+extern "C" void dWorldSetMaxContactsB200(dWorldID w, int n) { w->max_contacts = n < 1 ? 1 : (n > 8 ? 8 : n); }
+extern "C" void dWorldSetNumEnvsB200(dWorldID w, int n) { eng_set_num_envs(w->eng, n); }
+extern "C" void dWorldSetCapacityB200(dWorldID w, long mp, long mm) { eng_set_capacity(w->eng, mp, mm); }
+extern "C" void dWorldSetBigExtentB200(dWorldID w, float e) { eng_set_big_extent(w->eng, e); }
+extern "C" void dWorldWaitB200(dWorldID w) { eng_wait(w->eng); }
+extern "C" void dWorldEnableTimingB200(dWorldID w, int on) { eng_enable_timing(w->eng, on); }
+extern "C" void dWorldGetTimingsB200(dWorldID w, float out[4]) { eng_last_timings(w->eng, out); }
+extern "C" int dWorldGetNumBodiesB200(dWorldID w) { return eng_bodies(w->eng).n; }
+
+extern "C" void dWorldGetStatsB200(dWorldID w, dStepStatsB200 *out) {
+    static_assert(sizeof(dStepStatsB200) == sizeof(StepStats), "stats layout");
+    StepStats s = eng_stats(w->eng);
+    memcpy(out, &s, sizeof(s));
+}
+
+// ------------------------------------------------------------------ bodies
+
+static dxBody *new_body(dxWorld *w) {
+    const int idx = eng_add_body(w->eng);
+    w->bodies.push_back(dxBody{w, idx, nullptr, true});
+    return &w->bodies.back();
+}
+
+extern "C" dBodyID dBodyCreate(dWorldID w) {
+    fresh(w);
+    dxBody *b = new_body(w);
+    eng_bodies(w->eng).flags[b->idx] = BF_GYRO; // ODE >= 0.13: gyroscopic mode on by default
+    return b;
+}
+
+extern "C" void dBodyDestroy(dBodyID b) {
+    if (!b || !b->alive) return;
+    dxWorld *w = b->w;
+    fresh(w);
+    // ODE detaches the body's geoms; the slot stays as an inert kinematic body
+    for (dxGeom &g : w->geoms)
+        if (g.alive && g.body == b) {
+            g.body = nullptr;
+            eng_geoms(w->eng).body[g.idx] = -1;
+            eng_mark_geoms_dirty(w->eng);
+        }
+    HostBodies &hb = eng_bodies(w->eng);
+    hb.flags[b->idx] = BF_KINEMATIC | BF_NOGRAVITY;
+    hb.pos[4 * b->idx + 3] = 0.f;
+    for (int k = 0; k < 3; k++) { hb.lvel[4 * b->idx + k] = 0; hb.avel[4 * b->idx + k] = 0; }
+    for (int k = 0; k < 12; k++) hb.invI[12 * b->idx + k] = 0;
+    eng_mark_bodies_dirty(w->eng);
+    b->alive = false;
+}
+
+#define HB(b) eng_bodies((b)->w->eng)
+
+extern "C" void dBodySetPosition(dBodyID b, dReal x, dReal y, dReal z) {
+    fresh(b->w);
+    float *p = &HB(b).pos[4 * b->idx];
+    p[0] = x; p[1] = y; p[2] = z;
+    eng_mark_bodies_dirty(b->w->eng);
+}
+extern "C" void dBodySetRotation(dBodyID b, const dMatrix3 R) {
+    fresh(b->w);
+    float *r = &HB(b).R[12 * b->idx], *q = &HB(b).quat[4 * b->idx];
+    memcpy(r, R, 12 * sizeof(float));
+    r[3] = r[7] = r[11] = 0;
+    dRtoQ(r, q);
+    normalize4(q);
+    eng_mark_bodies_dirty(b->w->eng);
+}
+extern "C" void dBodySetQuaternion(dBodyID b, const dQuaternion qq) {
+    fresh(b->w);
+    float *r = &HB(b).R[12 * b->idx], *q = &HB(b).quat[4 * b->idx];
+    memcpy(q, qq, 4 * sizeof(float));
+    normalize4(q);
+    dQtoR(q, r);
+    eng_mark_bodies_dirty(b->w->eng);
+}
+extern "C" void dBodySetLinearVel(dBodyID b, dReal x, dReal y, dReal z) {
+    fresh(b->w);
+    float *p = &HB(b).lvel[4 * b->idx];
+    p[0] = x; p[1] = y; p[2] = z;
+    eng_mark_bodies_dirty(b->w->eng);
+}
+extern "C" void dBodySetAngularVel(dBodyID b, dReal x, dReal y, dReal z) {
+    fresh(b->w);
+    float *p = &HB(b).avel[4 * b->idx];
+    p[0] = x; p[1] = y; p[2] = z;
+    eng_mark_bodies_dirty(b->w->eng);
+}
+extern "C" const dReal *dBodyGetPosition(dBodyID b) { fresh(b->w); return &HB(b).pos[4 * b->idx]; }
+extern "C" const dReal *dBodyGetRotation(dBodyID b) { fresh(b->w); return &HB(b).R[12 * b->idx]; }
+extern "C" const dReal *dBodyGetQuaternion(dBodyID b) { fresh(b->w); return &HB(b).quat[4 * b->idx]; }
+extern "C" const dReal *dBodyGetLinearVel(dBodyID b) { fresh(b->w); return &HB(b).lvel[4 * b->idx]; }
+extern "C" const dReal *dBodyGetAngularVel(dBodyID b) { fresh(b->w); return &HB(b).avel[4 * b->idx]; }
+extern "C" const dReal *dBodyGetForce(dBodyID b) { fresh(b->w); return &HB(b).facc[4 * b->idx]; }
+extern "C" const dReal *dBodyGetTorque(dBodyID b) { fresh(b->w); return &HB(b).tacc[4 * b->idx]; }
+
+extern "C" void dBodySetMass(dBodyID b, const dMass *m) {
+    if (!(m->mass > 0)) fatal("dBodySetMass: mass must be > 0");
+    if (m->c[0] != 0 || m->c[1] != 0 || m->c[2] != 0) fatal("dBodySetMass: centre of mass must be at the origin");
+    fresh(b->w);
+    HostBodies &hb = HB(b);
+    hb.lvel[4 * b->idx + 3] = m->mass;
+    memcpy(&hb.I[12 * b->idx], m->I, 12 * sizeof(float));
+    if (!(hb.flags[b->idx] & BF_KINEMATIC)) {
+        hb.pos[4 * b->idx + 3] = 1.0f / m->mass;
+        invert3(m->I, &hb.invI[12 * b->idx]);
+    }
+    eng_mark_bodies_dirty(b->w->eng);
+}
+extern "C" void dBodyGetMass(dBodyID b, dMass *m) {
+    HostBodies &hb = HB(b);
+    dMassSetZero(m);
+    m->mass = hb.lvel[4 * b->idx + 3];
+    memcpy(m->I, &hb.I[12 * b->idx], 12 * sizeof(float));
+}
+extern "C" void dBodySetKinematic(dBodyID b) {
+    fresh(b->w);
+    HostBodies &hb = HB(b);
+    hb.flags[b->idx] |= BF_KINEMATIC;
+    hb.pos[4 * b->idx + 3] = 0.f; // invMass = 0, invI = 0
+    for (int k = 0; k < 12; k++) hb.invI[12 * b->idx + k] = 0;
+    eng_mark_bodies_dirty(b->w->eng);
+}
+extern "C" void dBodySetDynamic(dBodyID b) {
+    fresh(b->w);
+    HostBodies &hb = HB(b);
+    hb.flags[b->idx] &= ~BF_KINEMATIC;
+    hb.pos[4 * b->idx + 3] = 1.0f / hb.lvel[4 * b->idx + 3];
+    invert3(&hb.I[12 * b->idx], &hb.invI[12 * b->idx]);
+    eng_mark_bodies_dirty(b->w->eng);
+}
+extern "C" int dBodyIsKinematic(dBodyID b) { return (HB(b).flags[b->idx] & BF_KINEMATIC) != 0; }
+static void set_flag(dBodyID b, int flag, bool on) {
+    fresh(b->w);
+    int &f = HB(b).flags[b->idx];
+    f = on ? (f | flag) : (f & ~flag);
+    eng_mark_bodies_dirty(b->w->eng);
+}
+extern "C" void dBodySetGravityMode(dBodyID b, int mode) { set_flag(b, BF_NOGRAVITY, mode == 0); }
+extern "C" int dBodyGetGravityMode(dBodyID b) { return (HB(b).flags[b->idx] & BF_NOGRAVITY) == 0; }
+extern "C" void dBodySetGyroscopicMode(dBodyID b, int on) { set_flag(b, BF_GYRO, on != 0); }
+extern "C" int dBodyGetGyroscopicMode(dBodyID b) { return (HB(b).flags[b->idx] & BF_GYRO) != 0; }
+extern "C" void dBodyAddForce(dBodyID b, dReal fx, dReal fy, dReal fz) {
+    fresh(b->w);
+    float *f = &HB(b).facc[4 * b->idx];
+    f[0] += fx; f[1] += fy; f[2] += fz;
+    eng_mark_forces_dirty(b->w->eng);
+}
+extern "C" void dBodyAddTorque(dBodyID b, dReal fx, dReal fy, dReal fz) {
+    fresh(b->w);
+    float *f = &HB(b).tacc[4 * b->idx];
+    f[0] += fx; f[1] += fy; f[2] += fz;
+    eng_mark_forces_dirty(b->w->eng);
+}
+extern "C" void dBodySetData(dBodyID b, void *d) { b->data = d; }
+extern "C" void *dBodyGetData(dBodyID b) { return b->data; }
+extern "C" dWorldID dBodyGetWorld(dBodyID b) { return b->w; }
+extern "C" void dBodySetEnvB200(dBodyID b, int env) { HB(b).env[b->idx] = env; }
+extern "C" int dBodyGetIndexB200(dBodyID b) { return b->idx; }
+extern "C" dBodyID dWorldGetBodyB200(dWorldID w, int i) { return (i >= 0 && i < (int)w->bodies.size()) ? &w->bodies[i] : nullptr; }
+
+// ------------------------------------------------------------------ spaces and geoms
+
+extern "C" dSpaceID dHashSpaceCreate(dSpaceID) {
+    dxSpace *s = new dxSpace();
+    s->w = current_world();
+    if (s->w) s->w->spaces.push_back(s);
+    return s;
+}
+extern "C" dSpaceID dSimpleSpaceCreate(dSpaceID p) { return dHashSpaceCreate(p); }
+extern "C" void dSpaceDestroy(dSpaceID s) {
+    if (!s) return;
+    if (s->w) {
+        for (dxGeom *g : s->geoms)
+            if (g->alive) dGeomDestroy(g);
+        for (auto &p : s->w->spaces) if (p == s) p = nullptr;
+    }
+    delete s;
+}
+extern "C" int dSpaceGetNumGeoms(dSpaceID s) {
+    int n = 0;
+    for (dxGeom *g : s->geoms) n += g->alive ? 1 : 0;
+    return n;
+}
+extern "C" dGeomID dSpaceGetGeom(dSpaceID s, int i) {
+    for (dxGeom *g : s->geoms)
+        if (g->alive && i-- == 0) return g;
+    return nullptr;
+}
+extern "C" dGeomID dSpaceGetGeomB200(dSpaceID s, int i) { return (i >= 0 && i < (int)s->geoms.size()) ? s->geoms[i] : nullptr; }
+
+#define HG(g) eng_geoms((g)->space->w->eng)
+
+static dxGeom *new_geom(dxSpace *s, int type, float d0, float d1, float d2, float d3) {
+    if (!s) fatal("geoms must be created in a space (dSpaceID 0 is not supported)");
+    dxWorld *w = space_world(s);
+    const int idx = eng_add_geom(w->eng);
+    HostGeoms &hg = eng_geoms(w->eng);
+    hg.type[idx] = type;
+    hg.dims[4 * idx] = d0; hg.dims[4 * idx + 1] = d1; hg.dims[4 * idx + 2] = d2; hg.dims[4 * idx + 3] = d3;
+    hg.env[idx] = -1;
+    w->geoms.push_back(dxGeom{s, idx, nullptr, nullptr, true, {0, 0, 0, 0, 0, 0}});
+    dxGeom *g = &w->geoms.back();
+    s->geoms.push_back(g);
+    return g;
+}
+
+extern "C" dGeomID dCreateSphere(dSpaceID s, dReal r) { return new_geom(s, G_SPHERE, r, 0, 0, 0); }
+extern "C" dGeomID dCreateBox(dSpaceID s, dReal lx, dReal ly, dReal lz) { return new_geom(s, G_BOX, lx, ly, lz, 0); }
+static void plane_normalize(float *p) {
+    // make_sure_plane_normal_has_unit_length
+    float l = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+    if (l > 0) {
+        l = 1.0f / sqrtf(l);
+        p[0] *= l; p[1] *= l; p[2] *= l; p[3] *= l;
+    } else {
+        p[0] = 1; p[1] = 0; p[2] = 0; p[3] = 0;
+    }
+}
+extern "C" dGeomID dCreatePlane(dSpaceID s, dReal a, dReal b, dReal c, dReal d) {
+    float p[4] = {a, b, c, d};
+    plane_normalize(p);
+    return new_geom(s, G_PLANE, p[0], p[1], p[2], p[3]);
+}
+extern "C" void dGeomDestroy(dGeomID g) {
+    if (!g || !g->alive) return;
+    HG(g).alive[g->idx] = 0;
+    eng_mark_geoms_dirty(g->space->w->eng);
+    g->alive = false;
+}
+extern "C" void dGeomSetBody(dGeomID g, dBodyID b) {
+    if (b && b->w != g->space->w) fatal("dGeomSetBody: the body belongs to a different world than the geom's space");
+    g->body = b;
+    HostGeoms &hg = HG(g);
+    hg.body[g->idx] = b ? b->idx : -1;
+    if (b && hg.env[g->idx] < 0) hg.env[g->idx] = eng_bodies(b->w->eng).env[b->idx];
+    eng_mark_geoms_dirty(g->space->w->eng);
+}
+extern "C" dBodyID dGeomGetBody(dGeomID g) { return g->body; }
+extern "C" void dGeomSetPosition(dGeomID g, dReal x, dReal y, dReal z) {
+    if (g->body) { dBodySetPosition(g->body, x, y, z); return; }
+    float *p = &HG(g).pos[4 * g->idx];
+    p[0] = x; p[1] = y; p[2] = z;
+    eng_mark_geoms_dirty(g->space->w->eng);
+}
+extern "C" void dGeomSetRotation(dGeomID g, const dMatrix3 R) {
+    if (g->body) { dBodySetRotation(g->body, R); return; }
+    float *r = &HG(g).R[12 * g->idx];
+    memcpy(r, R, 12 * sizeof(float));
+    r[3] = r[7] = r[11] = 0;
+    eng_mark_geoms_dirty(g->space->w->eng);
+}
+extern "C" void dGeomSetQuaternion(dGeomID g, const dQuaternion q) {
+    if (g->body) { dBodySetQuaternion(g->body, q); return; }
+    dQuaternion qq = {q[0], q[1], q[2], q[3]};
+    normalize4(qq);
+    dQtoR(qq, &HG(g).R[12 * g->idx]);
+    eng_mark_geoms_dirty(g->space->w->eng);
+}
+extern "C" const dReal *dGeomGetPosition(dGeomID g) {
+    if (g->body) return dBodyGetPosition(g->body);
+    return &HG(g).pos[4 * g->idx];
+}
+extern "C" const dReal *dGeomGetRotation(dGeomID g) {
+    if (g->body) return dBodyGetRotation(g->body);
+    return &HG(g).R[12 * g->idx];
+}
+extern "C" void dGeomGetQuaternion(dGeomID g, dQuaternion q) {
+    if (g->body) { memcpy(q, dBodyGetQuaternion(g->body), 4 * sizeof(float)); return; }
+    dRtoQ(&HG(g).R[12 * g->idx], q);
+}
+extern "C" int dGeomGetClass(dGeomID g) { return HG(g).type[g->idx]; }
+extern "C" void dGeomSetCategoryBits(dGeomID g, unsigned long bits) {
+    HG(g).cat[g->idx] = (uint32_t)bits;
+    eng_mark_geoms_dirty(g->space->w->eng);
+}
+extern "C" void dGeomSetCollideBits(dGeomID g, unsigned long bits) {
+    HG(g).col[g->idx] = (uint32_t)bits;
+    eng_mark_geoms_dirty(g->space->w->eng);
+}
+extern "C" unsigned long dGeomGetCategoryBits(dGeomID g) { return HG(g).cat[g->idx]; }
+extern "C" unsigned long dGeomGetCollideBits(dGeomID g) { return HG(g).col[g->idx]; }
+extern "C" void dGeomSetData(dGeomID g, void *d) { g->data = d; }
+extern "C" void *dGeomGetData(dGeomID g) { return g->data; }
+extern "C" dSpaceID dGeomGetSpace(dGeomID g) { return g->space; }
+extern "C" dReal dGeomSphereGetRadius(dGeomID g) { return HG(g).dims[4 * g->idx]; }
+extern "C" void dGeomSphereSetRadius(dGeomID g, dReal r) {
+    HG(g).dims[4 * g->idx] = r;
+    eng_mark_geoms_dirty(g->space->w->eng);
+}
+extern "C" void dGeomBoxGetLengths(dGeomID g, dVector3 out) {
+    for (int k = 0; k < 3; k++) out[k] = HG(g).dims[4 * g->idx + k];
+    out[3] = 0;
+}
+extern "C" void dGeomBoxSetLengths(dGeomID g, dReal lx, dReal ly, dReal lz) {
+    float *d = &HG(g).dims[4 * g->idx];
+    d[0] = lx; d[1] = ly; d[2] = lz;
+    eng_mark_geoms_dirty(g->space->w->eng);
+}
+extern "C" void dGeomPlaneGetParams(dGeomID g, dVector4 out) {
+    for (int k = 0; k < 4; k++) out[k] = HG(g).dims[4 * g->idx + k];
+}
+extern "C" void dGeomPlaneSetParams(dGeomID g, dReal a, dReal b, dReal c, dReal d) {
+    float p[4] = {a, b, c, d};
+    plane_normalize(p);
+    memcpy(&HG(g).dims[4 * g->idx], p, sizeof(p));
+    eng_mark_geoms_dirty(g->space->w->eng);
+}
+extern "C" void dGeomSetEnvB200(dGeomID g, int env) {
+    HG(g).env[g->idx] = env;
+    eng_mark_geoms_dirty(g->space->w->eng);
+}
+extern "C" int dGeomGetIndexB200(dGeomID g) { return g->idx; }
+
+extern "C" void dGeomGetAABB(dGeomID g, dReal aabb[6]) {
+    // host restatement of the AABB rules for a single geom (debug accessor; not on the hot path)
+    const HostGeoms &hg = HG(g);
+    const float *pos = dGeomGetPosition(g), *R = dGeomGetRotation(g), *d = &hg.dims[4 * g->idx];
+    const int type = hg.type[g->idx];
+    for (int k = 0; k < 3; k++) { aabb[2 * k] = -INFINITY; aabb[2 * k + 1] = INFINITY; }
+    if (type == G_SPHERE) {
+        for (int k = 0; k < 3; k++) { aabb[2 * k] = pos[k] - d[0]; aabb[2 * k + 1] = pos[k] + d[0]; }
+    } else if (type == G_BOX) {
+        for (int k = 0; k < 3; k++) {
+            float range = 0.5f * (fabsf(R[k * 4] * d[0]) + fabsf(R[k * 4 + 1] * d[1]) + fabsf(R[k * 4 + 2] * d[2]));
+            aabb[2 * k] = pos[k] - range;
+            aabb[2 * k + 1] = pos[k] + range;
+        }
+    } else if (type == G_PLANE) {
+        if (d[1] == 0.0f && d[2] == 0.0f) { aabb[0] = (d[0] > 0) ? -INFINITY : -d[3]; aabb[1] = (d[0] > 0) ? d[3] : INFINITY; }
+        else if (d[0] == 0.0f && d[2] == 0.0f) { aabb[2] = (d[1] > 0) ? -INFINITY : -d[3]; aabb[3] = (d[1] > 0) ? d[3] : INFINITY; }
+        else if (d[0] == 0.0f && d[1] == 0.0f) { aabb[4] = (d[2] > 0) ? -INFINITY : -d[3]; aabb[5] = (d[2] > 0) ? d[3] : INFINITY; }
+    }
+}
+
+// trimesh
+extern "C" dTriMeshDataID dGeomTriMeshDataCreate(void) { return new dxTriMeshData(); }
+extern "C" void dGeomTriMeshDataDestroy(dTriMeshDataID d) { delete d; }
+extern "C" void dGeomTriMeshDataBuildSingle(dTriMeshDataID d, const void *Vertices, int VertexStride, int VertexCount,
+                                            const void *Indices, int IndexCount, int TriStride) {
+    d->verts.resize((size_t)VertexCount * 3);
+    for (int i = 0; i < VertexCount; i++) {
+        const float *v = (const float *)((const char *)Vertices + (size_t)i * VertexStride);
+        d->verts[3 * i] = v[0]; d->verts[3 * i + 1] = v[1]; d->verts[3 * i + 2] = v[2];
+    }
+    const int nt = IndexCount / 3;
+    d->tris.resize((size_t)nt * 3);
+    for (int t = 0; t < nt; t++) {
+        const dTriIndex *ix = (const dTriIndex *)((const char *)Indices + (size_t)t * TriStride);
+        d->tris[3 * t] = (int)ix[0]; d->tris[3 * t + 1] = (int)ix[1]; d->tris[3 * t + 2] = (int)ix[2];
+    }
+    d->bound_world = nullptr;
+    d->mesh_id = -1;
+}
+extern "C" dGeomID dCreateTriMesh(dSpaceID s, dTriMeshDataID d, dTriCallback *, dTriArrayCallback *, dTriRayCallback *) {
+    dxWorld *w = space_world(s);
+    if (d->bound_world != w || d->mesh_id < 0) {
+        d->mesh_id = eng_add_mesh(w->eng, d->verts.data(), (int)d->verts.size() / 3, d->tris.data(), (int)d->tris.size() / 3);
+        d->bound_world = w;
+    }
+    return new_geom(s, G_TRIMESH, (float)d->mesh_id, 0, 0, 0);
+}
+extern "C" int dWorldAddTriMeshB200(dWorldID w, const float *verts, int nv, const int *tris, int nt) {
+    return eng_add_mesh(w->eng, verts, nv, tris, nt);
+}
+
+// ------------------------------------------------------------------ bulk creation / state
+
+extern "C" int dWorldAddBodiesB200(dWorldID w, int n, const float *pos3, const float *quat4, const float *lvel3,
+                                   const float *avel3, const float *mass, const float *inertia9, const int *flags,
+                                   const int *env) {
+    fresh(w);
+    HostBodies &hb = eng_bodies(w->eng);
+    const int first = hb.n;
+    for (int i = 0; i < n; i++) {
+        dxBody *b = new_body(w);
+        const int k = b->idx;
+        for (int c = 0; c < 3; c++) hb.pos[4 * k + c] = pos3[3 * i + c];
+        if (quat4) {
+            float *q = &hb.quat[4 * k];
+            memcpy(q, quat4 + 4 * i, 16);
+            normalize4(q);
+            dQtoR(q, &hb.R[12 * k]);
+        }
+        if (lvel3) for (int c = 0; c < 3; c++) hb.lvel[4 * k + c] = lvel3[3 * i + c];
+        if (avel3) for (int c = 0; c < 3; c++) hb.avel[4 * k + c] = avel3[3 * i + c];
+        const int fl = flags ? flags[i] : 0;
+        hb.flags[k] = fl;
+        hb.env[k] = env ? env[i] : 0;
+        const float m = mass ? mass[i] : 1.0f;
+        hb.lvel[4 * k + 3] = m;
+        if (inertia9)
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) hb.I[12 * k + 4 * r + c] = inertia9[9 * i + 3 * r + c];
+        if (fl & BF_KINEMATIC) {
+            hb.pos[4 * k + 3] = 0.f;
+            for (int c = 0; c < 12; c++) hb.invI[12 * k + c] = 0.f;
+        } else {
+            hb.pos[4 * k + 3] = 1.0f / m;
+            if (inertia9) invert3(&hb.I[12 * k], &hb.invI[12 * k]);
+        }
+    }
+    eng_mark_bodies_dirty(w->eng);
+    return first;
+}
+
+extern "C" int dSpaceAddGeomsB200(dSpaceID s, dWorldID w, int n, const int *type, const float *dims4, const int *body,
+                                  const float *pos3, const float *R12, const unsigned *cat, const unsigned *col,
+                                  const int *env) {
+    if (!s->w) { s->w = w; w->spaces.push_back(s); }
+    if (s->w != w) fatal("dSpaceAddGeomsB200: the space is bound to another world");
+    HostGeoms &hg = eng_geoms(w->eng);
+    const int first = hg.n;
+    for (int i = 0; i < n; i++) {
+        float d[4] = {dims4[4 * i], dims4[4 * i + 1], dims4[4 * i + 2], dims4[4 * i + 3]};
+        if (type[i] == G_PLANE) plane_normalize(d);
+        dxGeom *g = new_geom(s, type[i], d[0], d[1], d[2], d[3]);
+        const int k = g->idx;
+        const int b = body ? body[i] : -1;
+        if (b >= 0) {
+            if (b >= (int)w->bodies.size()) fatal("dSpaceAddGeomsB200: body index out of range");
+            g->body = &w->bodies[b];
+            hg.body[k] = b;
+        } else {
+            if (pos3) for (int c = 0; c < 3; c++) hg.pos[4 * k + c] = pos3[3 * i + c];
+            if (R12) {
+                memcpy(&hg.R[12 * k], R12 + 12 * i, 48);
+                hg.R[12 * k + 3] = hg.R[12 * k + 7] = hg.R[12 * k + 11] = 0;
+            }
+        }
+        if (cat) hg.cat[k] = cat[i];
+        if (col) hg.col[k] = col[i];
+        hg.env[k] = env ? env[i] : (b >= 0 ? eng_bodies(w->eng).env[b] : -1);
+    }
+    eng_mark_geoms_dirty(w->eng);
+    return first;
+}
+
+extern "C" void dWorldGetStateB200(dWorldID w, float *pos3, float *quat4, float *lvel3, float *avel3, float *R12) {
+    fresh(w);
+    const HostBodies &hb = eng_bodies(w->eng);
+    for (int i = 0; i < hb.n; i++) {
+        if (pos3) for (int c = 0; c < 3; c++) pos3[3 * i + c] = hb.pos[4 * i + c];
+        if (quat4) memcpy(quat4 + 4 * i, &hb.quat[4 * i], 16);
+        if (lvel3) for (int c = 0; c < 3; c++) lvel3[3 * i + c] = hb.lvel[4 * i + c];
+        if (avel3) for (int c = 0; c < 3; c++) avel3[3 * i + c] = hb.avel[4 * i + c];
+        if (R12) memcpy(R12 + 12 * i, &hb.R[12 * i], 48);
+    }
+}
+
+extern "C" void dWorldSetForcesB200(dWorldID w, const float *f6, int n) { eng_set_forces(w->eng, f6, n); }
+extern "C" void dWorldGetSnapshotB200(dWorldID w, float *dst, int first, int count, int blocking) {
+    eng_snapshot_to_host(w->eng, dst, first, count, blocking != 0);
+}
+extern "C" const float *dWorldGetSnapshotDeviceB200(dWorldID w) { return eng_snapshot_device(w->eng); }
+
+// ------------------------------------------------------------------ collision
+
+extern "C" void dSpaceCollideDeviceB200(dSpaceID s, int max_contacts) {
+    dxWorld *w = space_world(s);
+    eng_collide(w->eng, max_contacts);
+    w->device_contacts_pending = true;
+}
+
+extern "C" void dSpaceCollide(dSpaceID s, void *data, dNearCallback *callback) {
+    dxWorld *w = space_world(s);
+    eng_collide(w->eng, w->max_contacts);
+    w->device_contacts_pending = false;
+    w->cb_pairs = eng_fetch_pairs(w->eng);
+    const HostPairs &hp = w->cb_pairs;
+    w->in_callback = true;
+    for (int p = 0; p < hp.n_pairs; p++) {
+        w->cb_g1 = hp.g1[p]; w->cb_g2 = hp.g2[p];
+        w->cb_first = hp.first[p]; w->cb_count = hp.count[p];
+        callback(data, &w->geoms[hp.g1[p]], &w->geoms[hp.g2[p]]);
+    }
+    w->in_callback = false;
+    w->cb_g1 = w->cb_g2 = -1;
+}
+
+static int copy_contacts(dxWorld *w, int first, int count, bool swapped, dGeomID o1, dGeomID o2, int maxc,
+                         dContactGeom *contact, int skip) {
+    const HostPairs &hp = w->cb_pairs;
+    const int n = count < maxc ? count : maxc;
+    for (int k = 0; k < n; k++) {
+        dContactGeom *c = (dContactGeom *)((char *)contact + (size_t)k * skip);
+        const float *pd = hp.pos_depth + 4 * (size_t)(first + k), *ns = hp.normal_side + 4 * (size_t)(first + k);
+        c->pos[0] = pd[0]; c->pos[1] = pd[1]; c->pos[2] = pd[2]; c->pos[3] = 0;
+        const float sg = swapped ? -1.f : 1.f;
+        c->normal[0] = sg * ns[0]; c->normal[1] = sg * ns[1]; c->normal[2] = sg * ns[2]; c->normal[3] = 0;
+        c->depth = pd[3];
+        c->g1 = o1; c->g2 = o2;
+        int side;
+        memcpy(&side, &ns[3], sizeof(int));
+        c->side1 = swapped ? side : -1;
+        c->side2 = swapped ? -1 : side;
+    }
+    return n;
+}
+
+extern "C" int dCollide(dGeomID o1, dGeomID o2, int flags, dContactGeom *contact, int skip) {
+    const int maxc = flags & 0xffff;
+    if (!o1 || !o2 || o1 == o2 || maxc < 1) return 0;
+    dxWorld *w = o1->space->w;
+    if (o2->space->w != w) return 0;
+    if (w->in_callback && ((o1->idx == w->cb_g1 && o2->idx == w->cb_g2) || (o1->idx == w->cb_g2 && o2->idx == w->cb_g1))) {
+        const bool swapped = o1->idx != w->cb_g1;
+        if (w->cb_count <= maxc || w->cb_count <= 1)
+            return copy_contacts(w, w->cb_first, w->cb_count, swapped, o1, o2, maxc, contact, skip);
+        // fewer contacts requested than were precomputed: ODE culls differently, so the exact
+        // answer needs the pair re-collided with that limit (set dWorldSetMaxContactsB200 to avoid)
+        fatal("dCollide: max contacts smaller than the world's precomputed limit; call dWorldSetMaxContactsB200 first");
+    }
+    fatal("dCollide outside dSpaceCollide's callback is not supported by this build");
+    return 0;
+}
+
+extern "C" int dSpaceGetPairsB200(dSpaceID s, int *pairs2, int cap) {
+    dxWorld *w = space_world(s);
+    HostPairs hp = eng_fetch_pairs(w->eng);
+    w->cb_pairs = hp;
+    for (int p = 0; p < hp.n_pairs && p < cap; p++) { pairs2[2 * p] = hp.g1[p]; pairs2[2 * p + 1] = hp.g2[p]; }
+    return hp.n_pairs;
+}
+
+extern "C" int dSpaceGetContactsB200(dSpaceID s, int *count_per_pair, int cap_pairs, float *pos_depth4,
+                                     float *normal_side4, int cap_contacts) {
+    dxWorld *w = space_world(s);
+    HostPairs hp = eng_fetch_pairs(w->eng);
+    w->cb_pairs = hp;
+    int total = 0;
+    for (int p = 0; p < hp.n_pairs; p++) {
+        if (p < cap_pairs) count_per_pair[p] = hp.count[p];
+        for (int k = 0; k < hp.count[p]; k++) {
+            if (total < cap_contacts) {
+                memcpy(pos_depth4 + 4 * (size_t)total, hp.pos_depth + 4 * (size_t)(hp.first[p] + k), 16);
+                memcpy(normal_side4 + 4 * (size_t)total, hp.normal_side + 4 * (size_t)(hp.first[p] + k), 16);
+            }
+            total++;
+        }
+    }
+    return total;
+}
+
+extern "C" int dWorldGetSolverOrderB200(dWorldID w, int *g1, int *g2, int *k, int cap) {
+    return eng_export_solver_order(w->eng, g1, g2, k, cap);
+}
+
+// ------------------------------------------------------------------ contact joints
+
+extern "C" dJointGroupID dJointGroupCreate(int) { return new dxJointGroup(); }
+extern "C" void dJointGroupEmpty(dJointGroupID g) {
+    if (g) g->joints.clear();
+}
+extern "C" void dJointGroupDestroy(dJointGroupID g) {
+    if (!g) return;
+    for (dxWorld *w : g_worlds)
+        if (w)
+            for (auto &p : w->groups) if (p == g) p = nullptr;
+    for (dxWorld *w : g_worlds)
+        if (w) {
+            std::vector<dxJointGroup *> keep;
+            for (auto p : w->groups) if (p) keep.push_back(p);
+            w->groups.swap(keep);
+        }
+    delete g;
+}
+
+static dxJointGroup g_default_group;
+
+extern "C" dJointID dJointCreateContact(dWorldID w, dJointGroupID g, const dContact *c) {
+    if (!g) g = &g_default_group;
+    bool known = false;
+    for (dxJointGroup *p : w->groups) if (p == g) known = true;
+    if (!known) w->groups.push_back(g);
+    dxJoint j;
+    j.w = w; j.b1 = j.b2 = nullptr;
+    j.hc.pos[0] = c->geom.pos[0]; j.hc.pos[1] = c->geom.pos[1]; j.hc.pos[2] = c->geom.pos[2];
+    j.hc.depth = c->geom.depth;
+    j.hc.normal[0] = c->geom.normal[0]; j.hc.normal[1] = c->geom.normal[1]; j.hc.normal[2] = c->geom.normal[2];
+    j.hc.b1 = j.hc.b2 = -1;
+    // only the fields the mode selects are read: the reference leaves the rest uninitialised (src/main.c:676)
+    const dSurfaceParameters &s = c->surface;
+    Surface &o = j.hc.surf;
+    memset(&o, 0, sizeof(o));
+    o.mode = s.mode;
+    o.mu = s.mu;
+    if (s.mode & dContactMu2) o.mu2 = s.mu2;
+    if (s.mode & dContactBounce) { o.bounce = s.bounce; o.bounce_vel = s.bounce_vel; }
+    if (s.mode & dContactSoftERP) o.soft_erp = s.soft_erp;
+    if (s.mode & dContactSoftCFM) o.soft_cfm = s.soft_cfm;
+    if (s.mode & dContactMotion1) o.motion1 = s.motion1;
+    if (s.mode & dContactMotion2) o.motion2 = s.motion2;
+    if (s.mode & dContactMotionN) o.motionN = s.motionN;
+    if (s.mode & dContactSlip1) o.slip1 = s.slip1;
+    if (s.mode & dContactSlip2) o.slip2 = s.slip2;
+    if (s.mode & dContactFDir1) fatal("dContactFDir1 is not supported (friction directions come from dPlaneSpace)");
+    g->joints.push_back(j);
+    return &g->joints.back();
+}
+extern "C" void dJointAttach(dJointID j, dBodyID b1, dBodyID b2) {
+    j->b1 = b1;
+    j->b2 = b2;
+}
+extern "C" dBodyID dJointGetBody(dJointID j, int index) { return index == 0 ? j->b1 : j->b2; }
+
+// ------------------------------------------------------------------ primitive test hooks
+// (host arrays in, host arrays out; used by tests/test_prims_gpu.py to check the hand-written scan
+// and radix sort against numpy at awkward sizes)
+#include "prims.cuh"
+
+extern "C" int dTestScanB200(const int *in, int *out, long n, int *total) {
+    OB_CUDA(cudaSetDevice(default_device()));
+    int *d = nullptr, *dt = nullptr;
+    OB_CUDA(cudaMalloc(&d, (size_t)(n > 0 ? n : 1) * sizeof(int)));
+    OB_CUDA(cudaMalloc(&dt, sizeof(int)));
+    OB_CUDA(cudaMemcpy(d, in, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    ScanWorkspace ws;
+    scan_exclusive(d, d, n, nullptr, dt, ws, 0);
+    OB_CUDA(cudaDeviceSynchronize());
+    OB_CUDA(cudaMemcpy(out, d, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    OB_CUDA(cudaMemcpy(total, dt, sizeof(int), cudaMemcpyDeviceToHost));
+    scan_workspace_free(ws);
+    cudaFree(d);
+    cudaFree(dt);
+    return 0;
+}
+
+extern "C" int dTestSortB200(unsigned *keys, int *vals, long n, int bits) {
+    OB_CUDA(cudaSetDevice(default_device()));
+    uint32_t *dk = nullptr;
+    int *dv = nullptr;
+    OB_CUDA(cudaMalloc(&dk, (size_t)(n > 0 ? n : 1) * sizeof(uint32_t)));
+    OB_CUDA(cudaMalloc(&dv, (size_t)(n > 0 ? n : 1) * sizeof(int)));
+    OB_CUDA(cudaMemcpy(dk, keys, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    OB_CUDA(cudaMemcpy(dv, vals, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    SortWorkspace ws;
+    sort_pairs(dk, dv, n, nullptr, bits, ws, 0);
+    OB_CUDA(cudaDeviceSynchronize());
+    OB_CUDA(cudaMemcpy(keys, dk, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    OB_CUDA(cudaMemcpy(vals, dv, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    sort_workspace_free(ws);
+    cudaFree(dk);
+    cudaFree(dv);
+    return 0;
+}

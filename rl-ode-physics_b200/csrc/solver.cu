@@ -1,0 +1,672 @@
+// solver.cu -- K5..K8: contact manifolds -> graph colouring -> row build -> SOR/PGS iterations with
+// the integrator and snapshot pack fused into the solver tail.
+//
+// Replaces what libode does inside dWorldStep/dWorldQuickStep (/root/reference/src/main.c:213) for
+// the contact joints the reference's NearCallback creates (src/main.c:683-691), plus the app-side
+// GetTransformMat pack (src/main.c:602-622, used at :236).
+//
+// Parallelisation: one thread owns one manifold (all contacts between one geom pair) and solves
+// its rows in order normal, tangent 1, tangent 2 per contact.  Manifolds are edge-coloured on the
+// body graph so that manifolds of one colour share no dynamic body; colours run one after the
+// other separated by grid-wide barriers inside one persistent cooperative kernel.  This is exactly
+// a sequential Gauss-Seidel sweep in (colour, manifold, contact, row) order -- the order the test
+// oracle is given -- so results match a CPU run of that order bit for bit.
+//
+// Rows are not stored as 12-float Jacobians: per contact the kernel streams the normal, the two
+// lever arms and 9 row scalars (96 B with lambda) and rebuilds J and M^-1 J^T from the bodies'
+// world inverse inertia each iteration; arithmetic is free on a kernel that is HBM-bound.
+#include <cooperative_groups.h>
+
+#include "engine_impl.h"
+
+namespace cg = cooperative_groups;
+
+namespace ob {
+
+constexpr int MODE_MU2 = 0x001, MODE_BOUNCE = 0x004, MODE_SOFT_ERP = 0x008, MODE_SOFT_CFM = 0x010,
+              MODE_MOTION1 = 0x020, MODE_MOTION2 = 0x040, MODE_MOTIONN = 0x080, MODE_SLIP1 = 0x100,
+              MODE_SLIP2 = 0x200, MODE_APPROX1_1 = 0x1000, MODE_APPROX1_2 = 0x2000;
+
+constexpr int REC_REV = 1 << 8, REC_DYN1 = 1 << 9, REC_DYN2 = 1 << 10;
+constexpr int OVERFLOW_COLOUR = 64;
+
+// ------------------------------------------------------------------ per-body step preparation
+
+// world-frame inverse inertia, gyroscopic torque, gravity, v/h + M^-1 f; clears the accumulators
+__global__ void __launch_bounds__(256) k_body_prep(BodyArrays B, StepConfig cfg, StepStats *__restrict__ stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        stats->n_rows = 0; stats->n_rows1 = 0; stats->n_rows2 = 0; stats->n_contacts = 0;
+        stats->n_manifolds = 0; stats->n_colours = 0; stats->n_overflow = 0; stats->colour_rounds = 0;
+    }
+    if (i >= B.n) return;
+    const float4 p = B.pos[i];
+    const float invM = p.w;
+    const M3 R = load_m3(B.R, i);
+    const M3 iIb = load_m3(B.invI, i);
+    const int flags = B.flags[i];
+    // dMultiply2_333(tmp, invI, R): tmp = invI * R^T ; dMultiply0_333(out, R, tmp)
+    M3 tmp;
+    tmp.r0 = v3(dot(iIb.r0, R.r0), dot(iIb.r0, R.r1), dot(iIb.r0, R.r2));
+    tmp.r1 = v3(dot(iIb.r1, R.r0), dot(iIb.r1, R.r1), dot(iIb.r1, R.r2));
+    tmp.r2 = v3(dot(iIb.r2, R.r0), dot(iIb.r2, R.r1), dot(iIb.r2, R.r2));
+    M3 iIw;
+    iIw.r0 = v3(dot(R.r0, col(tmp, 0)), dot(R.r0, col(tmp, 1)), dot(R.r0, col(tmp, 2)));
+    iIw.r1 = v3(dot(R.r1, col(tmp, 0)), dot(R.r1, col(tmp, 1)), dot(R.r1, col(tmp, 2)));
+    iIw.r2 = v3(dot(R.r2, col(tmp, 0)), dot(R.r2, col(tmp, 1)), dot(R.r2, col(tmp, 2)));
+    const float4 lv4 = B.lvel[i], av4 = B.avel[i];
+    const V3 lv = v3(lv4), av = v3(av4);
+    V3 f = v3(B.facc[i]), t = v3(B.tacc[i]);
+    if ((flags & BF_GYRO) && !(flags & BF_KINEMATIC)) {
+        const M3 Ib = load_m3(B.I, i);
+        M3 t2;
+        t2.r0 = v3(dot(Ib.r0, R.r0), dot(Ib.r0, R.r1), dot(Ib.r0, R.r2));
+        t2.r1 = v3(dot(Ib.r1, R.r0), dot(Ib.r1, R.r1), dot(Ib.r1, R.r2));
+        t2.r2 = v3(dot(Ib.r2, R.r0), dot(Ib.r2, R.r1), dot(Ib.r2, R.r2));
+        M3 Iw;
+        Iw.r0 = v3(dot(R.r0, col(t2, 0)), dot(R.r0, col(t2, 1)), dot(R.r0, col(t2, 2)));
+        Iw.r1 = v3(dot(R.r1, col(t2, 0)), dot(R.r1, col(t2, 1)), dot(R.r1, col(t2, 2)));
+        Iw.r2 = v3(dot(R.r2, col(t2, 0)), dot(R.r2, col(t2, 1)), dot(R.r2, col(t2, 2)));
+        const V3 L = mul(Iw, av);
+        const V3 gt = cross(av, L);
+        t = t - gt;
+    }
+    if (!(flags & BF_NOGRAVITY)) {
+        const float mass = lv4.w;
+        f.x += mass * cfg.gx; f.y += mass * cfg.gy; f.z += mass * cfg.gz;
+    }
+    B.facc[i] = make_float4(f.x, f.y, f.z, 0.f);
+    B.tacc[i] = make_float4(t.x, t.y, t.z, 0.f);
+    const float h1 = 1.0f / cfg.h;
+    const V3 it = mul(iIw, t);
+    B.tmp[2 * i] = make_float4(f.x * invM + lv.x * h1, f.y * invM + lv.y * h1, f.z * invM + lv.z * h1, 0.f);
+    B.tmp[2 * i + 1] = make_float4(it.x + av.x * h1, it.y + av.y * h1, it.z + av.z * h1, 0.f);
+    B.inv[3 * i] = make_float4(iIw.r0.x, iIw.r0.y, iIw.r0.z, invM);
+    B.inv[3 * i + 1] = make_float4(iIw.r1.x, iIw.r1.y, iIw.r1.z, 0.f);
+    B.inv[3 * i + 2] = make_float4(iIw.r2.x, iIw.r2.y, iIw.r2.z, 0.f);
+    B.fc[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    B.fc[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    B.colmask[i] = 0ull;
+    B.prio[i] = ~0ull;
+}
+
+// ------------------------------------------------------------------ manifolds from device contacts
+
+__global__ void __launch_bounds__(256) k_manifold_flags(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
+                                                         const int *__restrict__ g_body, const int *__restrict__ nc,
+                                                         int *__restrict__ flag) {
+    const int n = bc->n_pairs;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const int2 pr = pairs[p];
+        flag[p] = (nc[p] > 0 && (g_body[pr.x] >= 0 || g_body[pr.y] >= 0)) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_manifold_write(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
+                                                         const int *__restrict__ g_body, const int *__restrict__ nc,
+                                                         const int *__restrict__ scanned, const float4 *__restrict__ b_pos,
+                                                         ManifoldArrays M, StepStats *__restrict__ stats) {
+    const int n = bc->n_pairs;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const int2 pr = pairs[p];
+        int b1 = g_body[pr.x], b2 = g_body[pr.y];
+        const int c = nc[p];
+        if (!(c > 0 && (b1 >= 0 || b2 >= 0))) continue;
+        const int m = scanned[p];
+        if (m >= M.cap) { atomicOr(&stats->flags, SF_MANIFOLD_OVERFLOW); continue; }
+        int w = c;
+        if (b1 < 0) { b1 = b2; b2 = -1; w |= REC_REV; } // dJointAttach: NULL body1 swaps, REVERSE
+        if (b_pos[b1].w > 0.f) w |= REC_DYN1;
+        if (b2 >= 0 && b_pos[b2].w > 0.f) w |= REC_DYN2;
+        M.rec[m] = make_int4(b1, b2, p, w);
+    }
+}
+
+__global__ void k_manifold_count(const int *__restrict__ total, ManifoldArrays M, StepStats *__restrict__ stats) {
+    int n = *total;
+    if (n > M.cap) n = M.cap;
+    *M.count = n;
+    stats->n_manifolds = n;
+    M.meta[0] = 0; M.meta[1] = 0; M.meta[2] = 0; M.meta[3] = 0; M.meta[4] = 0;
+}
+
+// flag DYN bits for host-provided manifold records
+__global__ void __launch_bounds__(256) k_manifold_dynbits(ManifoldArrays M, const float4 *__restrict__ b_pos) {
+    const int n = *M.count;
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
+        int4 r = M.rec[m];
+        r.w &= ~(REC_DYN1 | REC_DYN2);
+        if (b_pos[r.x].w > 0.f) r.w |= REC_DYN1;
+        if (r.y >= 0 && b_pos[r.y].w > 0.f) r.w |= REC_DYN2;
+        M.rec[m] = r;
+    }
+}
+
+// ------------------------------------------------------------------ edge colouring
+
+__device__ __forceinline__ unsigned long long manifold_prio(int m) {
+    unsigned x = (unsigned)m * 0x9E3779B1u;
+    x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13; x *= 0xC2B2AE3Du; x ^= x >> 16;
+    return ((unsigned long long)x << 32) | (unsigned)m;
+}
+
+// Deterministic parallel greedy colouring: in every round an uncoloured manifold wins if it has
+// the smallest hashed priority among the uncoloured manifolds at both of its dynamic bodies; a
+// winner takes the lowest colour free at both bodies.  Only kinematic/static ends never conflict.
+__global__ void __launch_bounds__(256) k_colour(ManifoldArrays M, BodyArrays B) {
+    cg::grid_group grid = cg::this_grid();
+    const int n = *M.count;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+    for (int m = gt; m < n; m += gs) M.colour[m] = -1;
+    grid.sync();
+    int round = 0;
+    for (;; round++) {
+        int *rem_cur = &M.meta[2 + (round & 1)], *rem_next = &M.meta[2 + ((round + 1) & 1)];
+        if (gt == 0) *rem_next = 0;
+        for (int m = gt; m < n; m += gs) {
+            if (M.colour[m] >= 0) continue;
+            const int4 r = M.rec[m];
+            const unsigned long long pr = manifold_prio(m);
+            if (r.w & REC_DYN1) atomicMin(&B.prio[r.x], pr);
+            if (r.w & REC_DYN2) atomicMin(&B.prio[r.y], pr);
+        }
+        grid.sync();
+        int local = 0;
+        for (int m = gt; m < n; m += gs) {
+            if (M.colour[m] >= 0) continue;
+            const int4 r = M.rec[m];
+            const unsigned long long pr = manifold_prio(m);
+            const bool d1 = r.w & REC_DYN1, d2 = r.w & REC_DYN2;
+            const bool ok = (!d1 || B.prio[r.x] == pr) && (!d2 || B.prio[r.y] == pr);
+            if (ok) {
+                unsigned long long mask = 0ull;
+                if (d1) mask |= B.colmask[r.x];
+                if (d2) mask |= B.colmask[r.y];
+                int c;
+                if (~mask == 0ull) {
+                    c = OVERFLOW_COLOUR;
+                    atomicAdd(&M.meta[1], 1);
+                } else {
+                    c = __ffsll((long long)~mask) - 1;
+                    const unsigned long long bit = 1ull << c;
+                    if (d1) B.colmask[r.x] |= bit;
+                    if (d2) B.colmask[r.y] |= bit;
+                    atomicMax(&M.meta[0], c + 1);
+                }
+                M.colour[m] = c;
+            } else {
+                local++;
+            }
+        }
+        // warp-aggregate the remaining count
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0 && local) atomicAdd(rem_cur, local);
+        grid.sync();
+        const int rem = *rem_cur;
+        if (rem == 0) break;
+        for (int m = gt; m < n; m += gs) {
+            if (M.colour[m] >= 0) continue;
+            const int4 r = M.rec[m];
+            if (r.w & REC_DYN1) B.prio[r.x] = ~0ull;
+            if (r.w & REC_DYN2) B.prio[r.y] = ~0ull;
+        }
+        grid.sync();
+    }
+    if (gt == 0) M.meta[4] = round + 1;
+}
+
+__global__ void __launch_bounds__(256) k_colour_keys(ManifoldArrays M) {
+    const int n = *M.count;
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
+        const int nc = M.rec[m].w & 0xff;
+        M.skey[m] = ((uint32_t)M.colour[m] << 3) | (uint32_t)(8 - nc);
+        M.sidx[m] = m;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_colour_bounds(ManifoldArrays M) {
+    const int n = *M.count;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const int c = (int)(M.skey[s] >> 3);
+        if (s == 0 || (int)(M.skey[s - 1] >> 3) != c) M.colour_start[c] = s;
+    }
+}
+
+__global__ void k_colour_fixup(ManifoldArrays M, StepStats *__restrict__ stats) {
+    const int n = *M.count;
+    M.colour_start[OVERFLOW_COLOUR + 1] = n;
+    for (int c = OVERFLOW_COLOUR; c >= 0; c--)
+        if (M.colour_start[c] < 0) M.colour_start[c] = M.colour_start[c + 1];
+    stats->n_colours = M.meta[0];
+    stats->n_overflow = M.meta[1];
+    stats->colour_rounds = M.meta[4];
+}
+
+__global__ void k_colour_start_init(ManifoldArrays M) {
+    if (threadIdx.x < OVERFLOW_COLOUR + 2) M.colour_start[threadIdx.x] = -1;
+}
+
+// ------------------------------------------------------------------ row build
+
+struct ContactSource {
+    const float4 *pd, *ns;
+    const Surface *surf; // per contact (compat) or nullptr
+    int kstride;         // index = cbase + k * kstride
+};
+
+__device__ __forceinline__ int surface_rows(const Surface &s) {
+    // dxJointContact::getInfo1
+    int m = 1;
+    const float mu = s.mu < 0 ? 0 : s.mu;
+    if (s.mode & MODE_MU2) {
+        const float mu2 = s.mu2 < 0 ? 0 : s.mu2;
+        if (mu > 0) m++;
+        if (mu2 > 0) m++;
+    } else if (mu > 0) m += 2;
+    return m;
+}
+
+struct BodyKin {
+    V3 x, lv, av, tv, tw;
+    M3 iI;
+    float invM;
+};
+
+__device__ __forceinline__ BodyKin load_kin(const BodyArrays &B, int b) {
+    BodyKin k;
+    const float4 p = B.pos[b];
+    k.x = v3(p);
+    k.lv = v3(B.lvel[b]);
+    k.av = v3(B.avel[b]);
+    k.tv = v3(B.tmp[2 * b]);
+    k.tw = v3(B.tmp[2 * b + 1]);
+    const float4 i0 = B.inv[3 * b], i1 = B.inv[3 * b + 1], i2 = B.inv[3 * b + 2];
+    k.iI = M3{v3(i0), v3(i1), v3(i2)};
+    k.invM = i0.w;
+    return k;
+}
+
+// one constraint row of dxJointContact::getInfo2 + QuickStep's rhs / Ad
+__device__ __forceinline__ void build_row(V3 dir, V3 c1, V3 c2, const BodyKin &k1, const BodyKin &k2, bool two,
+                                          float cval, float cfm, const StepConfig &cfg, float &rhs_s, float &Ad,
+                                          float &Adcfm) {
+    const float h1 = 1.0f / cfg.h;
+    const V3 J1a = cross(c1, dir);
+    V3 J2l = v3(0.f, 0.f, 0.f), J2a = v3(0.f, 0.f, 0.f);
+    // rhs = c/h - J (v/h + invM fe)
+    float sum = 0.f;
+    sum += dir.x * k1.tv.x; sum += dir.y * k1.tv.y; sum += dir.z * k1.tv.z;
+    sum += J1a.x * k1.tw.x; sum += J1a.y * k1.tw.y; sum += J1a.z * k1.tw.z;
+    if (two) {
+        J2l = -dir;
+        J2a = -cross(c2, dir);
+        sum += J2l.x * k2.tv.x; sum += J2l.y * k2.tv.y; sum += J2l.z * k2.tv.z;
+        sum += J2a.x * k2.tw.x; sum += J2a.y * k2.tw.y; sum += J2a.z * k2.tw.z;
+    }
+    const float rhs = cval * h1 - sum;
+    const float cfm_h = cfm * h1;
+    // Ad = w / (J invM J^T + cfm)
+    const V3 iM1l = v3(k1.invM * dir.x, k1.invM * dir.y, k1.invM * dir.z);
+    const V3 iM1a = mul(k1.iI, J1a);
+    float d = 0.f;
+    d += iM1l.x * dir.x; d += iM1l.y * dir.y; d += iM1l.z * dir.z;
+    d += iM1a.x * J1a.x; d += iM1a.y * J1a.y; d += iM1a.z * J1a.z;
+    if (two) {
+        const V3 iM2l = v3(k2.invM * J2l.x, k2.invM * J2l.y, k2.invM * J2l.z);
+        const V3 iM2a = mul(k2.iI, J2a);
+        d += iM2l.x * J2l.x; d += iM2l.y * J2l.y; d += iM2l.z * J2l.z;
+        d += iM2a.x * J2a.x; d += iM2a.y * J2a.y; d += iM2a.z * J2a.z;
+    }
+    Ad = cfg.sor_w / (d + cfm_h);
+    rhs_s = rhs * Ad;
+    Adcfm = Ad * cfm_h;
+}
+
+__global__ void __launch_bounds__(128) k_rows(ManifoldArrays M, BodyArrays B, ContactSource src, Surface usurf,
+                                               SolverArrays S, StepConfig cfg, StepStats *__restrict__ stats) {
+    const int n = *M.count;
+    int rows1 = 0, rows2 = 0, ncont = 0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const int m = M.sidx[s];
+        const int4 rec = M.rec[m];
+        const int nc = rec.w & 0xff;
+        const bool rev = rec.w & REC_REV, two = rec.y >= 0;
+        S.mrec[s] = make_int4(rec.x, rec.y, nc, m);
+        const BodyKin k1 = load_kin(B, rec.x);
+        BodyKin k2;
+        if (two) k2 = load_kin(B, rec.y);
+        else {
+            k2.x = v3(0.f, 0.f, 0.f); k2.lv = k2.av = k2.tv = k2.tw = k2.x;
+            k2.iI = M3{k2.x, k2.x, k2.x}; k2.invM = 0.f;
+        }
+        for (int k = 0; k < nc; k++) {
+            const size_t ci = (size_t)rec.z + (size_t)k * src.kstride;
+            const float4 pd = src.pd[ci], ns = src.ns[ci];
+            const Surface sf = src.surf ? src.surf[ci] : usurf;
+            const int the_m = surface_rows(sf);
+            V3 normal = v3(ns);
+            if (rev) normal = -normal;
+            const V3 pos = v3(pd);
+            const V3 c1 = pos - k1.x;
+            const V3 c2 = two ? (pos - k2.x) : v3(0.f, 0.f, 0.f);
+            // normal row: pushout, max_vel cap, bounce
+            float erp = cfg.erp;
+            if (sf.mode & MODE_SOFT_ERP) erp = sf.soft_erp;
+            const float kk = (1.0f / cfg.h) * erp;
+            float depth = pd.w - cfg.min_depth;
+            if (depth < 0) depth = 0;
+            float cfmN = cfg.cfm;
+            if (sf.mode & MODE_SOFT_CFM) cfmN = sf.soft_cfm;
+            float motionN = 0.f;
+            if (sf.mode & MODE_MOTIONN) motionN = sf.motionN;
+            float cN = kk * depth + motionN;
+            if (cN > cfg.max_vel) cN = cfg.max_vel;
+            if (sf.mode & MODE_BOUNCE) {
+                const V3 J1a = cross(c1, normal);
+                float outgoing = dot(normal, k1.lv) + dot(J1a, k1.av);
+                if (two) {
+                    const V3 J2l = -normal;
+                    const V3 J2a = -cross(c2, normal);
+                    outgoing += dot(J2l, k2.lv) + dot(J2a, k2.av);
+                }
+                outgoing -= motionN;
+                if (sf.bounce_vel >= 0 && (-outgoing) > sf.bounce_vel) {
+                    const float newc = -sf.bounce * outgoing + motionN;
+                    if (newc > cN) cN = newc;
+                }
+            }
+            float rhsN, AdN, AdcfmN;
+            build_row(normal, c1, c2, k1, k2, two, cN, cfmN, cfg, rhsN, AdN, AdcfmN);
+            float4 q3 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = q3;
+            int lflags = the_m;
+            if (the_m >= 2) {
+                V3 t1, t2;
+                plane_space(normal, t1, t2);
+                const float mu = sf.mu < 0 ? 0 : sf.mu;
+                float c1v = (sf.mode & MODE_MOTION1) ? sf.motion1 : 0.f;
+                float cfm1 = (sf.mode & MODE_SLIP1) ? sf.slip1 : cfg.cfm;
+                build_row(t1, c1, c2, k1, k2, two, c1v, cfm1, cfg, q3.x, q3.y, q3.z);
+                q3.w = mu;
+                if (sf.mode & MODE_APPROX1_1) lflags |= 0x10;
+                if (the_m >= 3) {
+                    float c2v = (sf.mode & MODE_MOTION2) ? sf.motion2 : 0.f;
+                    float cfm2 = (sf.mode & MODE_SLIP2) ? sf.slip2 : cfg.cfm;
+                    build_row(t2, c1, c2, k1, k2, two, c2v, cfm2, cfg, q4.x, q4.y, q4.z);
+                    q4.w = (sf.mode & MODE_MU2) ? (sf.mu2 < 0 ? 0 : sf.mu2) : mu;
+                    if (sf.mode & MODE_APPROX1_2) lflags |= 0x20;
+                }
+            }
+            const size_t si = (size_t)k * S.cap + s;
+            S.q0[si] = make_float4(normal.x, normal.y, normal.z, rhsN);
+            S.q1[si] = make_float4(c1.x, c1.y, c1.z, AdN);
+            S.q2[si] = make_float4(c2.x, c2.y, c2.z, AdcfmN);
+            S.q3[si] = q3;
+            S.q4[si] = q4;
+            S.lam[si] = make_float4(0.f, 0.f, 0.f, __int_as_float(lflags));
+            if (two) rows2 += the_m; else rows1 += the_m;
+            ncont++;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        rows1 += __shfl_xor_sync(0xffffffffu, rows1, o);
+        rows2 += __shfl_xor_sync(0xffffffffu, rows2, o);
+        ncont += __shfl_xor_sync(0xffffffffu, ncont, o);
+    }
+    if ((threadIdx.x & 31) == 0 && (rows1 | rows2 | ncont)) {
+        atomicAdd(&stats->n_rows1, rows1);
+        atomicAdd(&stats->n_rows2, rows2);
+        atomicAdd(&stats->n_rows, rows1 + rows2);
+        atomicAdd(&stats->n_contacts, ncont);
+    }
+}
+
+// ------------------------------------------------------------------ SOR/PGS + fused tail
+
+struct FC {
+    V3 l, a;
+};
+
+// one row of ODE's SOR_LCP inner loop (quickstep.cpp), J rebuilt from (dir, c1, c2)
+__device__ __forceinline__ void solve_row(V3 dir, V3 c1, V3 c2, bool two, float invM1, const M3 &iI1, float invM2,
+                                          const M3 &iI2, float rhs_s, float Ad, float Adcfm, float lo, float hi,
+                                          float &lambda, FC &f1, FC &f2) {
+    const V3 J1a = cross(c1, dir);
+    const float old_lambda = lambda;
+    float delta = rhs_s - old_lambda * Adcfm;
+    // J is pre-scaled by Ad in ODE; scale component-wise so the products round identically
+    delta -= f1.l.x * (dir.x * Ad) + f1.l.y * (dir.y * Ad) + f1.l.z * (dir.z * Ad) + f1.a.x * (J1a.x * Ad) +
+             f1.a.y * (J1a.y * Ad) + f1.a.z * (J1a.z * Ad);
+    V3 J2l = v3(0.f, 0.f, 0.f), J2a = J2l;
+    if (two) {
+        J2l = -dir;
+        J2a = -cross(c2, dir);
+        delta -= f2.l.x * (J2l.x * Ad) + f2.l.y * (J2l.y * Ad) + f2.l.z * (J2l.z * Ad) + f2.a.x * (J2a.x * Ad) +
+                 f2.a.y * (J2a.y * Ad) + f2.a.z * (J2a.z * Ad);
+    }
+    const float new_lambda = old_lambda + delta;
+    if (new_lambda < lo) { delta = lo - old_lambda; lambda = lo; }
+    else if (new_lambda > hi) { delta = hi - old_lambda; lambda = hi; }
+    else lambda = new_lambda;
+    const V3 iM1a = mul(iI1, J1a);
+    f1.l.x += delta * (invM1 * dir.x); f1.l.y += delta * (invM1 * dir.y); f1.l.z += delta * (invM1 * dir.z);
+    f1.a.x += delta * iM1a.x; f1.a.y += delta * iM1a.y; f1.a.z += delta * iM1a.z;
+    if (two) {
+        const V3 iM2a = mul(iI2, J2a);
+        f2.l.x += delta * (invM2 * J2l.x); f2.l.y += delta * (invM2 * J2l.y); f2.l.z += delta * (invM2 * J2l.z);
+        f2.a.x += delta * iM2a.x; f2.a.y += delta * iM2a.y; f2.a.z += delta * iM2a.z;
+    }
+}
+
+__device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, const BodyArrays &B) {
+    const int4 rec = S.mrec[s];
+    const int b1 = rec.x, b2 = rec.y, nc = rec.z;
+    const bool two = b2 >= 0;
+    FC f1, f2;
+    {
+        const float4 a = B.fc[2 * b1], b = B.fc[2 * b1 + 1];
+        f1.l = v3(a); f1.a = v3(b);
+    }
+    const float4 i10 = B.inv[3 * b1], i11 = B.inv[3 * b1 + 1], i12 = B.inv[3 * b1 + 2];
+    const M3 iI1 = M3{v3(i10), v3(i11), v3(i12)};
+    const float invM1 = i10.w;
+    M3 iI2 = M3{v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f)};
+    float invM2 = 0.f;
+    f2.l = v3(0.f, 0.f, 0.f); f2.a = f2.l;
+    if (two) {
+        const float4 a = B.fc[2 * b2], b = B.fc[2 * b2 + 1];
+        f2.l = v3(a); f2.a = v3(b);
+        const float4 i20 = B.inv[3 * b2], i21 = B.inv[3 * b2 + 1], i22 = B.inv[3 * b2 + 2];
+        iI2 = M3{v3(i20), v3(i21), v3(i22)};
+        invM2 = i20.w;
+    }
+    for (int k = 0; k < nc; k++) {
+        const size_t si = (size_t)k * S.cap + s;
+        const float4 q0 = S.q0[si], q1 = S.q1[si], q2 = S.q2[si];
+        float4 lam = S.lam[si];
+        const int lflags = __float_as_int(lam.w);
+        const int the_m = lflags & 0xf;
+        const V3 n = v3(q0), c1 = v3(q1), c2 = v3(q2);
+        solve_row(n, c1, c2, two, invM1, iI1, invM2, iI2, q0.w, q1.w, q2.w, 0.f, INFINITY, lam.x, f1, f2);
+        if (the_m >= 2) {
+            const float4 q3 = S.q3[si];
+            V3 t1, t2;
+            plane_space(n, t1, t2);
+            float hi = q3.w, lo = -q3.w;
+            if (lflags & 0x10) { hi = fabsf(q3.w * lam.x); lo = -hi; }
+            solve_row(t1, c1, c2, two, invM1, iI1, invM2, iI2, q3.x, q3.y, q3.z, lo, hi, lam.y, f1, f2);
+            if (the_m >= 3) {
+                const float4 q4 = S.q4[si];
+                hi = q4.w; lo = -q4.w;
+                if (lflags & 0x20) { hi = fabsf(q4.w * lam.x); lo = -hi; }
+                solve_row(t2, c1, c2, two, invM1, iI1, invM2, iI2, q4.x, q4.y, q4.z, lo, hi, lam.z, f1, f2);
+            }
+        }
+        S.lam[si] = lam;
+    }
+    B.fc[2 * b1] = make_float4(f1.l.x, f1.l.y, f1.l.z, 0.f);
+    B.fc[2 * b1 + 1] = make_float4(f1.a.x, f1.a.y, f1.a.z, 0.f);
+    if (two) {
+        B.fc[2 * b2] = make_float4(f2.l.x, f2.l.y, f2.l.z, 0.f);
+        B.fc[2 * b2 + 1] = make_float4(f2.a.x, f2.a.y, f2.a.z, 0.f);
+    }
+}
+
+// velocity update, dxStepBody (semi-implicit Euler + quaternion renormalisation + dQtoR) and the
+// reference's GetTransformMat pack, for one body
+__device__ __forceinline__ void integrate_body(int i, const BodyArrays &B, float h) {
+    float4 p = B.pos[i];
+    float4 lv4 = B.lvel[i], av4 = B.avel[i];
+    const float4 fl = B.fc[2 * i], fa = B.fc[2 * i + 1];
+    const float4 f = B.facc[i], t = B.tacc[i];
+    const float invM = p.w;
+    lv4.x += h * fl.x; lv4.y += h * fl.y; lv4.z += h * fl.z;
+    av4.x += h * fa.x; av4.y += h * fa.y; av4.z += h * fa.z;
+    lv4.x += h * invM * f.x; lv4.y += h * invM * f.y; lv4.z += h * invM * f.z;
+    const float4 i0 = B.inv[3 * i], i1 = B.inv[3 * i + 1], i2 = B.inv[3 * i + 2];
+    const V3 th = v3(t.x * h, t.y * h, t.z * h);
+    av4.x += dot(v3(i0), th); av4.y += dot(v3(i1), th); av4.z += dot(v3(i2), th);
+    p.x += h * lv4.x; p.y += h * lv4.y; p.z += h * lv4.z;
+    float4 q = B.quat[i]; // (w,x,y,z) in x,y,z,w slots
+    const float q0 = q.x, q1 = q.y, q2 = q.z, q3 = q.w;
+    const float dq0 = 0.5f * (-av4.x * q1 - av4.y * q2 - av4.z * q3);
+    const float dq1 = 0.5f * (av4.x * q0 + av4.y * q3 - av4.z * q2);
+    const float dq2 = 0.5f * (-av4.x * q3 + av4.y * q0 + av4.z * q1);
+    const float dq3 = 0.5f * (av4.x * q2 - av4.y * q1 + av4.z * q0);
+    q.x = q0 + h * dq0; q.y = q1 + h * dq1; q.z = q2 + h * dq2; q.w = q3 + h * dq3;
+    float l = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+    if (l > 0) {
+        l = 1.0f / sqrtf(l);
+        q.x *= l; q.y *= l; q.z *= l; q.w *= l;
+    } else {
+        q = make_float4(1.f, 0.f, 0.f, 0.f);
+    }
+    const M3 R = q_to_r(q);
+    B.pos[i] = p;
+    B.lvel[i] = lv4;
+    B.avel[i] = av4;
+    B.quat[i] = q;
+    store_m3(B.R, i, R);
+    B.facc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    B.tacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // snapshot: column-major 4x4 = transpose of R, translation in 12..14 (src/main.c:602-622)
+    float4 *sn = reinterpret_cast<float4 *>(B.snap + 16 * (size_t)i);
+    sn[0] = make_float4(R.r0.x, R.r1.x, R.r2.x, 0.f);
+    sn[1] = make_float4(R.r0.y, R.r1.y, R.r2.y, 0.f);
+    sn[2] = make_float4(R.r0.z, R.r1.z, R.r2.z, 0.f);
+    sn[3] = make_float4(p.x, p.y, p.z, 1.f);
+}
+
+__global__ void __launch_bounds__(256) k_solve(ManifoldArrays M, SolverArrays S, BodyArrays B, StepConfig cfg) {
+    cg::grid_group grid = cg::this_grid();
+    const int n = *M.count;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+    if (n > 0) {
+        const int ncol = M.meta[0];
+        const int ovf0 = M.colour_start[OVERFLOW_COLOUR], ovf1 = M.colour_start[OVERFLOW_COLOUR + 1];
+        for (int it = 0; it < cfg.iters; it++) {
+            for (int c = 0; c < ncol; c++) {
+                const int s0 = M.colour_start[c], s1 = M.colour_start[c + 1];
+                for (int s = s0 + gt; s < s1; s += gs) solve_manifold(s, S, B);
+                grid.sync();
+            }
+            if (ovf1 > ovf0) {
+                // manifolds that found no free colour (> 64 neighbours): one thread, in order
+                if (gt == 0)
+                    for (int s = ovf0; s < ovf1; s++) solve_manifold(s, S, B);
+                grid.sync();
+            }
+        }
+    }
+    for (int i = gt; i < B.n; i += gs) integrate_body(i, B, cfg.h);
+}
+
+// ------------------------------------------------------------------ host orchestration
+
+static int coop_grid(Engine *e, const void *kernel, int threads, long work_items) {
+    int per_sm = 0;
+    OB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+    if (per_sm < 1) per_sm = 1;
+    long max_blocks = (long)per_sm * e->num_sms;
+    long want = (work_items + threads - 1) / threads;
+    if (want < 1) want = 1;
+    return (int)(want < max_blocks ? want : max_blocks);
+}
+
+void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_surface) {
+    cudaStream_t st = e->st;
+    BodyArrays B = e->B;
+    const int nb = B.n;
+    if (nb == 0) return;
+    StepConfig cfg;
+    cfg.h = h; cfg.erp = e->params.erp; cfg.cfm = e->params.cfm; cfg.sor_w = e->params.sor_w;
+    cfg.max_vel = e->params.max_vel; cfg.min_depth = e->params.min_depth;
+    cfg.gx = e->params.gravity[0]; cfg.gy = e->params.gravity[1]; cfg.gz = e->params.gravity[2];
+    cfg.iters = e->params.iters;
+
+    k_body_prep<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(B, cfg, e->d_stats);
+    OB_CHECK_KERNEL("k_body_prep", st);
+
+    ManifoldArrays M = e->M;
+    const unsigned pgrid = (unsigned)(e->num_sms * 8);
+    long max_manifolds;
+    ContactSource src;
+    Surface usurf{};
+    if (host_contacts) {
+        // records + contacts were uploaded by eng_step_host_contacts; *M.count set there
+        src.pd = e->hc_pd; src.ns = e->hc_ns; src.surf = e->hc_surf; src.kstride = 1;
+        k_manifold_dynbits<<<pgrid, 256, 0, st>>>(M, B.pos);
+        OB_CHECK_KERNEL("k_manifold_dynbits", st);
+        max_manifolds = (long)e->st_mrec.size();
+    } else {
+        if (uniform_surface) usurf = *uniform_surface;
+        src.pd = e->cs.pd; src.ns = e->cs.ns; src.surf = nullptr; src.kstride = e->cs.stride;
+        if (e->have_device_contacts) {
+            k_manifold_flags<<<pgrid, 256, 0, st>>>(e->bp.counters, e->bp.pairs, e->G.body, e->cs.nc, M.flag);
+            OB_CHECK_KERNEL("k_manifold_flags", st);
+            scan_exclusive(M.flag, M.flag, e->bp.cap_pairs, &e->bp.counters->n_pairs, &M.meta[5], e->scan, st);
+            k_manifold_write<<<pgrid, 256, 0, st>>>(e->bp.counters, e->bp.pairs, e->G.body, e->cs.nc, M.flag, B.pos, M,
+                                                    e->d_stats);
+            OB_CHECK_KERNEL("k_manifold_write", st);
+            k_manifold_count<<<1, 1, 0, st>>>(&M.meta[5], M, e->d_stats);
+            OB_CHECK_KERNEL("k_manifold_count", st);
+            max_manifolds = M.cap;
+        } else {
+            OB_CUDA(cudaMemsetAsync(M.count, 0, sizeof(int), st));
+            OB_CUDA(cudaMemsetAsync(M.meta, 0, 8 * sizeof(int), st));
+            max_manifolds = 0;
+        }
+    }
+    if (e->timing) OB_CUDA(cudaEventRecord(e->ev[2], st));
+
+    if (max_manifolds > 0) {
+        {
+            int grid = coop_grid(e, (const void *)k_colour, 256, max_manifolds);
+            void *args[] = {(void *)&M, (void *)&B};
+            OB_CUDA(cudaLaunchCooperativeKernel((const void *)k_colour, dim3((unsigned)grid), dim3(256), args, 0, st));
+        }
+        k_colour_keys<<<pgrid, 256, 0, st>>>(M);
+        OB_CHECK_KERNEL("k_colour_keys", st);
+        sort_pairs(M.skey, M.sidx, max_manifolds, M.count, 10, e->sort, st);
+        k_colour_start_init<<<1, 128, 0, st>>>(M);
+        OB_CHECK_KERNEL("k_colour_start_init", st);
+        k_colour_bounds<<<pgrid, 256, 0, st>>>(M);
+        OB_CHECK_KERNEL("k_colour_bounds", st);
+        k_colour_fixup<<<1, 1, 0, st>>>(M, e->d_stats);
+        OB_CHECK_KERNEL("k_colour_fixup", st);
+        k_rows<<<pgrid, 128, 0, st>>>(M, B, src, usurf, e->S, cfg, e->d_stats);
+        OB_CHECK_KERNEL("k_rows", st);
+    }
+    if (e->timing) OB_CUDA(cudaEventRecord(e->ev[3], st));
+    {
+        SolverArrays S = e->S;
+        long work = max_manifolds > nb ? max_manifolds : nb;
+        int grid = coop_grid(e, (const void *)k_solve, 256, work);
+        void *args[] = {(void *)&M, (void *)&S, (void *)&B, (void *)&cfg};
+        OB_CUDA(cudaLaunchCooperativeKernel((const void *)k_solve, dim3((unsigned)grid), dim3(256), args, 0, st));
+    }
+    if (e->timing) OB_CUDA(cudaEventRecord(e->ev[4], st));
+}
+
+} // namespace ob
