@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(256) k_np_none(const BroadCounters *__restrict
 // shared memory with a TMA bulk copy (cp.async.bulk global->shared completing on an mbarrier)
 // when it fits, which the reference's teapot.obj does (8884 triangles, 165 KB).  Lanes stride
 // over triangles; hits go to a per-warp candidate list; the <= 8 contacts are then chosen by the
-// order-independent rule documented in oracle/ode_oracle.c (depth desc, triangle index asc,
+// order-independent rule documented in DESIGN.md "sphere-trimesh" (depth desc, triangle index asc,
 // duplicates within 1e-3 r dropped).
 
 constexpr int TM_WARPS = 8;

@@ -151,10 +151,10 @@ def server_scene(seed=1, n_dropped=64, n_players=4, h=1.0 / 60.0, floor_plane=Fa
         pos, gtype, dims = _spawn(rng)
         if y_range is not None:
             pos = (pos[0], y_range[0] + (pos[1] - 20.0) / 30.0 * (y_range[1] - y_range[0]), pos[2])
-        b = _add_body(sc, pos)
+        b = _add_body(sc, pos, flags=BODY_GYRO)  # dBodyCreate: gyroscopic mode on (ODE >= 0.13)
         _add_geom(sc, gtype, dims, body=b, cat=CMASK_OBJ, col=CMASK_OBJ | CMASK_MAP, env=0)
     for i in range(n_players):
-        b = _add_body(sc, (0.0 + 1.5 * i, 2.0, -3.0), flags=BODY_KINEMATIC)
+        b = _add_body(sc, (0.0 + 1.5 * i, 2.0, -3.0), flags=BODY_KINEMATIC | BODY_GYRO)
         _add_geom(sc, SPHERE, (0.5,), body=b, cat=CMASK_OBJ, col=CMASK_OBJ | CMASK_MAP, env=0)
     return finalize(sc)
 
@@ -302,6 +302,38 @@ def trimesh_scene(n_side=100, seed=2, sphere_scale=5.0, h=1.0 / 60.0, mesh=None,
     }
     sg = _static_geoms([(TRIMESH, (0.0,), (0, 0, 0), IDENT_R, -1), (PLANE, (0, 1, 0, float(lo[1]) - 1.0), (0, 0, 0), IDENT_R, -1)])
     return from_arrays("C2", bodies, _concat([sg, geoms]), meshes=[(verts, tris)], h=h)
+
+
+def trimesh_contact_scene(n=256, seed=11, sphere_scale=5.0, mesh=None, h=1.0 / 60.0):
+    """Spheres placed in touch with a static trimesh (centre = triangle centroid + 0.8 r along the
+    face normal): exercises sphere-vs-trimesh contacts from step 0."""
+    verts, tris = mesh if mesh is not None else teapot_mesh()
+    rs = np.random.RandomState(seed)
+    pick = rs.choice(len(tris), size=n, replace=False)
+    a, b, c = verts[tris[pick, 0]], verts[tris[pick, 1]], verts[tris[pick, 2]]
+    cen = (a + b + c) / 3.0
+    nrm = np.cross(b - a, c - a)
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-20)
+    rad = rs.uniform(0.1, 0.4, size=n) * sphere_scale
+    pos = cen + nrm * (0.8 * rad)[:, None]
+    bodies = {
+        "pos": pos.astype(np.float32),
+        "quat": np.tile(np.array([1, 0, 0, 0], np.float32), (n, 1)),
+        "lvel": np.zeros((n, 3), np.float32), "avel": np.zeros((n, 3), np.float32),
+        "mass": np.ones(n, np.float32),
+        "inertia": np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1], np.float32), (n, 1)),
+        "flags": np.zeros(n, np.int32), "env": np.zeros(n, np.int32),
+    }
+    dims = np.zeros((n, 4), np.float32)
+    dims[:, 0] = rad
+    geoms = {
+        "type": np.full(n, SPHERE, np.int32), "dims": dims, "body": np.arange(n, dtype=np.int32),
+        "pos": np.zeros((n, 3), np.float32), "R": np.tile(np.array(IDENT_R, np.float32), (n, 1)),
+        "cat": np.full(n, CMASK_OBJ, np.uint32), "col": np.full(n, CMASK_OBJ | CMASK_MAP, np.uint32),
+        "env": np.zeros(n, np.int32),
+    }
+    sg = _static_geoms([(TRIMESH, (0.0,), (0, 0, 0), IDENT_R, -1)])
+    return from_arrays("trimesh-contact", bodies, _concat([sg, geoms]), meshes=[(verts, tris)], h=h)
 
 
 def random_soup(n=200, seed=7, extent=4.0, with_plane=True, with_static_box=True, rotated=True):

@@ -1,0 +1,245 @@
+"""GPU: parity of the CUDA path (through the C ABI of libode_b200.so) with the CPU oracle on the same
+seeded inputs, and with the committed golden fixtures.
+
+Bars (BASELINE.json north_star): broadphase pair lists and per-pair contact counts bit-exact as
+sorted sets; post-step position / orientation / velocity within relative 1e-4 after one step at
+equal iteration count (the oracle is run in the engine's Gauss-Seidel order); bounded
+constraint residual over 600 steps."""
+import os
+
+import numpy as np
+import pytest
+
+import util
+from odeb200 import scenes
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+STATE_RTOL = 1e-4  # north_star: relative 1e-4 in float32 after one step at equal iteration count
+
+
+def _scene(name):
+    return {
+        "c1_low": lambda: scenes.server_scene(seed=1, y_range=(1.0, 6.0)),
+        "c1p_low": lambda: scenes.server_scene(seed=1, y_range=(1.0, 6.0), floor_plane=True),
+        "soup200": lambda: scenes.random_soup(200, seed=7),
+        "soup_axis": lambda: scenes.random_soup(150, seed=9, rotated=False),
+        "teapot256": lambda: scenes.trimesh_contact_scene(256, seed=11),
+        "batch8": lambda: scenes.batched_worlds_scene(8, seed=4, spacing=0.7),
+        "soup1500": lambda: scenes.random_soup(1500, seed=21, extent=7.0),
+        "pile_dense": lambda: scenes.pile_scene(12, 12, 6, seed=5, spacing=0.6),
+    }[name]()
+
+
+GOLDEN = ["c1_low", "c1p_low", "soup200", "soup_axis", "teapot256", "batch8"]
+ALL = GOLDEN + ["soup1500", "pile_dense"]
+
+
+def _engine_contacts_by_pair(ew):
+    pr, cnt, pd, nrm, side = ew.contacts()
+    out, f = {}, 0
+    for (a, b), c in zip(pr.tolist(), cnt.tolist()):
+        out[(a, b)] = (pd[f:f + c], nrm[f:f + c], side[f:f + c])
+        f += c
+    return out
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_pairs_and_contacts_match_golden_bit_exact(name):
+    gold = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    ew = util.engine_world(_scene(name))
+    ew.collide(8)
+    assert np.array_equal(util.sorted_pair_set(ew.pairs()), gold["pairs"].astype(np.int64))
+    got = _engine_contacts_by_pair(ew)
+    f = 0
+    for (g1, g2), c in zip(gold["canon"].tolist(), gold["count"].tolist()):
+        pd, nrm, side = got[(g1, g2)]
+        assert len(pd) == c, (g1, g2)
+        assert np.array_equal(pd, gold["pos_depth"][f:f + c]), (g1, g2)
+        assert np.array_equal(nrm, gold["normal"][f:f + c]), (g1, g2)
+        assert np.array_equal(side, gold["side"][f:f + c]), (g1, g2)
+        f += c
+    assert ew.stats()["flags"] == 0
+    ew.close()
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_tick_parity_with_oracle(name):
+    sc = _scene(name)
+    ow, ew = util.load_both(sc)
+    for step in range(4):
+        ew.collide(8)
+        ep = util.sorted_pair_set(ew.pairs())
+        op = util.sorted_pair_set(ow.broadphase(0))
+        assert np.array_equal(ep, op), "step %d: broadphase pair sets differ" % step
+        got = _engine_contacts_by_pair(ew)
+        ref = util.oracle_contacts(ow)
+        assert set(got) == set(ref)
+        for key, cs in ref.items():
+            pd, nrm, side = got[key]
+            assert len(pd) == len(cs), (step, key)                      # contact counts: exact
+            for k, c in enumerate(cs):
+                assert np.array_equal(pd[k], np.array(list(c.pos) + [c.depth], np.float32)), (step, key, k)
+                assert np.array_equal(nrm[k], np.array(list(c.normal), np.float32)), (step, key, k)
+        ew.step(sc["h"])
+        util.oracle_tick_in_engine_order(ow, ew, sc["h"])
+        es, os_ = ew.state(), ow.state()
+        for k in ("pos", "quat", "lvel", "avel"):
+            assert util.rel_err(es[k], os_[k]).max() <= STATE_RTOL, (step, k)
+        st = ew.stats()
+        assert st["flags"] == 0 and st["n_overflow"] == 0
+    ew.close()
+
+
+def test_snapshot_is_the_reference_transform_layout():
+    sc = _scene("soup200")
+    ow, ew = util.load_both(sc)
+    ew.tick(sc["h"])
+    util.oracle_tick_in_engine_order(ow, ew, sc["h"])
+    snap = ew.snapshot()
+    ref = np.stack([ow.body_transform(i) for i in range(ow.num_bodies)])
+    assert np.allclose(snap, ref, rtol=STATE_RTOL, atol=1e-6)
+    st = ew.state()
+    R = st["R"].reshape(-1, 3, 4)
+    assert np.array_equal(snap[:, 0:3], R[:, :, 0]) and np.array_equal(snap[:, 4:7], R[:, :, 1])   # transpose of R
+    assert np.array_equal(snap[:, 12:15], st["pos"]) and (snap[:, 15] == 1).all() and (snap[:, 3] == 0).all()
+    # partial window copy
+    assert np.array_equal(ew.snapshot(first=10, count=5), snap[10:15])
+    ew.close()
+
+
+def test_engine_is_deterministic():
+    sc = _scene("soup1500")
+    outs = []
+    for _ in range(2):
+        ew = util.engine_world(sc)
+        for _ in range(10):
+            ew.tick(sc["h"])
+        outs.append(ew.state())
+        ew.close()
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def test_batched_worlds_are_independent_bit_exact():
+    """World w inside a batch evolves exactly as the same world stepped alone: the property that makes
+    sharding worlds over GPUs collective-free and bit-reproducible."""
+    batch = scenes.batched_worlds_scene(6, seed=4, spacing=0.7)
+    ew = util.engine_world(batch)
+    for _ in range(25):
+        ew.tick(batch["h"])
+    sb = ew.state()
+    st = ew.stats()
+    assert st["n_contacts"] > 100
+    ew.close()
+    for w in (0, 3, 5):
+        alone = scenes.batched_worlds_scene(1, seed=4, spacing=0.7, first_world=w)
+        e1 = util.engine_world(alone)
+        for _ in range(25):
+            e1.tick(alone["h"])
+        s1 = e1.state()
+        e1.close()
+        for k in ("pos", "quat", "lvel", "avel"):
+            assert np.array_equal(sb[k][w * 128:(w + 1) * 128], s1[k]), (w, k)
+
+
+def _max_penetration(ew):
+    pr, cnt, pd, nrm, side = ew.contacts()
+    return float(pd[:, 3].max()) if len(pd) else 0.0
+
+
+def test_c1_600_steps_bounded_residual():
+    sc = scenes.server_scene(seed=1)
+    ew = util.engine_world(sc)
+    n_dyn = 64
+    ke_peak, pen_max = 0.0, 0.0
+    for step in range(600):
+        ew.collide(8)
+        if step % 20 == 0:
+            pen_max = max(pen_max, _max_penetration(ew))
+        ew.step(sc["h"])
+        if step % 50 == 49:
+            s = ew.state()
+            assert np.isfinite(s["pos"]).all()
+            ke_peak = max(ke_peak, float((s["lvel"][:n_dyn] ** 2).sum()))
+    s = ew.state()
+    # dropped from y in [20,50]: impact speed <= sqrt(2 g 50) ~ 31 m/s; nothing may exceed it
+    assert np.abs(s["lvel"]).max() < 35.0
+    assert pen_max < 0.6                         # fast impacts penetrate, but stay bounded
+    # everything ends inside the arena, above the floor (top at y = 0.5), the kinematic spheres untouched
+    assert s["pos"][:n_dyn, 1].min() > 0.5 and s["pos"][:n_dyn, 1].max() < 12.0
+    assert np.array_equal(s["pos"][n_dyn:, 1], np.full(4, 2.0, np.float32))
+    assert np.allclose(np.linalg.norm(s["quat"], axis=1), 1.0, atol=1e-5)
+    ew.close()
+
+
+def test_c1_at_rest_constraint_residual():
+    """After settling, the solved velocities satisfy the contact rows: normal relative velocity at
+    every active contact stays within the ERP push-out bound and bodies stop moving."""
+    sc = scenes.server_scene(seed=1, y_range=(1.0, 4.0))
+    ew = util.engine_world(sc)
+    for _ in range(600):
+        ew.tick(sc["h"])
+    ew.collide(8)
+    pen = _max_penetration(ew)
+    s = ew.state()
+    assert pen < 0.02
+    assert np.abs(s["lvel"][:64]).max() < 0.25 and np.abs(s["avel"][:64]).max() < 2.5
+    ew.close()
+
+
+def test_full_size_pile_properties():
+    """BASELINE config 3 at full size (1,048,576 bodies): size-independent properties -- no capacity
+    overflow, finite state, unit quaternions, nothing below the floor beyond the contact slop, and
+    the pair list is duplicate-free and canonical."""
+    sc = scenes.pile_scene(256, 256, 16, seed=3)
+    ew = util.engine_world(sc)
+    for _ in range(120):
+        ew.tick(sc["h"])
+    ew.collide(8)
+    st = ew.stats()
+    assert st["flags"] == 0 and st["n_overflow"] == 0 and st["n_pairs"] > 100000
+    pr = ew.pairs()
+    key = pr[:, 0].astype(np.int64) * (1 << 32) + pr[:, 1]
+    assert len(np.unique(key)) == len(key)
+    types = sc["geoms"]["type"]
+    assert (types[pr[:, 0]] <= types[pr[:, 1]]).all()
+    ew.step(sc["h"])
+    s = ew.state()
+    assert np.isfinite(s["pos"]).all() and np.isfinite(s["lvel"]).all()
+    assert np.allclose(np.linalg.norm(s["quat"], axis=1), 1.0, atol=1e-5)
+    assert s["pos"][:, 1].min() > -0.5
+    assert np.abs(s["pos"][:, 0]).max() < 0.5 * 256 * 1.8 + 2.0
+    ew.close()
+
+
+def test_mass_and_inertia_parity():
+    """dMassSetBox-style inertia (non-identity, gyroscopic term active) against the oracle."""
+    rs = np.random.RandomState(3)
+    sc = scenes.random_soup(120, seed=33)
+    b = sc["bodies"]
+    g = sc["geoms"]
+    for gi in range(len(g["type"])):
+        bi = g["body"][gi]
+        if bi < 0:
+            continue
+        dens = 2.0 + rs.rand()
+        if g["type"][gi] == scenes.BOX:
+            lx, ly, lz = g["dims"][gi][:3]
+            m = dens * lx * ly * lz
+            I = np.diag([m / 12 * (ly * ly + lz * lz), m / 12 * (lx * lx + lz * lz), m / 12 * (lx * lx + ly * ly)])
+        else:
+            r = g["dims"][gi][0]
+            m = dens * 4.0 / 3.0 * np.pi * r ** 3
+            I = np.eye(3) * 0.4 * m * r * r
+        b["mass"][bi] = m
+        b["inertia"][bi] = I.reshape(9)
+        b["flags"][bi] = scenes.BODY_GYRO
+    ow, ew = util.load_both(sc)
+    for step in range(3):
+        ew.tick(sc["h"])
+        util.oracle_tick_in_engine_order(ow, ew, sc["h"])
+        es, os_ = ew.state(), ow.state()
+        for k in ("pos", "quat", "lvel", "avel"):
+            assert util.rel_err(es[k], os_[k]).max() <= STATE_RTOL, (step, k)
+    ew.close()
