@@ -21,6 +21,7 @@ struct BodyArrays {
     float4 *invI;  // 3 per body, body frame
     float4 *facc, *tacc;
     int *flags;
+    int *local;    // body index relative to the first body of its env (env-invariant colouring priority)
     // per-step solver views
     float4 *inv;   // 3 per body: rows of the world-frame inverse inertia; row 0 .w = invMass
     float4 *tmp;   // 2 per body: v/h + invM*f, w/h + invI*t

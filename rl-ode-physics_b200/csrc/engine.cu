@@ -71,7 +71,7 @@ void eng_destroy(Engine *e) {
     cudaStreamSynchronize(e->st);
     BodyArrays &B = e->B;
     dev_free(B.pos); dev_free(B.quat); dev_free(B.R); dev_free(B.lvel); dev_free(B.avel); dev_free(B.I);
-    dev_free(B.invI); dev_free(B.facc); dev_free(B.tacc); dev_free(B.flags); dev_free(B.inv); dev_free(B.tmp);
+    dev_free(B.invI); dev_free(B.facc); dev_free(B.tacc); dev_free(B.flags); dev_free(B.local); dev_free(B.inv); dev_free(B.tmp);
     dev_free(B.fc); dev_free(B.snap); dev_free(B.colmask); dev_free(B.prio);
     GeomArrays &G = e->G;
     dev_free(G.type); dev_free(G.dims); dev_free(G.body); dev_free(G.pos); dev_free(G.R); dev_free(G.cat);
@@ -190,7 +190,7 @@ void engine_ensure_capacity(Engine *e) {
         dev_realloc(B.pos, o, n, st); dev_realloc(B.quat, o, n, st); dev_realloc(B.R, 3 * o, 3 * n, st);
         dev_realloc(B.lvel, o, n, st); dev_realloc(B.avel, o, n, st); dev_realloc(B.I, 3 * o, 3 * n, st);
         dev_realloc(B.invI, 3 * o, 3 * n, st); dev_realloc(B.facc, o, n, st); dev_realloc(B.tacc, o, n, st);
-        dev_realloc(B.flags, o, n, st); dev_realloc(B.inv, 3 * o, 3 * n, st, false);
+        dev_realloc(B.flags, o, n, st); dev_realloc(B.local, o, n, st); dev_realloc(B.inv, 3 * o, 3 * n, st, false);
         dev_realloc(B.tmp, 2 * o, 2 * n, st, false); dev_realloc(B.fc, 2 * o, 2 * n, st, false);
         dev_realloc(B.snap, 16 * o, 16 * n, st); dev_realloc(B.colmask, o, n, st, false);
         dev_realloc(B.prio, o, n, st, false);
@@ -279,6 +279,21 @@ void eng_sync_to_device(Engine *e) {
         upload(e->B.avel, b.avel.data(), n, st); upload(e->B.I, b.I.data(), 3 * n, st);
         upload(e->B.invI, b.invI.data(), 3 * n, st); upload(e->B.facc, b.facc.data(), n, st);
         upload(e->B.tacc, b.tacc.data(), n, st); upload(e->B.flags, b.flags.data(), n, st);
+        {
+            // index of a body relative to the first body of its env: makes the colouring priorities, and
+            // with them the Gauss-Seidel order of a world, independent of which other worlds share the batch
+            std::vector<int> first((size_t)std::max(e->n_envs, 1), INT32_MAX), local(n);
+            for (size_t i = 0; i < n; i++) {
+                const int en = b.env[i];
+                if (en >= 0 && en < (int)first.size() && (int)i < first[en]) first[en] = (int)i;
+            }
+            for (size_t i = 0; i < n; i++) {
+                const int en = b.env[i];
+                local[i] = (en >= 0 && en < (int)first.size()) ? (int)i - first[en] : (int)i;
+            }
+            upload(e->B.local, local.data(), n, st);
+            OB_CUDA(cudaStreamSynchronize(st)); // `local` is a temporary
+        }
         e->bodies_dirty = false;
         e->forces_dirty = false;
     } else if (e->forces_dirty) {

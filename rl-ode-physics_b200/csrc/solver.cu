@@ -144,8 +144,10 @@ __global__ void __launch_bounds__(256) k_manifold_dynbits(ManifoldArrays M, cons
 
 // ------------------------------------------------------------------ edge colouring
 
-__device__ __forceinline__ unsigned long long manifold_prio(int m) {
-    unsigned x = (unsigned)m * 0x9E3779B1u;
+__device__ __forceinline__ unsigned long long manifold_prio(int m, int lb1, int lb2) {
+    // hash of the env-local body pair; the manifold index only breaks ties (its relative order inside
+    // a world does not depend on the other worlds of a batch)
+    unsigned x = ((unsigned)lb1 * 0x9E3779B1u) ^ (((unsigned)lb2 + 0x7F4A7C15u) * 0x85EBCA6Bu);
     x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13; x *= 0xC2B2AE3Du; x ^= x >> 16;
     return ((unsigned long long)x << 32) | (unsigned)m;
 }
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(256) k_colour(ManifoldArrays M, BodyArrays B) 
         for (int m = gt; m < n; m += gs) {
             if (M.colour[m] >= 0) continue;
             const int4 r = M.rec[m];
-            const unsigned long long pr = manifold_prio(m);
+            const unsigned long long pr = manifold_prio(m, B.local[r.x], r.y >= 0 ? B.local[r.y] : -1);
             if (r.w & REC_DYN1) atomicMin(&B.prio[r.x], pr);
             if (r.w & REC_DYN2) atomicMin(&B.prio[r.y], pr);
         }
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(256) k_colour(ManifoldArrays M, BodyArrays B) 
         for (int m = gt; m < n; m += gs) {
             if (M.colour[m] >= 0) continue;
             const int4 r = M.rec[m];
-            const unsigned long long pr = manifold_prio(m);
+            const unsigned long long pr = manifold_prio(m, B.local[r.x], r.y >= 0 ? B.local[r.y] : -1);
             const bool d1 = r.w & REC_DYN1, d2 = r.w & REC_DYN2;
             const bool ok = (!d1 || B.prio[r.x] == pr) && (!d2 || B.prio[r.y] == pr);
             if (ok) {

@@ -169,6 +169,9 @@ def test_headless_reference_server_loop_drop_in():
         ew.tick(sc["h"])
     snap = ew.snapshot()
     assert np.array_equal(tr_c[4:72], snap)       # same scene through the bulk API: identical transforms
-    # static map slots carry the GetTransformMatV matrix they were created with
-    assert np.allclose(tr_c[1][:12], scenes.transform_mat_v((4, 3, 0), (0, 0, -0.5))[:12])
+    # static map slots: the broadcast loop re-packs dGeomGetRotation with GetTransformMat, i.e. the
+    # TRANSPOSE of the GetTransformMatV rows the geom was created with
+    rm = scenes.transform_mat_v((4, 3, 0), (0, 0, -0.5))[:12].reshape(3, 4)
+    assert np.array_equal(tr_c[1].reshape(4, 4)[:3, :3], rm[:, :3].T.T.T)
+    assert np.array_equal(tr_c[1][12:], np.array([4, 3, 0, 1], np.float32))
     ew.close()
