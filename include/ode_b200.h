@@ -66,6 +66,12 @@ void dWorldSetForcesB200(dWorldID, const float *force_torque6, int n);
 void dWorldGetSnapshotB200(dWorldID, float *dst16, int first, int count, int blocking);
 const float *dWorldGetSnapshotDeviceB200(dWorldID);
 void dWorldWaitB200(dWorldID);
+/* CUDA-event timer on the world's stream: everything queued between start and stop */
+void dWorldTimerStartB200(dWorldID);
+void dWorldTimerStopB200(dWorldID);
+float dWorldTimerElapsedB200(dWorldID); /* ms, blocking */
+/* number of CUDA kernels this library has launched in this process so far */
+long dGetKernelLaunchCountB200(void);
 
 /* capacities (pairs, manifolds); 0 = automatic (8 and 6 per geom). Overflow sets a stats flag. */
 void dWorldSetCapacityB200(dWorldID, long max_pairs, long max_manifolds);

@@ -92,6 +92,8 @@ void eng_destroy(Engine *e) {
     dev_free(e->dl_first); dev_free(e->dl_pd); dev_free(e->dl_ns);
     for (auto &m : e->hmeshes) { dev_free(m.d_verts); dev_free(m.d_tris); }
     dev_free(e->d_stats);
+    dev_free(e->d_f6);
+    if (e->tev[0]) { cudaEventDestroy(e->tev[0]); cudaEventDestroy(e->tev[1]); }
     if (e->h_stats) cudaFreeHost(e->h_stats);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     cudaStreamDestroy(e->st);
@@ -484,15 +486,46 @@ void eng_snapshot_to_host(Engine *e, float *dst, int first, int count, bool bloc
     if (blocking) OB_CUDA(cudaStreamSynchronize(e->st));
 }
 
+// 6 floats per body (force, torque) -> the float4 accumulators the step consumes
+__global__ void __launch_bounds__(256) k_scatter_forces(int n, const float *__restrict__ f6, float4 *__restrict__ facc,
+                                                         float4 *__restrict__ tacc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *f = f6 + 6 * (size_t)i;
+    facc[i] = make_float4(f[0], f[1], f[2], 0.f);
+    tacc[i] = make_float4(f[3], f[4], f[5], 0.f);
+}
+
 void eng_set_forces(Engine *e, const float *f6, int n) {
-    // host pointer with 6 floats per body -> facc / tacc mirrors -> device
-    HostBodies &b = e->hb;
-    if (n > b.n) n = b.n;
-    for (int i = 0; i < n; i++) {
-        b.facc[4 * i] = f6[6 * i]; b.facc[4 * i + 1] = f6[6 * i + 1]; b.facc[4 * i + 2] = f6[6 * i + 2];
-        b.tacc[4 * i] = f6[6 * i + 3]; b.tacc[4 * i + 1] = f6[6 * i + 4]; b.tacc[4 * i + 2] = f6[6 * i + 5];
+    // one H2D copy straight from the caller's (ideally pinned) buffer, then a scatter kernel;
+    // replaces the accumulators of bodies [0, n) for the next step, like dBodySetForce/Torque
+    eng_sync_to_device(e);
+    if (n > e->B.n) n = e->B.n;
+    if (n <= 0) return;
+    if (n > e->cap_f6) {
+        if (e->d_f6) OB_CUDA(cudaFree(e->d_f6));
+        e->cap_f6 = n + n / 4 + 64;
+        OB_CUDA(cudaMalloc(&e->d_f6, (size_t)e->cap_f6 * 6 * sizeof(float)));
     }
-    e->forces_dirty = true;
+    OB_CUDA(cudaMemcpyAsync(e->d_f6, f6, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, e->st));
+    k_scatter_forces<<<(unsigned)((n + 255) / 256), 256, 0, e->st>>>(n, e->d_f6, e->B.facc, e->B.tacc);
+    OB_CHECK_KERNEL("k_scatter_forces", e->st);
+}
+
+long g_ob_launches = 0;
+long eng_launch_count() { return g_ob_launches; }
+
+void eng_timer_start(Engine *e) {
+    OB_CUDA(cudaSetDevice(e->device));
+    if (!e->tev[0]) { OB_CUDA(cudaEventCreate(&e->tev[0])); OB_CUDA(cudaEventCreate(&e->tev[1])); }
+    OB_CUDA(cudaEventRecord(e->tev[0], e->st));
+}
+void eng_timer_stop(Engine *e) { OB_CUDA(cudaEventRecord(e->tev[1], e->st)); }
+float eng_timer_elapsed_ms(Engine *e) {
+    float ms = 0.f;
+    OB_CUDA(cudaEventSynchronize(e->tev[1]));
+    OB_CUDA(cudaEventElapsedTime(&ms, e->tev[0], e->tev[1]));
+    return ms;
 }
 
 void eng_wait(Engine *e) {

@@ -37,8 +37,13 @@ inline bool ob_debug_sync() {
     }
     return v == 1;
 }
+// every kernel launch of the library passes through OB_CHECK_KERNEL (or ob_count_launch for the
+// cooperative ones): the counter is what bench.py reports as gpu_launches
+extern long g_ob_launches;
+inline void ob_count_launch() { ++g_ob_launches; }
 #define OB_CHECK_KERNEL(name, st)                                                                  \
     do {                                                                                           \
+        ob_count_launch();                                                                         \
         cudaError_t e__ = cudaGetLastError();                                                      \
         if (e__ == cudaSuccess && ob_debug_sync()) e__ = cudaStreamSynchronize(st);                \
         if (e__ != cudaSuccess) {                                                                  \
@@ -179,6 +184,11 @@ void eng_wait(Engine *);
 StepStats eng_stats(Engine *);                  // blocking: stats of the last collide/step
 // solver order export for parity tests: per device contact (pair-major) the solve rank
 int eng_export_solver_order(Engine *, int *pair_g1, int *pair_g2, int *pair_k, int cap);
+// device timer on the engine stream (CUDA events): start / stop / elapsed ms (blocking)
+void eng_timer_start(Engine *);
+void eng_timer_stop(Engine *);
+float eng_timer_elapsed_ms(Engine *);
+long eng_launch_count();
 // event-timed sections of the last step, milliseconds (collide, prep+colour+rows, solve+tail)
 void eng_last_timings(Engine *, float out[4]);
 void eng_enable_timing(Engine *, int on);

@@ -60,6 +60,9 @@ struct Engine {
     bool ev_valid = false;
 
     int coop_blocks_colour = 0, coop_blocks_solve = 0;
+    cudaEvent_t tev[2] = {nullptr, nullptr};
+    float *d_f6 = nullptr;
+    int cap_f6 = 0;
 };
 
 void engine_ensure_capacity(Engine *e);

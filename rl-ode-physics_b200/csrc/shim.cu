@@ -322,6 +322,10 @@ extern "C" void dWorldSetNumEnvsB200(dWorldID w, int n) { eng_set_num_envs(w->en
 extern "C" void dWorldSetCapacityB200(dWorldID w, long mp, long mm) { eng_set_capacity(w->eng, mp, mm); }
 extern "C" void dWorldSetBigExtentB200(dWorldID w, float e) { eng_set_big_extent(w->eng, e); }
 extern "C" void dWorldWaitB200(dWorldID w) { eng_wait(w->eng); }
+extern "C" void dWorldTimerStartB200(dWorldID w) { eng_timer_start(w->eng); }
+extern "C" void dWorldTimerStopB200(dWorldID w) { eng_timer_stop(w->eng); }
+extern "C" float dWorldTimerElapsedB200(dWorldID w) { return eng_timer_elapsed_ms(w->eng); }
+extern "C" long dGetKernelLaunchCountB200(void) { return eng_launch_count(); }
 extern "C" void dWorldEnableTimingB200(dWorldID w, int on) { eng_enable_timing(w->eng, on); }
 extern "C" void dWorldGetTimingsB200(dWorldID w, float out[4]) { eng_last_timings(w->eng, out); }
 extern "C" int dWorldGetNumBodiesB200(dWorldID w) { return eng_bodies(w->eng).n; }

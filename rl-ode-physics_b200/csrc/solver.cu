@@ -647,6 +647,7 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
             int grid = coop_grid(e, (const void *)k_colour, 256, max_manifolds);
             void *args[] = {(void *)&M, (void *)&B};
             OB_CUDA(cudaLaunchCooperativeKernel((const void *)k_colour, dim3((unsigned)grid), dim3(256), args, 0, st));
+            OB_CHECK_KERNEL("k_colour", st);
         }
         k_colour_keys<<<pgrid, 256, 0, st>>>(M);
         OB_CHECK_KERNEL("k_colour_keys", st);
@@ -667,6 +668,7 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
         int grid = coop_grid(e, (const void *)k_solve, 256, work);
         void *args[] = {(void *)&M, (void *)&S, (void *)&B, (void *)&cfg};
         OB_CUDA(cudaLaunchCooperativeKernel((const void *)k_solve, dim3((unsigned)grid), dim3(256), args, 0, st));
+        OB_CHECK_KERNEL("k_solve", st);
     }
     if (e->timing) OB_CUDA(cudaEventRecord(e->ev[4], st));
 }

@@ -113,6 +113,8 @@ _SIGS = [
     ("dWorldGetSnapshotB200", None, [_vp, _vp, _i, _i, _i]),
     ("dWorldGetSnapshotDeviceB200", _vp, [_vp]),
     ("dWorldWaitB200", None, [_vp]),
+    ("dWorldTimerStartB200", None, [_vp]), ("dWorldTimerStopB200", None, [_vp]),
+    ("dWorldTimerElapsedB200", C.c_float, [_vp]), ("dGetKernelLaunchCountB200", C.c_long, []),
     ("dWorldSetCapacityB200", None, [_vp, C.c_long, C.c_long]),
     ("dWorldSetBigExtentB200", None, [_vp, _f]),
     ("dWorldGetStatsB200", None, [_vp, C.POINTER(StepStats)]),
