@@ -86,6 +86,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """samples before this point (warm-up) are dropped"""
+        self.first = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -96,7 +100,7 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "first", 0):]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -108,7 +112,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples: timed region shorter than the sampling period"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
                 "power_w_max": float(max(power)), "samples": len(sm)}
 
@@ -239,11 +243,12 @@ def main():
 
     # ---------------- device-resident throughput: W warm-up ticks, then exactly K timed ticks
     ew.enable_timing(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()                  # nvidia-smi needs ~1 s to start; only samples taken under load are kept
     for _ in range(max(args.warmup, 3)):
         ew.tick(h)
     ew.wait()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     sharding.barrier()
     torch.cuda.synchronize()
     launches0 = L.dGetKernelLaunchCountB200()

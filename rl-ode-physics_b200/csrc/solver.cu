@@ -461,58 +461,95 @@ __device__ __forceinline__ void solve_row(V3 dir, V3 c1, V3 c2, bool two, float 
     }
 }
 
+// the six float4 records of one contact of one sorted manifold (DESIGN.md "solver rows")
+struct RowRec {
+    float4 q0, q1, q2, q3, q4, lam;
+};
+__device__ __forceinline__ RowRec load_rows(const SolverArrays &S, size_t si) {
+    RowRec r;
+    // rows are written by k_rows before this kernel starts: read-only path; lambda is thread-private
+    r.q0 = __ldg(&S.q0[si]); r.q1 = __ldg(&S.q1[si]); r.q2 = __ldg(&S.q2[si]);
+    r.q3 = __ldg(&S.q3[si]); r.q4 = __ldg(&S.q4[si]);
+    r.lam = S.lam[si];
+    return r;
+}
+
+// All rows of one manifold, in order (normal, tangent 1, tangent 2) per contact.  The loads of the
+// manifold's first contact are issued together with the body gathers, and contact k+1 is fetched
+// while contact k is being solved, so the dependent chain per manifold is: record -> {bodies, rows}
+// -> arithmetic, not one DRAM round trip per contact.  The body accumulators fc are exchanged
+// between SMs from one colour to the next, so they bypass L1 (ld.cg / st.cg).
 __device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, const BodyArrays &B) {
-    const int4 rec = S.mrec[s];
+    const int4 rec = __ldg(&S.mrec[s]);
     const int b1 = rec.x, b2 = rec.y, nc = rec.z;
     const bool two = b2 >= 0;
+    RowRec cur = load_rows(S, (size_t)s);
     FC f1, f2;
     {
-        const float4 a = B.fc[2 * b1], b = B.fc[2 * b1 + 1];
+        const float4 a = __ldcg(&B.fc[2 * b1]), b = __ldcg(&B.fc[2 * b1 + 1]);
         f1.l = v3(a); f1.a = v3(b);
     }
-    const float4 i10 = B.inv[3 * b1], i11 = B.inv[3 * b1 + 1], i12 = B.inv[3 * b1 + 2];
+    const float4 i10 = __ldg(&B.inv[3 * b1]), i11 = __ldg(&B.inv[3 * b1 + 1]), i12 = __ldg(&B.inv[3 * b1 + 2]);
     const M3 iI1 = M3{v3(i10), v3(i11), v3(i12)};
     const float invM1 = i10.w;
     M3 iI2 = M3{v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f)};
     float invM2 = 0.f;
     f2.l = v3(0.f, 0.f, 0.f); f2.a = f2.l;
     if (two) {
-        const float4 a = B.fc[2 * b2], b = B.fc[2 * b2 + 1];
+        const float4 a = __ldcg(&B.fc[2 * b2]), b = __ldcg(&B.fc[2 * b2 + 1]);
         f2.l = v3(a); f2.a = v3(b);
-        const float4 i20 = B.inv[3 * b2], i21 = B.inv[3 * b2 + 1], i22 = B.inv[3 * b2 + 2];
+        const float4 i20 = __ldg(&B.inv[3 * b2]), i21 = __ldg(&B.inv[3 * b2 + 1]), i22 = __ldg(&B.inv[3 * b2 + 2]);
         iI2 = M3{v3(i20), v3(i21), v3(i22)};
         invM2 = i20.w;
     }
     for (int k = 0; k < nc; k++) {
         const size_t si = (size_t)k * S.cap + s;
-        const float4 q0 = S.q0[si], q1 = S.q1[si], q2 = S.q2[si];
-        float4 lam = S.lam[si];
+        RowRec nxt = cur;
+        if (k + 1 < nc) nxt = load_rows(S, si + S.cap);
+        float4 lam = cur.lam;
         const int lflags = __float_as_int(lam.w);
         const int the_m = lflags & 0xf;
-        const V3 n = v3(q0), c1 = v3(q1), c2 = v3(q2);
-        solve_row(n, c1, c2, two, invM1, iI1, invM2, iI2, q0.w, q1.w, q2.w, 0.f, INFINITY, lam.x, f1, f2);
+        const V3 n = v3(cur.q0), c1 = v3(cur.q1), c2 = v3(cur.q2);
+        solve_row(n, c1, c2, two, invM1, iI1, invM2, iI2, cur.q0.w, cur.q1.w, cur.q2.w, 0.f, INFINITY, lam.x, f1, f2);
         if (the_m >= 2) {
-            const float4 q3 = S.q3[si];
+            const float4 q3 = cur.q3;
             V3 t1, t2;
             plane_space(n, t1, t2);
             float hi = q3.w, lo = -q3.w;
             if (lflags & 0x10) { hi = fabsf(q3.w * lam.x); lo = -hi; }
             solve_row(t1, c1, c2, two, invM1, iI1, invM2, iI2, q3.x, q3.y, q3.z, lo, hi, lam.y, f1, f2);
             if (the_m >= 3) {
-                const float4 q4 = S.q4[si];
+                const float4 q4 = cur.q4;
                 hi = q4.w; lo = -q4.w;
                 if (lflags & 0x20) { hi = fabsf(q4.w * lam.x); lo = -hi; }
                 solve_row(t2, c1, c2, two, invM1, iI1, invM2, iI2, q4.x, q4.y, q4.z, lo, hi, lam.z, f1, f2);
             }
         }
         S.lam[si] = lam;
+        cur = nxt;
     }
-    B.fc[2 * b1] = make_float4(f1.l.x, f1.l.y, f1.l.z, 0.f);
-    B.fc[2 * b1 + 1] = make_float4(f1.a.x, f1.a.y, f1.a.z, 0.f);
+    __stcg(&B.fc[2 * b1], make_float4(f1.l.x, f1.l.y, f1.l.z, 0.f));
+    __stcg(&B.fc[2 * b1 + 1], make_float4(f1.a.x, f1.a.y, f1.a.z, 0.f));
     if (two) {
-        B.fc[2 * b2] = make_float4(f2.l.x, f2.l.y, f2.l.z, 0.f);
-        B.fc[2 * b2 + 1] = make_float4(f2.a.x, f2.a.y, f2.a.z, 0.f);
+        __stcg(&B.fc[2 * b2], make_float4(f2.l.x, f2.l.y, f2.l.z, 0.f));
+        __stcg(&B.fc[2 * b2 + 1], make_float4(f2.a.x, f2.a.y, f2.a.z, 0.f));
     }
+}
+
+// grid-wide barrier of the persistent solver (all CTAs are co-resident: cooperative launch).  One
+// release-add per CTA on a monotone counter, thread 0 spins with acquire loads.
+__device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
 }
 
 // velocity update, dxStepBody (semi-implicit Euler + quaternion renormalisation + dQtoR) and the
@@ -520,7 +557,7 @@ __device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, con
 __device__ __forceinline__ void integrate_body(int i, const BodyArrays &B, float h) {
     float4 p = B.pos[i];
     float4 lv4 = B.lvel[i], av4 = B.avel[i];
-    const float4 fl = B.fc[2 * i], fa = B.fc[2 * i + 1];
+    const float4 fl = __ldcg(&B.fc[2 * i]), fa = __ldcg(&B.fc[2 * i + 1]);
     const float4 f = B.facc[i], t = B.tacc[i];
     const float invM = p.w;
     lv4.x += h * fl.x; lv4.y += h * fl.y; lv4.z += h * fl.z;
@@ -560,10 +597,11 @@ __device__ __forceinline__ void integrate_body(int i, const BodyArrays &B, float
     sn[3] = make_float4(p.x, p.y, p.z, 1.f);
 }
 
-__global__ void __launch_bounds__(256) k_solve(ManifoldArrays M, SolverArrays S, BodyArrays B, StepConfig cfg) {
-    cg::grid_group grid = cg::this_grid();
+__global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays S, BodyArrays B, StepConfig cfg) {
     const int n = *M.count;
     const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+    unsigned *bar = reinterpret_cast<unsigned *>(&M.meta[6]);
+    unsigned target = 0;
     if (n > 0) {
         const int ncol = M.meta[0];
         const int ovf0 = M.colour_start[OVERFLOW_COLOUR], ovf1 = M.colour_start[OVERFLOW_COLOUR + 1];
@@ -571,13 +609,13 @@ __global__ void __launch_bounds__(256) k_solve(ManifoldArrays M, SolverArrays S,
             for (int c = 0; c < ncol; c++) {
                 const int s0 = M.colour_start[c], s1 = M.colour_start[c + 1];
                 for (int s = s0 + gt; s < s1; s += gs) solve_manifold(s, S, B);
-                grid.sync();
+                grid_barrier(bar, target);
             }
             if (ovf1 > ovf0) {
                 // manifolds that found no free colour (> 64 neighbours): one thread, in order
                 if (gt == 0)
                     for (int s = ovf0; s < ovf1; s++) solve_manifold(s, S, B);
-                grid.sync();
+                grid_barrier(bar, target);
             }
         }
     }
@@ -664,6 +702,7 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
     if (e->timing) OB_CUDA(cudaEventRecord(e->ev[3], st));
     {
         SolverArrays S = e->S;
+        OB_CUDA(cudaMemsetAsync(&M.meta[6], 0, sizeof(int), st)); // grid barrier counter
         long work = max_manifolds > nb ? max_manifolds : nb;
         int grid = coop_grid(e, (const void *)k_solve, 256, work);
         void *args[] = {(void *)&M, (void *)&S, (void *)&B, (void *)&cfg};
