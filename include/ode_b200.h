@@ -75,6 +75,10 @@ long dGetKernelLaunchCountB200(void);
 
 /* capacities (pairs, manifolds); 0 = automatic (8 and 6 per geom). Overflow sets a stats flag. */
 void dWorldSetCapacityB200(dWorldID, long max_pairs, long max_manifolds);
+/* solver selection: mode 0 = automatic (island solver for batched worlds, grid-barrier solver
+ * otherwise), 1 = always the grid-barrier solver. env_group = lanes per env of the island solver
+ * (8, 16, 32; 0 = automatic). Both solvers produce bit-identical results. */
+void dWorldSetSolverModeB200(dWorldID, int mode, int env_group);
 /* dynamic geoms whose AABB extent exceeds this are treated like static "big" geoms (default inf) */
 void dWorldSetBigExtentB200(dWorldID, float extent);
 

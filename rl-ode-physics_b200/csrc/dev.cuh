@@ -22,6 +22,7 @@ struct BodyArrays {
     float4 *facc, *tacc;
     int *flags;
     int *local;    // body index relative to the first body of its env (env-invariant colouring priority)
+    int *env;      // env (independent world) of the body
     // per-step solver views
     float4 *inv;   // 3 per body: rows of the world-frame inverse inertia; row 0 .w = invMass
     float4 *tmp;   // 2 per body: v/h + invM*f, w/h + invI*t
@@ -112,6 +113,18 @@ struct ManifoldArrays {
     int *meta;        // [0] n_colours, [1] n_overflow, [2],[3] remaining (alternating), [4] rounds, [5] scan total
 };
 
+// batched independent worlds: manifolds bucketed per env for the island solver (one lane group per env)
+struct EnvArrays {
+    int n_envs;
+    int max_bodies;  // largest number of bodies in one env (host-known)
+    int *cnt;        // manifolds per env (n_envs + 1 for the scan)
+    int *start;      // exclusive scan of cnt, [n_envs] = total
+    int *fill;       // bucket cursors
+    int4 *rec;       // manifold records bucketed by env
+    int *perm;       // per env: bucket slots ordered by colour
+    unsigned char *col; // colour per bucket slot
+};
+
 // solver rows, k-major: contact k of sorted manifold s at [k * cap + s]
 struct SolverArrays {
     int cap;
@@ -131,5 +144,6 @@ struct StepConfig {
 };
 
 void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_surface);
+void solver_profile_dump();
 
 } // namespace ob

@@ -62,16 +62,18 @@ Engine *eng_create(int device) {
     OB_CUDA(cudaMalloc(&e->bp.counters, sizeof(BroadCounters)));
     OB_CUDA(cudaMemset(e->bp.counters, 0, sizeof(BroadCounters)));
     e->meshes.n = 0;
+    if (const char *g = getenv("ODE_B200_ENV_GROUP")) e->env_group = atoi(g);
     return e;
 }
 
 void eng_destroy(Engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    solver_profile_dump();
     cudaStreamSynchronize(e->st);
     BodyArrays &B = e->B;
     dev_free(B.pos); dev_free(B.quat); dev_free(B.R); dev_free(B.lvel); dev_free(B.avel); dev_free(B.I);
-    dev_free(B.invI); dev_free(B.facc); dev_free(B.tacc); dev_free(B.flags); dev_free(B.local); dev_free(B.inv); dev_free(B.tmp);
+    dev_free(B.invI); dev_free(B.facc); dev_free(B.tacc); dev_free(B.flags); dev_free(B.local); dev_free(B.env); dev_free(B.inv); dev_free(B.tmp);
     dev_free(B.fc); dev_free(B.snap); dev_free(B.colmask); dev_free(B.prio);
     GeomArrays &G = e->G;
     dev_free(G.type); dev_free(G.dims); dev_free(G.body); dev_free(G.pos); dev_free(G.R); dev_free(G.cat);
@@ -88,6 +90,7 @@ void eng_destroy(Engine *e) {
     SolverArrays &S = e->S;
     dev_free(S.q0); dev_free(S.q1); dev_free(S.q2); dev_free(S.q3); dev_free(S.q4); dev_free(S.lam); dev_free(S.mrec);
     sort_workspace_free(e->sort); scan_workspace_free(e->scan);
+    dev_free(e->E.cnt); dev_free(e->E.start); dev_free(e->E.fill); dev_free(e->E.rec); dev_free(e->E.perm); dev_free(e->E.col);
     dev_free(e->hc_pd); dev_free(e->hc_ns); dev_free(e->hc_surf); dev_free(e->hc_mrec);
     dev_free(e->dl_first); dev_free(e->dl_pd); dev_free(e->dl_ns);
     for (auto &m : e->hmeshes) { dev_free(m.d_verts); dev_free(m.d_tris); }
@@ -181,6 +184,7 @@ void eng_mark_forces_dirty(Engine *e) { e->forces_dirty = true; }
 void eng_set_num_envs(Engine *e, int n) { e->n_envs = n < 1 ? 1 : n; }
 void eng_set_capacity(Engine *e, long max_pairs, long max_manifolds) { e->want_pairs = max_pairs; e->want_manifolds = max_manifolds; }
 void eng_set_big_extent(Engine *e, float extent) { e->big_extent = extent; }
+void eng_set_solver_mode(Engine *e, int mode, int env_group) { e->solver_mode = mode; e->env_group = env_group; }
 void eng_enable_timing(Engine *e, int on) { e->timing = on != 0; }
 
 // grow body / geom arrays to hold the host mirrors
@@ -192,7 +196,7 @@ void engine_ensure_capacity(Engine *e) {
         dev_realloc(B.pos, o, n, st); dev_realloc(B.quat, o, n, st); dev_realloc(B.R, 3 * o, 3 * n, st);
         dev_realloc(B.lvel, o, n, st); dev_realloc(B.avel, o, n, st); dev_realloc(B.I, 3 * o, 3 * n, st);
         dev_realloc(B.invI, 3 * o, 3 * n, st); dev_realloc(B.facc, o, n, st); dev_realloc(B.tacc, o, n, st);
-        dev_realloc(B.flags, o, n, st); dev_realloc(B.local, o, n, st); dev_realloc(B.inv, 3 * o, 3 * n, st, false);
+        dev_realloc(B.flags, o, n, st); dev_realloc(B.local, o, n, st); dev_realloc(B.env, o, n, st); dev_realloc(B.inv, 3 * o, 3 * n, st, false);
         dev_realloc(B.tmp, 2 * o, 2 * n, st, false); dev_realloc(B.fc, 2 * o, 2 * n, st, false);
         dev_realloc(B.snap, 16 * o, 16 * n, st); dev_realloc(B.colmask, o, n, st, false);
         dev_realloc(B.prio, o, n, st, false);
@@ -258,6 +262,21 @@ void engine_ensure_pair_capacity(Engine *e) {
         dev_realloc(S.mrec, 0, n, st, false);
         S.cap = (int)n;
     }
+    if (e->n_envs > 1) {
+        if (e->M.cap > e->cap_env_rec) {
+            const size_t n = (size_t)e->M.cap;
+            dev_realloc(e->E.rec, 0, n, st, false); dev_realloc(e->E.perm, 0, n, st, false);
+            dev_realloc(e->E.col, 0, n, st, false);
+            e->cap_env_rec = (int)n;
+        }
+        if (e->n_envs + 1 > e->cap_envs) {
+            const size_t n = (size_t)e->n_envs + 1;
+            dev_realloc(e->E.cnt, 0, n, st, false); dev_realloc(e->E.start, 0, n, st, false);
+            dev_realloc(e->E.fill, 0, n, st, false);
+            e->cap_envs = (int)n;
+        }
+    }
+    e->E.n_envs = e->n_envs;
 }
 
 template <typename T>
@@ -293,7 +312,11 @@ void eng_sync_to_device(Engine *e) {
                 const int en = b.env[i];
                 local[i] = (en >= 0 && en < (int)first.size()) ? (int)i - first[en] : (int)i;
             }
+            int max_local = 0;
+            for (size_t i = 0; i < n; i++) max_local = std::max(max_local, local[i]);
+            e->E.max_bodies = max_local + 1;
             upload(e->B.local, local.data(), n, st);
+            upload(e->B.env, b.env.data(), n, st);
             OB_CUDA(cudaStreamSynchronize(st)); // `local` is a temporary
         }
         e->bodies_dirty = false;
@@ -558,17 +581,15 @@ int eng_export_solver_order(Engine *e, int *pair_g1, int *pair_g2, int *pair_k, 
     int nm = 0;
     OB_CUDA(cudaMemcpy(&nm, e->M.count, sizeof(int), cudaMemcpyDeviceToHost));
     if (nm <= 0) return 0;
-    std::vector<int4> mrec((size_t)nm), rec((size_t)nm);
+    std::vector<int4> mrec((size_t)nm);
     OB_CUDA(cudaMemcpy(mrec.data(), e->S.mrec, (size_t)nm * sizeof(int4), cudaMemcpyDeviceToHost));
-    OB_CUDA(cudaMemcpy(rec.data(), e->M.rec, (size_t)nm * sizeof(int4), cudaMemcpyDeviceToHost));
     BroadCounters bc;
     OB_CUDA(cudaMemcpy(&bc, e->bp.counters, sizeof(bc), cudaMemcpyDeviceToHost));
     std::vector<int2> pairs((size_t)std::max(bc.n_pairs, 1));
     if (bc.n_pairs) OB_CUDA(cudaMemcpy(pairs.data(), e->bp.pairs, (size_t)bc.n_pairs * sizeof(int2), cudaMemcpyDeviceToHost));
     int out = 0;
     for (int s = 0; s < nm; s++) {
-        const int m = mrec[s].w, nc = mrec[s].z;
-        const int p = rec[m].z;
+        const int p = mrec[s].w, nc = mrec[s].z; // .w = pair index of the manifold
         for (int k = 0; k < nc; k++) {
             if (out < cap) {
                 pair_g1[out] = (p < bc.n_pairs) ? pairs[p].x : -1;

@@ -32,6 +32,10 @@ struct Engine {
     bool have_device_contacts = false;
 
     ManifoldArrays M{};
+    EnvArrays E{};
+    int cap_envs = 0, cap_env_rec = 0;
+    int env_group = 0; // lanes per env of the island solver (0 = automatic)
+    int solver_mode = 0; // 0 automatic, 1 force the global (grid-barrier) solver
     SolverArrays S{};
     ScanWorkspace scan;
     SortWorkspace sort;

@@ -144,12 +144,12 @@ __global__ void __launch_bounds__(256) k_manifold_dynbits(ManifoldArrays M, cons
 
 // ------------------------------------------------------------------ edge colouring
 
-__device__ __forceinline__ unsigned long long manifold_prio(int m, int lb1, int lb2) {
-    // hash of the env-local body pair; the manifold index only breaks ties (its relative order inside
-    // a world does not depend on the other worlds of a batch)
+__device__ __forceinline__ unsigned long long manifold_prio(int tie, int lb1, int lb2) {
+    // hash of the env-local body pair; the pair index only breaks ties (its relative order inside a
+    // world does not depend on the other worlds of a batch)
     unsigned x = ((unsigned)lb1 * 0x9E3779B1u) ^ (((unsigned)lb2 + 0x7F4A7C15u) * 0x85EBCA6Bu);
     x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13; x *= 0xC2B2AE3Du; x ^= x >> 16;
-    return ((unsigned long long)x << 32) | (unsigned)m;
+    return ((unsigned long long)x << 32) | (unsigned)tie;
 }
 
 // Deterministic parallel greedy colouring: in every round an uncoloured manifold wins if it has
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) k_colour(ManifoldArrays M, BodyArrays B) 
         for (int m = gt; m < n; m += gs) {
             if (M.colour[m] >= 0) continue;
             const int4 r = M.rec[m];
-            const unsigned long long pr = manifold_prio(m, B.local[r.x], r.y >= 0 ? B.local[r.y] : -1);
+            const unsigned long long pr = manifold_prio(r.z, B.local[r.x], r.y >= 0 ? B.local[r.y] : -1);
             if (r.w & REC_DYN1) atomicMin(&B.prio[r.x], pr);
             if (r.w & REC_DYN2) atomicMin(&B.prio[r.y], pr);
         }
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) k_colour(ManifoldArrays M, BodyArrays B) 
         for (int m = gt; m < n; m += gs) {
             if (M.colour[m] >= 0) continue;
             const int4 r = M.rec[m];
-            const unsigned long long pr = manifold_prio(m, B.local[r.x], r.y >= 0 ? B.local[r.y] : -1);
+            const unsigned long long pr = manifold_prio(r.z, B.local[r.x], r.y >= 0 ? B.local[r.y] : -1);
             const bool d1 = r.w & REC_DYN1, d2 = r.w & REC_DYN2;
             const bool ok = (!d1 || B.prio[r.x] == pr) && (!d2 || B.prio[r.y] == pr);
             if (ok) {
@@ -325,91 +325,95 @@ __device__ __forceinline__ void build_row(V3 dir, V3 c1, V3 c2, const BodyKin &k
     Adcfm = Ad * cfm_h;
 }
 
+// all rows of one manifold -> solver slot s (getInfo2 + QuickStep rhs/Ad per row)
+__device__ __forceinline__ void build_manifold_rows(int s, const int4 rec, const BodyArrays &B, const ContactSource &src,
+                                                    const Surface &usurf, const SolverArrays &S, const StepConfig &cfg,
+                                                    int &rows1, int &rows2, int &ncont) {
+    const int nc = rec.w & 0xff;
+    const bool rev = rec.w & REC_REV, two = rec.y >= 0;
+    S.mrec[s] = make_int4(rec.x, rec.y, nc, rec.z);
+    const BodyKin k1 = load_kin(B, rec.x);
+    BodyKin k2;
+    if (two) k2 = load_kin(B, rec.y);
+    else {
+        k2.x = v3(0.f, 0.f, 0.f); k2.lv = k2.av = k2.tv = k2.tw = k2.x;
+        k2.iI = M3{k2.x, k2.x, k2.x}; k2.invM = 0.f;
+    }
+    for (int k = 0; k < nc; k++) {
+        const size_t ci = (size_t)rec.z + (size_t)k * src.kstride;
+        const float4 pd = src.pd[ci], ns = src.ns[ci];
+        const Surface sf = src.surf ? src.surf[ci] : usurf;
+        const int the_m = surface_rows(sf);
+        V3 normal = v3(ns);
+        if (rev) normal = -normal;
+        const V3 pos = v3(pd);
+        const V3 c1 = pos - k1.x;
+        const V3 c2 = two ? (pos - k2.x) : v3(0.f, 0.f, 0.f);
+        // normal row: pushout, max_vel cap, bounce
+        float erp = cfg.erp;
+        if (sf.mode & MODE_SOFT_ERP) erp = sf.soft_erp;
+        const float kk = (1.0f / cfg.h) * erp;
+        float depth = pd.w - cfg.min_depth;
+        if (depth < 0) depth = 0;
+        float cfmN = cfg.cfm;
+        if (sf.mode & MODE_SOFT_CFM) cfmN = sf.soft_cfm;
+        float motionN = 0.f;
+        if (sf.mode & MODE_MOTIONN) motionN = sf.motionN;
+        float cN = kk * depth + motionN;
+        if (cN > cfg.max_vel) cN = cfg.max_vel;
+        if (sf.mode & MODE_BOUNCE) {
+            const V3 J1a = cross(c1, normal);
+            float outgoing = dot(normal, k1.lv) + dot(J1a, k1.av);
+            if (two) {
+                const V3 J2l = -normal;
+                const V3 J2a = -cross(c2, normal);
+                outgoing += dot(J2l, k2.lv) + dot(J2a, k2.av);
+            }
+            outgoing -= motionN;
+            if (sf.bounce_vel >= 0 && (-outgoing) > sf.bounce_vel) {
+                const float newc = -sf.bounce * outgoing + motionN;
+                if (newc > cN) cN = newc;
+            }
+        }
+        float rhsN, AdN, AdcfmN;
+        build_row(normal, c1, c2, k1, k2, two, cN, cfmN, cfg, rhsN, AdN, AdcfmN);
+        float4 q3 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = q3;
+        int lflags = the_m;
+        if (the_m >= 2) {
+            V3 t1, t2;
+            plane_space(normal, t1, t2);
+            const float mu = sf.mu < 0 ? 0 : sf.mu;
+            float c1v = (sf.mode & MODE_MOTION1) ? sf.motion1 : 0.f;
+            float cfm1 = (sf.mode & MODE_SLIP1) ? sf.slip1 : cfg.cfm;
+            build_row(t1, c1, c2, k1, k2, two, c1v, cfm1, cfg, q3.x, q3.y, q3.z);
+            q3.w = mu;
+            if (sf.mode & MODE_APPROX1_1) lflags |= 0x10;
+            if (the_m >= 3) {
+                float c2v = (sf.mode & MODE_MOTION2) ? sf.motion2 : 0.f;
+                float cfm2 = (sf.mode & MODE_SLIP2) ? sf.slip2 : cfg.cfm;
+                build_row(t2, c1, c2, k1, k2, two, c2v, cfm2, cfg, q4.x, q4.y, q4.z);
+                q4.w = (sf.mode & MODE_MU2) ? (sf.mu2 < 0 ? 0 : sf.mu2) : mu;
+                if (sf.mode & MODE_APPROX1_2) lflags |= 0x20;
+            }
+        }
+        const size_t si = (size_t)k * S.cap + s;
+        S.q0[si] = make_float4(normal.x, normal.y, normal.z, rhsN);
+        S.q1[si] = make_float4(c1.x, c1.y, c1.z, AdN);
+        S.q2[si] = make_float4(c2.x, c2.y, c2.z, AdcfmN);
+        S.q3[si] = q3;
+        S.q4[si] = q4;
+        S.lam[si] = make_float4(0.f, 0.f, 0.f, __int_as_float(lflags));
+        if (two) rows2 += the_m; else rows1 += the_m;
+        ncont++;
+    }
+}
+
 __global__ void __launch_bounds__(128) k_rows(ManifoldArrays M, BodyArrays B, ContactSource src, Surface usurf,
                                                SolverArrays S, StepConfig cfg, StepStats *__restrict__ stats) {
     const int n = *M.count;
     int rows1 = 0, rows2 = 0, ncont = 0;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
-        const int m = M.sidx[s];
-        const int4 rec = M.rec[m];
-        const int nc = rec.w & 0xff;
-        const bool rev = rec.w & REC_REV, two = rec.y >= 0;
-        S.mrec[s] = make_int4(rec.x, rec.y, nc, m);
-        const BodyKin k1 = load_kin(B, rec.x);
-        BodyKin k2;
-        if (two) k2 = load_kin(B, rec.y);
-        else {
-            k2.x = v3(0.f, 0.f, 0.f); k2.lv = k2.av = k2.tv = k2.tw = k2.x;
-            k2.iI = M3{k2.x, k2.x, k2.x}; k2.invM = 0.f;
-        }
-        for (int k = 0; k < nc; k++) {
-            const size_t ci = (size_t)rec.z + (size_t)k * src.kstride;
-            const float4 pd = src.pd[ci], ns = src.ns[ci];
-            const Surface sf = src.surf ? src.surf[ci] : usurf;
-            const int the_m = surface_rows(sf);
-            V3 normal = v3(ns);
-            if (rev) normal = -normal;
-            const V3 pos = v3(pd);
-            const V3 c1 = pos - k1.x;
-            const V3 c2 = two ? (pos - k2.x) : v3(0.f, 0.f, 0.f);
-            // normal row: pushout, max_vel cap, bounce
-            float erp = cfg.erp;
-            if (sf.mode & MODE_SOFT_ERP) erp = sf.soft_erp;
-            const float kk = (1.0f / cfg.h) * erp;
-            float depth = pd.w - cfg.min_depth;
-            if (depth < 0) depth = 0;
-            float cfmN = cfg.cfm;
-            if (sf.mode & MODE_SOFT_CFM) cfmN = sf.soft_cfm;
-            float motionN = 0.f;
-            if (sf.mode & MODE_MOTIONN) motionN = sf.motionN;
-            float cN = kk * depth + motionN;
-            if (cN > cfg.max_vel) cN = cfg.max_vel;
-            if (sf.mode & MODE_BOUNCE) {
-                const V3 J1a = cross(c1, normal);
-                float outgoing = dot(normal, k1.lv) + dot(J1a, k1.av);
-                if (two) {
-                    const V3 J2l = -normal;
-                    const V3 J2a = -cross(c2, normal);
-                    outgoing += dot(J2l, k2.lv) + dot(J2a, k2.av);
-                }
-                outgoing -= motionN;
-                if (sf.bounce_vel >= 0 && (-outgoing) > sf.bounce_vel) {
-                    const float newc = -sf.bounce * outgoing + motionN;
-                    if (newc > cN) cN = newc;
-                }
-            }
-            float rhsN, AdN, AdcfmN;
-            build_row(normal, c1, c2, k1, k2, two, cN, cfmN, cfg, rhsN, AdN, AdcfmN);
-            float4 q3 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = q3;
-            int lflags = the_m;
-            if (the_m >= 2) {
-                V3 t1, t2;
-                plane_space(normal, t1, t2);
-                const float mu = sf.mu < 0 ? 0 : sf.mu;
-                float c1v = (sf.mode & MODE_MOTION1) ? sf.motion1 : 0.f;
-                float cfm1 = (sf.mode & MODE_SLIP1) ? sf.slip1 : cfg.cfm;
-                build_row(t1, c1, c2, k1, k2, two, c1v, cfm1, cfg, q3.x, q3.y, q3.z);
-                q3.w = mu;
-                if (sf.mode & MODE_APPROX1_1) lflags |= 0x10;
-                if (the_m >= 3) {
-                    float c2v = (sf.mode & MODE_MOTION2) ? sf.motion2 : 0.f;
-                    float cfm2 = (sf.mode & MODE_SLIP2) ? sf.slip2 : cfg.cfm;
-                    build_row(t2, c1, c2, k1, k2, two, c2v, cfm2, cfg, q4.x, q4.y, q4.z);
-                    q4.w = (sf.mode & MODE_MU2) ? (sf.mu2 < 0 ? 0 : sf.mu2) : mu;
-                    if (sf.mode & MODE_APPROX1_2) lflags |= 0x20;
-                }
-            }
-            const size_t si = (size_t)k * S.cap + s;
-            S.q0[si] = make_float4(normal.x, normal.y, normal.z, rhsN);
-            S.q1[si] = make_float4(c1.x, c1.y, c1.z, AdN);
-            S.q2[si] = make_float4(c2.x, c2.y, c2.z, AdcfmN);
-            S.q3[si] = q3;
-            S.q4[si] = q4;
-            S.lam[si] = make_float4(0.f, 0.f, 0.f, __int_as_float(lflags));
-            if (two) rows2 += the_m; else rows1 += the_m;
-            ncont++;
-        }
-    }
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
+        build_manifold_rows(s, M.rec[M.sidx[s]], B, src, usurf, S, cfg, rows1, rows2, ncont);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         rows1 += __shfl_xor_sync(0xffffffffu, rows1, o);
@@ -479,6 +483,14 @@ __device__ __forceinline__ RowRec load_rows(const SolverArrays &S, size_t si) {
 // while contact k is being solved, so the dependent chain per manifold is: record -> {bodies, rows}
 // -> arithmetic, not one DRAM round trip per contact.  The body accumulators fc are exchanged
 // between SMs from one colour to the next, so they bypass L1 (ld.cg / st.cg).
+template <bool L2ONLY>
+__device__ __forceinline__ float4 ld_fc(const float4 *p) { return L2ONLY ? __ldcg(p) : *p; }
+template <bool L2ONLY>
+__device__ __forceinline__ void st_fc(float4 *p, float4 v) {
+    if (L2ONLY) __stcg(p, v); else *p = v;
+}
+
+template <bool L2ONLY>
 __device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, const BodyArrays &B) {
     const int4 rec = __ldg(&S.mrec[s]);
     const int b1 = rec.x, b2 = rec.y, nc = rec.z;
@@ -486,7 +498,7 @@ __device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, con
     RowRec cur = load_rows(S, (size_t)s);
     FC f1, f2;
     {
-        const float4 a = __ldcg(&B.fc[2 * b1]), b = __ldcg(&B.fc[2 * b1 + 1]);
+        const float4 a = ld_fc<L2ONLY>(&B.fc[2 * b1]), b = ld_fc<L2ONLY>(&B.fc[2 * b1 + 1]);
         f1.l = v3(a); f1.a = v3(b);
     }
     const float4 i10 = __ldg(&B.inv[3 * b1]), i11 = __ldg(&B.inv[3 * b1 + 1]), i12 = __ldg(&B.inv[3 * b1 + 2]);
@@ -496,7 +508,7 @@ __device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, con
     float invM2 = 0.f;
     f2.l = v3(0.f, 0.f, 0.f); f2.a = f2.l;
     if (two) {
-        const float4 a = __ldcg(&B.fc[2 * b2]), b = __ldcg(&B.fc[2 * b2 + 1]);
+        const float4 a = ld_fc<L2ONLY>(&B.fc[2 * b2]), b = ld_fc<L2ONLY>(&B.fc[2 * b2 + 1]);
         f2.l = v3(a); f2.a = v3(b);
         const float4 i20 = __ldg(&B.inv[3 * b2]), i21 = __ldg(&B.inv[3 * b2 + 1]), i22 = __ldg(&B.inv[3 * b2 + 2]);
         iI2 = M3{v3(i20), v3(i21), v3(i22)};
@@ -528,11 +540,11 @@ __device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, con
         S.lam[si] = lam;
         cur = nxt;
     }
-    __stcg(&B.fc[2 * b1], make_float4(f1.l.x, f1.l.y, f1.l.z, 0.f));
-    __stcg(&B.fc[2 * b1 + 1], make_float4(f1.a.x, f1.a.y, f1.a.z, 0.f));
+    st_fc<L2ONLY>(&B.fc[2 * b1], make_float4(f1.l.x, f1.l.y, f1.l.z, 0.f));
+    st_fc<L2ONLY>(&B.fc[2 * b1 + 1], make_float4(f1.a.x, f1.a.y, f1.a.z, 0.f));
     if (two) {
-        __stcg(&B.fc[2 * b2], make_float4(f2.l.x, f2.l.y, f2.l.z, 0.f));
-        __stcg(&B.fc[2 * b2 + 1], make_float4(f2.a.x, f2.a.y, f2.a.z, 0.f));
+        st_fc<L2ONLY>(&B.fc[2 * b2], make_float4(f2.l.x, f2.l.y, f2.l.z, 0.f));
+        st_fc<L2ONLY>(&B.fc[2 * b2 + 1], make_float4(f2.a.x, f2.a.y, f2.a.z, 0.f));
     }
 }
 
@@ -608,18 +620,217 @@ __global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays
         for (int it = 0; it < cfg.iters; it++) {
             for (int c = 0; c < ncol; c++) {
                 const int s0 = M.colour_start[c], s1 = M.colour_start[c + 1];
-                for (int s = s0 + gt; s < s1; s += gs) solve_manifold(s, S, B);
+                for (int s = s0 + gt; s < s1; s += gs) solve_manifold<true>(s, S, B);
                 grid_barrier(bar, target);
             }
             if (ovf1 > ovf0) {
                 // manifolds that found no free colour (> 64 neighbours): one thread, in order
                 if (gt == 0)
-                    for (int s = ovf0; s < ovf1; s++) solve_manifold(s, S, B);
+                    for (int s = ovf0; s < ovf1; s++) solve_manifold<true>(s, S, B);
                 grid_barrier(bar, target);
             }
         }
     }
     for (int i = gt; i < B.n; i += gs) integrate_body(i, B, cfg.h);
+}
+
+// ------------------------------------------------------------------ island solver for batched worlds
+//
+// Scenes made of many small independent worlds ("envs", BASELINE config 4) do not need grid-wide
+// barriers: an env is an island.  Manifolds are bucketed per env, and one group of G lanes of a warp
+// owns one env for the whole solve: it colours the env's manifolds (same rule and priorities as
+// k_colour, so the colours -- and therefore the Gauss-Seidel order and every result bit -- are the
+// same as on the global path), orders them by colour, builds their rows and runs all iterations
+// with __syncwarp() between colours.  Rows and accumulators of an env stay in L1/L2 for its 20
+// iterations instead of being streamed from HBM 20 times.
+
+__global__ void __launch_bounds__(256) k_env_count(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
+                                                    const int *__restrict__ g_body, const int *__restrict__ nc,
+                                                    const int *__restrict__ b_env, int *__restrict__ env_cnt) {
+    const int n = bc->n_pairs;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const int2 pr = pairs[p];
+        const int b1 = g_body[pr.x], b2 = g_body[pr.y];
+        if (nc[p] > 0 && (b1 >= 0 || b2 >= 0)) atomicAdd(&env_cnt[b_env[b1 >= 0 ? b1 : b2]], 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_env_bucket(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
+                                                     const int *__restrict__ g_body, const int *__restrict__ nc,
+                                                     const float4 *__restrict__ b_pos, const int *__restrict__ b_env,
+                                                     EnvArrays E, StepStats *__restrict__ stats) {
+    const int n = bc->n_pairs;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const int2 pr = pairs[p];
+        int b1 = g_body[pr.x], b2 = g_body[pr.y];
+        const int c = nc[p];
+        if (!(c > 0 && (b1 >= 0 || b2 >= 0))) continue;
+        int w = c;
+        if (b1 < 0) { b1 = b2; b2 = -1; w |= REC_REV; }
+        if (b_pos[b1].w > 0.f) w |= REC_DYN1;
+        if (b2 >= 0 && b_pos[b2].w > 0.f) w |= REC_DYN2;
+        const int e = b_env[b1];
+        const int slot = E.start[e] + atomicAdd(&E.fill[e], 1);
+        E.rec[slot] = make_int4(b1, b2, p, w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) stats->n_manifolds = E.start[E.n_envs];
+}
+
+#ifdef OB_ENV_PROFILE
+__device__ unsigned long long g_env_prof[8];
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(i, a, b) if (g == 0) atomicAdd(&g_env_prof[i], (unsigned long long)((b) - (a)))
+#else
+#define PROF_T(var)
+#define PROF_ADD(i, a, b)
+#endif
+
+template <int G>
+__global__ void __launch_bounds__(128) k_env_solve(EnvArrays E, BodyArrays B, ContactSource src, Surface usurf,
+                                                    SolverArrays S, StepConfig cfg, StepStats *__restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char env_smem[];
+    constexpr int GROUPS = 128 / G;
+    const int grp = threadIdx.x / G, g = threadIdx.x % G;
+    const int lane = threadIdx.x & 31;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
+    const int mb = (E.max_bodies + 31) & ~31;
+    // per group: colour masks + priorities of the env's bodies, colour bucket starts and cursors
+    unsigned long long *masks = reinterpret_cast<unsigned long long *>(env_smem) + (size_t)grp * 2 * mb;
+    unsigned long long *prio = masks + mb;
+    int *cstart = reinterpret_cast<int *>(env_smem + (size_t)GROUPS * 2 * mb * sizeof(unsigned long long)) + grp * 136;
+    int *cursor = cstart + 68;
+    int rows1 = 0, rows2 = 0, ncont = 0, max_col = 0, max_rounds = 0;
+    for (int env = blockIdx.x * GROUPS + grp; env < E.n_envs; env += gridDim.x * GROUPS) {
+        const int ms = E.start[env], me = E.start[env + 1];
+        if (me > ms) {
+            PROF_T(t0);
+            // ---- colouring (rule of k_colour, at group scope)
+            for (int i = g; i < mb; i += G) { masks[i] = 0ull; prio[i] = ~0ull; }
+            for (int i = g; i < 68; i += G) { cstart[i] = 0; cursor[i] = 0; }
+            for (int m = ms + g; m < me; m += G) E.col[m] = 255;
+            __syncwarp(gmask);
+            int rounds = 0;
+            for (;; rounds++) {
+                for (int m = ms + g; m < me; m += G) {
+                    if (E.col[m] != 255) continue;
+                    const int4 r = E.rec[m];
+                    const int l1 = B.local[r.x], l2 = r.y >= 0 ? B.local[r.y] : -1;
+                    const unsigned long long pr = manifold_prio(r.z, l1, l2);
+                    if (r.w & REC_DYN1) atomicMin(&prio[l1], pr);
+                    if (r.w & REC_DYN2) atomicMin(&prio[l2], pr);
+                }
+                __syncwarp(gmask);
+                bool left = false;
+                for (int m = ms + g; m < me; m += G) {
+                    if (E.col[m] != 255) continue;
+                    const int4 r = E.rec[m];
+                    const int l1 = B.local[r.x], l2 = r.y >= 0 ? B.local[r.y] : -1;
+                    const unsigned long long pr = manifold_prio(r.z, l1, l2);
+                    const bool d1 = r.w & REC_DYN1, d2 = r.w & REC_DYN2;
+                    if ((!d1 || prio[l1] == pr) && (!d2 || prio[l2] == pr)) {
+                        unsigned long long mask = 0ull;
+                        if (d1) mask |= masks[l1];
+                        if (d2) mask |= masks[l2];
+                        int c;
+                        if (~mask == 0ull) c = OVERFLOW_COLOUR;
+                        else {
+                            c = __ffsll((long long)~mask) - 1;
+                            const unsigned long long bit = 1ull << c;
+                            if (d1) masks[l1] |= bit;
+                            if (d2) masks[l2] |= bit;
+                        }
+                        E.col[m] = (unsigned char)c;
+                        atomicAdd(&cstart[c + 1], 1);
+                    } else left = true;
+                }
+                __syncwarp(gmask);
+                if (!__any_sync(gmask, left)) break;
+                for (int m = ms + g; m < me; m += G) {
+                    if (E.col[m] != 255) continue;
+                    const int4 r = E.rec[m];
+                    if (r.w & REC_DYN1) prio[B.local[r.x]] = ~0ull;
+                    if (r.w & REC_DYN2) prio[B.local[r.y]] = ~0ull;
+                }
+                __syncwarp(gmask);
+            }
+            PROF_T(t1);
+            // ---- order the env's manifolds by colour (counting sort at group scope)
+            if (g == 0) {
+                int acc = 0;
+                for (int c = 0; c <= OVERFLOW_COLOUR + 1; c++) { acc += cstart[c]; cstart[c] = acc; }
+            }
+            __syncwarp(gmask);
+            int ncol = 0;
+            for (int m = ms + g; m < me; m += G) {
+                const int c = E.col[m];
+                const int r = atomicAdd(&cursor[c], 1);
+                E.perm[ms + cstart[c] + r] = m;
+                if (c < OVERFLOW_COLOUR && c + 1 > ncol) ncol = c + 1;
+            }
+            __syncwarp(gmask);
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) ncol = max(ncol, __shfl_xor_sync(gmask, ncol, o));
+            PROF_T(t2);
+            // ---- rows
+            for (int s = ms + g; s < me; s += G) build_manifold_rows(s, E.rec[E.perm[s]], B, src, usurf, S, cfg, rows1, rows2, ncont);
+            __syncwarp(gmask);
+            PROF_T(t3);
+            // ---- SOR/PGS iterations, colours separated by group-level barriers only
+            const int ovf0 = ms + cstart[OVERFLOW_COLOUR], ovf1 = ms + cstart[OVERFLOW_COLOUR + 1];
+            for (int it = 0; it < cfg.iters; it++) {
+                for (int c = 0; c < ncol; c++) {
+                    const int s1 = ms + cstart[c + 1];
+                    for (int s = ms + cstart[c] + g; s < s1; s += G) solve_manifold<false>(s, S, B);
+                    __syncwarp(gmask);
+                }
+                if (ovf1 > ovf0) {
+                    if (g == 0)
+                        for (int s = ovf0; s < ovf1; s++) solve_manifold<false>(s, S, B);
+                    __syncwarp(gmask);
+                }
+            }
+            PROF_T(t4);
+            PROF_ADD(0, t0, t1); PROF_ADD(1, t1, t2); PROF_ADD(2, t2, t3); PROF_ADD(3, t3, t4); PROF_ADD(4, 0, 1);
+            max_col = max(max_col, ncol);
+            max_rounds = max(max_rounds, rounds + 1);
+            if (g == 0 && ovf1 > ovf0) atomicAdd(&stats->n_overflow, ovf1 - ovf0);
+        }
+        __syncwarp(gmask);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        rows1 += __shfl_xor_sync(0xffffffffu, rows1, o);
+        rows2 += __shfl_xor_sync(0xffffffffu, rows2, o);
+        ncont += __shfl_xor_sync(0xffffffffu, ncont, o);
+        max_col = max(max_col, __shfl_xor_sync(0xffffffffu, max_col, o));
+        max_rounds = max(max_rounds, __shfl_xor_sync(0xffffffffu, max_rounds, o));
+    }
+    if (lane == 0) {
+        if (rows1 | rows2 | ncont) {
+            atomicAdd(&stats->n_rows1, rows1);
+            atomicAdd(&stats->n_rows2, rows2);
+            atomicAdd(&stats->n_rows, rows1 + rows2);
+            atomicAdd(&stats->n_contacts, ncont);
+        }
+        atomicMax(&stats->n_colours, max_col);
+        atomicMax(&stats->colour_rounds, max_rounds);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_integrate(BodyArrays B, StepConfig cfg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B.n) integrate_body(i, B, cfg.h);
+}
+
+void solver_profile_dump() {
+#ifdef OB_ENV_PROFILE
+    unsigned long long h[8];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, g_env_prof, sizeof(h));
+    if (h[4])
+        fprintf(stderr, "env-solve profile (avg cycles per env-solve): colour %.0f  sort %.0f  rows %.0f  iterations %.0f  (n=%llu)\n",
+                (double)h[0] / h[4], (double)h[1] / h[4], (double)h[2] / h[4], (double)h[3] / h[4], h[4]);
+#endif
 }
 
 // ------------------------------------------------------------------ host orchestration
@@ -653,6 +864,50 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
     long max_manifolds;
     ContactSource src;
     Surface usurf{};
+    // batched independent worlds with device-resident contacts take the island path
+    const bool env_path = !host_contacts && e->have_device_contacts && e->n_envs > 1 && e->E.max_bodies <= 1024 &&
+                          e->solver_mode != 1;
+    if (env_path) {
+        if (uniform_surface) usurf = *uniform_surface;
+        src.pd = e->cs.pd; src.ns = e->cs.ns; src.surf = nullptr; src.kstride = e->cs.stride;
+        EnvArrays E = e->E;
+        const int ne = E.n_envs;
+        OB_CUDA(cudaMemsetAsync(E.cnt, 0, ((size_t)ne + 1) * sizeof(int), st));
+        OB_CUDA(cudaMemsetAsync(E.fill, 0, ((size_t)ne + 1) * sizeof(int), st));
+        k_env_count<<<pgrid, 256, 0, st>>>(e->bp.counters, e->bp.pairs, e->G.body, e->cs.nc, B.env, E.cnt);
+        OB_CHECK_KERNEL("k_env_count", st);
+        scan_exclusive(E.cnt, E.start, (long)ne + 1, nullptr, nullptr, e->scan, st);
+        k_env_bucket<<<pgrid, 256, 0, st>>>(e->bp.counters, e->bp.pairs, e->G.body, e->cs.nc, B.pos, B.env, E, e->d_stats);
+        OB_CHECK_KERNEL("k_env_bucket", st);
+        OB_CUDA(cudaMemcpyAsync(M.count, E.start + ne, sizeof(int), cudaMemcpyDeviceToDevice, st));
+        if (e->timing) {
+            OB_CUDA(cudaEventRecord(e->ev[2], st));
+            OB_CUDA(cudaEventRecord(e->ev[3], st));
+        }
+        // lanes per env (8, 16 or 32): measured on C4, a full warp per env is fastest
+        int G = e->env_group;
+        if (G != 8 && G != 16 && G != 32) G = 32;
+        const int groups = 128 / G;
+        const int mb = (E.max_bodies + 31) & ~31;
+        const size_t smem = (size_t)groups * (2 * (size_t)mb * sizeof(unsigned long long) + 136 * sizeof(int));
+        const unsigned grid = (unsigned)((ne + groups - 1) / groups);
+        SolverArrays S = e->S;
+        if (G == 8) {
+            if (smem > 48 * 1024) OB_CUDA(cudaFuncSetAttribute(k_env_solve<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_env_solve<8><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->d_stats);
+        } else if (G == 16) {
+            if (smem > 48 * 1024) OB_CUDA(cudaFuncSetAttribute(k_env_solve<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_env_solve<16><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->d_stats);
+        } else {
+            if (smem > 48 * 1024) OB_CUDA(cudaFuncSetAttribute(k_env_solve<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_env_solve<32><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->d_stats);
+        }
+        OB_CHECK_KERNEL("k_env_solve", st);
+        k_integrate<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(B, cfg);
+        OB_CHECK_KERNEL("k_integrate", st);
+        if (e->timing) OB_CUDA(cudaEventRecord(e->ev[4], st));
+        return;
+    }
     if (host_contacts) {
         // records + contacts were uploaded by eng_step_host_contacts; *M.count set there
         src.pd = e->hc_pd; src.ns = e->hc_ns; src.surf = e->hc_surf; src.kstride = 1;

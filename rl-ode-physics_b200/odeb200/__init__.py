@@ -117,6 +117,7 @@ _SIGS = [
     ("dWorldTimerElapsedB200", C.c_float, [_vp]), ("dGetKernelLaunchCountB200", C.c_long, []),
     ("dWorldSetCapacityB200", None, [_vp, C.c_long, C.c_long]),
     ("dWorldSetBigExtentB200", None, [_vp, _f]),
+    ("dWorldSetSolverModeB200", None, [_vp, _i, _i]),
     ("dWorldGetStatsB200", None, [_vp, C.POINTER(StepStats)]),
     ("dWorldEnableTimingB200", None, [_vp, _i]),
     ("dWorldGetTimingsB200", None, [_vp, _fp]),
@@ -131,7 +132,7 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = os.path.abspath(LIB_PATH)
+    path = os.path.abspath(os.environ.get("ODE_B200_LIB", LIB_PATH))  # override only for instrumented builds
     if not os.path.exists(path):
         raise RuntimeError("libode_b200.so is not built (%s): run `python __graft_entry__.py` or make -C "
                            "rl-ode-physics_b200/csrc; there is no CPU fallback" % path)
@@ -223,6 +224,9 @@ class World:
 
     def set_surface(self, s):
         self.L.dWorldSetSurfaceB200(self.w, C.byref(s))
+
+    def set_solver_mode(self, mode=0, env_group=0):
+        self.L.dWorldSetSolverModeB200(self.w, int(mode), int(env_group))
 
     def set_capacity(self, max_pairs, max_manifolds):
         self.L.dWorldSetCapacityB200(self.w, int(max_pairs), int(max_manifolds))

@@ -251,3 +251,24 @@ def test_mass_and_inertia_parity():
         for k in ("pos", "quat", "lvel", "avel"):
             assert util.rel_err(es[k], os_[k]).max() <= STATE_RTOL, (step, k)
     ew.close()
+
+
+@pytest.mark.parametrize("group", [8, 16, 32])
+def test_island_solver_equals_grid_barrier_solver(group):
+    """Batched worlds take the island solver (one lane group per env, no grid barriers); it must give
+    the same bits as the global graph-coloured solver."""
+    sc = scenes.batched_worlds_scene(24, seed=4, spacing=0.7)
+    outs = []
+    for mode, g in ((1, 0), (0, group)):
+        ew = util.engine_world(sc)
+        ew.set_solver_mode(mode, g)
+        for _ in range(30):
+            ew.tick(sc["h"])
+        outs.append((ew.state(), ew.stats()))
+        ew.close()
+    (a, sa), (b, sb) = outs
+    for k in ("pos", "quat", "lvel", "avel"):
+        assert np.array_equal(a[k], b[k]), k
+    for k in ("n_contacts", "n_manifolds", "n_rows1", "n_rows2", "n_colours"):
+        assert sa[k] == sb[k], k
+    assert sa["n_contacts"] > 500
