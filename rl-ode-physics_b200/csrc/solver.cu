@@ -685,14 +685,18 @@ __device__ unsigned long long g_env_prof[8];
 #define PROF_ADD(i, a, b)
 #endif
 
+// The W = 32/G envs that share a warp run in LOCKSTEP: every loop bound is made warp-uniform (the
+// maximum over the warp's groups) and lanes without work are predicated off, so the groups never
+// diverge into serialised code paths.  The solver is issue-bound (ncu: 67 % issue-active, DRAM 8 %),
+// so what matters is how many lanes of each issued instruction do useful work.
 template <int G>
 __global__ void __launch_bounds__(128) k_env_solve(EnvArrays E, BodyArrays B, ContactSource src, Surface usurf,
                                                     SolverArrays S, StepConfig cfg, StepStats *__restrict__ stats) {
     extern __shared__ __align__(16) unsigned char env_smem[];
-    constexpr int GROUPS = 128 / G;
+    constexpr int GROUPS = 128 / G;   // envs per CTA
+    constexpr unsigned FULL = 0xffffffffu;
     const int grp = threadIdx.x / G, g = threadIdx.x % G;
     const int lane = threadIdx.x & 31;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((lane / G) * G));
     const int mb = (E.max_bodies + 31) & ~31;
     // per group: colour masks + priorities of the env's bodies, colour bucket starts and cursors
     unsigned long long *masks = reinterpret_cast<unsigned long long *>(env_smem) + (size_t)grp * 2 * mb;
@@ -700,29 +704,39 @@ __global__ void __launch_bounds__(128) k_env_solve(EnvArrays E, BodyArrays B, Co
     int *cstart = reinterpret_cast<int *>(env_smem + (size_t)GROUPS * 2 * mb * sizeof(unsigned long long)) + grp * 136;
     int *cursor = cstart + 68;
     int rows1 = 0, rows2 = 0, ncont = 0, max_col = 0, max_rounds = 0;
-    for (int env = blockIdx.x * GROUPS + grp; env < E.n_envs; env += gridDim.x * GROUPS) {
-        const int ms = E.start[env], me = E.start[env + 1];
-        if (me > ms) {
-            PROF_T(t0);
-            // ---- colouring (rule of k_colour, at group scope)
-            for (int i = g; i < mb; i += G) { masks[i] = 0ull; prio[i] = ~0ull; }
-            for (int i = g; i < 68; i += G) { cstart[i] = 0; cursor[i] = 0; }
-            for (int m = ms + g; m < me; m += G) E.col[m] = 255;
-            __syncwarp(gmask);
-            int rounds = 0;
-            for (;; rounds++) {
-                for (int m = ms + g; m < me; m += G) {
-                    if (E.col[m] != 255) continue;
+    const int n_env_rounds = (E.n_envs + gridDim.x * GROUPS - 1) / (gridDim.x * GROUPS);
+    for (int er = 0; er < n_env_rounds; er++) {
+        const int env = (er * gridDim.x + blockIdx.x) * GROUPS + grp;
+        const bool have = env < E.n_envs;
+        const int ms = have ? E.start[env] : 0, me = have ? E.start[env + 1] : 0;
+        const int trips = (__reduce_max_sync(FULL, me - ms) + G - 1) / G; // warp-uniform
+        if (trips == 0) continue;
+        PROF_T(t0);
+        // ---- colouring (rule of k_colour, at group scope)
+        for (int i = g; i < mb; i += G) { masks[i] = 0ull; prio[i] = ~0ull; }
+        for (int i = g; i < 68; i += G) { cstart[i] = 0; cursor[i] = 0; }
+        for (int j = 0; j < trips; j++) {
+            const int m = ms + g + j * G;
+            if (m < me) E.col[m] = 255;
+        }
+        __syncwarp();
+        int rounds = 0;
+        for (;; rounds++) {
+            for (int j = 0; j < trips; j++) {
+                const int m = ms + g + j * G;
+                if (m < me && E.col[m] == 255) {
                     const int4 r = E.rec[m];
                     const int l1 = B.local[r.x], l2 = r.y >= 0 ? B.local[r.y] : -1;
                     const unsigned long long pr = manifold_prio(r.z, l1, l2);
                     if (r.w & REC_DYN1) atomicMin(&prio[l1], pr);
                     if (r.w & REC_DYN2) atomicMin(&prio[l2], pr);
                 }
-                __syncwarp(gmask);
-                bool left = false;
-                for (int m = ms + g; m < me; m += G) {
-                    if (E.col[m] != 255) continue;
+            }
+            __syncwarp();
+            bool left = false;
+            for (int j = 0; j < trips; j++) {
+                const int m = ms + g + j * G;
+                if (m < me && E.col[m] == 255) {
                     const int4 r = E.rec[m];
                     const int l1 = B.local[r.x], l2 = r.y >= 0 ? B.local[r.y] : -1;
                     const unsigned long long pr = manifold_prio(r.z, l1, l2);
@@ -743,67 +757,81 @@ __global__ void __launch_bounds__(128) k_env_solve(EnvArrays E, BodyArrays B, Co
                         atomicAdd(&cstart[c + 1], 1);
                     } else left = true;
                 }
-                __syncwarp(gmask);
-                if (!__any_sync(gmask, left)) break;
-                for (int m = ms + g; m < me; m += G) {
-                    if (E.col[m] != 255) continue;
+            }
+            __syncwarp();
+            if (!__any_sync(FULL, left)) break;
+            for (int j = 0; j < trips; j++) {
+                const int m = ms + g + j * G;
+                if (m < me && E.col[m] == 255) {
                     const int4 r = E.rec[m];
                     if (r.w & REC_DYN1) prio[B.local[r.x]] = ~0ull;
                     if (r.w & REC_DYN2) prio[B.local[r.y]] = ~0ull;
                 }
-                __syncwarp(gmask);
             }
-            PROF_T(t1);
-            // ---- order the env's manifolds by colour (counting sort at group scope)
-            if (g == 0) {
-                int acc = 0;
-                for (int c = 0; c <= OVERFLOW_COLOUR + 1; c++) { acc += cstart[c]; cstart[c] = acc; }
-            }
-            __syncwarp(gmask);
-            int ncol = 0;
-            for (int m = ms + g; m < me; m += G) {
+            __syncwarp();
+        }
+        PROF_T(t1);
+        // ---- order the env's manifolds by colour (counting sort at group scope)
+        if (g == 0) {
+            int acc = 0;
+            for (int c = 0; c <= OVERFLOW_COLOUR + 1; c++) { acc += cstart[c]; cstart[c] = acc; }
+        }
+        __syncwarp();
+        int ncol = 0;
+        for (int j = 0; j < trips; j++) {
+            const int m = ms + g + j * G;
+            if (m < me) {
                 const int c = E.col[m];
                 const int r = atomicAdd(&cursor[c], 1);
                 E.perm[ms + cstart[c] + r] = m;
                 if (c < OVERFLOW_COLOUR && c + 1 > ncol) ncol = c + 1;
             }
-            __syncwarp(gmask);
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) ncol = max(ncol, __shfl_xor_sync(gmask, ncol, o));
-            PROF_T(t2);
-            // ---- rows
-            for (int s = ms + g; s < me; s += G) build_manifold_rows(s, E.rec[E.perm[s]], B, src, usurf, S, cfg, rows1, rows2, ncont);
-            __syncwarp(gmask);
-            PROF_T(t3);
-            // ---- SOR/PGS iterations, colours separated by group-level barriers only
-            const int ovf0 = ms + cstart[OVERFLOW_COLOUR], ovf1 = ms + cstart[OVERFLOW_COLOUR + 1];
-            for (int it = 0; it < cfg.iters; it++) {
-                for (int c = 0; c < ncol; c++) {
-                    const int s1 = ms + cstart[c + 1];
-                    for (int s = ms + cstart[c] + g; s < s1; s += G) solve_manifold<false>(s, S, B);
-                    __syncwarp(gmask);
-                }
-                if (ovf1 > ovf0) {
-                    if (g == 0)
-                        for (int s = ovf0; s < ovf1; s++) solve_manifold<false>(s, S, B);
-                    __syncwarp(gmask);
-                }
-            }
-            PROF_T(t4);
-            PROF_ADD(0, t0, t1); PROF_ADD(1, t1, t2); PROF_ADD(2, t2, t3); PROF_ADD(3, t3, t4); PROF_ADD(4, 0, 1);
-            max_col = max(max_col, ncol);
-            max_rounds = max(max_rounds, rounds + 1);
-            if (g == 0 && ovf1 > ovf0) atomicAdd(&stats->n_overflow, ovf1 - ovf0);
         }
-        __syncwarp(gmask);
+        __syncwarp();
+        ncol = __reduce_max_sync(FULL, ncol); // colours of the busiest env of the warp
+        PROF_T(t2);
+        // ---- rows
+        for (int j = 0; j < trips; j++) {
+            const int s = ms + g + j * G;
+            if (s < me) build_manifold_rows(s, E.rec[E.perm[s]], B, src, usurf, S, cfg, rows1, rows2, ncont);
+        }
+        __syncwarp();
+        PROF_T(t3);
+        // ---- SOR/PGS iterations, colours separated by warp-level barriers only
+        const int novf = cstart[OVERFLOW_COLOUR + 1] - cstart[OVERFLOW_COLOUR];
+        const bool any_ovf = __any_sync(FULL, novf > 0);
+        for (int it = 0; it < cfg.iters; it++) {
+            for (int c = 0; c < ncol; c++) {
+                const int s0 = ms + cstart[c], s1 = ms + cstart[c + 1];
+                const int t = (__reduce_max_sync(FULL, s1 - s0) + G - 1) / G;
+                for (int j = 0; j < t; j++) {
+                    const int s = s0 + g + j * G;
+                    if (s < s1) solve_manifold<false>(s, S, B);
+                }
+                __syncwarp();
+            }
+            if (any_ovf) {
+                // manifolds that found no free colour (> 64 neighbours): one lane per env, in order
+                if (g == 0)
+                    for (int s = ms + cstart[OVERFLOW_COLOUR]; s < ms + cstart[OVERFLOW_COLOUR + 1]; s++)
+                        solve_manifold<false>(s, S, B);
+                __syncwarp();
+            }
+        }
+        PROF_T(t4);
+        PROF_ADD(0, t0, t1); PROF_ADD(1, t1, t2); PROF_ADD(2, t2, t3); PROF_ADD(3, t3, t4); PROF_ADD(4, 0, 1);
+        max_col = max(max_col, ncol);
+        max_rounds = max(max_rounds, rounds + 1);
+        if (g == 0 && novf > 0) atomicAdd(&stats->n_overflow, novf);
+        __syncwarp();
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        rows1 += __shfl_xor_sync(0xffffffffu, rows1, o);
-        rows2 += __shfl_xor_sync(0xffffffffu, rows2, o);
-        ncont += __shfl_xor_sync(0xffffffffu, ncont, o);
-        max_col = max(max_col, __shfl_xor_sync(0xffffffffu, max_col, o));
-        max_rounds = max(max_rounds, __shfl_xor_sync(0xffffffffu, max_rounds, o));
+        rows1 += __shfl_xor_sync(FULL, rows1, o);
+        rows2 += __shfl_xor_sync(FULL, rows2, o);
+        ncont += __shfl_xor_sync(FULL, ncont, o);
+        max_col = max(max_col, __shfl_xor_sync(FULL, max_col, o));
+        max_rounds = max(max_rounds, __shfl_xor_sync(FULL, max_rounds, o));
     }
     if (lane == 0) {
         if (rows1 | rows2 | ncont) {
@@ -884,9 +912,9 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
             OB_CUDA(cudaEventRecord(e->ev[2], st));
             OB_CUDA(cudaEventRecord(e->ev[3], st));
         }
-        // lanes per env (8, 16 or 32): measured on C4, a full warp per env is fastest
+        // lanes per env (8, 16 or 32): the 32/G envs of a warp run in lockstep
         int G = e->env_group;
-        if (G != 8 && G != 16 && G != 32) G = 32;
+        if (G != 8 && G != 16 && G != 32) G = ne >= 4096 ? 8 : (ne >= 1024 ? 16 : 32);
         const int groups = 128 / G;
         const int mb = (E.max_bodies + 31) & ~31;
         const size_t smem = (size_t)groups * (2 * (size_t)mb * sizeof(unsigned long long) + 136 * sizeof(int));
