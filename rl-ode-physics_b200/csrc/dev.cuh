@@ -131,8 +131,9 @@ struct SolverArrays {
     float4 *q0; // n.xyz, rhsN
     float4 *q1; // r1.xyz, AdN
     float4 *q2; // r2.xyz, AdcfmN
-    float4 *q3; // rhsT1, AdT1, AdcfmT1, hi1
-    float4 *q4; // rhsT2, AdT2, AdcfmT2, hi2
+    float4 *q3; // rhsT1, AdT1, AdcfmT1, k = 1/sqrt(.) of dPlaneSpace(n)
+    float4 *q4; // rhsT2, AdT2, AdcfmT2, mu
+    float4 *q5; // (mu2, -, -, -): only written/read for dContactMu2 contacts
     float4 *lam; // lambdaN, lambdaT1, lambdaT2, bitcast(rows | findex flags)
     int4 *mrec;  // per sorted manifold: b1, b2, nc, manifold id
 };

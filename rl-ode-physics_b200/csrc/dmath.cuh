@@ -69,20 +69,24 @@ __host__ __device__ __forceinline__ M3 q_to_r(float4 q) { // q = (w,x,y,z) in (x
     return R;
 }
 
-// dPlaneSpace
-__host__ __device__ __forceinline__ void plane_space(V3 n, V3 &p, V3 &q) {
+// dPlaneSpace, split in two: the only expensive part is k = 1/sqrt(a) (IEEE sqrt + divide); the
+// solver computes it once per contact in the row builder and reuses it every iteration.
+__host__ __device__ __forceinline__ float plane_space_k(V3 n) {
+    if (fabsf(n.z) > 0.70710678118654752440f) return 1.0f / sqrtf(n.y * n.y + n.z * n.z);
+    return 1.0f / sqrtf(n.x * n.x + n.y * n.y);
+}
+__host__ __device__ __forceinline__ void plane_space_with_k(V3 n, float k, V3 &p, V3 &q) {
     if (fabsf(n.z) > 0.70710678118654752440f) {
         float a = n.y * n.y + n.z * n.z;
-        float k = 1.0f / sqrtf(a);
         p = V3{0, -n.z * k, n.y * k};
         q = V3{a * k, -n.x * p.z, n.x * p.y};
     } else {
         float a = n.x * n.x + n.y * n.y;
-        float k = 1.0f / sqrtf(a);
         p = V3{-n.y * k, n.x * k, 0};
         q = V3{-n.z * p.y, n.z * p.x, a * k};
     }
 }
+__host__ __device__ __forceinline__ void plane_space(V3 n, V3 &p, V3 &q) { plane_space_with_k(n, plane_space_k(n), p, q); }
 
 __device__ __forceinline__ M3 load_m3(const float4 *__restrict__ R, int i) {
     float4 a = R[3 * i], b = R[3 * i + 1], c = R[3 * i + 2];

@@ -88,7 +88,7 @@ void eng_destroy(Engine *e) {
     dev_free(M.rec); dev_free(M.colour); dev_free(M.skey); dev_free(M.sidx); dev_free(M.flag); dev_free(M.count);
     dev_free(M.colour_start); dev_free(M.meta);
     SolverArrays &S = e->S;
-    dev_free(S.q0); dev_free(S.q1); dev_free(S.q2); dev_free(S.q3); dev_free(S.q4); dev_free(S.lam); dev_free(S.mrec);
+    dev_free(S.q0); dev_free(S.q1); dev_free(S.q2); dev_free(S.q3); dev_free(S.q4); dev_free(S.q5); dev_free(S.lam); dev_free(S.mrec);
     sort_workspace_free(e->sort); scan_workspace_free(e->scan);
     dev_free(e->E.cnt); dev_free(e->E.start); dev_free(e->E.fill); dev_free(e->E.rec); dev_free(e->E.perm); dev_free(e->E.col);
     dev_free(e->hc_pd); dev_free(e->hc_ns); dev_free(e->hc_surf); dev_free(e->hc_mrec);
@@ -258,7 +258,8 @@ void engine_ensure_pair_capacity(Engine *e) {
         SolverArrays &S = e->S;
         dev_realloc(S.q0, 0, n * 8, st, false); dev_realloc(S.q1, 0, n * 8, st, false);
         dev_realloc(S.q2, 0, n * 8, st, false); dev_realloc(S.q3, 0, n * 8, st, false);
-        dev_realloc(S.q4, 0, n * 8, st, false); dev_realloc(S.lam, 0, n * 8, st, false);
+        dev_realloc(S.q4, 0, n * 8, st, false); dev_realloc(S.q5, 0, n * 8, st, false);
+        dev_realloc(S.lam, 0, n * 8, st, false);
         dev_realloc(S.mrec, 0, n, st, false);
         S.cap = (int)n;
     }

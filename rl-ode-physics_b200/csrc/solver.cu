@@ -381,18 +381,23 @@ __device__ __forceinline__ void build_manifold_rows(int s, const int4 rec, const
         int lflags = the_m;
         if (the_m >= 2) {
             V3 t1, t2;
-            plane_space(normal, t1, t2);
+            const float psk = plane_space_k(normal);
+            plane_space_with_k(normal, psk, t1, t2);
             const float mu = sf.mu < 0 ? 0 : sf.mu;
             float c1v = (sf.mode & MODE_MOTION1) ? sf.motion1 : 0.f;
             float cfm1 = (sf.mode & MODE_SLIP1) ? sf.slip1 : cfg.cfm;
             build_row(t1, c1, c2, k1, k2, two, c1v, cfm1, cfg, q3.x, q3.y, q3.z);
-            q3.w = mu;
+            q3.w = psk; // 1/sqrt of dPlaneSpace, reused by every iteration
+            q4.w = mu;
             if (sf.mode & MODE_APPROX1_1) lflags |= 0x10;
             if (the_m >= 3) {
                 float c2v = (sf.mode & MODE_MOTION2) ? sf.motion2 : 0.f;
                 float cfm2 = (sf.mode & MODE_SLIP2) ? sf.slip2 : cfg.cfm;
                 build_row(t2, c1, c2, k1, k2, two, c2v, cfm2, cfg, q4.x, q4.y, q4.z);
-                q4.w = (sf.mode & MODE_MU2) ? (sf.mu2 < 0 ? 0 : sf.mu2) : mu;
+                if (sf.mode & MODE_MU2) { // second friction limit differs: rare, kept out of the streamed records
+                    lflags |= 0x40;
+                    S.q5[(size_t)k * S.cap + s] = make_float4(sf.mu2 < 0 ? 0 : sf.mu2, 0.f, 0.f, 0.f);
+                }
                 if (sf.mode & MODE_APPROX1_2) lflags |= 0x20;
             }
         }
@@ -525,15 +530,17 @@ __device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, con
         solve_row(n, c1, c2, two, invM1, iI1, invM2, iI2, cur.q0.w, cur.q1.w, cur.q2.w, 0.f, INFINITY, lam.x, f1, f2);
         if (the_m >= 2) {
             const float4 q3 = cur.q3;
+            const float mu = cur.q4.w;
             V3 t1, t2;
-            plane_space(n, t1, t2);
-            float hi = q3.w, lo = -q3.w;
-            if (lflags & 0x10) { hi = fabsf(q3.w * lam.x); lo = -hi; }
+            plane_space_with_k(n, q3.w, t1, t2);
+            float hi = mu, lo = -mu;
+            if (lflags & 0x10) { hi = fabsf(mu * lam.x); lo = -hi; }
             solve_row(t1, c1, c2, two, invM1, iI1, invM2, iI2, q3.x, q3.y, q3.z, lo, hi, lam.y, f1, f2);
             if (the_m >= 3) {
                 const float4 q4 = cur.q4;
-                hi = q4.w; lo = -q4.w;
-                if (lflags & 0x20) { hi = fabsf(q4.w * lam.x); lo = -hi; }
+                const float mu2 = (lflags & 0x40) ? S.q5[si].x : mu;
+                hi = mu2; lo = -mu2;
+                if (lflags & 0x20) { hi = fabsf(mu2 * lam.x); lo = -hi; }
                 solve_row(t2, c1, c2, two, invM1, iI1, invM2, iI2, q4.x, q4.y, q4.z, lo, hi, lam.z, f1, f2);
             }
         }
