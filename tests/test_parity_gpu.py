@@ -272,3 +272,69 @@ def test_island_solver_equals_grid_barrier_solver(group):
     for k in ("n_contacts", "n_manifolds", "n_rows1", "n_rows2", "n_colours"):
         assert sa[k] == sb[k], k
     assert sa["n_contacts"] > 500
+
+
+def _surface(mode=0, **kw):
+    import oracle as O
+    import odeb200
+    so, se = O.Surface(), odeb200.SurfaceParameters()
+    so.mode = se.mode = mode
+    for k, v in kw.items():
+        setattr(so, k, v)
+        setattr(se, k, v)
+    return so, se
+
+
+@pytest.mark.parametrize("case", ["mu0", "mu_finite", "mu2", "approx1", "soft", "slip_motion"])
+def test_surface_modes_parity(case):
+    """dSurfaceParameters variants beyond the reference's (bounce, mu=inf): frictionless (1 row),
+    box friction, mu2, friction pyramid approximation (findex), soft ERP/CFM, slip and motion."""
+    B, MU2, SOFT_ERP, SOFT_CFM = 0x004, 0x001, 0x008, 0x010
+    M1, M2, MN, S1, S2, A1 = 0x020, 0x040, 0x080, 0x100, 0x200, 0x3000
+    so, se = {
+        "mu0": _surface(B, mu=0.0, bounce=0.1, bounce_vel=0.05),
+        "mu_finite": _surface(B, mu=0.7, bounce=0.3, bounce_vel=0.2),
+        "mu2": _surface(MU2, mu=0.9, mu2=0.2),
+        "approx1": _surface(A1 | B, mu=0.5, bounce=0.2, bounce_vel=0.1),
+        "soft": _surface(SOFT_ERP | SOFT_CFM | B, mu=float("inf"), soft_erp=0.5, soft_cfm=1e-3, bounce=0.2, bounce_vel=0.1),
+        "slip_motion": _surface(S1 | S2 | M1 | M2 | MN, mu=2.0, slip1=0.01, slip2=0.02, motion1=0.1, motion2=-0.2, motionN=0.05),
+    }[case]
+    sc = scenes.random_soup(160, seed=13)
+    ow, ew = util.load_both(sc)
+    ew.set_surface(se)
+    for step in range(3):
+        ew.tick(sc["h"])
+        util.oracle_tick_in_engine_order(ow, ew, sc["h"], surf=so, rows_per_contact=1 if case == "mu0" else 3)
+        es, os_ = ew.state(), ow.state()
+        for k in ("pos", "quat", "lvel", "avel"):
+            assert util.rel_err(es[k], os_[k]).max() <= STATE_RTOL, (case, step, k)
+    ew.close()
+
+
+def test_full_size_trimesh_scene():
+    """BASELINE config 2 at full size: teapot.obj (8884 triangles) vs 10,000 spheres.  Contact counts of a
+    sample of sphere-mesh pairs are checked against the oracle; the rest through properties."""
+    sc = scenes.trimesh_scene(100, seed=2)
+    ow, ew = util.load_both(sc)
+    for _ in range(150):
+        ew.tick(sc["h"])
+    ew.collide(8)
+    st = ew.stats()
+    assert st["flags"] == 0 and st["class_count"][5] > 1000            # sphere-trimesh pairs
+    pr, cnt, pd, nrm, side = ew.contacts()
+    s = ew.state()
+    for i in range(len(s["pos"])):
+        ow.set_body_state(i, pos=s["pos"][i], q=s["quat"][i], lvel=s["lvel"][i], avel=s["avel"][i])
+    types = sc["geoms"]["type"]
+    first = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+    mesh_pairs = [i for i in range(len(pr)) if types[pr[i, 1]] == scenes.TRIMESH and cnt[i] > 0]
+    assert len(mesh_pairs) > 200
+    ntri = 8884
+    for i in mesh_pairs[::max(1, len(mesh_pairs) // 150)]:
+        ref = ow.collide(int(pr[i, 0]), int(pr[i, 1]), 8)
+        assert len(ref) == cnt[i]
+        for k, c in enumerate(ref):
+            assert np.array_equal(pd[first[i] + k], np.array(list(c.pos) + [c.depth], np.float32))
+            assert side[first[i] + k] == c.side2 and 0 <= c.side2 < ntri
+    assert np.isfinite(s["pos"]).all() and s["pos"][:, 1].min() > -2.0     # nothing fell through the mesh + plane
+    ew.close()

@@ -51,7 +51,7 @@ def load_both(sc, iters=20):
     return ow, ew
 
 
-def oracle_tick_in_engine_order(ow, ew, h, maxc=8, surf=None):
+def oracle_tick_in_engine_order(ow, ew, h, maxc=8, surf=None, rows_per_contact=3):
     """Run the oracle's collide + QuickStep with the row order the engine used for its last step.
     Returns the number of oracle contacts."""
     surf = surf or O.reference_surface()
@@ -74,7 +74,7 @@ def oracle_tick_in_engine_order(ow, ew, h, maxc=8, surf=None):
             joint_of[(g1, g2, k)] = j
             if active:
                 row0[j] = rows
-                rows += 3
+                rows += rows_per_contact
             j += 1
     assert j == nc
     eg1, eg2, ek = ew.solver_order()
@@ -82,7 +82,7 @@ def oracle_tick_in_engine_order(ow, ew, h, maxc=8, surf=None):
     for a, b, k in zip(eg1, eg2, ek):
         jj = joint_of[(int(a), int(b), int(k))]
         r = row0[jj]
-        perm += [r, r + 1, r + 2]
+        perm += [r + i for i in range(rows_per_contact)]
     assert len(perm) == rows, (len(perm), rows)
     assert sorted(perm) == list(range(rows))
     ow.quickstep(h, order_mode=2, perm=np.asarray(perm, np.int32))
