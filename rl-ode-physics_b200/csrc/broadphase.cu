@@ -94,17 +94,24 @@ __global__ void __launch_bounds__(256) k_geom_update(GeomArrays g, const float4 
             }
         }
     }
-    // block reduction -> 7 atomics per warp leader
+    // warp shuffle reduction, then one set of atomics per CTA (not per warp: 32k warps hammering
+    // seven addresses serialise in the L2 atomic unit)
+    __shared__ float red[8][7];
     for (int k = 0; k < 3; k++) { cmin[k] = warp_min(cmin[k]); cmax[k] = warp_max(cmax[k]); }
     ext = warp_max(ext);
+    const int wid = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) {
-        for (int k = 0; k < 3; k++) {
-            if (cmin[k] <= cmax[k]) {
-                atomicMin(&acc[k], f2ord(cmin[k]));
-                atomicMax(&acc[3 + k], f2ord(cmax[k]));
-            }
-        }
-        if (ext > 0.f) atomicMax(&acc[6], f2ord(ext));
+        for (int k = 0; k < 3; k++) { red[wid][k] = cmin[k]; red[wid][3 + k] = cmax[k]; }
+        red[wid][6] = ext;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        const int k = threadIdx.x;
+        float v = red[0][k];
+        for (int w = 1; w < 8; w++) v = (k < 3) ? fminf(v, red[w][k]) : fmaxf(v, red[w][k]);
+        if (k < 3) { if (v < INFINITY) atomicMin(&acc[k], f2ord(v)); }
+        else if (k < 6) { if (v > -INFINITY) atomicMax(&acc[k], f2ord(v)); }
+        else if (v > 0.f) atomicMax(&acc[6], f2ord(v));
     }
 }
 

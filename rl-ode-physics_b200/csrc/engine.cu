@@ -63,6 +63,7 @@ Engine *eng_create(int device) {
     OB_CUDA(cudaMemset(e->bp.counters, 0, sizeof(BroadCounters)));
     e->meshes.n = 0;
     if (const char *g = getenv("ODE_B200_ENV_GROUP")) e->env_group = atoi(g);
+    if (const char *g = getenv("ODE_B200_COLOUR_SPREAD")) eng_set_colour_spread(e, atoi(g));
     return e;
 }
 
@@ -181,10 +182,15 @@ int eng_add_mesh(Engine *e, const float *verts, int nv, const int *tris, int nt)
 void eng_mark_bodies_dirty(Engine *e) { e->bodies_dirty = true; }
 void eng_mark_geoms_dirty(Engine *e) { e->geoms_dirty = true; }
 void eng_mark_forces_dirty(Engine *e) { e->forces_dirty = true; }
-void eng_set_num_envs(Engine *e, int n) { e->n_envs = n < 1 ? 1 : n; }
+void eng_set_num_envs(Engine *e, int n) {
+    e->n_envs = n < 1 ? 1 : n;
+    // batched worlds: equalise the colour classes (island solver lanes); single worlds: fewest colours
+    if (e->colour_spread_auto) e->colour_spread = e->n_envs > 1 ? 8 : 0;
+}
 void eng_set_capacity(Engine *e, long max_pairs, long max_manifolds) { e->want_pairs = max_pairs; e->want_manifolds = max_manifolds; }
 void eng_set_big_extent(Engine *e, float extent) { e->big_extent = extent; }
 void eng_set_solver_mode(Engine *e, int mode, int env_group) { e->solver_mode = mode; e->env_group = env_group; }
+void eng_set_colour_spread(Engine *e, int k) { e->colour_spread = k < 0 ? 0 : (k > 32 ? 32 : k); e->colour_spread_auto = false; }
 void eng_enable_timing(Engine *e, int on) { e->timing = on != 0; }
 
 // grow body / geom arrays to hold the host mirrors

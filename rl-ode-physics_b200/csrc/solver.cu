@@ -152,10 +152,28 @@ __device__ __forceinline__ unsigned long long manifold_prio(int tie, int lb1, in
     return ((unsigned long long)x << 32) | (unsigned)tie;
 }
 
+// colour choice of a winner: lowest free colour, or -- with spread K > 0 -- the first free colour at or
+// after a hashed start within [0, K) (cyclic), falling back to the lowest free colour >= K.  The
+// spread rule equalises the colour classes (greedy lowest-first makes the first colours large and the
+// last ones tiny, which leaves most lanes of the island solver idle in the late colours).
+__device__ __forceinline__ int pick_colour(unsigned long long mask, unsigned long long pr, int K) {
+    const unsigned long long fre = ~mask;
+    if (fre == 0ull) return OVERFLOW_COLOUR;
+    if (K > 0) {
+        const unsigned long long low = fre & ((1ull << K) - 1ull);
+        if (low) {
+            const int start = (int)((pr >> 32) % (unsigned)K);
+            const unsigned long long at = low >> start;
+            return at ? start + __ffsll((long long)at) - 1 : __ffsll((long long)low) - 1;
+        }
+    }
+    return __ffsll((long long)fre) - 1;
+}
+
 // Deterministic parallel greedy colouring: in every round an uncoloured manifold wins if it has
 // the smallest hashed priority among the uncoloured manifolds at both of its dynamic bodies; a
 // winner takes the lowest colour free at both bodies.  Only kinematic/static ends never conflict.
-__global__ void __launch_bounds__(256) k_colour(ManifoldArrays M, BodyArrays B) {
+__global__ void __launch_bounds__(256) k_colour(ManifoldArrays M, BodyArrays B, int spread) {
     cg::grid_group grid = cg::this_grid();
     const int n = *M.count;
     const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
@@ -184,12 +202,10 @@ __global__ void __launch_bounds__(256) k_colour(ManifoldArrays M, BodyArrays B) 
                 unsigned long long mask = 0ull;
                 if (d1) mask |= B.colmask[r.x];
                 if (d2) mask |= B.colmask[r.y];
-                int c;
-                if (~mask == 0ull) {
-                    c = OVERFLOW_COLOUR;
+                const int c = pick_colour(mask, pr, spread);
+                if (c == OVERFLOW_COLOUR) {
                     atomicAdd(&M.meta[1], 1);
                 } else {
-                    c = __ffsll((long long)~mask) - 1;
                     const unsigned long long bit = 1ull << c;
                     if (d1) B.colmask[r.x] |= bit;
                     if (d2) B.colmask[r.y] |= bit;
@@ -698,7 +714,8 @@ __device__ unsigned long long g_env_prof[8];
 // so what matters is how many lanes of each issued instruction do useful work.
 template <int G>
 __global__ void __launch_bounds__(128) k_env_solve(EnvArrays E, BodyArrays B, ContactSource src, Surface usurf,
-                                                    SolverArrays S, StepConfig cfg, StepStats *__restrict__ stats) {
+                                                    SolverArrays S, StepConfig cfg, int spread,
+                                                    StepStats *__restrict__ stats) {
     extern __shared__ __align__(16) unsigned char env_smem[];
     constexpr int GROUPS = 128 / G;   // envs per CTA
     constexpr unsigned FULL = 0xffffffffu;
@@ -752,10 +769,8 @@ __global__ void __launch_bounds__(128) k_env_solve(EnvArrays E, BodyArrays B, Co
                         unsigned long long mask = 0ull;
                         if (d1) mask |= masks[l1];
                         if (d2) mask |= masks[l2];
-                        int c;
-                        if (~mask == 0ull) c = OVERFLOW_COLOUR;
-                        else {
-                            c = __ffsll((long long)~mask) - 1;
+                        const int c = pick_colour(mask, pr, spread);
+                        if (c != OVERFLOW_COLOUR) {
                             const unsigned long long bit = 1ull << c;
                             if (d1) masks[l1] |= bit;
                             if (d2) masks[l2] |= bit;
@@ -921,7 +936,7 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
         }
         // lanes per env (8, 16 or 32): the 32/G envs of a warp run in lockstep
         int G = e->env_group;
-        if (G != 8 && G != 16 && G != 32) G = ne >= 4096 ? 8 : (ne >= 1024 ? 16 : 32);
+        if (G != 8 && G != 16 && G != 32) G = ne >= 1024 ? 16 : 32; // measured on C4: 16 ~ 32 > 8
         const int groups = 128 / G;
         const int mb = (E.max_bodies + 31) & ~31;
         const size_t smem = (size_t)groups * (2 * (size_t)mb * sizeof(unsigned long long) + 136 * sizeof(int));
@@ -929,13 +944,13 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
         SolverArrays S = e->S;
         if (G == 8) {
             if (smem > 48 * 1024) OB_CUDA(cudaFuncSetAttribute(k_env_solve<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_env_solve<8><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->d_stats);
+            k_env_solve<8><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->colour_spread, e->d_stats);
         } else if (G == 16) {
             if (smem > 48 * 1024) OB_CUDA(cudaFuncSetAttribute(k_env_solve<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_env_solve<16><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->d_stats);
+            k_env_solve<16><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->colour_spread, e->d_stats);
         } else {
             if (smem > 48 * 1024) OB_CUDA(cudaFuncSetAttribute(k_env_solve<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_env_solve<32><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->d_stats);
+            k_env_solve<32><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->colour_spread, e->d_stats);
         }
         OB_CHECK_KERNEL("k_env_solve", st);
         k_integrate<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(B, cfg);
@@ -973,7 +988,8 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
     if (max_manifolds > 0) {
         {
             int grid = coop_grid(e, (const void *)k_colour, 256, max_manifolds);
-            void *args[] = {(void *)&M, (void *)&B};
+            int spread = e->colour_spread;
+            void *args[] = {(void *)&M, (void *)&B, (void *)&spread};
             OB_CUDA(cudaLaunchCooperativeKernel((const void *)k_colour, dim3((unsigned)grid), dim3(256), args, 0, st));
             OB_CHECK_KERNEL("k_colour", st);
         }
