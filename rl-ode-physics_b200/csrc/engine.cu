@@ -184,8 +184,8 @@ void eng_mark_geoms_dirty(Engine *e) { e->geoms_dirty = true; }
 void eng_mark_forces_dirty(Engine *e) { e->forces_dirty = true; }
 void eng_set_num_envs(Engine *e, int n) {
     e->n_envs = n < 1 ? 1 : n;
-    // batched worlds: equalise the colour classes (island solver lanes); single worlds: fewest colours
-    if (e->colour_spread_auto) e->colour_spread = e->n_envs > 1 ? 8 : 0;
+    // measured on C4 (profiles/README.md): spreading the colours makes MORE phases whose cost is set by
+    // the longest manifold in the phase, so lowest-free colouring stays the default for batched worlds too
 }
 void eng_set_capacity(Engine *e, long max_pairs, long max_manifolds) { e->want_pairs = max_pairs; e->want_manifolds = max_manifolds; }
 void eng_set_big_extent(Engine *e, float extent) { e->big_extent = extent; }
