@@ -79,6 +79,10 @@ void dWorldSetCapacityB200(dWorldID, long max_pairs, long max_manifolds);
  * otherwise), 1 = always the grid-barrier solver. env_group = lanes per env of the island solver
  * (8, 16, 32; 0 = automatic). Both solvers produce bit-identical results. */
 void dWorldSetSolverModeB200(dWorldID, int mode, int env_group);
+/* Gauss-Seidel unit of the device-resident solver: 0 = one manifold (all contacts of a geom pair),
+ * 1 = one contact, -1 = automatic (per contact for batched worlds, per manifold otherwise).  Either is a
+ * valid row order; results differ in the last bits between the two settings. */
+void dWorldSetContactUnitsB200(dWorldID, int per_contact);
 /* dynamic geoms whose AABB extent exceeds this are treated like static "big" geoms (default inf) */
 void dWorldSetBigExtentB200(dWorldID, float extent);
 

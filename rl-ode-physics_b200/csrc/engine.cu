@@ -64,6 +64,7 @@ Engine *eng_create(int device) {
     e->meshes.n = 0;
     if (const char *g = getenv("ODE_B200_ENV_GROUP")) e->env_group = atoi(g);
     if (const char *g = getenv("ODE_B200_COLOUR_SPREAD")) eng_set_colour_spread(e, atoi(g));
+    if (const char *g = getenv("ODE_B200_CONTACT_UNITS")) e->contact_units = atoi(g);
     return e;
 }
 
@@ -190,6 +191,7 @@ void eng_set_num_envs(Engine *e, int n) {
 void eng_set_capacity(Engine *e, long max_pairs, long max_manifolds) { e->want_pairs = max_pairs; e->want_manifolds = max_manifolds; }
 void eng_set_big_extent(Engine *e, float extent) { e->big_extent = extent; }
 void eng_set_solver_mode(Engine *e, int mode, int env_group) { e->solver_mode = mode; e->env_group = env_group; }
+void eng_set_contact_units(Engine *e, int per_contact) { e->contact_units = per_contact; }
 void eng_set_colour_spread(Engine *e, int k) { e->colour_spread = k < 0 ? 0 : (k > 32 ? 32 : k); e->colour_spread_auto = false; }
 void eng_enable_timing(Engine *e, int on) { e->timing = on != 0; }
 
@@ -252,8 +254,10 @@ void engine_ensure_pair_capacity(Engine *e) {
         e->cs.stride = (int)n;
         e->have_device_contacts = false;
     }
-    long wantm = e->want_manifolds > 0 ? e->want_manifolds : (long)e->hg.n * 6 + 1024;
-    if (wantm > bp.cap_pairs) wantm = bp.cap_pairs;
+    // solver units: manifolds (<= pairs) or, with per-contact units, contacts
+    const bool per_contact = e->contact_units >= 0 ? e->contact_units == 1 : e->n_envs > 1;
+    long wantm = e->want_manifolds > 0 ? e->want_manifolds : (long)e->hg.n * (per_contact ? 8 : 6) + 1024;
+    if (!per_contact && wantm > bp.cap_pairs) wantm = bp.cap_pairs;
     if ((long)e->st_mrec.size() > wantm) wantm = (long)e->st_mrec.size();
     if (wantm > e->M.cap) {
         const size_t n = (size_t)wantm;
@@ -596,12 +600,14 @@ int eng_export_solver_order(Engine *e, int *pair_g1, int *pair_g2, int *pair_k, 
     if (bc.n_pairs) OB_CUDA(cudaMemcpy(pairs.data(), e->bp.pairs, (size_t)bc.n_pairs * sizeof(int2), cudaMemcpyDeviceToHost));
     int out = 0;
     for (int s = 0; s < nm; s++) {
-        const int p = mrec[s].w, nc = mrec[s].z; // .w = pair index of the manifold
+        // .w = slot index of the unit's first contact = pair + k0 * stride
+        const int stride = e->cs.stride > 0 ? e->cs.stride : 1;
+        const int p = mrec[s].w % stride, k0 = mrec[s].w / stride, nc = mrec[s].z;
         for (int k = 0; k < nc; k++) {
             if (out < cap) {
                 pair_g1[out] = (p < bc.n_pairs) ? pairs[p].x : -1;
                 pair_g2[out] = (p < bc.n_pairs) ? pairs[p].y : -1;
-                pair_k[out] = k;
+                pair_k[out] = k0 + k;
             }
             out++;
         }

@@ -158,6 +158,7 @@ void eng_set_capacity(Engine *, long max_pairs, long max_manifolds);
 void eng_set_big_extent(Engine *, float extent);
 void eng_set_solver_mode(Engine *, int mode, int env_group);
 void eng_set_colour_spread(Engine *, int k);
+void eng_set_contact_units(Engine *, int per_contact);
 
 // device ops (all asynchronous on the engine stream unless stated)
 void eng_sync_to_device(Engine *);              // upload dirty mirrors

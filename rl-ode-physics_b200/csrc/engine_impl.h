@@ -36,6 +36,7 @@ struct Engine {
     int cap_envs = 0, cap_env_rec = 0;
     int env_group = 0; // lanes per env of the island solver (0 = automatic)
     int solver_mode = 0; // 0 automatic, 1 force the global (grid-barrier) solver
+    int contact_units = -1; // -1 automatic (per contact for batched worlds), 0 manifold units, 1 contact units
     int colour_spread = 0; // 0: lowest free colour; K > 0: hashed start within the first K colours
     bool colour_spread_auto = true;
     SolverArrays S{};

@@ -94,18 +94,21 @@ __global__ void __launch_bounds__(256) k_body_prep(BodyArrays B, StepConfig cfg,
 
 __global__ void __launch_bounds__(256) k_manifold_flags(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
                                                          const int *__restrict__ g_body, const int *__restrict__ nc,
-                                                         int *__restrict__ flag) {
+                                                         int *__restrict__ flag, int per_contact) {
     const int n = bc->n_pairs;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         const int2 pr = pairs[p];
-        flag[p] = (nc[p] > 0 && (g_body[pr.x] >= 0 || g_body[pr.y] >= 0)) ? 1 : 0;
+        const int c = nc[p];
+        // solver units of this pair: one manifold, or one unit per contact
+        flag[p] = (c > 0 && (g_body[pr.x] >= 0 || g_body[pr.y] >= 0)) ? (per_contact ? c : 1) : 0;
     }
 }
 
 __global__ void __launch_bounds__(256) k_manifold_write(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
                                                          const int *__restrict__ g_body, const int *__restrict__ nc,
                                                          const int *__restrict__ scanned, const float4 *__restrict__ b_pos,
-                                                         ManifoldArrays M, StepStats *__restrict__ stats) {
+                                                         ManifoldArrays M, StepStats *__restrict__ stats, int per_contact,
+                                                         int kstride) {
     const int n = bc->n_pairs;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         const int2 pr = pairs[p];
@@ -113,12 +116,14 @@ __global__ void __launch_bounds__(256) k_manifold_write(const BroadCounters *__r
         const int c = nc[p];
         if (!(c > 0 && (b1 >= 0 || b2 >= 0))) continue;
         const int m = scanned[p];
-        if (m >= M.cap) { atomicOr(&stats->flags, SF_MANIFOLD_OVERFLOW); continue; }
-        int w = c;
+        const int units = per_contact ? c : 1;
+        if (m + units > M.cap) { atomicOr(&stats->flags, SF_MANIFOLD_OVERFLOW); continue; }
+        int w = per_contact ? 1 : c;
         if (b1 < 0) { b1 = b2; b2 = -1; w |= REC_REV; } // dJointAttach: NULL body1 swaps, REVERSE
         if (b_pos[b1].w > 0.f) w |= REC_DYN1;
         if (b2 >= 0 && b_pos[b2].w > 0.f) w |= REC_DYN2;
-        M.rec[m] = make_int4(b1, b2, p, w);
+        // .z = index of the unit's first contact in the slot arrays (contact k of pair p: p + k * stride)
+        for (int u = 0; u < units; u++) M.rec[m + u] = make_int4(b1, b2, p + u * kstride, w);
     }
 }
 
@@ -669,32 +674,35 @@ __global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays
 
 __global__ void __launch_bounds__(256) k_env_count(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
                                                     const int *__restrict__ g_body, const int *__restrict__ nc,
-                                                    const int *__restrict__ b_env, int *__restrict__ env_cnt) {
+                                                    const int *__restrict__ b_env, int *__restrict__ env_cnt,
+                                                    int per_contact) {
     const int n = bc->n_pairs;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         const int2 pr = pairs[p];
         const int b1 = g_body[pr.x], b2 = g_body[pr.y];
-        if (nc[p] > 0 && (b1 >= 0 || b2 >= 0)) atomicAdd(&env_cnt[b_env[b1 >= 0 ? b1 : b2]], 1);
+        const int c = nc[p];
+        if (c > 0 && (b1 >= 0 || b2 >= 0)) atomicAdd(&env_cnt[b_env[b1 >= 0 ? b1 : b2]], per_contact ? c : 1);
     }
 }
 
 __global__ void __launch_bounds__(256) k_env_bucket(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
                                                      const int *__restrict__ g_body, const int *__restrict__ nc,
                                                      const float4 *__restrict__ b_pos, const int *__restrict__ b_env,
-                                                     EnvArrays E, StepStats *__restrict__ stats) {
+                                                     EnvArrays E, StepStats *__restrict__ stats, int per_contact, int kstride) {
     const int n = bc->n_pairs;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         const int2 pr = pairs[p];
         int b1 = g_body[pr.x], b2 = g_body[pr.y];
         const int c = nc[p];
         if (!(c > 0 && (b1 >= 0 || b2 >= 0))) continue;
-        int w = c;
+        const int units = per_contact ? c : 1;
+        int w = per_contact ? 1 : c;
         if (b1 < 0) { b1 = b2; b2 = -1; w |= REC_REV; }
         if (b_pos[b1].w > 0.f) w |= REC_DYN1;
         if (b2 >= 0 && b_pos[b2].w > 0.f) w |= REC_DYN2;
         const int e = b_env[b1];
-        const int slot = E.start[e] + atomicAdd(&E.fill[e], 1);
-        E.rec[slot] = make_int4(b1, b2, p, w);
+        const int slot = E.start[e] + atomicAdd(&E.fill[e], units);
+        for (int u = 0; u < units; u++) E.rec[slot + u] = make_int4(b1, b2, p + u * kstride, w);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) stats->n_manifolds = E.start[E.n_envs];
 }
@@ -914,6 +922,9 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
     long max_manifolds;
     ContactSource src;
     Surface usurf{};
+    // solver unit: a whole manifold (all contacts of a pair, fewest colours) or a single contact (more
+    // colours, but every phase costs one contact instead of the longest manifold of the phase)
+    const int per_contact = e->contact_units >= 0 ? e->contact_units : (e->n_envs > 1 ? 1 : 0);
     // batched independent worlds with device-resident contacts take the island path
     const bool env_path = !host_contacts && e->have_device_contacts && e->n_envs > 1 && e->E.max_bodies <= 1024 &&
                           e->solver_mode != 1;
@@ -924,10 +935,11 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
         const int ne = E.n_envs;
         OB_CUDA(cudaMemsetAsync(E.cnt, 0, ((size_t)ne + 1) * sizeof(int), st));
         OB_CUDA(cudaMemsetAsync(E.fill, 0, ((size_t)ne + 1) * sizeof(int), st));
-        k_env_count<<<pgrid, 256, 0, st>>>(e->bp.counters, e->bp.pairs, e->G.body, e->cs.nc, B.env, E.cnt);
+        k_env_count<<<pgrid, 256, 0, st>>>(e->bp.counters, e->bp.pairs, e->G.body, e->cs.nc, B.env, E.cnt, per_contact);
         OB_CHECK_KERNEL("k_env_count", st);
         scan_exclusive(E.cnt, E.start, (long)ne + 1, nullptr, nullptr, e->scan, st);
-        k_env_bucket<<<pgrid, 256, 0, st>>>(e->bp.counters, e->bp.pairs, e->G.body, e->cs.nc, B.pos, B.env, E, e->d_stats);
+        k_env_bucket<<<pgrid, 256, 0, st>>>(e->bp.counters, e->bp.pairs, e->G.body, e->cs.nc, B.pos, B.env, E, e->d_stats,
+                                            per_contact, e->cs.stride);
         OB_CHECK_KERNEL("k_env_bucket", st);
         OB_CUDA(cudaMemcpyAsync(M.count, E.start + ne, sizeof(int), cudaMemcpyDeviceToDevice, st));
         if (e->timing) {
@@ -968,11 +980,11 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
         if (uniform_surface) usurf = *uniform_surface;
         src.pd = e->cs.pd; src.ns = e->cs.ns; src.surf = nullptr; src.kstride = e->cs.stride;
         if (e->have_device_contacts) {
-            k_manifold_flags<<<pgrid, 256, 0, st>>>(e->bp.counters, e->bp.pairs, e->G.body, e->cs.nc, M.flag);
+            k_manifold_flags<<<pgrid, 256, 0, st>>>(e->bp.counters, e->bp.pairs, e->G.body, e->cs.nc, M.flag, per_contact);
             OB_CHECK_KERNEL("k_manifold_flags", st);
             scan_exclusive(M.flag, M.flag, e->bp.cap_pairs, &e->bp.counters->n_pairs, &M.meta[5], e->scan, st);
             k_manifold_write<<<pgrid, 256, 0, st>>>(e->bp.counters, e->bp.pairs, e->G.body, e->cs.nc, M.flag, B.pos, M,
-                                                    e->d_stats);
+                                                    e->d_stats, per_contact, e->cs.stride);
             OB_CHECK_KERNEL("k_manifold_write", st);
             k_manifold_count<<<1, 1, 0, st>>>(&M.meta[5], M, e->d_stats);
             OB_CHECK_KERNEL("k_manifold_count", st);

@@ -118,6 +118,7 @@ _SIGS = [
     ("dWorldSetCapacityB200", None, [_vp, C.c_long, C.c_long]),
     ("dWorldSetBigExtentB200", None, [_vp, _f]),
     ("dWorldSetSolverModeB200", None, [_vp, _i, _i]),
+    ("dWorldSetContactUnitsB200", None, [_vp, _i]),
     ("dWorldGetStatsB200", None, [_vp, C.POINTER(StepStats)]),
     ("dWorldEnableTimingB200", None, [_vp, _i]),
     ("dWorldGetTimingsB200", None, [_vp, _fp]),
@@ -227,6 +228,9 @@ class World:
 
     def set_solver_mode(self, mode=0, env_group=0):
         self.L.dWorldSetSolverModeB200(self.w, int(mode), int(env_group))
+
+    def set_contact_units(self, per_contact):
+        self.L.dWorldSetContactUnitsB200(self.w, int(per_contact))
 
     def set_capacity(self, max_pairs, max_manifolds):
         self.L.dWorldSetCapacityB200(self.w, int(max_pairs), int(max_manifolds))

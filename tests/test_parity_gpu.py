@@ -135,6 +135,7 @@ def test_batched_worlds_are_independent_bit_exact():
     for w in (0, 3, 5):
         alone = scenes.batched_worlds_scene(1, seed=4, spacing=0.7, first_world=w)
         e1 = util.engine_world(alone)
+        e1.set_contact_units(1)          # same Gauss-Seidel unit as the batch default
         for _ in range(25):
             e1.tick(alone["h"])
         s1 = e1.state()
