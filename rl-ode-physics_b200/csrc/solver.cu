@@ -516,10 +516,10 @@ __device__ __forceinline__ void st_fc(float4 *p, float4 v) {
     if (L2ONLY) __stcg(p, v); else *p = v;
 }
 
-template <bool L2ONLY>
+template <bool L2ONLY, bool SINGLE = false>
 __device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, const BodyArrays &B) {
     const int4 rec = __ldg(&S.mrec[s]);
-    const int b1 = rec.x, b2 = rec.y, nc = rec.z;
+    const int b1 = rec.x, b2 = rec.y, nc = SINGLE ? 1 : rec.z; // SINGLE: per-contact units, no contact loop
     const bool two = b2 >= 0;
     RowRec cur = load_rows(S, (size_t)s);
     FC f1, f2;
@@ -543,7 +543,7 @@ __device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, con
     for (int k = 0; k < nc; k++) {
         const size_t si = (size_t)k * S.cap + s;
         RowRec nxt = cur;
-        if (k + 1 < nc) nxt = load_rows(S, si + S.cap);
+        if (!SINGLE && k + 1 < nc) nxt = load_rows(S, si + S.cap);
         float4 lam = cur.lam;
         const int lflags = __float_as_int(lam.w);
         const int the_m = lflags & 0xf;
@@ -566,7 +566,7 @@ __device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, con
             }
         }
         S.lam[si] = lam;
-        cur = nxt;
+        if (!SINGLE) cur = nxt;
     }
     st_fc<L2ONLY>(&B.fc[2 * b1], make_float4(f1.l.x, f1.l.y, f1.l.z, 0.f));
     st_fc<L2ONLY>(&B.fc[2 * b1 + 1], make_float4(f1.a.x, f1.a.y, f1.a.z, 0.f));
@@ -720,7 +720,7 @@ __device__ unsigned long long g_env_prof[8];
 // maximum over the warp's groups) and lanes without work are predicated off, so the groups never
 // diverge into serialised code paths.  The solver is issue-bound (ncu: 67 % issue-active, DRAM 8 %),
 // so what matters is how many lanes of each issued instruction do useful work.
-template <int G>
+template <int G, bool SINGLE>
 __global__ void __launch_bounds__(128) k_env_solve(EnvArrays E, BodyArrays B, ContactSource src, Surface usurf,
                                                     SolverArrays S, StepConfig cfg, int spread,
                                                     StepStats *__restrict__ stats) {
@@ -836,7 +836,7 @@ __global__ void __launch_bounds__(128) k_env_solve(EnvArrays E, BodyArrays B, Co
                 const int t = (__reduce_max_sync(FULL, s1 - s0) + G - 1) / G;
                 for (int j = 0; j < t; j++) {
                     const int s = s0 + g + j * G;
-                    if (s < s1) solve_manifold<false>(s, S, B);
+                    if (s < s1) solve_manifold<false, SINGLE>(s, S, B);
                 }
                 __syncwarp();
             }
@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(128) k_env_solve(EnvArrays E, BodyArrays B, Co
                 // manifolds that found no free colour (> 64 neighbours): one lane per env, in order
                 if (g == 0)
                     for (int s = ms + cstart[OVERFLOW_COLOUR]; s < ms + cstart[OVERFLOW_COLOUR + 1]; s++)
-                        solve_manifold<false>(s, S, B);
+                        solve_manifold<false, SINGLE>(s, S, B);
                 __syncwarp();
             }
         }
@@ -948,22 +948,24 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
         }
         // lanes per env (8, 16 or 32): the 32/G envs of a warp run in lockstep
         int G = e->env_group;
-        if (G != 8 && G != 16 && G != 32) G = ne >= 1024 ? 16 : 32; // measured on C4: 16 ~ 32 > 8
+        if (G != 8 && G != 16 && G != 32) G = 32; // measured on C4: 32 >= 16 > 8
         const int groups = 128 / G;
         const int mb = (E.max_bodies + 31) & ~31;
         const size_t smem = (size_t)groups * (2 * (size_t)mb * sizeof(unsigned long long) + 136 * sizeof(int));
         const unsigned grid = (unsigned)((ne + groups - 1) / groups);
         SolverArrays S = e->S;
-        if (G == 8) {
-            if (smem > 48 * 1024) OB_CUDA(cudaFuncSetAttribute(k_env_solve<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_env_solve<8><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->colour_spread, e->d_stats);
-        } else if (G == 16) {
-            if (smem > 48 * 1024) OB_CUDA(cudaFuncSetAttribute(k_env_solve<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_env_solve<16><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->colour_spread, e->d_stats);
+#define OB_LAUNCH_ENV(GG, SS)                                                                                        \
+    do {                                                                                                             \
+        if (smem > 48 * 1024)                                                                                        \
+            OB_CUDA(cudaFuncSetAttribute(k_env_solve<GG, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_env_solve<GG, SS><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->colour_spread, e->d_stats);        \
+    } while (0)
+        if (per_contact) {
+            if (G == 8) OB_LAUNCH_ENV(8, true); else if (G == 16) OB_LAUNCH_ENV(16, true); else OB_LAUNCH_ENV(32, true);
         } else {
-            if (smem > 48 * 1024) OB_CUDA(cudaFuncSetAttribute(k_env_solve<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_env_solve<32><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->colour_spread, e->d_stats);
+            if (G == 8) OB_LAUNCH_ENV(8, false); else if (G == 16) OB_LAUNCH_ENV(16, false); else OB_LAUNCH_ENV(32, false);
         }
+#undef OB_LAUNCH_ENV
         OB_CHECK_KERNEL("k_env_solve", st);
         k_integrate<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(B, cfg);
         OB_CHECK_KERNEL("k_integrate", st);
