@@ -721,7 +721,7 @@ __device__ unsigned long long g_env_prof[8];
 // diverge into serialised code paths.  The solver is issue-bound (ncu: 67 % issue-active, DRAM 8 %),
 // so what matters is how many lanes of each issued instruction do useful work.
 template <int G, bool SINGLE>
-__global__ void __launch_bounds__(128) k_env_solve(EnvArrays E, BodyArrays B, ContactSource src, Surface usurf,
+__global__ void __launch_bounds__(128, 5) k_env_solve(EnvArrays E, BodyArrays B, ContactSource src, Surface usurf,
                                                     SolverArrays S, StepConfig cfg, int spread,
                                                     StepStats *__restrict__ stats) {
     extern __shared__ __align__(16) unsigned char env_smem[];
