@@ -248,25 +248,31 @@ __device__ __forceinline__ int test_pair(const float4 &lo1, const float4 &hi1, c
     return pair_class(ta, tb);
 }
 
+// The count pass also parks each thread's first SWEEP_TCAP hits (k-major, coalesced) so that the fill
+// pass is a pure compaction for almost every thread instead of a second traversal of the grid.
+constexpr int SWEEP_TCAP = 8;
+
 struct PairSink {
     int cnt[PC_COUNT];
+    int total;
 };
 
 template <bool FILL>
 __device__ __forceinline__ void emit(int cls, int i, int n, const float4 &lo1, const uint4 &f1, const float4 &lo2,
                                      const uint4 &f2, PairSink &sink, const int *__restrict__ off,
-                                     int2 *__restrict__ pairs, int cap_pairs) {
+                                     int2 *__restrict__ pairs, int cap_pairs, int2 *__restrict__ tmp) {
+    int ga = __float_as_int(lo1.w), gb = __float_as_int(lo2.w);
+    const int ta = (int)f1.w, tb = (int)f2.w;
+    // canonical callback order: lower class first, then lower geom id
+    if (ta > tb || (ta == tb && ga > gb)) { int t = ga; ga = gb; gb = t; }
     if (FILL) {
-        int pos = off[cls * n + i] + sink.cnt[cls];
-        if (pos < cap_pairs) {
-            int ga = __float_as_int(lo1.w), gb = __float_as_int(lo2.w);
-            int ta = (int)f1.w, tb = (int)f2.w;
-            // canonical callback order: lower class first, then lower geom id
-            if (ta > tb || (ta == tb && ga > gb)) { int t = ga; ga = gb; gb = t; }
-            pairs[pos] = make_int2(ga, gb);
-        }
+        const int pos = off[cls * n + i] + sink.cnt[cls];
+        if (pos < cap_pairs) pairs[pos] = make_int2(ga, gb);
+    } else if (sink.total < SWEEP_TCAP) {
+        tmp[(size_t)sink.total * n + i] = make_int2(ga | (cls << 28), gb);
     }
     sink.cnt[cls]++;
+    sink.total++;
 }
 
 // K3b: the sweep. Thread i owns sorted record i and visits only records after it in sort order:
@@ -278,13 +284,27 @@ __global__ void __launch_bounds__(128) k_sweep(int n, const uint32_t *__restrict
                                                 const uint4 *__restrict__ s_flt, const int *__restrict__ cell_start,
                                                 const int *__restrict__ cell_end, const GridParams *__restrict__ gpp,
                                                 const BroadCounters *__restrict__ bc, int *__restrict__ cnt,
-                                                const int *__restrict__ off, int2 *__restrict__ pairs, int cap_pairs) {
+                                                const int *__restrict__ off, int2 *__restrict__ pairs, int cap_pairs,
+                                                int2 *__restrict__ tmp, int *__restrict__ tot) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int first_big = bc->first_big, first_dead = bc->first_dead;
     PairSink sink;
 #pragma unroll
     for (int c = 0; c < PC_COUNT; c++) sink.cnt[c] = 0;
+    sink.total = 0;
+    if (FILL) {
+        const int t = tot[i];
+        if (t <= SWEEP_TCAP) { // every hit of this thread was parked by the count pass: compact, in order
+            for (int k = 0; k < t; k++) {
+                const int2 e = tmp[(size_t)k * n + i];
+                const int cls = e.x >> 28;
+                const int pos = off[cls * n + i] + sink.cnt[cls]++;
+                if (pos < cap_pairs) pairs[pos] = make_int2(e.x & 0x0fffffff, e.y);
+            }
+            return;
+        }
+    }
     if (i < first_dead) {
         const float4 lo1 = s_min[i], hi1 = s_max[i];
         const uint4 f1 = s_flt[i];
@@ -306,7 +326,7 @@ __global__ void __launch_bounds__(128) k_sweep(int n, const uint32_t *__restrict
                     const float4 lo2 = s_min[j], hi2 = s_max[j];
                     const uint4 f2 = s_flt[j];
                     int cls = test_pair(lo1, hi1, f1, lo2, hi2, f2);
-                    if (cls >= 0) emit<FILL>(cls, i, n, lo1, f1, lo2, f2, sink, off, pairs, cap_pairs);
+                    if (cls >= 0) emit<FILL>(cls, i, n, lo1, f1, lo2, f2, sink, off, pairs, cap_pairs, tmp);
                 }
             }
             const int x0 = max(x - 1, 0), x1 = min(x + 1, gp.dx - 1);
@@ -328,27 +348,28 @@ __global__ void __launch_bounds__(128) k_sweep(int n, const uint32_t *__restrict
                     const float4 lo2 = s_min[j], hi2 = s_max[j];
                     const uint4 f2 = s_flt[j];
                     int cls = test_pair(lo1, hi1, f1, lo2, hi2, f2);
-                    if (cls >= 0) emit<FILL>(cls, i, n, lo1, f1, lo2, f2, sink, off, pairs, cap_pairs);
+                    if (cls >= 0) emit<FILL>(cls, i, n, lo1, f1, lo2, f2, sink, off, pairs, cap_pairs, tmp);
                 }
             }
             for (int j = first_big; j < first_dead; j++) {
                 const float4 lo2 = s_min[j], hi2 = s_max[j];
                 const uint4 f2 = s_flt[j];
                 int cls = test_pair(lo1, hi1, f1, lo2, hi2, f2);
-                if (cls >= 0) emit<FILL>(cls, i, n, lo1, f1, lo2, f2, sink, off, pairs, cap_pairs);
+                if (cls >= 0) emit<FILL>(cls, i, n, lo1, f1, lo2, f2, sink, off, pairs, cap_pairs, tmp);
             }
         } else {
             for (int j = i + 1; j < first_dead; j++) {
                 const float4 lo2 = s_min[j], hi2 = s_max[j];
                 const uint4 f2 = s_flt[j];
                 int cls = test_pair(lo1, hi1, f1, lo2, hi2, f2);
-                if (cls >= 0) emit<FILL>(cls, i, n, lo1, f1, lo2, f2, sink, off, pairs, cap_pairs);
+                if (cls >= 0) emit<FILL>(cls, i, n, lo1, f1, lo2, f2, sink, off, pairs, cap_pairs, tmp);
             }
         }
     }
     if (!FILL) {
 #pragma unroll
         for (int c = 0; c < PC_COUNT; c++) cnt[c * n + i] = sink.cnt[c];
+        tot[i] = sink.total;
     }
 }
 
@@ -396,12 +417,12 @@ void broadphase_run(BroadPhase &bp, GeomArrays g, const float4 *b_pos, const flo
     OB_CHECK_KERNEL("k_sorted_records", st);
     const unsigned nb2 = (unsigned)((n + 127) / 128);
     k_sweep<false><<<nb2, 128, 0, st>>>(n, bp.keys, bp.s_min, bp.s_max, bp.s_flt, bp.cell_start, bp.cell_end, bp.gp,
-                                        bp.counters, bp.cnt, nullptr, nullptr, 0);
+                                        bp.counters, bp.cnt, nullptr, nullptr, 0, bp.sweep_tmp, bp.sweep_tot);
     OB_CHECK_KERNEL("k_sweep", st);
     OB_CUDA(cudaMemsetAsync(bp.cnt + (size_t)PC_COUNT * n, 0, sizeof(int), st));
     scan_exclusive(bp.cnt, bp.cnt, (long)PC_COUNT * n + 1, nullptr, nullptr, bp.scan, st);
     k_sweep<true><<<nb2, 128, 0, st>>>(n, bp.keys, bp.s_min, bp.s_max, bp.s_flt, bp.cell_start, bp.cell_end, bp.gp,
-                                       bp.counters, nullptr, bp.cnt, bp.pairs, bp.cap_pairs);
+                                       bp.counters, nullptr, bp.cnt, bp.pairs, bp.cap_pairs, bp.sweep_tmp, bp.sweep_tot);
     OB_CHECK_KERNEL("k_sweep", st);
     k_pairs_finish<<<1, 1, 0, st>>>(n, bp.cnt, bp.cap_pairs, bp.counters, d_stats, bp.gp);
     OB_CHECK_KERNEL("k_pairs_finish", st);

@@ -80,6 +80,8 @@ struct BroadPhase {
     uint4 *s_flt = nullptr;
     int *cell_start = nullptr, *cell_end = nullptr;
     int *cnt = nullptr; // PC_COUNT * n + 1
+    int2 *sweep_tmp = nullptr; // SWEEP_TCAP layers of n parked hits
+    int *sweep_tot = nullptr;  // hits per sweep thread
     int2 *pairs = nullptr;
     SortWorkspace sort;
     ScanWorkspace scan;

@@ -154,7 +154,8 @@ __device__ __forceinline__ unsigned long long manifold_prio(int tie, int lb1, in
     // world does not depend on the other worlds of a batch)
     unsigned x = ((unsigned)lb1 * 0x9E3779B1u) ^ (((unsigned)lb2 + 0x7F4A7C15u) * 0x85EBCA6Bu);
     x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13; x *= 0xC2B2AE3Du; x ^= x >> 16;
-    return ((unsigned long long)x << 32) | (unsigned)tie;
+    // 24 hash bits + 32 tie bits: the top byte is left free for k_colour's round stamp
+    return ((unsigned long long)(x >> 8) << 32) | (unsigned)tie;
 }
 
 // colour choice of a winner: lowest free colour, or -- with spread K > 0 -- the first free colour at or
@@ -188,10 +189,14 @@ __global__ void __launch_bounds__(256) k_colour(ManifoldArrays M, BodyArrays B, 
     for (;; round++) {
         int *rem_cur = &M.meta[2 + (round & 1)], *rem_next = &M.meta[2 + ((round + 1) & 1)];
         if (gt == 0) *rem_next = 0;
+        // Later rounds stamp their priorities with a smaller top byte, so atomicMin prefers them over
+        // whatever earlier rounds left behind and no reset pass (and no third grid barrier) is needed.
+        const bool stamped = round < 254;
+        const unsigned long long stamp = stamped ? ((unsigned long long)(254 - round) << 56) : 0ull;
         for (int m = gt; m < n; m += gs) {
             if (M.colour[m] >= 0) continue;
             const int4 r = M.rec[m];
-            const unsigned long long pr = manifold_prio(r.z, B.local[r.x], r.y >= 0 ? B.local[r.y] : -1);
+            const unsigned long long pr = stamp | manifold_prio(r.z, B.local[r.x], r.y >= 0 ? B.local[r.y] : -1);
             if (r.w & REC_DYN1) atomicMin(&B.prio[r.x], pr);
             if (r.w & REC_DYN2) atomicMin(&B.prio[r.y], pr);
         }
@@ -200,14 +205,15 @@ __global__ void __launch_bounds__(256) k_colour(ManifoldArrays M, BodyArrays B, 
         for (int m = gt; m < n; m += gs) {
             if (M.colour[m] >= 0) continue;
             const int4 r = M.rec[m];
-            const unsigned long long pr = manifold_prio(r.z, B.local[r.x], r.y >= 0 ? B.local[r.y] : -1);
+            const unsigned long long base = manifold_prio(r.z, B.local[r.x], r.y >= 0 ? B.local[r.y] : -1);
+            const unsigned long long pr = stamp | base;
             const bool d1 = r.w & REC_DYN1, d2 = r.w & REC_DYN2;
             const bool ok = (!d1 || B.prio[r.x] == pr) && (!d2 || B.prio[r.y] == pr);
             if (ok) {
                 unsigned long long mask = 0ull;
                 if (d1) mask |= B.colmask[r.x];
                 if (d2) mask |= B.colmask[r.y];
-                const int c = pick_colour(mask, pr, spread);
+                const int c = pick_colour(mask, base, spread);
                 if (c == OVERFLOW_COLOUR) {
                     atomicAdd(&M.meta[1], 1);
                 } else {
@@ -228,13 +234,15 @@ __global__ void __launch_bounds__(256) k_colour(ManifoldArrays M, BodyArrays B, 
         grid.sync();
         const int rem = *rem_cur;
         if (rem == 0) break;
-        for (int m = gt; m < n; m += gs) {
-            if (M.colour[m] >= 0) continue;
-            const int4 r = M.rec[m];
-            if (r.w & REC_DYN1) B.prio[r.x] = ~0ull;
-            if (r.w & REC_DYN2) B.prio[r.y] = ~0ull;
+        if (!stamped) { // out of stamps (> 254 rounds): fall back to resetting the priorities
+            for (int m = gt; m < n; m += gs) {
+                if (M.colour[m] >= 0) continue;
+                const int4 r = M.rec[m];
+                if (r.w & REC_DYN1) B.prio[r.x] = ~0ull;
+                if (r.w & REC_DYN2) B.prio[r.y] = ~0ull;
+            }
+            grid.sync();
         }
-        grid.sync();
     }
     if (gt == 0) M.meta[4] = round + 1;
 }
