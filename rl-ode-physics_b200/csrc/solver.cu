@@ -132,7 +132,7 @@ __global__ void k_manifold_count(const int *__restrict__ total, ManifoldArrays M
     if (n > M.cap) n = M.cap;
     *M.count = n;
     stats->n_manifolds = n;
-    M.meta[0] = 0; M.meta[1] = 0; M.meta[2] = 0; M.meta[3] = 0; M.meta[4] = 0;
+    M.meta[0] = 0; M.meta[1] = 0; M.meta[2] = 0; M.meta[3] = 0; M.meta[4] = 0; M.meta[7] = 0;
 }
 
 // flag DYN bits for host-provided manifold records
@@ -187,7 +187,9 @@ __global__ void __launch_bounds__(256) k_colour(ManifoldArrays M, BodyArrays B, 
     grid.sync();
     int round = 0;
     for (;; round++) {
-        int *rem_cur = &M.meta[2 + (round & 1)], *rem_next = &M.meta[2 + ((round + 1) & 1)];
+        // three rotating counters: the one zeroed here was last read two grid barriers ago
+        const int slot[3] = {2, 3, 7};
+        int *rem_cur = &M.meta[slot[round % 3]], *rem_next = &M.meta[slot[(round + 1) % 3]];
         if (gt == 0) *rem_next = 0;
         // Later rounds stamp their priorities with a smaller top byte, so atomicMin prefers them over
         // whatever earlier rounds left behind and no reset pass (and no third grid barrier) is needed.
