@@ -9,6 +9,10 @@
 
 namespace ob {
 
+static void step_begin(Engine *e);
+static void step_end(Engine *e);
+static void apply_pending_forces(Engine *e);
+
 template <typename T>
 static void dev_realloc(T *&p, size_t old_n, size_t new_n, cudaStream_t st, bool keep = true) {
     T *q = nullptr;
@@ -47,6 +51,13 @@ Engine *eng_create(int device) {
     }
     OB_CUDA(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     OB_CUDA(cudaStreamCreateWithFlags(&e->copy_st, cudaStreamNonBlocking));
+    OB_CUDA(cudaStreamCreateWithFlags(&e->h2d_st, cudaStreamNonBlocking));
+    OB_CUDA(cudaEventCreateWithFlags(&e->ev_step_done, cudaEventDisableTiming));
+    OB_CUDA(cudaEventCreateWithFlags(&e->ev_snap_copied[0], cudaEventDisableTiming));
+    OB_CUDA(cudaEventCreateWithFlags(&e->ev_snap_copied[1], cudaEventDisableTiming));
+    OB_CUDA(cudaEventCreateWithFlags(&e->ev_f6, cudaEventDisableTiming));
+    OB_CUDA(cudaEventCreateWithFlags(&e->ev_f6_consumed[0], cudaEventDisableTiming));
+    OB_CUDA(cudaEventCreateWithFlags(&e->ev_f6_consumed[1], cudaEventDisableTiming));
     OB_CUDA(cudaMalloc(&e->d_stats, sizeof(StepStats)));
     OB_CUDA(cudaMemset(e->d_stats, 0, sizeof(StepStats)));
     OB_CUDA(cudaMallocHost(&e->h_stats, sizeof(StepStats)));
@@ -73,10 +84,12 @@ void eng_destroy(Engine *e) {
     cudaSetDevice(e->device);
     solver_profile_dump();
     cudaStreamSynchronize(e->st);
+    cudaStreamSynchronize(e->copy_st);
+    cudaStreamSynchronize(e->h2d_st);
     BodyArrays &B = e->B;
     dev_free(B.pos); dev_free(B.quat); dev_free(B.R); dev_free(B.lvel); dev_free(B.avel); dev_free(B.I);
     dev_free(B.invI); dev_free(B.facc); dev_free(B.tacc); dev_free(B.flags); dev_free(B.local); dev_free(B.env); dev_free(B.inv); dev_free(B.tmp);
-    dev_free(B.fc); dev_free(B.snap); dev_free(B.colmask); dev_free(B.prio);
+    dev_free(B.fc); dev_free(e->snap_buf[0]); dev_free(e->snap_buf[1]); dev_free(B.colmask); dev_free(B.prio);
     GeomArrays &G = e->G;
     dev_free(G.type); dev_free(G.dims); dev_free(G.body); dev_free(G.pos); dev_free(G.R); dev_free(G.cat);
     dev_free(G.col); dev_free(G.env); dev_free(G.mesh); dev_free(G.alive); dev_free(G.amin); dev_free(G.amax);
@@ -97,12 +110,15 @@ void eng_destroy(Engine *e) {
     dev_free(e->dl_first); dev_free(e->dl_pd); dev_free(e->dl_ns);
     for (auto &m : e->hmeshes) { dev_free(m.d_verts); dev_free(m.d_tris); }
     dev_free(e->d_stats);
-    dev_free(e->d_f6);
+    dev_free(e->d_f6[0]); dev_free(e->d_f6[1]);
     if (e->tev[0]) { cudaEventDestroy(e->tev[0]); cudaEventDestroy(e->tev[1]); }
     if (e->h_stats) cudaFreeHost(e->h_stats);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     cudaStreamDestroy(e->st);
     cudaStreamDestroy(e->copy_st);
+    cudaStreamDestroy(e->h2d_st);
+    cudaEventDestroy(e->ev_step_done); cudaEventDestroy(e->ev_snap_copied[0]); cudaEventDestroy(e->ev_snap_copied[1]);
+    cudaEventDestroy(e->ev_f6); cudaEventDestroy(e->ev_f6_consumed[0]); cudaEventDestroy(e->ev_f6_consumed[1]);
     delete e;
 }
 
@@ -206,7 +222,10 @@ void engine_ensure_capacity(Engine *e) {
         dev_realloc(B.invI, 3 * o, 3 * n, st); dev_realloc(B.facc, o, n, st); dev_realloc(B.tacc, o, n, st);
         dev_realloc(B.flags, o, n, st); dev_realloc(B.local, o, n, st); dev_realloc(B.env, o, n, st); dev_realloc(B.inv, 3 * o, 3 * n, st, false);
         dev_realloc(B.tmp, 2 * o, 2 * n, st, false); dev_realloc(B.fc, 2 * o, 2 * n, st, false);
-        dev_realloc(B.snap, 16 * o, 16 * n, st); dev_realloc(B.colmask, o, n, st, false);
+        OB_CUDA(cudaStreamSynchronize(e->copy_st));
+        dev_realloc(e->snap_buf[0], 16 * o, 16 * n, st); dev_realloc(e->snap_buf[1], 16 * o, 16 * n, st);
+        B.snap = e->snap_buf[e->snap_cur];
+        dev_realloc(B.colmask, o, n, st, false);
         dev_realloc(B.prio, o, n, st, false);
         e->cap_b = (int)n;
     }
@@ -459,7 +478,10 @@ void eng_step_device_contacts(Engine *e, float h, const Surface &surf) {
         OB_CUDA(cudaEventRecord(e->ev[0], e->st));
         OB_CUDA(cudaEventRecord(e->ev[1], e->st));
     }
+    apply_pending_forces(e);
+    step_begin(e);
     solver_step(e, h, false, &surf);
+    step_end(e);
     e->have_device_contacts = false;
     e->host_stale = true;
     e->ev_valid = e->timing;
@@ -506,20 +528,42 @@ void eng_step_host_contacts(Engine *e, float h, const HostContact *contacts, int
         OB_CUDA(cudaEventRecord(e->ev[0], st));
         OB_CUDA(cudaEventRecord(e->ev[1], st));
     }
+    apply_pending_forces(e);
+    step_begin(e);
     solver_step(e, h, true, nullptr);
+    step_end(e);
     OB_CUDA(cudaStreamSynchronize(st)); // staging vectors and &nm must outlive the copies
     e->have_device_contacts = false;
     e->host_stale = true;
     e->ev_valid = e->timing;
 }
 
-const float *eng_snapshot_device(Engine *e) { return e->B.snap; }
+const float *eng_snapshot_device(Engine *e) { return e->snap_buf[e->snap_cur]; }
+
+// called by both step entry points around solver_step: flip the snapshot buffer, make the kernel that
+// will overwrite it wait for a still-draining copy, apply pending force uploads
+static void step_begin(Engine *e) {
+    const int next = e->snap_cur ^ 1;
+    if (e->snap_copy_pending[next]) {
+        OB_CUDA(cudaStreamWaitEvent(e->st, e->ev_snap_copied[next], 0));
+        e->snap_copy_pending[next] = false;
+    }
+    e->snap_cur = next;
+    e->B.snap = e->snap_buf[next];
+}
+static void step_end(Engine *e) { OB_CUDA(cudaEventRecord(e->ev_step_done, e->st)); }
 
 void eng_snapshot_to_host(Engine *e, float *dst, int first, int count, bool blocking) {
     OB_CUDA(cudaSetDevice(e->device));
     if (count <= 0) return;
-    OB_CUDA(cudaMemcpyAsync(dst, e->B.snap + 16 * (size_t)first, (size_t)count * 64, cudaMemcpyDeviceToHost, e->st));
-    if (blocking) OB_CUDA(cudaStreamSynchronize(e->st));
+    // the copy runs on the copy stream, after the step that produced the snapshot, and overlaps later ticks
+    const int cur = e->snap_cur;
+    OB_CUDA(cudaEventRecord(e->ev_step_done, e->st));
+    OB_CUDA(cudaStreamWaitEvent(e->copy_st, e->ev_step_done, 0));
+    OB_CUDA(cudaMemcpyAsync(dst, e->snap_buf[cur] + 16 * (size_t)first, (size_t)count * 64, cudaMemcpyDeviceToHost, e->copy_st));
+    OB_CUDA(cudaEventRecord(e->ev_snap_copied[cur], e->copy_st));
+    e->snap_copy_pending[cur] = true;
+    if (blocking) OB_CUDA(cudaStreamSynchronize(e->copy_st));
 }
 
 // 6 floats per body (force, torque) -> the float4 accumulators the step consumes
@@ -533,19 +577,41 @@ __global__ void __launch_bounds__(256) k_scatter_forces(int n, const float *__re
 }
 
 void eng_set_forces(Engine *e, const float *f6, int n) {
-    // one H2D copy straight from the caller's (ideally pinned) buffer, then a scatter kernel;
-    // replaces the accumulators of bodies [0, n) for the next step, like dBodySetForce/Torque
+    // One H2D copy straight from the caller's (ideally pinned) buffer on the upload stream; the scatter
+    // into the float4 accumulators is deferred to the start of the next step, so the copy overlaps the
+    // collide phase.  Replaces the accumulators of bodies [0, n), like dBodySetForce/Torque.
     eng_sync_to_device(e);
     if (n > e->B.n) n = e->B.n;
     if (n <= 0) return;
     if (n > e->cap_f6) {
-        if (e->d_f6) OB_CUDA(cudaFree(e->d_f6));
+        OB_CUDA(cudaStreamSynchronize(e->st));
+        OB_CUDA(cudaStreamSynchronize(e->h2d_st));
         e->cap_f6 = n + n / 4 + 64;
-        OB_CUDA(cudaMalloc(&e->d_f6, (size_t)e->cap_f6 * 6 * sizeof(float)));
+        for (int i = 0; i < 2; i++) {
+            if (e->d_f6[i]) OB_CUDA(cudaFree(e->d_f6[i]));
+            OB_CUDA(cudaMalloc(&e->d_f6[i], (size_t)e->cap_f6 * 6 * sizeof(float)));
+            e->f6_inflight[i] = false;
+        }
     }
-    OB_CUDA(cudaMemcpyAsync(e->d_f6, f6, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, e->st));
-    k_scatter_forces<<<(unsigned)((n + 255) / 256), 256, 0, e->st>>>(n, e->d_f6, e->B.facc, e->B.tacc);
+    // the scatter that last read this staging buffer (two uploads ago) must be done
+    const int cur = e->f6_cur ^ 1;
+    if (e->f6_inflight[cur]) OB_CUDA(cudaStreamWaitEvent(e->h2d_st, e->ev_f6_consumed[cur], 0));
+    OB_CUDA(cudaMemcpyAsync(e->d_f6[cur], f6, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, e->h2d_st));
+    OB_CUDA(cudaEventRecord(e->ev_f6, e->h2d_st));
+    e->f6_cur = cur;
+    e->pending_f6 = n;
+}
+
+// before a step consumes the accumulators: wait for the upload and scatter it
+static void apply_pending_forces(Engine *e) {
+    if (e->pending_f6 <= 0) return;
+    const int n = e->pending_f6;
+    OB_CUDA(cudaStreamWaitEvent(e->st, e->ev_f6, 0));
+    k_scatter_forces<<<(unsigned)((n + 255) / 256), 256, 0, e->st>>>(n, e->d_f6[e->f6_cur], e->B.facc, e->B.tacc);
     OB_CHECK_KERNEL("k_scatter_forces", e->st);
+    OB_CUDA(cudaEventRecord(e->ev_f6_consumed[e->f6_cur], e->st));
+    e->f6_inflight[e->f6_cur] = true;
+    e->pending_f6 = 0;
 }
 
 long g_ob_launches = 0;
@@ -567,6 +633,8 @@ float eng_timer_elapsed_ms(Engine *e) {
 void eng_wait(Engine *e) {
     OB_CUDA(cudaSetDevice(e->device));
     OB_CUDA(cudaStreamSynchronize(e->st));
+    OB_CUDA(cudaStreamSynchronize(e->copy_st));
+    OB_CUDA(cudaStreamSynchronize(e->h2d_st));
 }
 
 StepStats eng_stats(Engine *e) {

@@ -68,8 +68,20 @@ struct Engine {
 
     int coop_blocks_colour = 0, coop_blocks_solve = 0;
     cudaEvent_t tev[2] = {nullptr, nullptr};
-    float *d_f6 = nullptr;
-    int cap_f6 = 0;
+    // host <-> device traffic of the tick runs on its own streams so it overlaps the next tick's kernels:
+    // snapshots are double-buffered (the tail of tick t+1 writes the other buffer while tick t's copy drains)
+    cudaStream_t h2d_st = nullptr;
+    float *snap_buf[2] = {nullptr, nullptr};
+    int snap_cur = 0;                 // buffer the last step wrote (B.snap points at it)
+    cudaEvent_t ev_step_done = nullptr;
+    cudaEvent_t ev_snap_copied[2] = {nullptr, nullptr};
+    bool snap_copy_pending[2] = {false, false};
+    float *d_f6[2] = {nullptr, nullptr};   // double-buffered staging of the 6-float force records
+    int f6_cur = 0;
+    int cap_f6 = 0, pending_f6 = 0;   // pending_f6 > 0: forces uploaded on h2d_st, scatter before the next step
+    cudaEvent_t ev_f6 = nullptr;
+    cudaEvent_t ev_f6_consumed[2] = {nullptr, nullptr};
+    bool f6_inflight[2] = {false, false};
 };
 
 void engine_ensure_capacity(Engine *e);
