@@ -28,7 +28,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "body_steps_per_sec"
 UNIT = "body-steps/s"
-SETTLE = {"C4": 100, "C3": 300, "C2": 120, "C1": 200}
+SETTLE = {"C4": 100, "C3": 300, "C2": 120, "C1": 200, "C5": 300}
 
 
 def parse_args():
@@ -36,12 +36,13 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--workload", default="C4", choices=["C4", "C3", "C2", "C1"])
+    ap.add_argument("--workload", default="C4", choices=["C4", "C3", "C2", "C1", "C5"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--worlds-per-gpu", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--settle", type=int, default=-1)
+    ap.add_argument("--slab-cols", type=int, default=128, help="C5: lattice columns (x) per GPU; z = 1024, y = 16")
     return ap.parse_args()
 
 
@@ -230,15 +231,33 @@ def main():
     dev = "cuda:%d" % local_rank
     L = odeb200.lib()
 
-    sc, desc = build_scene(args.workload, rank, args.worlds_per_gpu)
-    n_bodies = len(sc["bodies"]["pos"])
+    slab = None
+    if args.workload == "C5":
+        # one slab of the 1024(z) x 16(y) lattice per GPU, halo exchange of boundary bodies over NCCL
+        from odeb200 import slabs
+        sc, halo = slabs.slab_scene(rank, world, nx_per_slab=args.slab_cols, nz=1024, ny=16, seed=5, margin_cols=4)
+        desc = ("C5: slab-decomposed single world, %d x 1024 x 16 lattice columns per GPU (%d bodies/GPU), NCCL halo exchange "
+                "of boundary-body states each tick, dt=1/60, QuickStep 20 iters" % (args.slab_cols, args.slab_cols * 1024 * 16))
+        n_bodies = sc["n_owned"]
+    else:
+        sc, desc = build_scene(args.workload, rank, args.worlds_per_gpu)
+        n_bodies = len(sc["bodies"]["pos"])
     n_geoms = len(sc["geoms"]["type"])
     ew = odeb200.World(gravity=sc["gravity"], device=local_rank)
     ew.load_scene(sc)
     h = sc["h"]
+    if args.workload == "C5":
+        slab = slabs.SlabWorld(ew, halo, dev)
+        exch = (lambda: slabs.exchange_nccl(slab, rank, world)) if world > 1 else (lambda: None)
+
+        def do_tick():
+            slabs.tick(slab, exch, h)
+    else:
+        def do_tick():
+            ew.tick(h)
     settle = SETTLE[args.workload] if args.settle < 0 else args.settle
     for _ in range(settle):          # scene preparation (bodies dropped onto the ground), untimed
-        ew.tick(h)
+        do_tick()
     ew.wait()
 
     # ---------------- device-resident throughput: W warm-up ticks, then exactly K timed ticks
@@ -246,7 +265,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()                  # nvidia-smi needs ~1 s to start; only samples taken under load are kept
     for _ in range(max(args.warmup, 3)):
-        ew.tick(h)
+        do_tick()
     ew.wait()
     sampler.mark()
     sharding.barrier()
@@ -255,7 +274,7 @@ def main():
     solve_ms = []
     L.dWorldTimerStartB200(ew.w)
     for _ in range(args.steps):
-        ew.tick(h)
+        do_tick()
     L.dWorldTimerStopB200(ew.w)
     ew.wait()
     torch.cuda.synchronize()
@@ -266,7 +285,7 @@ def main():
     st = ew.stats()
     # per-kernel duration of the dominant kernel (k_solve): CUDA events on the engine's stream, a few live ticks
     for _ in range(8):
-        ew.tick(h)
+        do_tick()
         ew.wait()
         solve_ms.append(ew.timings()["solve_ms"])
     tm = ew.timings()
@@ -283,7 +302,7 @@ def main():
         fp = odeb200.C.cast(f6.data_ptr(), odeb200.C.POINTER(odeb200.C.c_float))
         for i in range(3):
             L.dWorldSetForcesB200(ew.w, fp, n_bodies)
-            ew.tick(h)
+            do_tick()
             L.dWorldGetSnapshotB200(ew.w, snap[i & 1].data_ptr(), 0, n_bodies, 0)
         ew.wait()
         sharding.barrier()
@@ -291,7 +310,7 @@ def main():
         t0 = time.perf_counter()
         for i in range(args.steps):
             L.dWorldSetForcesB200(ew.w, fp, n_bodies)
-            ew.tick(h)
+            do_tick()
             L.dWorldGetSnapshotB200(ew.w, snap[i & 1].data_ptr(), 0, n_bodies, 0)
         ew.wait()
         torch.cuda.synchronize()
@@ -338,6 +357,7 @@ def main():
             "ms_per_step": t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": desc, "bodies_per_gpu": n_bodies, "settle_steps": settle,
+                       "halo_bytes_per_tick_per_gpu": (slab.halo_bytes() if slab else 0),
                        "l2": "inputs larger than L2: ~%.0f MB of body, contact and row arrays are streamed per tick (126 MB L2)"
                              % ((sum(ab.values()) / 20 + 200 * n_bodies) / 1e6),
                        "counts": {k: st[k] for k in ("n_pairs", "n_contacts", "n_manifolds", "n_rows1", "n_rows2", "n_colours")}},

@@ -66,6 +66,12 @@ void dWorldSetForcesB200(dWorldID, const float *force_torque6, int n);
 void dWorldGetSnapshotB200(dWorldID, float *dst16, int first, int count, int blocking);
 const float *dWorldGetSnapshotDeviceB200(dWorldID);
 void dWorldWaitB200(dWorldID);
+/* halo exchange of a slab-decomposed world: gather the states of the listed
+ * bodies into a DEVICE buffer / scatter received states into the listed (ghost) bodies.  16 floats per
+ * body: pos3 pad, quat4, lvel3 pad, avel3 pad.  d_idx and the buffers are device pointers (so NCCL can
+ * send them GPU to GPU); asynchronous on the world's stream. */
+void dWorldPackStatesDeviceB200(dWorldID, const int *d_idx, int n, float *d_out16);
+void dWorldUnpackStatesDeviceB200(dWorldID, const int *d_idx, int n, const float *d_in16);
 /* CUDA-event timer on the world's stream: everything queued between start and stop */
 void dWorldTimerStartB200(dWorldID);
 void dWorldTimerStopB200(dWorldID);

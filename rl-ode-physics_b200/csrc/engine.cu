@@ -614,6 +614,47 @@ static void apply_pending_forces(Engine *e) {
     e->pending_f6 = 0;
 }
 
+// ---- halo exchange support (slab-decomposed worlds): gather / scatter of body states through DEVICE
+// buffers, so NCCL can move them GPU to GPU without touching the host.  16 floats per body:
+// pos(3) pad, quat(4), lvel(3) pad, avel(3) pad.
+__global__ void __launch_bounds__(256) k_pack_states(int n, const int *__restrict__ idx, BodyArrays B, float4 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = idx[i];
+    const float4 p = B.pos[b], q = B.quat[b], lv = B.lvel[b], av = B.avel[b];
+    out[4 * (size_t)i] = make_float4(p.x, p.y, p.z, 0.f);
+    out[4 * (size_t)i + 1] = q;
+    out[4 * (size_t)i + 2] = make_float4(lv.x, lv.y, lv.z, 0.f);
+    out[4 * (size_t)i + 3] = make_float4(av.x, av.y, av.z, 0.f);
+}
+
+__global__ void __launch_bounds__(256) k_unpack_states(int n, const int *__restrict__ idx, BodyArrays B, const float4 *__restrict__ in) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = idx[i];
+    const float4 p = in[4 * (size_t)i], q = in[4 * (size_t)i + 1], lv = in[4 * (size_t)i + 2], av = in[4 * (size_t)i + 3];
+    const float invM = B.pos[b].w, mass = B.lvel[b].w;
+    B.pos[b] = make_float4(p.x, p.y, p.z, invM);
+    B.quat[b] = q;
+    store_m3(B.R, b, q_to_r(q));
+    B.lvel[b] = make_float4(lv.x, lv.y, lv.z, mass);
+    B.avel[b] = make_float4(av.x, av.y, av.z, 0.f);
+}
+
+void eng_pack_states_device(Engine *e, const int *d_idx, int n, float *d_out) {
+    eng_sync_to_device(e);
+    if (n <= 0) return;
+    k_pack_states<<<(unsigned)((n + 255) / 256), 256, 0, e->st>>>(n, d_idx, e->B, reinterpret_cast<float4 *>(d_out));
+    OB_CHECK_KERNEL("k_pack_states", e->st);
+}
+void eng_unpack_states_device(Engine *e, const int *d_idx, int n, const float *d_in) {
+    eng_sync_to_device(e);
+    if (n <= 0) return;
+    k_unpack_states<<<(unsigned)((n + 255) / 256), 256, 0, e->st>>>(n, d_idx, e->B, reinterpret_cast<const float4 *>(d_in));
+    OB_CHECK_KERNEL("k_unpack_states", e->st);
+    e->host_stale = true;
+}
+
 long g_ob_launches = 0;
 long eng_launch_count() { return g_ob_launches; }
 

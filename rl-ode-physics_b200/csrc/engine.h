@@ -182,6 +182,9 @@ const float *eng_snapshot_device(Engine *);
 void eng_snapshot_to_host(Engine *, float *dst, int first, int count, bool blocking);
 // upload per-body external force/torque (6 floats per body) for the next step
 void eng_set_forces(Engine *, const float *f6, int n);
+// halo exchange: gather / scatter body states (16 floats each) through device buffers (async)
+void eng_pack_states_device(Engine *, const int *d_idx, int n, float *d_out);
+void eng_unpack_states_device(Engine *, const int *d_idx, int n, const float *d_in);
 // wait for everything queued on the engine stream
 void eng_wait(Engine *);
 StepStats eng_stats(Engine *);                  // blocking: stats of the last collide/step

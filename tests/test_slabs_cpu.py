@@ -1,0 +1,50 @@
+"""CPU: host logic of the slab decomposition (BASELINE config 5): ownership, ghost mirrors and halo lists
+of neighbouring ranks line up."""
+import numpy as np
+
+from odeb200 import scenes, slabs
+
+
+def test_neighbouring_slabs_agree_on_the_halo():
+    n_slabs, nx, nz, ny, mc = 3, 6, 5, 3, 2
+    built = [slabs.slab_scene(r, n_slabs, nx_per_slab=nx, nz=nz, ny=ny, seed=5, margin_cols=mc) for r in range(n_slabs)]
+    for r, (sc, halo) in enumerate(built):
+        n_own = sc["n_owned"]
+        assert n_own == nx * nz * ny
+        b, g = sc["bodies"], sc["geoms"]
+        assert (b["flags"][:n_own] == 0).all() and (b["flags"][n_own:] == scenes.BODY_KINEMATIC).all()
+        assert (halo["left"] is None) == (r == 0) and (halo["right"] is None) == (r == n_slabs - 1)
+        # geoms: 5 planes, then one geom per body in body order
+        assert np.array_equal(g["body"][5:], np.arange(len(b["pos"])))
+        assert (g["cat"][5:5 + n_own] == slabs.CAT_OBJ).all() and (g["cat"][5 + n_own:] == slabs.CAT_GHOST).all()
+        if halo["right"] is not None:
+            send, _ = halo["right"]
+            _, recv = built[r + 1][1]["left"]
+            nb, ng = built[r + 1][0]["bodies"], built[r + 1][0]["geoms"]
+            assert len(send) == len(recv) == mc * nz * ny
+            # the neighbour's ghosts mirror exactly the bodies we send, in the same order
+            assert np.array_equal(b["pos"][send], nb["pos"][recv])
+            assert np.array_equal(g["dims"][5 + send], ng["dims"][5 + recv])
+            assert np.array_equal(g["type"][5 + send], ng["type"][5 + recv])
+            # and they are the columns nearest the shared face
+            face = 0.5 * (b["pos"][:n_own, 0].max() + nb["pos"][:built[r + 1][0]["n_owned"], 0].min())
+            assert (np.abs(b["pos"][send, 0] - face) < (mc + 0.5) * 1.8).all()
+        if halo["left"] is not None:
+            send, _ = halo["left"]
+            _, recv = built[r - 1][1]["right"]
+            assert np.array_equal(b["pos"][send], built[r - 1][0]["bodies"]["pos"][recv])
+    # slabs tile x without gaps: owned x ranges are disjoint and ordered
+    xs = [(sc["bodies"]["pos"][:sc["n_owned"], 0].min(), sc["bodies"]["pos"][:sc["n_owned"], 0].max()) for sc, _ in built]
+    assert xs[0][1] < xs[1][0] and xs[1][1] < xs[2][0]
+
+
+def test_ghosts_only_collide_with_owned_bodies():
+    sc, halo = slabs.slab_scene(0, 2, nx_per_slab=4, nz=4, ny=2, margin_cols=2)
+    g = sc["geoms"]
+
+    def passes(i, j):
+        return bool((g["cat"][i] & g["col"][j]) or (g["cat"][j] & g["col"][i]))
+    n_own = sc["n_owned"]
+    plane, owned, ghost = 0, 5, 5 + n_own
+    assert passes(owned, owned + 1) and passes(owned, ghost) and passes(owned, plane)
+    assert not passes(ghost, ghost + 1) and not passes(ghost, plane) and not passes(plane, plane + 1)
