@@ -119,6 +119,9 @@ struct ManifoldArrays {
 struct EnvArrays {
     int n_envs;
     int max_bodies;  // largest number of bodies in one env (host-known)
+    int contiguous;  // 1: every env's bodies are one contiguous index range (enables shared-memory staging)
+    int *first_body; // first body of each env
+    int *n_body;     // bodies of each env
     int *cnt;        // manifolds per env (n_envs + 1 for the scan)
     int *start;      // exclusive scan of cnt, [n_envs] = total
     int *fill;       // bucket cursors

@@ -76,6 +76,7 @@ Engine *eng_create(int device) {
     if (const char *g = getenv("ODE_B200_ENV_GROUP")) e->env_group = atoi(g);
     if (const char *g = getenv("ODE_B200_COLOUR_SPREAD")) eng_set_colour_spread(e, atoi(g));
     if (const char *g = getenv("ODE_B200_CONTACT_UNITS")) e->contact_units = atoi(g);
+    if (const char *g = getenv("ODE_B200_ENV_STAGE")) e->env_stage = atoi(g);
     return e;
 }
 
@@ -105,7 +106,7 @@ void eng_destroy(Engine *e) {
     SolverArrays &S = e->S;
     dev_free(S.q0); dev_free(S.q1); dev_free(S.q2); dev_free(S.q3); dev_free(S.q4); dev_free(S.q5); dev_free(S.lam); dev_free(S.mrec);
     sort_workspace_free(e->sort); scan_workspace_free(e->scan);
-    dev_free(e->E.cnt); dev_free(e->E.start); dev_free(e->E.fill); dev_free(e->E.rec); dev_free(e->E.perm); dev_free(e->E.col);
+    dev_free(e->E.first_body); dev_free(e->E.n_body); dev_free(e->E.cnt); dev_free(e->E.start); dev_free(e->E.fill); dev_free(e->E.rec); dev_free(e->E.perm); dev_free(e->E.col);
     dev_free(e->hc_pd); dev_free(e->hc_ns); dev_free(e->hc_surf); dev_free(e->hc_mrec);
     dev_free(e->dl_first); dev_free(e->dl_pd); dev_free(e->dl_ns);
     for (auto &m : e->hmeshes) { dev_free(m.d_verts); dev_free(m.d_tris); }
@@ -347,6 +348,23 @@ void eng_sync_to_device(Engine *e) {
             int max_local = 0;
             for (size_t i = 0; i < n; i++) max_local = std::max(max_local, local[i]);
             e->E.max_bodies = max_local + 1;
+            // per-env body ranges; contiguous envs let the island solver stage body data in shared memory
+            std::vector<int> cnt(first.size(), 0);
+            for (size_t i = 0; i < n; i++) if (b.env[i] >= 0 && b.env[i] < (int)first.size()) cnt[b.env[i]]++;
+            bool contiguous = true;
+            for (size_t i = 0; i < n && contiguous; i++) {
+                const int en = b.env[i];
+                if (en < 0 || en >= (int)first.size() || local[i] >= cnt[en]) contiguous = false;
+            }
+            for (auto &f : first) if (f == INT32_MAX) f = 0;
+            e->E.contiguous = contiguous ? 1 : 0;
+            if ((int)first.size() > e->cap_env_bodies) {
+                dev_realloc(e->E.first_body, 0, first.size() + 1, st, false);
+                dev_realloc(e->E.n_body, 0, first.size() + 1, st, false);
+                e->cap_env_bodies = (int)first.size();
+            }
+            upload(e->E.first_body, first.data(), first.size(), st);
+            upload(e->E.n_body, cnt.data(), cnt.size(), st);
             upload(e->B.local, local.data(), n, st);
             upload(e->B.env, b.env.data(), n, st);
             OB_CUDA(cudaStreamSynchronize(st)); // `local` is a temporary

@@ -33,8 +33,9 @@ struct Engine {
 
     ManifoldArrays M{};
     EnvArrays E{};
-    int cap_envs = 0, cap_env_rec = 0;
+    int cap_envs = 0, cap_env_rec = 0, cap_env_bodies = 0;
     int env_group = 0; // lanes per env of the island solver (0 = automatic)
+    int env_stage = 1; // island solver: stage body data in shared memory when possible
     int solver_mode = 0; // 0 automatic, 1 force the global (grid-barrier) solver
     int contact_units = -1; // -1 automatic (per contact for batched worlds), 0 manifold units, 1 contact units
     int colour_spread = 0; // 0: lowest free colour; K > 0: hashed start within the first K colours

@@ -526,27 +526,29 @@ __device__ __forceinline__ void st_fc(float4 *p, float4 v) {
     if (L2ONLY) __stcg(p, v); else *p = v;
 }
 
+// fcp / invp: where the accumulators and world inverse inertias of the unit's bodies live -- the global
+// arrays (indexed by body) or, on the island path, the env's copy in shared memory (indexed by local body)
 template <bool L2ONLY, bool SINGLE = false>
-__device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, const BodyArrays &B) {
+__device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, float4 *fcp, const float4 *invp) {
     const int4 rec = __ldg(&S.mrec[s]);
     const int b1 = rec.x, b2 = rec.y, nc = SINGLE ? 1 : rec.z; // SINGLE: per-contact units, no contact loop
     const bool two = b2 >= 0;
     RowRec cur = load_rows(S, (size_t)s);
     FC f1, f2;
     {
-        const float4 a = ld_fc<L2ONLY>(&B.fc[2 * b1]), b = ld_fc<L2ONLY>(&B.fc[2 * b1 + 1]);
+        const float4 a = ld_fc<L2ONLY>(&fcp[2 * b1]), b = ld_fc<L2ONLY>(&fcp[2 * b1 + 1]);
         f1.l = v3(a); f1.a = v3(b);
     }
-    const float4 i10 = __ldg(&B.inv[3 * b1]), i11 = __ldg(&B.inv[3 * b1 + 1]), i12 = __ldg(&B.inv[3 * b1 + 2]);
+    const float4 i10 = invp[3 * b1], i11 = invp[3 * b1 + 1], i12 = invp[3 * b1 + 2];
     const M3 iI1 = M3{v3(i10), v3(i11), v3(i12)};
     const float invM1 = i10.w;
     M3 iI2 = M3{v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f)};
     float invM2 = 0.f;
     f2.l = v3(0.f, 0.f, 0.f); f2.a = f2.l;
     if (two) {
-        const float4 a = ld_fc<L2ONLY>(&B.fc[2 * b2]), b = ld_fc<L2ONLY>(&B.fc[2 * b2 + 1]);
+        const float4 a = ld_fc<L2ONLY>(&fcp[2 * b2]), b = ld_fc<L2ONLY>(&fcp[2 * b2 + 1]);
         f2.l = v3(a); f2.a = v3(b);
-        const float4 i20 = __ldg(&B.inv[3 * b2]), i21 = __ldg(&B.inv[3 * b2 + 1]), i22 = __ldg(&B.inv[3 * b2 + 2]);
+        const float4 i20 = invp[3 * b2], i21 = invp[3 * b2 + 1], i22 = invp[3 * b2 + 2];
         iI2 = M3{v3(i20), v3(i21), v3(i22)};
         invM2 = i20.w;
     }
@@ -578,11 +580,11 @@ __device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, con
         S.lam[si] = lam;
         if (!SINGLE) cur = nxt;
     }
-    st_fc<L2ONLY>(&B.fc[2 * b1], make_float4(f1.l.x, f1.l.y, f1.l.z, 0.f));
-    st_fc<L2ONLY>(&B.fc[2 * b1 + 1], make_float4(f1.a.x, f1.a.y, f1.a.z, 0.f));
+    st_fc<L2ONLY>(&fcp[2 * b1], make_float4(f1.l.x, f1.l.y, f1.l.z, 0.f));
+    st_fc<L2ONLY>(&fcp[2 * b1 + 1], make_float4(f1.a.x, f1.a.y, f1.a.z, 0.f));
     if (two) {
-        st_fc<L2ONLY>(&B.fc[2 * b2], make_float4(f2.l.x, f2.l.y, f2.l.z, 0.f));
-        st_fc<L2ONLY>(&B.fc[2 * b2 + 1], make_float4(f2.a.x, f2.a.y, f2.a.z, 0.f));
+        st_fc<L2ONLY>(&fcp[2 * b2], make_float4(f2.l.x, f2.l.y, f2.l.z, 0.f));
+        st_fc<L2ONLY>(&fcp[2 * b2 + 1], make_float4(f2.a.x, f2.a.y, f2.a.z, 0.f));
     }
 }
 
@@ -658,13 +660,13 @@ __global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays
         for (int it = 0; it < cfg.iters; it++) {
             for (int c = 0; c < ncol; c++) {
                 const int s0 = M.colour_start[c], s1 = M.colour_start[c + 1];
-                for (int s = s0 + gt; s < s1; s += gs) solve_manifold<true>(s, S, B);
+                for (int s = s0 + gt; s < s1; s += gs) solve_manifold<true>(s, S, B.fc, B.inv);
                 grid_barrier(bar, target);
             }
             if (ovf1 > ovf0) {
                 // manifolds that found no free colour (> 64 neighbours): one thread, in order
                 if (gt == 0)
-                    for (int s = ovf0; s < ovf1; s++) solve_manifold<true>(s, S, B);
+                    for (int s = ovf0; s < ovf1; s++) solve_manifold<true>(s, S, B.fc, B.inv);
                 grid_barrier(bar, target);
             }
         }
@@ -732,7 +734,7 @@ __device__ unsigned long long g_env_prof[8];
 // so what matters is how many lanes of each issued instruction do useful work.
 template <int G, bool SINGLE>
 __global__ void __launch_bounds__(128, 5) k_env_solve(EnvArrays E, BodyArrays B, ContactSource src, Surface usurf,
-                                                    SolverArrays S, StepConfig cfg, int spread,
+                                                    SolverArrays S, StepConfig cfg, int spread, int stage,
                                                     StepStats *__restrict__ stats) {
     extern __shared__ __align__(16) unsigned char env_smem[];
     constexpr int GROUPS = 128 / G;   // envs per CTA
@@ -740,10 +742,15 @@ __global__ void __launch_bounds__(128, 5) k_env_solve(EnvArrays E, BodyArrays B,
     const int grp = threadIdx.x / G, g = threadIdx.x % G;
     const int lane = threadIdx.x & 31;
     const int mb = (E.max_bodies + 31) & ~31;
-    // per group: colour masks + priorities of the env's bodies, colour bucket starts and cursors
-    unsigned long long *masks = reinterpret_cast<unsigned long long *>(env_smem) + (size_t)grp * 2 * mb;
+    // per group: a body region -- colour masks + priorities while colouring (16 B per body), then, with
+    // `stage`, the env's accumulators fc and world inverse inertias (80 B per body) for the iterations --
+    // followed by the colour bucket starts and cursors
+    const size_t region = (size_t)mb * (stage ? 80 : 16);
+    unsigned long long *masks = reinterpret_cast<unsigned long long *>(env_smem + (size_t)grp * region);
     unsigned long long *prio = masks + mb;
-    int *cstart = reinterpret_cast<int *>(env_smem + (size_t)GROUPS * 2 * mb * sizeof(unsigned long long)) + grp * 136;
+    float4 *sm_fc = reinterpret_cast<float4 *>(env_smem + (size_t)grp * region);
+    float4 *sm_inv = sm_fc + 2 * (size_t)mb;
+    int *cstart = reinterpret_cast<int *>(env_smem + (size_t)GROUPS * region) + grp * 136;
     int *cursor = cstart + 68;
     int rows1 = 0, rows2 = 0, ncont = 0, max_col = 0, max_rounds = 0;
     const int n_env_rounds = (E.n_envs + gridDim.x * GROUPS - 1) / (gridDim.x * GROUPS);
@@ -833,9 +840,28 @@ __global__ void __launch_bounds__(128, 5) k_env_solve(EnvArrays E, BodyArrays B,
         // ---- rows
         for (int j = 0; j < trips; j++) {
             const int s = ms + g + j * G;
-            if (s < me) build_manifold_rows(s, E.rec[E.perm[s]], B, src, usurf, S, cfg, rows1, rows2, ncont);
+            if (s < me) {
+                const int4 r = E.rec[E.perm[s]];
+                build_manifold_rows(s, r, B, src, usurf, S, cfg, rows1, rows2, ncont);
+                if (stage) { // the iterations index the shared-memory copies by env-local body
+                    int4 mr = S.mrec[s];
+                    mr.x = B.local[r.x];
+                    mr.y = r.y >= 0 ? B.local[r.y] : -1;
+                    S.mrec[s] = mr;
+                }
+            }
         }
         __syncwarp();
+        float4 *fcp = B.fc;
+        const float4 *invp = B.inv;
+        const int fb = have ? E.first_body[env] : 0, nbod = have ? E.n_body[env] : 0;
+        if (stage) { // colouring scratch is dead: reuse the region for fc (zero) and inv (copied once)
+            for (int i = g; i < 2 * nbod; i += G) sm_fc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = g; i < 3 * nbod; i += G) sm_inv[i] = B.inv[3 * (size_t)fb + i];
+            fcp = sm_fc;
+            invp = sm_inv;
+            __syncwarp();
+        }
         PROF_T(t3);
         // ---- SOR/PGS iterations, colours separated by warp-level barriers only
         const int novf = cstart[OVERFLOW_COLOUR + 1] - cstart[OVERFLOW_COLOUR];
@@ -846,7 +872,7 @@ __global__ void __launch_bounds__(128, 5) k_env_solve(EnvArrays E, BodyArrays B,
                 const int t = (__reduce_max_sync(FULL, s1 - s0) + G - 1) / G;
                 for (int j = 0; j < t; j++) {
                     const int s = s0 + g + j * G;
-                    if (s < s1) solve_manifold<false, SINGLE>(s, S, B);
+                    if (s < s1) solve_manifold<false, SINGLE>(s, S, fcp, invp);
                 }
                 __syncwarp();
             }
@@ -854,9 +880,13 @@ __global__ void __launch_bounds__(128, 5) k_env_solve(EnvArrays E, BodyArrays B,
                 // manifolds that found no free colour (> 64 neighbours): one lane per env, in order
                 if (g == 0)
                     for (int s = ms + cstart[OVERFLOW_COLOUR]; s < ms + cstart[OVERFLOW_COLOUR + 1]; s++)
-                        solve_manifold<false, SINGLE>(s, S, B);
+                        solve_manifold<false, SINGLE>(s, S, fcp, invp);
                 __syncwarp();
             }
+        }
+        if (stage) { // hand the accumulators to k_integrate
+            for (int i = g; i < 2 * nbod; i += G) B.fc[2 * (size_t)fb + i] = sm_fc[i];
+            __syncwarp();
         }
         PROF_T(t4);
         PROF_ADD(0, t0, t1); PROF_ADD(1, t1, t2); PROF_ADD(2, t2, t3); PROF_ADD(3, t3, t4); PROF_ADD(4, 0, 1);
@@ -961,14 +991,16 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
         if (G != 8 && G != 16 && G != 32) G = 32; // measured on C4: 32 >= 16 > 8
         const int groups = 128 / G;
         const int mb = (E.max_bodies + 31) & ~31;
-        const size_t smem = (size_t)groups * (2 * (size_t)mb * sizeof(unsigned long long) + 136 * sizeof(int));
+        // stage the env's body data in shared memory when its bodies are one index range and it fits
+        const int stage = (E.contiguous && mb <= 160 && e->env_stage != 0) ? 1 : 0;
+        const size_t smem = (size_t)groups * ((size_t)mb * (stage ? 80 : 16) + 136 * sizeof(int));
         const unsigned grid = (unsigned)((ne + groups - 1) / groups);
         SolverArrays S = e->S;
 #define OB_LAUNCH_ENV(GG, SS)                                                                                        \
     do {                                                                                                             \
         if (smem > 48 * 1024)                                                                                        \
             OB_CUDA(cudaFuncSetAttribute(k_env_solve<GG, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_env_solve<GG, SS><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->colour_spread, e->d_stats);        \
+        k_env_solve<GG, SS><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->colour_spread, stage, e->d_stats);        \
     } while (0)
         if (per_contact) {
             if (G == 8) OB_LAUNCH_ENV(8, true); else if (G == 16) OB_LAUNCH_ENV(16, true); else OB_LAUNCH_ENV(32, true);
