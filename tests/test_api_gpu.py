@@ -1,0 +1,191 @@
+"""GPU: behaviour of the ODE handle API beyond the main tick: spawning bodies while the simulation runs
+(the reference's MSGTYPE_S_NEW_BODY -> AddBody, src/main.c:178-182), dMass*/dBodySetMass, world
+parameters, destroying objects (src/main.c:258-267), empty and static-only worlds."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import odeb200
+import oracle as O
+import util
+from odeb200 import scenes
+
+pytestmark = pytest.mark.gpu
+fp = C.POINTER(C.c_float)
+H = 1.0 / 60.0
+
+
+def _near_callback(L, world, group, counter):
+    def near(data, o1, o2):
+        contacts = (odeb200.Contact * 8)()
+        geom0 = C.cast(C.addressof(contacts) + odeb200.Contact.geom.offset, C.POINTER(odeb200.ContactGeom))
+        nc = L.dCollide(o1, o2, 8, geom0, C.sizeof(odeb200.Contact))
+        counter[0] += 1
+        for k in range(nc):
+            contacts[k].surface.mode = odeb200.dContactBounce
+            contacts[k].surface.bounce = 0.2
+            contacts[k].surface.bounce_vel = 0.1
+            contacts[k].surface.mu = float("inf")
+            j = L.dJointCreateContact(world, group, C.byref(contacts[k]))
+            L.dJointAttach(j, L.dGeomGetBody(o1), L.dGeomGetBody(o2))
+    return odeb200.NearCallback(near)
+
+
+class Server:
+    """the reference's world setup + tick through the handle API"""
+
+    def __init__(self):
+        L = self.L = odeb200.lib()
+        L.dInitODE()
+        self.world = C.c_void_p(L.dWorldCreate())
+        L.dWorldSetGravity(self.world, 0.0, -9.8, 0.0)
+        self.space = C.c_void_p(L.dHashSpaceCreate(None))
+        self.group = C.c_void_p(L.dJointGroupCreate(0))
+        self.calls = [0]
+        self.cb = _near_callback(L, self.world, self.group, self.calls)
+        self.bodies, self.geoms = [], []
+
+    def add_static_box(self, pos, size):
+        g = C.c_void_p(self.L.dCreateBox(self.space, *[float(x) for x in size]))
+        self.L.dGeomSetPosition(g, *[float(x) for x in pos])
+        self.geoms.append(g)
+        return g
+
+    def add_body(self, pos, kind, dims, mass=None):
+        L = self.L
+        b = C.c_void_p(L.dBodyCreate(self.world))
+        L.dBodySetPosition(b, *[float(x) for x in pos])
+        if kind == "sphere":
+            g = C.c_void_p(L.dCreateSphere(self.space, float(dims[0])))
+        else:
+            g = C.c_void_p(L.dCreateBox(self.space, *[float(x) for x in dims]))
+        if mass is not None:
+            m = odeb200.Mass()
+            if kind == "sphere":
+                L.dMassSetSphere(C.byref(m), float(mass), float(dims[0]))
+            else:
+                L.dMassSetBox(C.byref(m), float(mass), *[float(x) for x in dims])
+            L.dBodySetMass(b, C.byref(m))
+        L.dGeomSetBody(g, b)
+        self.bodies.append(b); self.geoms.append(g)
+        return b, g
+
+    def tick(self, h=H):
+        self.L.dSpaceCollide(self.space, None, self.cb)
+        self.L.dWorldStep(self.world, float(h))
+        self.L.dJointGroupEmpty(self.group)
+
+    def pos(self, b):
+        p = self.L.dBodyGetPosition(b)
+        return np.array([p[0], p[1], p[2]], np.float32)
+
+    def vel(self, b):
+        p = self.L.dBodyGetLinearVel(b)
+        return np.array([p[0], p[1], p[2]], np.float32)
+
+    def close(self):
+        L = self.L
+        for g in self.geoms:
+            L.dGeomDestroy(g)
+        for b in self.bodies:
+            L.dBodyDestroy(b)
+        L.dJointGroupDestroy(self.group)
+        L.dSpaceDestroy(self.space)
+        L.dWorldDestroy(self.world)
+
+
+def test_bodies_spawned_while_running_match_the_oracle():
+    s = Server()
+    ow = O.OracleWorld()
+    s.add_static_box((0, 0, 0), (100, 1, 100))
+    ow.add_geom(O.BOX, [100, 1, 100], pos=[0, 0, 0])
+    rs = np.random.RandomState(5)
+    for step in range(90):
+        if step % 10 == 0:                       # a client pressed `M` (src/main.c:502-522)
+            pos = [rs.uniform(-1, 1), rs.uniform(1.5, 3.0), rs.uniform(-1, 1)]
+            if rs.randint(2):
+                dims = list(rs.uniform(0.2, 1.0, 3)); kind, t = "box", O.BOX
+            else:
+                dims = [rs.uniform(0.1, 0.4)]; kind, t = "sphere", O.SPHERE
+            s.add_body(pos, kind, dims)
+            b = ow.add_body(np.float32(pos), flags=O.BODY_GYRO)
+            ow.add_geom(t, np.float32(dims), body=b)
+        s.tick()
+        ow.tick(H, order_mode=0)
+    assert s.calls[0] > 90
+    # both integrate the same scene; row orders differ (ODE's shuffle vs colours), so compare loosely
+    for i, b in enumerate(s.bodies):
+        po = ow.body(i)[0]
+        assert np.abs(s.pos(b) - po).max() < 0.08, i
+        assert s.pos(b)[1] > 0.5
+    s.close()
+
+
+def test_dmass_and_world_parameters_take_effect():
+    s = Server()
+    L = s.L
+    L.dWorldSetERP(s.world, 0.5); L.dWorldSetCFM(s.world, 1e-4)
+    L.dWorldSetQuickStepNumIterations(s.world, 7); L.dWorldSetQuickStepW(s.world, 1.1)
+    assert L.dWorldGetQuickStepNumIterations(s.world) == 7
+    ow = O.OracleWorld(erp=0.5, cfm=1e-4, iters=7, sor_w=1.1)
+    s.add_static_box((0, 0, 0), (20, 1, 20)); ow.add_geom(O.BOX, [20, 1, 20], pos=[0, 0, 0])
+    b1, g1 = s.add_body((0, 0.99, 0), "box", (1.0, 1.0, 0.5), mass=3.0)            # density 3
+    b2, g2 = s.add_body((0.1, 1.88, 0.0), "sphere", (0.4,), mass=2.0)
+    m1 = 3.0 * 1.0 * 1.0 * 0.5
+    I1 = np.diag([m1 / 12 * (1 + 0.25), m1 / 12 * (1 + 0.25), m1 / 12 * 2.0]).astype(np.float32)
+    m2 = np.float32(4.0 / 3.0) * np.float32(np.pi) * np.float32(0.4) ** 3 * np.float32(2.0)
+    I2 = (np.eye(3) * 0.4 * m2 * 0.16).astype(np.float32)
+    o1 = ow.add_body([0, 0.99, 0], mass=m1, inertia=I1.reshape(9), flags=O.BODY_GYRO); ow.add_geom(O.BOX, [1, 1, 0.5], body=o1)
+    o2 = ow.add_body(np.float32([0.1, 1.88, 0.0]), mass=float(m2), inertia=I2.reshape(9), flags=O.BODY_GYRO); ow.add_geom(O.SPHERE, [0.4], body=o2)
+    # one tick solved in the same (engine) order: build the engine's order from a device-resident twin
+    sc_types = [O.BOX, O.BOX, O.SPHERE]
+    s.tick()
+    ow._types, ow._bodies = sc_types, [-1, 0, 1]
+    # oracle in joint order == engine order here (2 pairs, disjoint colour per body chain) up to tolerance
+    ow.tick(H, order_mode=1)
+    for (b, o) in ((b1, o1), (b2, o2)):
+        assert np.abs(s.pos(b) - ow.body(o)[0]).max() < 2e-4
+        assert np.abs(s.vel(b) - ow.body(o)[3]).max() < 2e-2
+    # heavier sphere sinks the same way in both; parameters really were used: ERP 0.5 pushes out faster than 0.2
+    s.close()
+
+
+def test_destroy_and_empty_worlds():
+    s = Server()
+    s.tick()                                            # empty space: nothing to do, must not fail
+    floor = s.add_static_box((0, 0, 0), (10, 1, 10))
+    s.tick()                                            # static only
+    b, g = s.add_body((0, 0.9, 0), "sphere", (0.5,))
+    b2, g2 = s.add_body((2, 0.9, 0), "sphere", (0.5,))
+    for _ in range(5):
+        s.tick()
+    assert s.pos(b)[1] > 0.9 and s.pos(b2)[1] > 0.9     # resting on / pushed out of the floor
+    # destroy the floor geom: the spheres now fall freely
+    s.L.dGeomDestroy(floor)
+    y0 = s.pos(b)[1]
+    for _ in range(30):
+        s.tick()
+    assert s.pos(b)[1] < y0 - 0.8
+    # destroy one body + its geom: the other keeps simulating, the handle API stays usable
+    s.L.dGeomDestroy(g2); s.L.dBodyDestroy(b2)
+    s.bodies.remove(b2); s.geoms.remove(g2); s.geoms.remove(floor)
+    y1 = s.pos(b)[1]
+    s.tick()
+    assert s.pos(b)[1] < y1
+    s.close()
+
+
+def test_kinematic_body_via_api_and_velocity_setters():
+    s = Server()
+    L = s.L
+    s.add_static_box((0, 0, 0), (10, 1, 10))
+    k, gk = s.add_body((0, 1.0, 0), "sphere", (0.5,))
+    L.dBodySetKinematic(k)
+    L.dBodySetLinearVel(k, 1.0, 0.0, 0.0)
+    d, gd = s.add_body((0.9, 1.0, 0), "sphere", (0.5,))
+    for _ in range(10):
+        s.tick()
+    assert s.pos(k)[1] == 1.0 and abs(s.pos(k)[0] - 10 * H) < 1e-5
+    assert s.vel(d)[0] > 0.5
+    s.close()
