@@ -199,6 +199,7 @@ struct orc_world {
     omesh *m; int nm, capm;
     ojoint *j; int nj, capj;
     unsigned long lcg_seed; /* ODE dRand state */
+    int perturb_fma;        /* experiment: FMA-contracted solver arithmetic (not ODE's rounding) */
     float *last_lambda; int nrows;
 };
 
@@ -218,6 +219,7 @@ void orc_set_gravity(orc_world *w, float x, float y, float z) { w->gravity[0] = 
 void orc_set_params(orc_world *w, float erp, float cfm, int iters, float sor_w) {
     w->erp = erp; w->cfm = cfm; w->iters = iters; w->sor_w = sor_w;
 }
+void orc_set_perturb_fma(orc_world *w, int on) { w->perturb_fma = on; }
 void orc_set_contact_params(orc_world *w, float max_vel, float min_depth) { w->max_vel = max_vel; w->min_depth = min_depth; }
 
 static void invert3_sym(const float *I, float *inv) {
@@ -1389,11 +1391,25 @@ int orc_quickstep(orc_world *w, float h, int order_mode, const int *perm) {
                 float old_lambda = lambda[i];
                 float delta = rhs[i] - old_lambda * Adcfm[i];
                 float *fc1 = fc + 6 * b1, *Ji = J + 12 * i;
-                delta -= fc1[0] * Ji[0] + fc1[1] * Ji[1] + fc1[2] * Ji[2] + fc1[3] * Ji[3] + fc1[4] * Ji[4] + fc1[5] * Ji[5];
                 float *fc2 = 0;
+                if (w->perturb_fma) {
+                    /* sensitivity experiment only (tests/test_oracle_kat.py): contract the dot products with
+                     * fused multiply-adds, the rounding a GPU build with FMA contraction would produce */
+                    float a1 = fc1[0] * Ji[0];
+                    for (int k = 1; k < 6; k++) a1 = fmaf(fc1[k], Ji[k], a1);
+                    delta -= a1;
+                    if (b2 >= 0) {
+                        fc2 = fc + 6 * b2;
+                        float a2 = fc2[0] * Ji[6];
+                        for (int k = 1; k < 6; k++) a2 = fmaf(fc2[k], Ji[6 + k], a2);
+                        delta -= a2;
+                    }
+                } else {
+                delta -= fc1[0] * Ji[0] + fc1[1] * Ji[1] + fc1[2] * Ji[2] + fc1[3] * Ji[3] + fc1[4] * Ji[4] + fc1[5] * Ji[5];
                 if (b2 >= 0) {
                     fc2 = fc + 6 * b2;
                     delta -= fc2[0] * Ji[6] + fc2[1] * Ji[7] + fc2[2] * Ji[8] + fc2[3] * Ji[9] + fc2[4] * Ji[10] + fc2[5] * Ji[11];
+                }
                 }
                 float hi_act, lo_act;
                 if (findex[i] >= 0) { hi_act = fabsf(hi[i] * lambda[findex[i]]); lo_act = -hi_act; }
@@ -1403,8 +1419,13 @@ int orc_quickstep(orc_world *w, float h, int order_mode, const int *perm) {
                 else if (new_lambda > hi_act) { delta = hi_act - old_lambda; lambda[i] = hi_act; }
                 else lambda[i] = new_lambda;
                 const float *im = iMJ + 12 * i;
+                if (w->perturb_fma) {
+                    for (int k = 0; k < 6; k++) fc1[k] = fmaf(delta, im[k], fc1[k]);
+                    if (fc2) for (int k = 0; k < 6; k++) fc2[k] = fmaf(delta, im[6 + k], fc2[k]);
+                } else {
                 for (int k = 0; k < 6; k++) fc1[k] += delta * im[k];
                 if (fc2) for (int k = 0; k < 6; k++) fc2[k] += delta * im[6 + k];
+                }
             }
         }
         /* velocity update: v += h * cforce */

@@ -54,6 +54,8 @@ void orc_destroy(orc_world *);
 void orc_set_gravity(orc_world *, float x, float y, float z);
 void orc_set_params(orc_world *, float erp, float cfm, int iters, float sor_w);
 void orc_set_contact_params(orc_world *, float max_vel, float min_depth);
+/* sensitivity experiment: solve with FMA-contracted dot products instead of ODE's rounding */
+void orc_set_perturb_fma(orc_world *, int on);
 
 /* bodies: default mass 1, I = identity (dBodyCreate). q = (w,x,y,z). R optional (NULL -> dQtoR(q)).
  * inertia: 9 floats row-major (NULL -> identity). returns body index */

@@ -314,3 +314,25 @@ def test_trimesh_sphere_rule(oracle_lib):
     assert c[0].depth == pytest.approx(0.5 - math.hypot(0.3, 0.2), abs=1e-6)
     w.set_body_state(b, pos=[1.6, 0.2, 0.5])
     assert len(w.collide(gs, gm)) == 0
+
+
+def test_one_step_tolerance_is_meaningful_under_fma_rounding(oracle_lib):
+    """Why the engine keeps --fmad=false: contracting the solver's dot products into FMAs (what nvcc would do
+    by default) moves one-step velocities by up to ~1e-5 relative -- inside north_star's 1e-4 bar after ONE
+    step, but the drift compounds over steps.  The GPU path avoids the question by rounding exactly like the
+    oracle, so its parity tests use zero tolerance on state as well."""
+    import ctypes as C
+    from odeb200 import scenes
+    L = O.lib()
+    L.orc_set_perturb_fma.argtypes = [C.c_void_p, C.c_int]
+    sc = scenes.random_soup(400, seed=21, extent=4.5)
+    a = O.OracleWorld(); a.load_scene(sc)
+    b = O.OracleWorld(); b.load_scene(sc)
+    L.orc_set_perturb_fma(b.w, 1)
+    a.tick(sc["h"], order_mode=1); b.tick(sc["h"], order_mode=1)
+    sa, sb = a.state(), b.state()
+    assert a.num_rows > 300
+    for k, floor in (("pos", 1.0), ("quat", 1.0), ("lvel", 0.1), ("avel", 0.1)):
+        d = np.abs(sa[k].astype(np.float64) - sb[k]) / np.maximum(np.abs(sa[k]), floor)
+        assert d.max() < 1e-4, k
+    assert np.abs(sa["lvel"] - sb["lvel"]).max() > 0          # ... but it is not bit-identical
