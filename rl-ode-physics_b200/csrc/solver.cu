@@ -529,11 +529,10 @@ __device__ __forceinline__ void st_fc(float4 *p, float4 v) {
 // fcp / invp: where the accumulators and world inverse inertias of the unit's bodies live -- the global
 // arrays (indexed by body) or, on the island path, the env's copy in shared memory (indexed by local body)
 template <bool L2ONLY, bool SINGLE = false>
-__device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, float4 *fcp, const float4 *invp) {
-    const int4 rec = __ldg(&S.mrec[s]);
+__device__ __forceinline__ void solve_manifold_core(int s, const int4 rec, RowRec cur, const SolverArrays &S, float4 *fcp,
+                                                    const float4 *invp) {
     const int b1 = rec.x, b2 = rec.y, nc = SINGLE ? 1 : rec.z; // SINGLE: per-contact units, no contact loop
     const bool two = b2 >= 0;
-    RowRec cur = load_rows(S, (size_t)s);
     FC f1, f2;
     {
         const float4 a = ld_fc<L2ONLY>(&fcp[2 * b1]), b = ld_fc<L2ONLY>(&fcp[2 * b1 + 1]);
@@ -586,6 +585,18 @@ __device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, flo
         st_fc<L2ONLY>(&fcp[2 * b2], make_float4(f2.l.x, f2.l.y, f2.l.z, 0.f));
         st_fc<L2ONLY>(&fcp[2 * b2 + 1], make_float4(f2.a.x, f2.a.y, f2.a.z, 0.f));
     }
+}
+
+template <bool L2ONLY, bool SINGLE = false>
+__device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, float4 *fcp, const float4 *invp) {
+    const int4 rec = __ldg(&S.mrec[s]);
+    solve_manifold_core<L2ONLY, SINGLE>(s, rec, load_rows(S, (size_t)s), S, fcp, invp);
+}
+
+// cp.async (LDGSTS) of one 16-byte record into this thread's prefetch slot
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 
 // grid-wide barrier of the persistent solver (all CTAs are co-resident: cooperative launch).  One
@@ -649,18 +660,49 @@ __device__ __forceinline__ void integrate_body(int i, const BodyArrays &B, float
     sn[3] = make_float4(p.x, p.y, p.z, 1.f);
 }
 
+// Persistent solver of one big world.  Colour phases are separated by grid barriers; what a thread will
+// need FIRST in the next phase -- the record and the contact-0 rows of its first manifold there, all
+// immutable during the solve except the thread-private lambda -- is prefetched into shared memory with
+// cp.async BEFORE the barrier, so after the barrier only the accumulators (just written by other SMs,
+// in L2) and the inverse inertias stand between the thread and its arithmetic.
 __global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays S, BodyArrays B, StepConfig cfg) {
+    __shared__ __align__(16) float4 pf[256 * 7]; // per thread: mrec, q0..q4, lam
     const int n = *M.count;
     const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
     unsigned *bar = reinterpret_cast<unsigned *>(&M.meta[6]);
     unsigned target = 0;
+    float4 *slot = pf + threadIdx.x * 7;
+    auto prefetch = [&](int s) {
+        cp_async16(slot + 0, &S.mrec[s]);
+        cp_async16(slot + 1, &S.q0[s]); cp_async16(slot + 2, &S.q1[s]); cp_async16(slot + 3, &S.q2[s]);
+        cp_async16(slot + 4, &S.q3[s]); cp_async16(slot + 5, &S.q4[s]); cp_async16(slot + 6, &S.lam[s]);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     if (n > 0) {
         const int ncol = M.meta[0];
         const int ovf0 = M.colour_start[OVERFLOW_COLOUR], ovf1 = M.colour_start[OVERFLOW_COLOUR + 1];
+        bool have_pf = false;
+        if (ncol > 0 && M.colour_start[0] + gt < M.colour_start[1]) { prefetch(M.colour_start[0] + gt); have_pf = true; }
         for (int it = 0; it < cfg.iters; it++) {
             for (int c = 0; c < ncol; c++) {
                 const int s0 = M.colour_start[c], s1 = M.colour_start[c + 1];
-                for (int s = s0 + gt; s < s1; s += gs) solve_manifold<true>(s, S, B.fc, B.inv);
+                int s = s0 + gt;
+                if (have_pf) { // first manifold of this phase: its record and rows are already on chip
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    const int4 rec = *reinterpret_cast<const int4 *>(slot);
+                    RowRec cur;
+                    cur.q0 = slot[1]; cur.q1 = slot[2]; cur.q2 = slot[3]; cur.q3 = slot[4]; cur.q4 = slot[5]; cur.lam = slot[6];
+                    solve_manifold_core<true>(s, rec, cur, S, B.fc, B.inv);
+                    s += gs;
+                }
+                for (; s < s1; s += gs) solve_manifold<true>(s, S, B.fc, B.inv);
+                // next phase: next colour, or colour 0 of the next iteration
+                int cn = c + 1;
+                bool more = true;
+                if (cn == ncol) { cn = 0; more = it + 1 < cfg.iters; }
+                const int sn = M.colour_start[cn] + gt;
+                have_pf = more && sn < M.colour_start[cn + 1];
+                if (have_pf) prefetch(sn);
                 grid_barrier(bar, target);
             }
             if (ovf1 > ovf0) {
