@@ -151,5 +151,6 @@ struct StepConfig {
 
 void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_surface);
 void solver_profile_dump();
+float solver_barrier_bench(Engine *e, int iters);
 
 } // namespace ob

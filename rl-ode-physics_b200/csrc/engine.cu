@@ -673,6 +673,8 @@ void eng_unpack_states_device(Engine *e, const int *d_idx, int n, const float *d
     e->host_stale = true;
 }
 
+float eng_barrier_bench(Engine *e, int iters) { return solver_barrier_bench(e, iters); }
+
 long g_ob_launches = 0;
 long eng_launch_count() { return g_ob_launches; }
 

@@ -195,6 +195,7 @@ void eng_timer_start(Engine *);
 void eng_timer_stop(Engine *);
 float eng_timer_elapsed_ms(Engine *);
 long eng_launch_count();
+float eng_barrier_bench(Engine *, int iters); // microseconds per grid barrier (diagnostic)
 // event-timed sections of the last step, milliseconds (collide, prep+colour+rows, solve+tail)
 void eng_last_timings(Engine *, float out[4]);
 void eng_enable_timing(Engine *, int on);

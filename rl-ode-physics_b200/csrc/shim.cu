@@ -330,6 +330,7 @@ extern "C" void dWorldTimerStartB200(dWorldID w) { eng_timer_start(w->eng); }
 extern "C" void dWorldTimerStopB200(dWorldID w) { eng_timer_stop(w->eng); }
 extern "C" float dWorldTimerElapsedB200(dWorldID w) { return eng_timer_elapsed_ms(w->eng); }
 extern "C" long dGetKernelLaunchCountB200(void) { return eng_launch_count(); }
+extern "C" float dTestGridBarrierB200(dWorldID w, int iters) { return eng_barrier_bench(w->eng, iters); }
 extern "C" void dWorldEnableTimingB200(dWorldID w, int on) { eng_enable_timing(w->eng, on); }
 extern "C" void dWorldGetTimingsB200(dWorldID w, float out[4]) { eng_last_timings(w->eng, out); }
 extern "C" int dWorldGetNumBodiesB200(dWorldID w) { return eng_bodies(w->eng).n; }

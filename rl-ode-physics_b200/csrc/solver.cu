@@ -716,6 +716,36 @@ __global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays
     for (int i = gt; i < B.n; i += gs) integrate_body(i, B, cfg.h);
 }
 
+// micro-benchmark hook: cost of one grid barrier at the solver's launch shape
+__global__ void __launch_bounds__(256, 2) k_barrier_bench(unsigned *bar, int iters) {
+    unsigned target = 0;
+    for (int i = 0; i < iters; i++) grid_barrier(bar, target);
+}
+
+float solver_barrier_bench(Engine *e, int iters) {
+    unsigned *bar = nullptr;
+    OB_CUDA(cudaMalloc(&bar, sizeof(unsigned)));
+    OB_CUDA(cudaMemset(bar, 0, sizeof(unsigned)));
+    int per_sm = 0;
+    OB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)k_barrier_bench, 256, 0));
+    if (per_sm > 2) per_sm = 2;
+    int grid = per_sm * e->num_sms;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    void *args[] = {(void *)&bar, (void *)&iters};
+    OB_CUDA(cudaLaunchCooperativeKernel((const void *)k_barrier_bench, dim3((unsigned)grid), dim3(256), args, 0, e->st));
+    OB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), e->st));
+    OB_CUDA(cudaEventRecord(a, e->st));
+    OB_CUDA(cudaLaunchCooperativeKernel((const void *)k_barrier_bench, dim3((unsigned)grid), dim3(256), args, 0, e->st));
+    OB_CUDA(cudaEventRecord(b, e->st));
+    OB_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(bar);
+    return ms * 1000.f / iters; // microseconds per barrier
+}
+
 // ------------------------------------------------------------------ island solver for batched worlds
 //
 // Scenes made of many small independent worlds ("envs", BASELINE config 4) do not need grid-wide
