@@ -660,6 +660,16 @@ __device__ __forceinline__ void integrate_body(int i, const BodyArrays &B, float
     sn[3] = make_float4(p.x, p.y, p.z, 1.f);
 }
 
+#ifdef OB_ENV_PROFILE
+__device__ unsigned long long g_phase_t[256];
+__device__ int g_phase_n[256];
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 // Persistent solver of one big world.  Colour phases are separated by grid barriers; what a thread will
 // need FIRST in the next phase -- the record and the contact-0 rows of its first manifold there, all
 // immutable during the solve except the thread-private lambda -- is prefetched into shared memory with
@@ -681,6 +691,9 @@ __global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays
     if (n > 0) {
         const int ncol = M.meta[0];
         const int ovf0 = M.colour_start[OVERFLOW_COLOUR], ovf1 = M.colour_start[OVERFLOW_COLOUR + 1];
+#ifdef OB_ENV_PROFILE
+        if (gt == 0) g_phase_t[0] = gtimer();
+#endif
         bool have_pf = false;
         if (ncol > 0 && M.colour_start[0] + gt < M.colour_start[1]) { prefetch(M.colour_start[0] + gt); have_pf = true; }
         for (int it = 0; it < cfg.iters; it++) {
@@ -704,6 +717,9 @@ __global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays
                 have_pf = more && sn < M.colour_start[cn + 1];
                 if (have_pf) prefetch(sn);
                 grid_barrier(bar, target);
+#ifdef OB_ENV_PROFILE
+                if (gt == 0 && it * ncol + c < 255) { g_phase_t[it * ncol + c + 1] = gtimer(); g_phase_n[it * ncol + c + 1] = s1 - s0; }
+#endif
             }
             if (ovf1 > ovf0) {
                 // manifolds that found no free colour (> 64 neighbours): one thread, in order
@@ -997,6 +1013,17 @@ void solver_profile_dump() {
     unsigned long long h[8];
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(h, g_env_prof, sizeof(h));
+    {
+        unsigned long long t[256];
+        int nn[256];
+        cudaMemcpyFromSymbol(t, g_phase_t, sizeof(t));
+        cudaMemcpyFromSymbol(nn, g_phase_n, sizeof(nn));
+        if (t[1]) {
+            fprintf(stderr, "k_solve phases (manifolds: microseconds):");
+            for (int i = 1; i < 40 && t[i]; i++) fprintf(stderr, " %d:%.1f", nn[i], (double)(t[i] - t[i - 1]) / 1000.0);
+            fprintf(stderr, "\n");
+        }
+    }
     if (h[4])
         fprintf(stderr, "env-solve profile (avg cycles per env-solve): colour %.0f  sort %.0f  rows %.0f  iterations %.0f  (n=%llu)\n",
                 (double)h[0] / h[4], (double)h[1] / h[4], (double)h[2] / h[4], (double)h[3] / h[4], h[4]);
