@@ -593,12 +593,6 @@ __device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, flo
     solve_manifold_core<L2ONLY, SINGLE>(s, rec, load_rows(S, (size_t)s), S, fcp, invp);
 }
 
-// cp.async (LDGSTS) of one 16-byte record into this thread's prefetch slot
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-
 // grid-wide barrier of the persistent solver (all CTAs are co-resident: cooperative launch).  One
 // release-add per CTA on a monotone counter, thread 0 spins with acquire loads.
 __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &target) {
@@ -670,52 +664,26 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 #endif
 
-// Persistent solver of one big world.  Colour phases are separated by grid barriers; what a thread will
-// need FIRST in the next phase -- the record and the contact-0 rows of its first manifold there, all
-// immutable during the solve except the thread-private lambda -- is prefetched into shared memory with
-// cp.async BEFORE the barrier, so after the barrier only the accumulators (just written by other SMs,
-// in L2) and the inverse inertias stand between the thread and its arithmetic.
+// Persistent solver of one big world: colour phases separated by grid barriers (1.35 us each at 296 CTAs,
+// measured).  Per-phase timing on the 1 M-body pile (profiles/README.md): the large early colours run at
+// ~4.9 TB/s of rows + body data, the small late colours sit on a ~6 us latency floor.  (Prefetching the
+// next phase's rows with cp.async before the barrier, L2 evict-first hints on the rows and a persisting-L2
+// window on the body data were all measured and did not help; they are not in the code.)
 __global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays S, BodyArrays B, StepConfig cfg) {
-    __shared__ __align__(16) float4 pf[256 * 7]; // per thread: mrec, q0..q4, lam
     const int n = *M.count;
     const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
     unsigned *bar = reinterpret_cast<unsigned *>(&M.meta[6]);
     unsigned target = 0;
-    float4 *slot = pf + threadIdx.x * 7;
-    auto prefetch = [&](int s) {
-        cp_async16(slot + 0, &S.mrec[s]);
-        cp_async16(slot + 1, &S.q0[s]); cp_async16(slot + 2, &S.q1[s]); cp_async16(slot + 3, &S.q2[s]);
-        cp_async16(slot + 4, &S.q3[s]); cp_async16(slot + 5, &S.q4[s]); cp_async16(slot + 6, &S.lam[s]);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
     if (n > 0) {
         const int ncol = M.meta[0];
         const int ovf0 = M.colour_start[OVERFLOW_COLOUR], ovf1 = M.colour_start[OVERFLOW_COLOUR + 1];
 #ifdef OB_ENV_PROFILE
         if (gt == 0) g_phase_t[0] = gtimer();
 #endif
-        bool have_pf = false;
-        if (ncol > 0 && M.colour_start[0] + gt < M.colour_start[1]) { prefetch(M.colour_start[0] + gt); have_pf = true; }
         for (int it = 0; it < cfg.iters; it++) {
             for (int c = 0; c < ncol; c++) {
                 const int s0 = M.colour_start[c], s1 = M.colour_start[c + 1];
-                int s = s0 + gt;
-                if (have_pf) { // first manifold of this phase: its record and rows are already on chip
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    const int4 rec = *reinterpret_cast<const int4 *>(slot);
-                    RowRec cur;
-                    cur.q0 = slot[1]; cur.q1 = slot[2]; cur.q2 = slot[3]; cur.q3 = slot[4]; cur.q4 = slot[5]; cur.lam = slot[6];
-                    solve_manifold_core<true>(s, rec, cur, S, B.fc, B.inv);
-                    s += gs;
-                }
-                for (; s < s1; s += gs) solve_manifold<true>(s, S, B.fc, B.inv);
-                // next phase: next colour, or colour 0 of the next iteration
-                int cn = c + 1;
-                bool more = true;
-                if (cn == ncol) { cn = 0; more = it + 1 < cfg.iters; }
-                const int sn = M.colour_start[cn] + gt;
-                have_pf = more && sn < M.colour_start[cn + 1];
-                if (have_pf) prefetch(sn);
+                for (int s = s0 + gt; s < s1; s += gs) solve_manifold<true>(s, S, B.fc, B.inv);
                 grid_barrier(bar, target);
 #ifdef OB_ENV_PROFILE
                 if (gt == 0 && it * ncol + c < 255) { g_phase_t[it * ncol + c + 1] = gtimer(); g_phase_n[it * ncol + c + 1] = s1 - s0; }
