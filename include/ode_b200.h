@@ -10,6 +10,8 @@
 #ifndef ODE_B200_EXT_H
 #define ODE_B200_EXT_H
 
+#include <stddef.h>
+
 #include "ode/ode.h"
 
 #ifdef __cplusplus
@@ -78,6 +80,15 @@ void dWorldTimerStopB200(dWorldID);
 float dWorldTimerElapsedB200(dWorldID); /* ms, blocking */
 /* number of CUDA kernels this library has launched in this process so far */
 long dGetKernelLaunchCountB200(void);
+
+/* Wire image of the reference's MsgUpdateBodies (inc/msgs.h:30-33; what src/main.c:221-242 assembles with a
+ * 512-iteration host loop + memcpy): bind the application's slot table once -- per slot the dBodyID (or
+ * NULL), the dGeomID (static slots), BodyType, size[3] and RGBA colour, i.e. the fields of Body/BodyState
+ * (inc/body.h:20-31) -- then, after any step, one kernel writes {int msg; BodyState bodies[n_slots]} (84 bytes
+ * per slot) and one copy brings it to `dst`.  Returns the image size in bytes (4 + 84 * n_slots). */
+void dWorldBindSnapshotSlotsB200(dWorldID, int n_slots, const dBodyID *bodies, const dGeomID *geoms, const int *types,
+                                 const float *size3, const unsigned *rgba);
+size_t dWorldPackMsgUpdateBodiesB200(dWorldID, void *dst, int msg_type, int blocking);
 
 /* capacities (pairs, manifolds); 0 = automatic (8 and 6 per geom). Overflow sets a stats flag. */
 void dWorldSetCapacityB200(dWorldID, long max_pairs, long max_manifolds);

@@ -112,6 +112,7 @@ void eng_destroy(Engine *e) {
     dev_free(e->dl_first); dev_free(e->dl_pd); dev_free(e->dl_ns);
     for (auto &m : e->hmeshes) { dev_free(m.d_verts); dev_free(m.d_tris); }
     dev_free(e->d_stats);
+    dev_free(e->msg_body); dev_free(e->msg_geom); dev_free(e->msg_type); dev_free(e->msg_size); dev_free(e->msg_col); dev_free(e->msg_out);
     dev_free(e->d_f6[0]); dev_free(e->d_f6[1]);
     if (e->tev[0]) { cudaEventDestroy(e->tev[0]); cudaEventDestroy(e->tev[1]); }
     if (e->h_stats) cudaFreeHost(e->h_stats);
@@ -695,6 +696,72 @@ void eng_unpack_states_device(Engine *e, const int *d_idx, int n, const float *d
     k_unpack_states<<<(unsigned)((n + 255) / 256), 256, 0, e->st>>>(n, d_idx, e->B, reinterpret_cast<const float4 *>(d_in));
     OB_CHECK_KERNEL("k_unpack_states", e->st);
     e->host_stale = true;
+}
+
+// ---- wire image of the reference's MsgUpdateBodies (inc/msgs.h:30-33): int msg type, then n_slots BodyState
+// records of 84 bytes {int type; float transform[16]; float size[3]; uchar col[4]} (inc/body.h:26-31).
+// Slot -> body (transform from the fused snapshot) or static geom (GetTransformMat of its pose).
+__global__ void __launch_bounds__(256) k_pack_msg(int n_slots, const int *__restrict__ slot_body, const int *__restrict__ slot_geom,
+                                                   const int *__restrict__ slot_type, const float *__restrict__ slot_size,
+                                                   const unsigned *__restrict__ slot_col, const float *__restrict__ snap,
+                                                   const float4 *__restrict__ g_pos, const float4 *__restrict__ g_R, int msg_type,
+                                                   unsigned *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) out[0] = (unsigned)msg_type;
+    if (i >= n_slots) return;
+    unsigned *rec = out + 1 + (size_t)i * 21; // 84 bytes = 21 words
+    const int type = slot_type[i];
+    rec[0] = (unsigned)type;
+    float t[16];
+    for (int k = 0; k < 16; k++) t[k] = 0.f;
+    if (type != 0) {
+        const int b = slot_body[i], g = slot_geom[i];
+        if (b >= 0) {
+            for (int k = 0; k < 16; k++) t[k] = snap[16 * (size_t)b + k];
+        } else if (g >= 0) { // GetTransformMat(pos, rot): columns of the result = rows of ODE's R
+            const float4 p = g_pos[g], r0 = g_R[3 * g], r1 = g_R[3 * g + 1], r2 = g_R[3 * g + 2];
+            t[0] = r0.x; t[1] = r1.x; t[2] = r2.x;
+            t[4] = r0.y; t[5] = r1.y; t[6] = r2.y;
+            t[8] = r0.z; t[9] = r1.z; t[10] = r2.z;
+            t[12] = p.x; t[13] = p.y; t[14] = p.z; t[15] = 1.f;
+        }
+    }
+    for (int k = 0; k < 16; k++) rec[1 + k] = __float_as_uint(t[k]);
+    for (int k = 0; k < 3; k++) rec[17 + k] = __float_as_uint(slot_size[3 * i + k]);
+    rec[20] = slot_col[i];
+}
+
+void eng_bind_msg_slots(Engine *e, int n_slots, const int *body, const int *geom, const int *type, const float *size3,
+                        const unsigned *rgba) {
+    OB_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = e->st;
+    OB_CUDA(cudaStreamSynchronize(st));
+    dev_free(e->msg_body); dev_free(e->msg_geom); dev_free(e->msg_type); dev_free(e->msg_size); dev_free(e->msg_col);
+    dev_free(e->msg_out);
+    e->msg_slots = n_slots;
+    if (n_slots <= 0) return;
+    const size_t n = (size_t)n_slots;
+    OB_CUDA(cudaMalloc(&e->msg_body, n * 4)); OB_CUDA(cudaMalloc(&e->msg_geom, n * 4)); OB_CUDA(cudaMalloc(&e->msg_type, n * 4));
+    OB_CUDA(cudaMalloc(&e->msg_size, n * 12)); OB_CUDA(cudaMalloc(&e->msg_col, n * 4));
+    OB_CUDA(cudaMalloc(&e->msg_out, 4 + n * 84));
+    OB_CUDA(cudaMemcpy(e->msg_body, body, n * 4, cudaMemcpyHostToDevice));
+    OB_CUDA(cudaMemcpy(e->msg_geom, geom, n * 4, cudaMemcpyHostToDevice));
+    OB_CUDA(cudaMemcpy(e->msg_type, type, n * 4, cudaMemcpyHostToDevice));
+    OB_CUDA(cudaMemcpy(e->msg_size, size3, n * 12, cudaMemcpyHostToDevice));
+    OB_CUDA(cudaMemcpy(e->msg_col, rgba, n * 4, cudaMemcpyHostToDevice));
+}
+
+size_t eng_pack_msg(Engine *e, void *dst, int msg_type, bool blocking) {
+    if (e->msg_slots <= 0) return 0;
+    eng_sync_to_device(e);
+    const size_t bytes = 4 + (size_t)e->msg_slots * 84;
+    k_pack_msg<<<(unsigned)((e->msg_slots + 255) / 256), 256, 0, e->st>>>(e->msg_slots, e->msg_body, e->msg_geom, e->msg_type,
+                                                                       e->msg_size, e->msg_col, e->snap_buf[e->snap_cur], e->G.pos,
+                                                                       e->G.R, msg_type, e->msg_out);
+    OB_CHECK_KERNEL("k_pack_msg", e->st);
+    OB_CUDA(cudaMemcpyAsync(dst, e->msg_out, bytes, cudaMemcpyDeviceToHost, e->st));
+    if (blocking) OB_CUDA(cudaStreamSynchronize(e->st));
+    return bytes;
 }
 
 float eng_barrier_bench(Engine *e, int iters) { return solver_barrier_bench(e, iters); }

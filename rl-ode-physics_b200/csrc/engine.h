@@ -195,6 +195,10 @@ void eng_timer_start(Engine *);
 void eng_timer_stop(Engine *);
 float eng_timer_elapsed_ms(Engine *);
 long eng_launch_count();
+// wire image of the reference's MsgUpdateBodies: bind the slot table once, pack after any step
+void eng_bind_msg_slots(Engine *, int n_slots, const int *body, const int *geom, const int *type, const float *size3,
+                        const unsigned *rgba);
+size_t eng_pack_msg(Engine *, void *dst, int msg_type, bool blocking);
 float eng_barrier_bench(Engine *, int iters); // microseconds per grid barrier (diagnostic)
 // event-timed sections of the last step, milliseconds (collide, prep+colour+rows, solve+tail)
 void eng_last_timings(Engine *, float out[4]);

@@ -35,6 +35,11 @@ struct Engine {
     EnvArrays E{};
     int cap_envs = 0, cap_env_rec = 0, cap_env_bodies = 0;
     int env_group = 0; // lanes per env of the island solver (0 = automatic)
+    // wire image of MsgUpdateBodies (slot table bound by the host)
+    int msg_slots = 0;
+    int *msg_body = nullptr, *msg_geom = nullptr, *msg_type = nullptr;
+    float *msg_size = nullptr;
+    unsigned *msg_col = nullptr, *msg_out = nullptr;
     float4 *body_hot = nullptr; // fc (2 per body) followed by inv (3 per body)
     int l2_persist = 0;        // measured: the persisting carve-out costs more than it gives (profiles/README.md)        // keep body_hot resident in L2 through an access-policy window
     int env_stage = 1; // island solver: stage body data in shared memory when possible

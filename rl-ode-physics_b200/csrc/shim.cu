@@ -330,6 +330,18 @@ extern "C" void dWorldTimerStartB200(dWorldID w) { eng_timer_start(w->eng); }
 extern "C" void dWorldTimerStopB200(dWorldID w) { eng_timer_stop(w->eng); }
 extern "C" float dWorldTimerElapsedB200(dWorldID w) { return eng_timer_elapsed_ms(w->eng); }
 extern "C" long dGetKernelLaunchCountB200(void) { return eng_launch_count(); }
+extern "C" void dWorldBindSnapshotSlotsB200(dWorldID w, int n_slots, const dBodyID *bodies, const dGeomID *geoms, const int *types,
+                                            const float *size3, const unsigned *rgba) {
+    std::vector<int> bi((size_t)n_slots, -1), gi((size_t)n_slots, -1);
+    for (int i = 0; i < n_slots; i++) {
+        if (bodies && bodies[i] && bodies[i]->alive) bi[i] = bodies[i]->idx;
+        if (geoms && geoms[i] && geoms[i]->alive) gi[i] = geoms[i]->idx;
+    }
+    eng_bind_msg_slots(w->eng, n_slots, bi.data(), gi.data(), types, size3, rgba);
+}
+extern "C" size_t dWorldPackMsgUpdateBodiesB200(dWorldID w, void *dst, int msg_type, int blocking) {
+    return eng_pack_msg(w->eng, dst, msg_type, blocking != 0);
+}
 extern "C" float dTestGridBarrierB200(dWorldID w, int iters) { return eng_barrier_bench(w->eng, iters); }
 extern "C" void dWorldEnableTimingB200(dWorldID w, int on) { eng_enable_timing(w->eng, on); }
 extern "C" void dWorldGetTimingsB200(dWorldID w, float out[4]) { eng_last_timings(w->eng, out); }

@@ -7,7 +7,8 @@
  * this repo's <ode/ode.h> and links libode_b200.so, i.e. it is the drop-in test of the boundary:
  * the only thing that changed for the host code is the library behind the ODE names.
  *
- * usage: physics_server <seed> <n_spawn> <n_kinematic> <ticks> <dt> <mode: compat|device> <out.bin>
+ * usage: physics_server <seed> <n_spawn> <n_kinematic> <ticks> <dt> <mode: compat|device|wire> <out.bin>
+ * (wire = device-resident tick + the MsgUpdateBodies image packed on the GPU, dWorldPackMsgUpdateBodiesB200)
  * Writes the MsgUpdateBodies image (inc/msgs.h:30-33) after the last tick to out.bin.
  */
 #include <stdint.h>
@@ -150,7 +151,8 @@ int main(int argc, char **argv) {
     randState = (uint32_t)strtoul(argv[1], 0, 10);
     const int n_spawn = atoi(argv[2]), n_kin = atoi(argv[3]), ticks = atoi(argv[4]);
     const float dt = (float)atof(argv[5]);
-    const int device_mode = strcmp(argv[6], "device") == 0;
+    const int wire_mode = strcmp(argv[6], "wire") == 0;
+    const int device_mode = wire_mode || strcmp(argv[6], "device") == 0;
 
     dInitODE();                                  /* src/main.c:94-98 */
     world = dWorldCreate();
@@ -206,6 +208,25 @@ int main(int argc, char **argv) {
         dJointGroupEmpty(contactGroup);
     }
 
+    static MsgUpdateBodies updatedBodies;        /* src/main.c:239-240 */
+    if (wire_mode) {
+        /* the whole of src/main.c:221-240 as one kernel + one copy */
+        static dBodyID slot_body[MAX_BODIES];
+        static dGeomID slot_geom[MAX_BODIES];
+        static int slot_type[MAX_BODIES];
+        static float slot_size[MAX_BODIES][3];
+        static unsigned slot_col[MAX_BODIES];
+        for (int i = 0; i < MAX_BODIES; i++) {
+            slot_type[i] = bodyStates[i].type;
+            slot_body[i] = bodies[i].type != BODYTYPE_NULL ? bodies[i].body : NULL;
+            slot_geom[i] = bodies[i].type != BODYTYPE_NULL ? bodies[i].geom : NULL;
+            slot_size[i][0] = bodyStates[i].size.x; slot_size[i][1] = bodyStates[i].size.y; slot_size[i][2] = bodyStates[i].size.z;
+            memcpy(&slot_col[i], &bodyStates[i].col, 4);
+        }
+        dWorldBindSnapshotSlotsB200(world, MAX_BODIES, slot_body, slot_geom, slot_type, &slot_size[0][0], slot_col);
+        const size_t nbytes = dWorldPackMsgUpdateBodiesB200(world, &updatedBodies, MSGTYPE_C_UPDATE_BODIES, 1);
+        if (nbytes != sizeof(updatedBodies)) { fprintf(stderr, "wire image size %zu != %zu\n", nbytes, sizeof(updatedBodies)); return 1; }
+    } else {
     for (int i = 0; i < MAX_BODIES; i++) {       /* src/main.c:221-237 */
         if (BODYTYPE_NULL == bodies[i].type) continue;
         const dReal *pos, *rot;
@@ -218,10 +239,10 @@ int main(int argc, char **argv) {
         }
         GetTransformMat(bodyStates[i].transform, pos, rot);
     }
-    static MsgUpdateBodies updatedBodies;        /* src/main.c:239-240 */
     memset(&updatedBodies, 0, sizeof(updatedBodies));
     updatedBodies.msg = MSGTYPE_C_UPDATE_BODIES;
     memcpy(updatedBodies.bodies, bodyStates, sizeof(bodyStates));
+    }
     FILE *f = fopen(argv[7], "wb");
     if (!f) { perror("out"); return 1; }
     fwrite(&updatedBodies, sizeof(updatedBodies), 1, f);

@@ -158,8 +158,14 @@ def test_headless_reference_server_loop_drop_in():
     with tempfile.TemporaryDirectory() as d:
         msg_c, types_c, tr_c, sz_c = _run_server("compat", ticks, os.path.join(d, "c.bin"))
         msg_d, types_d, tr_d, sz_d = _run_server("device", ticks, os.path.join(d, "d.bin"))
+        raw_c = np.fromfile(os.path.join(d, "c.bin"), dtype=np.uint8)
+        _run_server("wire", ticks, os.path.join(d, "w.bin"))
+        raw_w = np.fromfile(os.path.join(d, "w.bin"), dtype=np.uint8)
     assert msg_c == 3 and msg_d == 3              # MSGTYPE_C_UPDATE_BODIES
     assert np.array_equal(types_c, types_d) and np.array_equal(tr_c, tr_d)
+    # the GPU-packed wire image (dWorldPackMsgUpdateBodiesB200) equals the host-assembled one byte for byte,
+    # except the unused padding-free NULL slots, which both leave zeroed
+    assert np.array_equal(raw_c, raw_w)
     # slots: 4 map boxes, 64 spawned bodies, 4 kinematic spheres, the rest BODYTYPE_NULL
     assert (types_c[:4] == 2).all() and (types_c[72:] == 0).all() and set(types_c[4:68].tolist()) <= {1, 2}
     sc = scenes.server_scene(seed=1)
