@@ -367,3 +367,52 @@ def test_forces_and_async_snapshot_pipeline():
     for k in ("pos", "quat", "lvel", "avel"):
         assert np.array_equal(es[k], os_[k]), k
     ew.close()
+
+
+def _crowded_scene(n_small=90, batched=False):
+    """One big dynamic slab carrying n_small spheres: the slab has more than 64 contact neighbours, so some of
+    its manifolds cannot get one of the 64 colours and go through the solvers' serial overflow class."""
+    sc = scenes._empty_scene("crowded")
+    scenes._add_geom(sc, scenes.PLANE, (0, 1, 0, 0.0), cat=scenes.CMASK_ALL & ~scenes.CMASK_MAP)
+    n_env = 2 if batched else 1
+    for e in range(n_env):
+        slab = scenes._add_body(sc, (0.0, 0.26, 0.0), mass=50.0, inertia=(400, 0, 0, 0, 800, 0, 0, 0, 400), env=e)
+        scenes._add_geom(sc, scenes.BOX, (10.0, 0.5, 10.0), body=slab, cat=scenes.CMASK_OBJ, col=scenes.CMASK_OBJ | scenes.CMASK_MAP, env=e)
+        k = 0
+        for ix in range(10):
+            for iz in range(10):
+                if k >= n_small:
+                    break
+                b = scenes._add_body(sc, (-4.5 + ix * 1.0, 0.51 + 0.29, -4.5 + iz * 1.0), env=e)
+                scenes._add_geom(sc, scenes.SPHERE, (0.3,), body=b, cat=scenes.CMASK_OBJ, col=scenes.CMASK_OBJ | scenes.CMASK_MAP, env=e)
+                k += 1
+    return scenes.finalize(sc)
+
+
+@pytest.mark.parametrize("batched", [False, True])
+def test_more_than_64_neighbours_overflow_class(batched):
+    sc = _crowded_scene(90, batched)
+    ow, ew = util.load_both(sc)
+    if batched:
+        ew.set_contact_units(0)          # manifold units on the island path too: 90 + 4 manifolds on the slab
+    for step in range(3):
+        ew.tick(sc["h"])
+        st = ew.stats()
+        assert st["n_overflow"] > 0 and st["n_colours"] == 64 and st["flags"] == 0
+        util.oracle_tick_in_engine_order(ow, ew, sc["h"])
+        es, os_ = ew.state(), ow.state()
+        for k in ("pos", "quat", "lvel", "avel"):
+            assert util.rel_err(es[k], os_[k]).max() <= STATE_RTOL, (step, k)
+    ew.close()
+
+
+def test_capacity_overflow_is_flagged_not_silent():
+    sc = scenes.random_soup(300, seed=3, extent=3.0)
+    ew = util.engine_world(sc)
+    ew.set_capacity(64, 32)              # far too small on purpose
+    ew.tick(sc["h"])
+    st = ew.stats()
+    assert st["flags"] & 1 and st["n_pairs"] == 64          # SF_PAIR_OVERFLOW, list truncated at capacity
+    s = ew.state()
+    assert np.isfinite(s["pos"]).all()
+    ew.close()
