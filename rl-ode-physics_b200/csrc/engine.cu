@@ -78,6 +78,7 @@ Engine *eng_create(int device) {
     if (const char *g = getenv("ODE_B200_CONTACT_UNITS")) e->contact_units = atoi(g);
     if (const char *g = getenv("ODE_B200_ENV_STAGE")) e->env_stage = atoi(g);
     if (const char *g = getenv("ODE_B200_L2_PERSIST")) e->l2_persist = atoi(g);
+    if (const char *g = getenv("ODE_B200_ENV_FUSE")) e->env_fuse = atoi(g);
     return e;
 }
 

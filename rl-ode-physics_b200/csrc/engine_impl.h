@@ -42,6 +42,7 @@ struct Engine {
     unsigned *msg_col = nullptr, *msg_out = nullptr;
     float4 *body_hot = nullptr; // fc (2 per body) followed by inv (3 per body)
     int l2_persist = 0;        // measured: the persisting carve-out costs more than it gives (profiles/README.md)        // keep body_hot resident in L2 through an access-policy window
+    int env_fuse = 1;  // island solver: run body preparation and the integrate/pack tail inside k_env_solve
     int env_stage = 1; // island solver: stage body data in shared memory when possible
     int solver_mode = 0; // 0 automatic, 1 force the global (grid-barrier) solver
     int contact_units = -1; // -1 automatic (per contact for batched worlds), 0 manifold units, 1 contact units

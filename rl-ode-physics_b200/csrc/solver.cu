@@ -33,13 +33,7 @@ constexpr int OVERFLOW_COLOUR = 64;
 // ------------------------------------------------------------------ per-body step preparation
 
 // world-frame inverse inertia, gyroscopic torque, gravity, v/h + M^-1 f; clears the accumulators
-__global__ void __launch_bounds__(256) k_body_prep(BodyArrays B, StepConfig cfg, StepStats *__restrict__ stats) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) {
-        stats->n_rows = 0; stats->n_rows1 = 0; stats->n_rows2 = 0; stats->n_contacts = 0;
-        stats->n_manifolds = 0; stats->n_colours = 0; stats->n_overflow = 0; stats->colour_rounds = 0;
-    }
-    if (i >= B.n) return;
+__device__ __forceinline__ void body_prep(int i, const BodyArrays &B, const StepConfig &cfg) {
     const float4 p = B.pos[i];
     const float invM = p.w;
     const M3 R = load_m3(B.R, i);
@@ -88,6 +82,16 @@ __global__ void __launch_bounds__(256) k_body_prep(BodyArrays B, StepConfig cfg,
     B.fc[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
     B.colmask[i] = 0ull;
     B.prio[i] = ~0ull;
+}
+
+__global__ void k_stats_reset(StepStats *__restrict__ stats) {
+    stats->n_rows = 0; stats->n_rows1 = 0; stats->n_rows2 = 0; stats->n_contacts = 0;
+    stats->n_manifolds = 0; stats->n_colours = 0; stats->n_overflow = 0; stats->colour_rounds = 0;
+}
+
+__global__ void __launch_bounds__(256) k_body_prep(BodyArrays B, StepConfig cfg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B.n) body_prep(i, B, cfg);
 }
 
 // ------------------------------------------------------------------ manifolds from device contacts
@@ -611,10 +615,9 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &target) {
 
 // velocity update, dxStepBody (semi-implicit Euler + quaternion renormalisation + dQtoR) and the
 // reference's GetTransformMat pack, for one body
-__device__ __forceinline__ void integrate_body(int i, const BodyArrays &B, float h) {
+__device__ __forceinline__ void integrate_body(int i, const BodyArrays &B, float h, float4 fl, float4 fa) {
     float4 p = B.pos[i];
     float4 lv4 = B.lvel[i], av4 = B.avel[i];
-    const float4 fl = __ldcg(&B.fc[2 * i]), fa = __ldcg(&B.fc[2 * i + 1]);
     const float4 f = B.facc[i], t = B.tacc[i];
     const float invM = p.w;
     lv4.x += h * fl.x; lv4.y += h * fl.y; lv4.z += h * fl.z;
@@ -697,7 +700,7 @@ __global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays
             }
         }
     }
-    for (int i = gt; i < B.n; i += gs) integrate_body(i, B, cfg.h);
+    for (int i = gt; i < B.n; i += gs) integrate_body(i, B, cfg.h, __ldcg(&B.fc[2 * i]), __ldcg(&B.fc[2 * i + 1]));
 }
 
 // micro-benchmark hook: cost of one grid barrier at the solver's launch shape
@@ -790,7 +793,7 @@ __device__ unsigned long long g_env_prof[8];
 // so what matters is how many lanes of each issued instruction do useful work.
 template <int G, bool SINGLE>
 __global__ void __launch_bounds__(128, 5) k_env_solve(EnvArrays E, BodyArrays B, ContactSource src, Surface usurf,
-                                                    SolverArrays S, StepConfig cfg, int spread, int stage,
+                                                    SolverArrays S, StepConfig cfg, int spread, int stage, int fused,
                                                     StepStats *__restrict__ stats) {
     extern __shared__ __align__(16) unsigned char env_smem[];
     constexpr int GROUPS = 128 / G;   // envs per CTA
@@ -815,7 +818,16 @@ __global__ void __launch_bounds__(128, 5) k_env_solve(EnvArrays E, BodyArrays B,
         const bool have = env < E.n_envs;
         const int ms = have ? E.start[env] : 0, me = have ? E.start[env + 1] : 0;
         const int trips = (__reduce_max_sync(FULL, me - ms) + G - 1) / G; // warp-uniform
-        if (trips == 0) continue;
+        const int fb = have ? E.first_body[env] : 0, nbod = have ? E.n_body[env] : 0;
+        if (fused) { // per-body step preparation of this env (k_body_prep's work), fused in
+            for (int i = g; i < nbod; i += G) body_prep(fb + i, B, cfg);
+            __syncwarp();
+        }
+        if (trips == 0) { // no contacts in any env of this warp: free flight
+            if (fused)
+                for (int i = g; i < nbod; i += G) integrate_body(fb + i, B, cfg.h, make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f));
+            continue;
+        }
         PROF_T(t0);
         // ---- colouring (rule of k_colour, at group scope)
         for (int i = g; i < mb; i += G) { masks[i] = 0ull; prio[i] = ~0ull; }
@@ -910,7 +922,6 @@ __global__ void __launch_bounds__(128, 5) k_env_solve(EnvArrays E, BodyArrays B,
         __syncwarp();
         float4 *fcp = B.fc;
         const float4 *invp = B.inv;
-        const int fb = have ? E.first_body[env] : 0, nbod = have ? E.n_body[env] : 0;
         if (stage) { // colouring scratch is dead: reuse the region for fc (zero) and inv (copied once)
             for (int i = g; i < 2 * nbod; i += G) sm_fc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int i = g; i < 3 * nbod; i += G) sm_inv[i] = B.inv[3 * (size_t)fb + i];
@@ -940,7 +951,14 @@ __global__ void __launch_bounds__(128, 5) k_env_solve(EnvArrays E, BodyArrays B,
                 __syncwarp();
             }
         }
-        if (stage) { // hand the accumulators to k_integrate
+        if (fused) { // solver tail: velocity update, dxStepBody, snapshot pack for this env's bodies
+            for (int i = g; i < nbod; i += G) {
+                const float4 fl = stage ? sm_fc[2 * i] : B.fc[2 * (size_t)(fb + i)];
+                const float4 fa = stage ? sm_fc[2 * i + 1] : B.fc[2 * (size_t)(fb + i) + 1];
+                integrate_body(fb + i, B, cfg.h, fl, fa);
+            }
+            __syncwarp();
+        } else if (stage) { // hand the accumulators to k_integrate
             for (int i = g; i < 2 * nbod; i += G) B.fc[2 * (size_t)fb + i] = sm_fc[i];
             __syncwarp();
         }
@@ -973,7 +991,7 @@ __global__ void __launch_bounds__(128, 5) k_env_solve(EnvArrays E, BodyArrays B,
 
 __global__ void __launch_bounds__(256) k_integrate(BodyArrays B, StepConfig cfg) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B.n) integrate_body(i, B, cfg.h);
+    if (i < B.n) integrate_body(i, B, cfg.h, __ldcg(&B.fc[2 * i]), __ldcg(&B.fc[2 * i + 1]));
 }
 
 void solver_profile_dump() {
@@ -1021,8 +1039,16 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
     cfg.gx = e->params.gravity[0]; cfg.gy = e->params.gravity[1]; cfg.gz = e->params.gravity[2];
     cfg.iters = e->params.iters;
 
-    k_body_prep<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(B, cfg, e->d_stats);
-    OB_CHECK_KERNEL("k_body_prep", st);
+    k_stats_reset<<<1, 1, 0, st>>>(e->d_stats);
+    OB_CHECK_KERNEL("k_stats_reset", st);
+    // island path with contiguous envs: per-body preparation and the integrate/pack tail run inside
+    // k_env_solve, env by env; otherwise they are separate passes over all bodies
+    const bool island = !host_contacts && e->have_device_contacts && e->n_envs > 1 && e->E.max_bodies <= 1024 && e->solver_mode != 1;
+    const int fused = (island && e->E.contiguous && e->env_fuse) ? 1 : 0;
+    if (!fused) {
+        k_body_prep<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(B, cfg);
+        OB_CHECK_KERNEL("k_body_prep", st);
+    }
 
     ManifoldArrays M = e->M;
     const unsigned pgrid = (unsigned)(e->num_sms * 8);
@@ -1033,8 +1059,7 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
     // colours, but every phase costs one contact instead of the longest manifold of the phase)
     const int per_contact = e->contact_units >= 0 ? e->contact_units : (e->n_envs > 1 ? 1 : 0);
     // batched independent worlds with device-resident contacts take the island path
-    const bool env_path = !host_contacts && e->have_device_contacts && e->n_envs > 1 && e->E.max_bodies <= 1024 &&
-                          e->solver_mode != 1;
+    const bool env_path = island;
     if (env_path) {
         if (uniform_surface) usurf = *uniform_surface;
         src.pd = e->cs.pd; src.ns = e->cs.ns; src.surf = nullptr; src.kstride = e->cs.stride;
@@ -1067,7 +1092,7 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
     do {                                                                                                             \
         if (smem > 48 * 1024)                                                                                        \
             OB_CUDA(cudaFuncSetAttribute(k_env_solve<GG, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_env_solve<GG, SS><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->colour_spread, stage, e->d_stats);        \
+        k_env_solve<GG, SS><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->colour_spread, stage, fused, e->d_stats);        \
     } while (0)
         if (per_contact) {
             if (G == 8) OB_LAUNCH_ENV(8, true); else if (G == 16) OB_LAUNCH_ENV(16, true); else OB_LAUNCH_ENV(32, true);
@@ -1076,8 +1101,10 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
         }
 #undef OB_LAUNCH_ENV
         OB_CHECK_KERNEL("k_env_solve", st);
-        k_integrate<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(B, cfg);
-        OB_CHECK_KERNEL("k_integrate", st);
+        if (!fused) {
+            k_integrate<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(B, cfg);
+            OB_CHECK_KERNEL("k_integrate", st);
+        }
         if (e->timing) OB_CUDA(cudaEventRecord(e->ev[4], st));
         return;
     }
