@@ -373,6 +373,114 @@ __global__ void __launch_bounds__(128) k_sweep(int n, const uint32_t *__restrict
     }
 }
 
+
+// ---- all pairs per env -------------------------------------------------------------------------
+// Batched worlds have a few hundred geoms each, so "which geoms share a world" already is the
+// broadphase partition: no keys, no sort, no cell table.  Thread i owns geom i and tests the next
+// floor((c-1)/2) geoms of its env's index range cyclically (plus the opposite one for even c, from the
+// lower half only), which visits each unordered pair exactly once with equal trip counts across a warp;
+// then the geoms shared by all envs.  A bounding-sphere record (16 B) screens each candidate before
+// the two AABB loads.  Same collideAABBs filter, same count -> scan -> fill emission as the grid path.
+__global__ void __launch_bounds__(256) k_env_bounds(GeomArrays g, float4 *__restrict__ cr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    const float4 lo = g.amin[i], hi = g.amax[i];
+    const float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
+    const float hx = 0.5f * (hi.x - lo.x), hy = 0.5f * (hi.y - lo.y), hz = 0.5f * (hi.z - lo.z);
+    // inflated so that rounding can never reject a pair whose AABBs overlap
+    const float r = sqrtf(hx * hx + hy * hy + hz * hz) * 1.0001f + 1e-6f * (fabsf(cx) + fabsf(cy) + fabsf(cz)) + 1e-6f;
+    cr[i] = make_float4(cx, cy, cz, r);
+}
+
+struct GeomRec {
+    float4 lo, hi; // lo.w = geom index, hi.w = body
+    uint4 f;       // cat, col, env, type
+};
+
+__device__ __forceinline__ GeomRec load_rec(const GeomArrays &g, int j, bool single) {
+    GeomRec r;
+    r.lo = g.amin[j]; r.hi = g.amax[j];
+    r.lo.w = __int_as_float(j);
+    r.hi.w = __int_as_float(g.body[j]);
+    r.f = make_uint4(g.cat[j], g.col[j], single ? 0u : (unsigned)g.env[j], (unsigned)g.type[j]);
+    return r;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_env_sweep(GeomArrays g, const float4 *__restrict__ cr,
+                                                    const int *__restrict__ efirst, const int *__restrict__ ecount,
+                                                    const int *__restrict__ shared, int n_shared, int single,
+                                                    int *__restrict__ cnt, const int *__restrict__ off,
+                                                    int2 *__restrict__ pairs, int cap_pairs, int2 *__restrict__ tmp,
+                                                    int *__restrict__ tot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = g.n;
+    if (i >= n) return;
+    PairSink sink;
+#pragma unroll
+    for (int c = 0; c < PC_COUNT; c++) sink.cnt[c] = 0;
+    sink.total = 0;
+    if (FILL) {
+        const int t = tot[i];
+        if (t <= SWEEP_TCAP) {
+            for (int k = 0; k < t; k++) {
+                const int2 e = tmp[(size_t)k * n + i];
+                const int cls = e.x >> 28;
+                const int pos = off[cls * n + i] + sink.cnt[cls]++;
+                if (pos < cap_pairs) pairs[pos] = make_int2(e.x & 0x0fffffff, e.y);
+            }
+            return;
+        }
+    }
+    if (g.alive[i]) {
+        const GeomRec me = load_rec(g, i, single != 0);
+        const float4 c1 = cr[i];
+        const int env = (int)me.f.z;
+        auto visit = [&](int j) {
+            const float4 c2 = cr[j];
+            const float dx = c1.x - c2.x, dy = c1.y - c2.y, dz = c1.z - c2.z, rr = c1.w + c2.w;
+            if (dx * dx + dy * dy + dz * dz > rr * rr) return; // NaN/inf (planes) fall through to the AABB test
+            const float4 lo2 = g.amin[j], hi2 = g.amax[j];
+            if (me.lo.x > hi2.x || me.hi.x < lo2.x || me.lo.y > hi2.y || me.hi.y < lo2.y || me.lo.z > hi2.z ||
+                me.hi.z < lo2.z)
+                return;
+            if (!g.alive[j]) return;
+            const GeomRec o = load_rec(g, j, single != 0);
+            const int cls = test_pair(me.lo, me.hi, me.f, o.lo, o.hi, o.f);
+            if (cls >= 0) emit<FILL>(cls, i, n, me.lo, me.f, o.lo, o.f, sink, off, pairs, cap_pairs, tmp);
+        };
+        if (env >= 0) {
+            const int first = efirst[env], c = ecount[env], li = i - first;
+            const int half = (c - 1) >> 1;
+            int lj = li;
+            for (int d = 1; d <= half; d++) {
+                lj = (lj + 1 == c) ? 0 : lj + 1;
+                visit(first + lj);
+            }
+            if (!(c & 1) && li < (c >> 1)) visit(first + li + (c >> 1));
+            for (int s = 0; s < n_shared; s++) visit(shared[s]);
+        } else {
+            for (int s = 0; s < n_shared; s++) {
+                const int j = shared[s];
+                if (j > i) visit(j);
+            }
+        }
+    }
+    if (!FILL) {
+#pragma unroll
+        for (int c = 0; c < PC_COUNT; c++) cnt[c * n + i] = sink.cnt[c];
+        tot[i] = sink.total;
+    }
+}
+
+__global__ void k_env_counters(BroadCounters *__restrict__ bc, GridParams *__restrict__ gp, int n_alive, int n_shared,
+                               int n_envs) {
+    bc->first_dead = n_alive;
+    bc->first_big = n_alive - n_shared;
+    bc->n_pairs = 0;
+    gp->cell = 0.f; gp->dx = gp->dy = gp->dz = 0; gp->n_envs = n_envs;
+}
+
 __global__ void k_pairs_finish(int n, const int *__restrict__ off, int cap_pairs, BroadCounters *__restrict__ bc,
                                StepStats *__restrict__ stats, const GridParams *__restrict__ gp) {
     int total = off[PC_COUNT * n];
@@ -395,7 +503,7 @@ __global__ void k_pairs_finish(int n, const int *__restrict__ off, int cap_pairs
 }
 
 void broadphase_run(BroadPhase &bp, GeomArrays g, const float4 *b_pos, const float4 *b_R, MeshTable meshes,
-                    int n_envs, float big_extent, StepStats *d_stats, cudaStream_t st) {
+                    int n_envs, float big_extent, const EnvBroad &eb, StepStats *d_stats, cudaStream_t st) {
     const int n = g.n;
     if (n == 0) {
         OB_CUDA(cudaMemsetAsync(bp.counters, 0, sizeof(BroadCounters), st));
@@ -407,6 +515,25 @@ void broadphase_run(BroadPhase &bp, GeomArrays g, const float4 *b_pos, const flo
     OB_CUDA(cudaMemcpyAsync(bp.acc, acc_init, sizeof(acc_init), cudaMemcpyHostToDevice, st));
     k_geom_update<<<nb, 256, 0, st>>>(g, b_pos, b_R, meshes, big_extent, bp.acc);
     OB_CHECK_KERNEL("k_geom_update", st);
+    if (eb.enabled) {
+        const unsigned nb2 = (unsigned)((n + 127) / 128);
+        float4 *cr = bp.s_min;
+        k_env_bounds<<<nb, 256, 0, st>>>(g, cr);
+        OB_CHECK_KERNEL("k_env_bounds", st);
+        k_env_counters<<<1, 1, 0, st>>>(bp.counters, bp.gp, eb.n_alive, eb.n_shared, n_envs);
+        OB_CHECK_KERNEL("k_env_counters", st);
+        k_env_sweep<false><<<nb2, 128, 0, st>>>(g, cr, eb.first, eb.count, eb.shared, eb.n_shared, eb.single, bp.cnt,
+                                                nullptr, nullptr, 0, bp.sweep_tmp, bp.sweep_tot);
+        OB_CHECK_KERNEL("k_env_sweep", st);
+        OB_CUDA(cudaMemsetAsync(bp.cnt + (size_t)PC_COUNT * n, 0, sizeof(int), st));
+        scan_exclusive(bp.cnt, bp.cnt, (long)PC_COUNT * n + 1, nullptr, nullptr, bp.scan, st);
+        k_env_sweep<true><<<nb2, 128, 0, st>>>(g, cr, eb.first, eb.count, eb.shared, eb.n_shared, eb.single, nullptr,
+                                               bp.cnt, bp.pairs, bp.cap_pairs, bp.sweep_tmp, bp.sweep_tot);
+        OB_CHECK_KERNEL("k_env_sweep", st);
+        k_pairs_finish<<<1, 1, 0, st>>>(n, bp.cnt, bp.cap_pairs, bp.counters, d_stats, bp.gp);
+        OB_CHECK_KERNEL("k_pairs_finish", st);
+        return;
+    }
     k_grid_params<<<1, 1, 0, st>>>(bp.acc, bp.gp, n_envs, bp.cap_cells, n, bp.counters);
     OB_CHECK_KERNEL("k_grid_params", st);
     k_cell_keys<<<nb, 256, 0, st>>>(g, bp.gp, bp.cap_cells, bp.keys, bp.idx);

@@ -87,8 +87,17 @@ struct BroadPhase {
     ScanWorkspace scan;
 };
 
+// all-pairs-per-env broadphase (batched worlds, or one small world): no sort, no grid.  Geoms of env e are
+// the index range [first[e], first[e] + count[e]); geoms shared by every env are listed in `shared`.
+struct EnvBroad {
+    int enabled = 0;
+    int single = 0;      // one world: every geom belongs to the one range, env ids are ignored
+    int n_shared = 0, n_alive = 0;
+    int *first = nullptr, *count = nullptr, *shared = nullptr;
+};
+
 void broadphase_run(BroadPhase &bp, GeomArrays g, const float4 *b_pos, const float4 *b_R, MeshTable meshes,
-                    int n_envs, float big_extent, StepStats *d_stats, cudaStream_t st);
+                    int n_envs, float big_extent, const EnvBroad &eb, StepStats *d_stats, cudaStream_t st);
 
 // contact slot storage: contact k of pair p lives at [k * stride + p]
 struct ContactSlots {

@@ -79,6 +79,7 @@ Engine *eng_create(int device) {
     if (const char *g = getenv("ODE_B200_ENV_STAGE")) e->env_stage = atoi(g);
     if (const char *g = getenv("ODE_B200_L2_PERSIST")) e->l2_persist = atoi(g);
     if (const char *g = getenv("ODE_B200_ENV_FUSE")) e->env_fuse = atoi(g);
+    if (const char *g = getenv("ODE_B200_BROADPHASE")) e->broad_mode = !strcmp(g, "grid") ? 0 : !strcmp(g, "env") ? 1 : -1;
     return e;
 }
 
@@ -97,6 +98,7 @@ void eng_destroy(Engine *e) {
     dev_free(G.type); dev_free(G.dims); dev_free(G.body); dev_free(G.pos); dev_free(G.R); dev_free(G.cat);
     dev_free(G.col); dev_free(G.env); dev_free(G.mesh); dev_free(G.alive); dev_free(G.amin); dev_free(G.amax);
     BroadPhase &bp = e->bp;
+    dev_free(e->EB.first); dev_free(e->EB.count); dev_free(e->EB.shared);
     dev_free(bp.acc); dev_free(bp.gp); dev_free(bp.counters); dev_free(bp.keys); dev_free(bp.idx);
     dev_free(bp.s_min); dev_free(bp.s_max); dev_free(bp.s_flt); dev_free(bp.cell_start); dev_free(bp.cell_end);
     dev_free(bp.cnt); dev_free(bp.pairs); dev_free(bp.sweep_tmp); dev_free(bp.sweep_tot);
@@ -205,6 +207,7 @@ void eng_mark_geoms_dirty(Engine *e) { e->geoms_dirty = true; }
 void eng_mark_forces_dirty(Engine *e) { e->forces_dirty = true; }
 void eng_set_num_envs(Engine *e, int n) {
     e->n_envs = n < 1 ? 1 : n;
+    e->geoms_dirty = true; // the per-env geom ranges depend on the env count
     // measured on C4 (profiles/README.md): spreading the colours makes MORE phases whose cost is set by
     // the longest manifold in the phase, so lowest-free colouring stays the default for batched worlds too
 }
@@ -414,7 +417,49 @@ void eng_sync_to_device(Engine *e) {
         upload(e->G.col, g.col.data(), n, st); upload(e->G.env, g.env.data(), n, st);
         upload(e->G.alive, g.alive.data(), n, st);
         upload(e->G.mesh, mesh.data(), n, st);
-        OB_CUDA(cudaStreamSynchronize(st)); // `mesh` is a temporary
+        // all-pairs-per-env broadphase: usable when every env's geoms are one index range of modest size
+        {
+            EnvBroad &eb = e->EB;
+            eb.enabled = 0;
+            const int ne = std::max(e->n_envs, 1);
+            std::vector<int> first((size_t)ne, 0), cnt((size_t)ne, 0), shared;
+            int n_alive = 0;
+            for (size_t i = 0; i < n; i++) n_alive += g.alive[i] ? 1 : 0;
+            bool ok = e->broad_mode != 0 && n > 0;
+            if (ok && ne == 1) {
+                ok = n <= (e->broad_mode == 1 ? 4096u : 1024u);
+                first[0] = 0; cnt[0] = (int)n;
+            } else if (ok) {
+                int maxc = 0;
+                for (size_t i = 0; i < n && ok; i++) {
+                    const int en = g.env[i];
+                    if (en < 0) { shared.push_back((int)i); continue; }
+                    if (en >= ne) { ok = false; break; }
+                    if (cnt[en] == 0) first[en] = (int)i;
+                    else if (first[en] + cnt[en] != (int)i) ok = false; // not one contiguous range
+                    cnt[en]++;
+                    maxc = std::max(maxc, cnt[en]);
+                }
+                ok = ok && maxc <= 2048 && shared.size() <= 256;
+            }
+            if (ok) {
+                if (ne > e->cap_eb_envs) {
+                    dev_realloc(eb.first, 0, (size_t)ne, st, false); dev_realloc(eb.count, 0, (size_t)ne, st, false);
+                    e->cap_eb_envs = ne;
+                }
+                if ((int)shared.size() > e->cap_eb_shared) {
+                    dev_realloc(eb.shared, 0, shared.size(), st, false);
+                    e->cap_eb_shared = (int)shared.size();
+                }
+                upload(eb.first, first.data(), (size_t)ne, st); upload(eb.count, cnt.data(), (size_t)ne, st);
+                upload(eb.shared, shared.data(), shared.size(), st);
+                eb.enabled = 1;
+                eb.single = ne == 1 ? 1 : 0;
+                eb.n_shared = (int)shared.size();
+                eb.n_alive = n_alive;
+            }
+            OB_CUDA(cudaStreamSynchronize(st)); // `mesh`, `first`, `cnt`, `shared` are temporaries
+        }
         e->geoms_dirty = false;
     }
 }
@@ -446,7 +491,7 @@ void eng_collide(Engine *e, int max_contacts) {
     if (max_contacts > 8) max_contacts = 8;
     e->max_contacts = max_contacts;
     if (e->timing) OB_CUDA(cudaEventRecord(e->ev[0], e->st));
-    broadphase_run(e->bp, e->G, e->B.pos, e->B.R, e->meshes, e->n_envs, e->big_extent, e->d_stats, e->st);
+    broadphase_run(e->bp, e->G, e->B.pos, e->B.R, e->meshes, e->n_envs, e->big_extent, e->EB, e->d_stats, e->st);
     narrowphase_run(e->bp, e->G, e->meshes, e->hmeshes, e->cs, max_contacts, e->d_stats, e->num_sms, e->st);
     if (e->timing) OB_CUDA(cudaEventRecord(e->ev[1], e->st));
     e->have_device_contacts = true;

@@ -46,6 +46,9 @@ struct Engine {
     int env_stage = 1; // island solver: stage body data in shared memory when possible
     int solver_mode = 0; // 0 automatic, 1 force the global (grid-barrier) solver
     int contact_units = -1; // -1 automatic (per contact for batched worlds), 0 manifold units, 1 contact units
+    int broad_mode = -1;   // -1 auto, 0 uniform grid, 1 all pairs per env
+    EnvBroad EB;
+    int cap_eb_envs = 0, cap_eb_shared = 0;
     int colour_spread = 0; // 0: lowest free colour; K > 0: hashed start within the first K colours
     bool colour_spread_auto = true;
     SolverArrays S{};
