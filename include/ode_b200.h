@@ -102,6 +102,10 @@ void dWorldSetSolverModeB200(dWorldID, int mode, int env_group);
 void dWorldSetContactUnitsB200(dWorldID, int per_contact);
 /* dynamic geoms whose AABB extent exceeds this are treated like static "big" geoms (default inf) */
 void dWorldSetBigExtentB200(dWorldID, float extent);
+/* broadphase layout: -1 automatic (default), 0 uniform grid (sort + cell sweep), 1 all pairs per env (batched
+ * worlds whose geoms were added env by env, or one world of <= 4096 geoms; falls back to the grid
+ * otherwise).  Both emit the same pair SET; the order inside the list differs. */
+void dWorldSetBroadphaseB200(dWorldID, int mode);
 
 typedef struct dStepStatsB200 {
     int n_geoms, n_big, n_pairs, n_contacts, n_manifolds, n_colours, n_overflow, flags;

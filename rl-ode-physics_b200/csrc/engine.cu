@@ -213,6 +213,7 @@ void eng_set_num_envs(Engine *e, int n) {
 }
 void eng_set_capacity(Engine *e, long max_pairs, long max_manifolds) { e->want_pairs = max_pairs; e->want_manifolds = max_manifolds; }
 void eng_set_big_extent(Engine *e, float extent) { e->big_extent = extent; }
+void eng_set_broadphase(Engine *e, int mode) { e->broad_mode = mode; e->geoms_dirty = true; }
 void eng_set_solver_mode(Engine *e, int mode, int env_group) { e->solver_mode = mode; e->env_group = env_group; }
 void eng_set_contact_units(Engine *e, int per_contact) { e->contact_units = per_contact; }
 void eng_set_colour_spread(Engine *e, int k) { e->colour_spread = k < 0 ? 0 : (k > 32 ? 32 : k); e->colour_spread_auto = false; }

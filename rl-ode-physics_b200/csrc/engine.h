@@ -156,6 +156,7 @@ void eng_mark_forces_dirty(Engine *);
 void eng_set_num_envs(Engine *, int n);
 void eng_set_capacity(Engine *, long max_pairs, long max_manifolds);
 void eng_set_big_extent(Engine *, float extent);
+void eng_set_broadphase(Engine *, int mode);
 void eng_set_solver_mode(Engine *, int mode, int env_group);
 void eng_set_colour_spread(Engine *, int k);
 void eng_set_contact_units(Engine *, int per_contact);

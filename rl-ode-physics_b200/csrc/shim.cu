@@ -321,6 +321,7 @@ extern "C" void dWorldSetMaxContactsB200(dWorldID w, int n) { w->max_contacts = 
 extern "C" void dWorldSetNumEnvsB200(dWorldID w, int n) { eng_set_num_envs(w->eng, n); }
 extern "C" void dWorldSetCapacityB200(dWorldID w, long mp, long mm) { eng_set_capacity(w->eng, mp, mm); }
 extern "C" void dWorldSetBigExtentB200(dWorldID w, float e) { eng_set_big_extent(w->eng, e); }
+extern "C" void dWorldSetBroadphaseB200(dWorldID w, int mode) { eng_set_broadphase(w->eng, mode); }
 extern "C" void dWorldSetSolverModeB200(dWorldID w, int mode, int env_group) { eng_set_solver_mode(w->eng, mode, env_group); }
 extern "C" void dWorldSetContactUnitsB200(dWorldID w, int per_contact) { eng_set_contact_units(w->eng, per_contact); }
 extern "C" void dWorldWaitB200(dWorldID w) { eng_wait(w->eng); }

@@ -787,12 +787,40 @@ __device__ unsigned long long g_env_prof[8];
 #define PROF_ADD(i, a, b)
 #endif
 
+#ifndef OB_ENV_PIPE
+#define OB_ENV_PIPE 0
+#endif
+#ifndef OB_ENV_CTAS
+#define OB_ENV_CTAS 5 // CTAs per SM the register budget is sized for (measured: 5 > 4, 6, 8 on C4)
+#endif
+struct EnvPre {
+    int s; // solver slot, -1: this lane has no unit in the pass
+    int4 rec;
+    float4 q0, q1, q2;
+#if OB_ENV_PIPE >= 2
+    float4 q3, q4;
+#endif
+};
+__device__ __forceinline__ EnvPre env_fetch(const SolverArrays &S, int ms, const int *cstart, int c, int j, int g, int G) {
+    EnvPre p;
+    const int s = ms + cstart[c] + g + j * G;
+    p.s = (s < ms + cstart[c + 1]) ? s : -1;
+    if (p.s >= 0) {
+        p.rec = __ldg(&S.mrec[s]);
+        p.q0 = __ldg(&S.q0[s]); p.q1 = __ldg(&S.q1[s]); p.q2 = __ldg(&S.q2[s]);
+#if OB_ENV_PIPE >= 2
+        p.q3 = __ldg(&S.q3[s]); p.q4 = __ldg(&S.q4[s]);
+#endif
+    }
+    return p;
+}
+
 // The W = 32/G envs that share a warp run in LOCKSTEP: every loop bound is made warp-uniform (the
 // maximum over the warp's groups) and lanes without work are predicated off, so the groups never
 // diverge into serialised code paths.  The solver is issue-bound (ncu: 67 % issue-active, DRAM 8 %),
 // so what matters is how many lanes of each issued instruction do useful work.
 template <int G, bool SINGLE>
-__global__ void __launch_bounds__(128, 5) k_env_solve(EnvArrays E, BodyArrays B, ContactSource src, Surface usurf,
+__global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, BodyArrays B, ContactSource src, Surface usurf,
                                                     SolverArrays S, StepConfig cfg, int spread, int stage, int fused,
                                                     StepStats *__restrict__ stats) {
     extern __shared__ __align__(16) unsigned char env_smem[];
@@ -934,6 +962,36 @@ __global__ void __launch_bounds__(128, 5) k_env_solve(EnvArrays E, BodyArrays B,
         const int novf = cstart[OVERFLOW_COLOUR + 1] - cstart[OVERFLOW_COLOUR];
         const bool any_ovf = __any_sync(FULL, novf > 0);
         for (int it = 0; it < cfg.iters; it++) {
+#if OB_ENV_PIPE
+            if (SINGLE) {
+                // software pipeline over the flattened (colour, pass) sequence: the read-only part of the
+                // NEXT pass's records is in flight while this pass is solved (rows and mrec never change
+                // during the iterations; lambda is read at use)
+                EnvPre cur = env_fetch(S, ms, cstart, 0, 0, g, G);
+                for (int c = 0; c < ncol; c++) {
+                    const int t = (__reduce_max_sync(FULL, cstart[c + 1] - cstart[c]) + G - 1) / G;
+                    for (int j = 0; j < t; j++) {
+                        EnvPre nxt;
+                        nxt.s = -1;
+                        if (j + 1 < t) nxt = env_fetch(S, ms, cstart, c, j + 1, g, G);
+                        else if (c + 1 < ncol) nxt = env_fetch(S, ms, cstart, c + 1, 0, g, G);
+                        if (cur.s >= 0) {
+                            RowRec r;
+                            r.q0 = cur.q0; r.q1 = cur.q1; r.q2 = cur.q2;
+#if OB_ENV_PIPE >= 2
+                            r.q3 = cur.q3; r.q4 = cur.q4;
+#else
+                            r.q3 = __ldg(&S.q3[cur.s]); r.q4 = __ldg(&S.q4[cur.s]);
+#endif
+                            r.lam = S.lam[cur.s];
+                            solve_manifold_core<false, true>(cur.s, cur.rec, r, S, fcp, invp);
+                        }
+                        cur = nxt;
+                    }
+                    __syncwarp();
+                }
+            } else
+#endif
             for (int c = 0; c < ncol; c++) {
                 const int s0 = ms + cstart[c], s1 = ms + cstart[c + 1];
                 const int t = (__reduce_max_sync(FULL, s1 - s0) + G - 1) / G;

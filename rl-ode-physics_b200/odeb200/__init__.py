@@ -118,6 +118,7 @@ _SIGS = [
     ("dWorldTimerElapsedB200", C.c_float, [_vp]), ("dGetKernelLaunchCountB200", C.c_long, []),
     ("dWorldSetCapacityB200", None, [_vp, C.c_long, C.c_long]),
     ("dWorldSetBigExtentB200", None, [_vp, _f]),
+    ("dWorldSetBroadphaseB200", None, [_vp, _i]),
     ("dWorldSetSolverModeB200", None, [_vp, _i, _i]),
     ("dWorldSetContactUnitsB200", None, [_vp, _i]),
     ("dWorldGetStatsB200", None, [_vp, C.POINTER(StepStats)]),
@@ -229,6 +230,9 @@ class World:
 
     def set_solver_mode(self, mode=0, env_group=0):
         self.L.dWorldSetSolverModeB200(self.w, int(mode), int(env_group))
+
+    def set_broadphase(self, mode):
+        self.L.dWorldSetBroadphaseB200(self.w, int(mode))
 
     def set_contact_units(self, per_contact):
         self.L.dWorldSetContactUnitsB200(self.w, int(per_contact))

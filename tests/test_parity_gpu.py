@@ -144,6 +144,30 @@ def test_batched_worlds_are_independent_bit_exact():
             assert np.array_equal(sb[k][w * 128:(w + 1) * 128], s1[k]), (w, k)
 
 
+@pytest.mark.parametrize("name", ["batch8", "c1_low", "soup200"])
+def test_env_broadphase_equals_grid_broadphase(name):
+    """The all-pairs-per-env sweep and the uniform-grid sweep must hand the narrowphase the same pair SET
+    (dxHashSpace::collide's, per the golden test) and therefore the same contacts; only list order differs."""
+    sc = _scene(name)
+    got = []
+    for mode in (0, 1):
+        ew = util.engine_world(sc)
+        ew.set_broadphase(mode)
+        ew.collide()      # same input state for both (a tick would let the list order reach the last bits)
+        by_pair = _engine_contacts_by_pair(ew)
+        st = ew.stats()
+        got.append((by_pair, st))
+        ew.close()
+    (a, sa), (b, sb) = got
+    assert sa["n_pairs"] == sb["n_pairs"] and sa["n_contacts"] == sb["n_contacts"]
+    assert sorted(a) == sorted(b)
+    for k in a:
+        for x, y in zip(a[k], b[k]):
+            assert np.array_equal(x, y), k
+    if name != "batch8":
+        assert sa["grid_dims"][0] > 0 and sb["grid_dims"][0] == 0  # the second run really took the env path
+
+
 def _max_penetration(ew, sc):
     """deepest contact among pairs that involve a dynamic body (the static map boxes overlap each
     other, and a kinematic player sphere sits inside the slanted wall by construction)"""
