@@ -534,12 +534,12 @@ __device__ __forceinline__ void st_fc(float4 *p, float4 v) {
 // arrays (indexed by body) or, on the island path, the env's copy in shared memory (indexed by local body)
 template <bool L2ONLY, bool SINGLE = false>
 __device__ __forceinline__ void solve_manifold_core(int s, const int4 rec, RowRec cur, const SolverArrays &S, float4 *fcp,
-                                                    const float4 *invp) {
+                                                    const float4 *invp, int fs = 2, int fo = 1) {
     const int b1 = rec.x, b2 = rec.y, nc = SINGLE ? 1 : rec.z; // SINGLE: per-contact units, no contact loop
     const bool two = b2 >= 0;
     FC f1, f2;
     {
-        const float4 a = ld_fc<L2ONLY>(&fcp[2 * b1]), b = ld_fc<L2ONLY>(&fcp[2 * b1 + 1]);
+        const float4 a = ld_fc<L2ONLY>(&fcp[fs * b1]), b = ld_fc<L2ONLY>(&fcp[fs * b1 + fo]);
         f1.l = v3(a); f1.a = v3(b);
     }
     const float4 i10 = invp[3 * b1], i11 = invp[3 * b1 + 1], i12 = invp[3 * b1 + 2];
@@ -549,7 +549,7 @@ __device__ __forceinline__ void solve_manifold_core(int s, const int4 rec, RowRe
     float invM2 = 0.f;
     f2.l = v3(0.f, 0.f, 0.f); f2.a = f2.l;
     if (two) {
-        const float4 a = ld_fc<L2ONLY>(&fcp[2 * b2]), b = ld_fc<L2ONLY>(&fcp[2 * b2 + 1]);
+        const float4 a = ld_fc<L2ONLY>(&fcp[fs * b2]), b = ld_fc<L2ONLY>(&fcp[fs * b2 + fo]);
         f2.l = v3(a); f2.a = v3(b);
         const float4 i20 = invp[3 * b2], i21 = invp[3 * b2 + 1], i22 = invp[3 * b2 + 2];
         iI2 = M3{v3(i20), v3(i21), v3(i22)};
@@ -583,18 +583,19 @@ __device__ __forceinline__ void solve_manifold_core(int s, const int4 rec, RowRe
         S.lam[si] = lam;
         if (!SINGLE) cur = nxt;
     }
-    st_fc<L2ONLY>(&fcp[2 * b1], make_float4(f1.l.x, f1.l.y, f1.l.z, 0.f));
-    st_fc<L2ONLY>(&fcp[2 * b1 + 1], make_float4(f1.a.x, f1.a.y, f1.a.z, 0.f));
+    st_fc<L2ONLY>(&fcp[fs * b1], make_float4(f1.l.x, f1.l.y, f1.l.z, 0.f));
+    st_fc<L2ONLY>(&fcp[fs * b1 + fo], make_float4(f1.a.x, f1.a.y, f1.a.z, 0.f));
     if (two) {
-        st_fc<L2ONLY>(&fcp[2 * b2], make_float4(f2.l.x, f2.l.y, f2.l.z, 0.f));
-        st_fc<L2ONLY>(&fcp[2 * b2 + 1], make_float4(f2.a.x, f2.a.y, f2.a.z, 0.f));
+        st_fc<L2ONLY>(&fcp[fs * b2], make_float4(f2.l.x, f2.l.y, f2.l.z, 0.f));
+        st_fc<L2ONLY>(&fcp[fs * b2 + fo], make_float4(f2.a.x, f2.a.y, f2.a.z, 0.f));
     }
 }
 
 template <bool L2ONLY, bool SINGLE = false>
-__device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, float4 *fcp, const float4 *invp) {
+__device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, float4 *fcp, const float4 *invp, int fs = 2,
+                                               int fo = 1) {
     const int4 rec = __ldg(&S.mrec[s]);
-    solve_manifold_core<L2ONLY, SINGLE>(s, rec, load_rows(S, (size_t)s), S, fcp, invp);
+    solve_manifold_core<L2ONLY, SINGLE>(s, rec, load_rows(S, (size_t)s), S, fcp, invp, fs, fo);
 }
 
 // grid-wide barrier of the persistent solver (all CTAs are co-resident: cooperative launch).  One
@@ -787,33 +788,9 @@ __device__ unsigned long long g_env_prof[8];
 #define PROF_ADD(i, a, b)
 #endif
 
-#ifndef OB_ENV_PIPE
-#define OB_ENV_PIPE 0
-#endif
 #ifndef OB_ENV_CTAS
-#define OB_ENV_CTAS 5 // CTAs per SM the register budget is sized for (measured: 5 > 4, 6, 8 on C4)
+#define OB_ENV_CTAS 5 // CTAs per SM the register budget is sized for (measured on C4: 5 >= 4 > 6, 8)
 #endif
-struct EnvPre {
-    int s; // solver slot, -1: this lane has no unit in the pass
-    int4 rec;
-    float4 q0, q1, q2;
-#if OB_ENV_PIPE >= 2
-    float4 q3, q4;
-#endif
-};
-__device__ __forceinline__ EnvPre env_fetch(const SolverArrays &S, int ms, const int *cstart, int c, int j, int g, int G) {
-    EnvPre p;
-    const int s = ms + cstart[c] + g + j * G;
-    p.s = (s < ms + cstart[c + 1]) ? s : -1;
-    if (p.s >= 0) {
-        p.rec = __ldg(&S.mrec[s]);
-        p.q0 = __ldg(&S.q0[s]); p.q1 = __ldg(&S.q1[s]); p.q2 = __ldg(&S.q2[s]);
-#if OB_ENV_PIPE >= 2
-        p.q3 = __ldg(&S.q3[s]); p.q4 = __ldg(&S.q4[s]);
-#endif
-    }
-    return p;
-}
 
 // The W = 32/G envs that share a warp run in LOCKSTEP: every loop bound is made warp-uniform (the
 // maximum over the warp's groups) and lanes without work are predicated off, so the groups never
@@ -949,11 +926,15 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
         }
         __syncwarp();
         float4 *fcp = B.fc;
+        int fs = 2, fo = 1; // fc layout: linear part at fs * b, angular part fo further on
         const float4 *invp = B.inv;
         if (stage) { // colouring scratch is dead: reuse the region for fc (zero) and inv (copied once)
-            for (int i = g; i < 2 * nbod; i += G) sm_fc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = g; i < 2 * mb; i += G) sm_fc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int i = g; i < 3 * nbod; i += G) sm_inv[i] = B.inv[3 * (size_t)fb + i];
             fcp = sm_fc;
+            // split layout in shared memory: with the linear and angular parts interleaved (32 B per body) a
+            // quarter-warp's 16-byte accesses can only reach every other bank group -- a built-in 2-way conflict
+            fs = 1; fo = mb;
             invp = sm_inv;
             __syncwarp();
         }
@@ -962,42 +943,12 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
         const int novf = cstart[OVERFLOW_COLOUR + 1] - cstart[OVERFLOW_COLOUR];
         const bool any_ovf = __any_sync(FULL, novf > 0);
         for (int it = 0; it < cfg.iters; it++) {
-#if OB_ENV_PIPE
-            if (SINGLE) {
-                // software pipeline over the flattened (colour, pass) sequence: the read-only part of the
-                // NEXT pass's records is in flight while this pass is solved (rows and mrec never change
-                // during the iterations; lambda is read at use)
-                EnvPre cur = env_fetch(S, ms, cstart, 0, 0, g, G);
-                for (int c = 0; c < ncol; c++) {
-                    const int t = (__reduce_max_sync(FULL, cstart[c + 1] - cstart[c]) + G - 1) / G;
-                    for (int j = 0; j < t; j++) {
-                        EnvPre nxt;
-                        nxt.s = -1;
-                        if (j + 1 < t) nxt = env_fetch(S, ms, cstart, c, j + 1, g, G);
-                        else if (c + 1 < ncol) nxt = env_fetch(S, ms, cstart, c + 1, 0, g, G);
-                        if (cur.s >= 0) {
-                            RowRec r;
-                            r.q0 = cur.q0; r.q1 = cur.q1; r.q2 = cur.q2;
-#if OB_ENV_PIPE >= 2
-                            r.q3 = cur.q3; r.q4 = cur.q4;
-#else
-                            r.q3 = __ldg(&S.q3[cur.s]); r.q4 = __ldg(&S.q4[cur.s]);
-#endif
-                            r.lam = S.lam[cur.s];
-                            solve_manifold_core<false, true>(cur.s, cur.rec, r, S, fcp, invp);
-                        }
-                        cur = nxt;
-                    }
-                    __syncwarp();
-                }
-            } else
-#endif
             for (int c = 0; c < ncol; c++) {
                 const int s0 = ms + cstart[c], s1 = ms + cstart[c + 1];
                 const int t = (__reduce_max_sync(FULL, s1 - s0) + G - 1) / G;
                 for (int j = 0; j < t; j++) {
                     const int s = s0 + g + j * G;
-                    if (s < s1) solve_manifold<false, SINGLE>(s, S, fcp, invp);
+                    if (s < s1) solve_manifold<false, SINGLE>(s, S, fcp, invp, fs, fo);
                 }
                 __syncwarp();
             }
@@ -1005,19 +956,22 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
                 // manifolds that found no free colour (> 64 neighbours): one lane per env, in order
                 if (g == 0)
                     for (int s = ms + cstart[OVERFLOW_COLOUR]; s < ms + cstart[OVERFLOW_COLOUR + 1]; s++)
-                        solve_manifold<false, SINGLE>(s, S, fcp, invp);
+                        solve_manifold<false, SINGLE>(s, S, fcp, invp, fs, fo);
                 __syncwarp();
             }
         }
         if (fused) { // solver tail: velocity update, dxStepBody, snapshot pack for this env's bodies
             for (int i = g; i < nbod; i += G) {
-                const float4 fl = stage ? sm_fc[2 * i] : B.fc[2 * (size_t)(fb + i)];
-                const float4 fa = stage ? sm_fc[2 * i + 1] : B.fc[2 * (size_t)(fb + i) + 1];
+                const float4 fl = stage ? sm_fc[i] : B.fc[2 * (size_t)(fb + i)];
+                const float4 fa = stage ? sm_fc[mb + i] : B.fc[2 * (size_t)(fb + i) + 1];
                 integrate_body(fb + i, B, cfg.h, fl, fa);
             }
             __syncwarp();
         } else if (stage) { // hand the accumulators to k_integrate
-            for (int i = g; i < 2 * nbod; i += G) B.fc[2 * (size_t)fb + i] = sm_fc[i];
+            for (int i = g; i < nbod; i += G) {
+                B.fc[2 * (size_t)(fb + i)] = sm_fc[i];
+                B.fc[2 * (size_t)(fb + i) + 1] = sm_fc[mb + i];
+            }
             __syncwarp();
         }
         PROF_T(t4);
