@@ -672,21 +672,25 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // measured).  Per-phase timing on the 1 M-body pile (profiles/README.md): the large early colours run at
 // ~4.9 TB/s of rows + body data, the small late colours sit on a ~6 us latency floor.  (Prefetching the
 // next phase's rows with cp.async before the barrier, L2 evict-first hints on the rows and a persisting-L2
-// window on the body data were all measured and did not help; they are not in the code.)
+// window on the body data, and fetching each thread's first record + rows of the next phase into registers
+// before the barrier, were all measured and did not help; they are not in the code.)
 __global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays S, BodyArrays B, StepConfig cfg) {
     const int n = *M.count;
     const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
     unsigned *bar = reinterpret_cast<unsigned *>(&M.meta[6]);
     unsigned target = 0;
+    __shared__ int cs[OVERFLOW_COLOUR + 2]; // colour bucket starts: read once, not once per phase
+    if (threadIdx.x < OVERFLOW_COLOUR + 2) cs[threadIdx.x] = M.colour_start[threadIdx.x];
+    __syncthreads();
     if (n > 0) {
         const int ncol = M.meta[0];
-        const int ovf0 = M.colour_start[OVERFLOW_COLOUR], ovf1 = M.colour_start[OVERFLOW_COLOUR + 1];
+        const int ovf0 = cs[OVERFLOW_COLOUR], ovf1 = cs[OVERFLOW_COLOUR + 1];
 #ifdef OB_ENV_PROFILE
         if (gt == 0) g_phase_t[0] = gtimer();
 #endif
         for (int it = 0; it < cfg.iters; it++) {
             for (int c = 0; c < ncol; c++) {
-                const int s0 = M.colour_start[c], s1 = M.colour_start[c + 1];
+                const int s0 = cs[c], s1 = cs[c + 1];
                 for (int s = s0 + gt; s < s1; s += gs) solve_manifold<true>(s, S, B.fc, B.inv);
                 grid_barrier(bar, target);
 #ifdef OB_ENV_PROFILE
