@@ -99,6 +99,9 @@ void eng_destroy(Engine *e) {
     dev_free(G.col); dev_free(G.env); dev_free(G.mesh); dev_free(G.alive); dev_free(G.amin); dev_free(G.amax);
     BroadPhase &bp = e->bp;
     dev_free(e->EB.first); dev_free(e->EB.count); dev_free(e->EB.shared);
+    if (e->h_patch) cudaFreeHost(e->h_patch);
+    if (e->d_patch) cudaFree(e->d_patch);
+    if (e->ev_patch) cudaEventDestroy(e->ev_patch);
     dev_free(bp.acc); dev_free(bp.gp); dev_free(bp.counters); dev_free(bp.keys); dev_free(bp.idx);
     dev_free(bp.s_min); dev_free(bp.s_max); dev_free(bp.s_flt); dev_free(bp.cell_start); dev_free(bp.cell_end);
     dev_free(bp.cnt); dev_free(bp.pairs); dev_free(bp.sweep_tmp); dev_free(bp.sweep_tot);
@@ -149,7 +152,8 @@ int eng_add_body(Engine *e) {
     b.tacc.insert(b.tacc.end(), {0.f, 0.f, 0.f, 0.f});
     b.flags.push_back(0);
     b.env.push_back(0);
-    e->bodies_dirty = true;
+    if (e->n_b_dev == 0) e->bodies_dirty = true; // nothing on the device yet: the first sync uploads everything
+    else eng_mark_body_fields(e, i, FLD_ALL);
     return i;
 }
 
@@ -166,7 +170,8 @@ int eng_add_geom(Engine *e) {
     g.col.push_back(0xffffffffu);
     g.env.push_back(-1);
     g.alive.push_back(1);
-    e->geoms_dirty = true;
+    if (e->n_g_dev == 0) e->geoms_dirty = true;
+    else eng_mark_geom(e, i);
     return i;
 }
 
@@ -206,8 +211,11 @@ void eng_mark_bodies_dirty(Engine *e) { e->bodies_dirty = true; }
 void eng_mark_geoms_dirty(Engine *e) { e->geoms_dirty = true; }
 void eng_mark_forces_dirty(Engine *e) { e->forces_dirty = true; }
 void eng_set_num_envs(Engine *e, int n) {
+    if ((n < 1 ? 1 : n) == e->n_envs) return;
+    eng_sync_to_host(e);
     e->n_envs = n < 1 ? 1 : n;
-    e->geoms_dirty = true; // the per-env geom ranges depend on the env count
+    e->geoms_dirty = true; // the per-env body and geom ranges depend on the env count
+    e->bodies_dirty = true;
     // measured on C4 (profiles/README.md): spreading the colours makes MORE phases whose cost is set by
     // the longest manifold in the phase, so lowest-free colouring stays the default for batched worlds too
 }
@@ -347,11 +355,181 @@ static void upload(T *dst, const void *src, size_t count, cudaStream_t st) {
     if (count) OB_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
 }
 
+// ---- incremental ingestion --------------------------------------------------------------------
+// A spawn (reference: MSGTYPE_S_NEW_BODY -> AddBody, src/main.c:178-182, 695-733) or a per-tick setter
+// (dBodySetPosition of a player body) touches a handful of entries of a world that may hold millions.
+// Such edits are queued as (index, field mask); the next collide/step packs them into one pinned
+// staging buffer, sends it with one copy and applies it with one scatter kernel -- no device-to-host
+// refresh, no re-upload of the arrays, no synchronisation per body.
+struct BodyPatch {
+    int idx, mask, flags, env;
+    int local, pad0, pad1, pad2;
+    float4 pos, quat, lvel, avel, facc, tacc;
+    float4 R[3], I[3], invI[3];
+};
+struct GeomPatch {
+    int idx, type, body, env;
+    unsigned cat, col;
+    int alive, mesh;
+    float4 dims, pos;
+    float4 R[3];
+};
+
+__global__ void __launch_bounds__(128) k_patch_bodies(BodyArrays B, const BodyPatch *__restrict__ p, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const BodyPatch q = p[t];
+    const int i = q.idx, m = q.mask;
+    const bool fresh_body = m & 64;
+    float4 pos = fresh_body ? q.pos : B.pos[i], lv = fresh_body ? q.lvel : B.lvel[i];
+    if (m & FLD_POS) { pos.x = q.pos.x; pos.y = q.pos.y; pos.z = q.pos.z; }
+    if (m & FLD_LVEL) { lv.x = q.lvel.x; lv.y = q.lvel.y; lv.z = q.lvel.z; }
+    if (m & FLD_MASS) {
+        pos.w = q.pos.w; lv.w = q.lvel.w; // inverse mass rides in pos.w, mass in lvel.w
+        B.flags[i] = q.flags;
+        for (int k = 0; k < 3; k++) { B.I[3 * i + k] = q.I[k]; B.invI[3 * i + k] = q.invI[k]; }
+    }
+    if (m & (FLD_POS | FLD_MASS)) B.pos[i] = pos;
+    if (m & (FLD_LVEL | FLD_MASS)) B.lvel[i] = lv;
+    if (m & FLD_ROT) {
+        B.quat[i] = q.quat;
+        for (int k = 0; k < 3; k++) B.R[3 * i + k] = q.R[k];
+    }
+    if (m & FLD_AVEL) B.avel[i] = q.avel;
+    if (m & FLD_FORCE) { B.facc[i] = q.facc; B.tacc[i] = q.tacc; }
+    if (fresh_body) { B.env[i] = q.env; B.local[i] = q.local; }
+}
+
+__global__ void __launch_bounds__(128) k_patch_geoms(GeomArrays G, const GeomPatch *__restrict__ p, int n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const GeomPatch q = p[t];
+    const int i = q.idx;
+    G.type[i] = q.type; G.body[i] = q.body; G.env[i] = q.env; G.cat[i] = q.cat; G.col[i] = q.col;
+    G.alive[i] = q.alive; G.mesh[i] = q.mesh; G.dims[i] = q.dims;
+    if (q.body < 0) { // body-attached geoms take their pose from the body at every collide
+        G.pos[i] = q.pos;
+        for (int k = 0; k < 3; k++) G.R[3 * i + k] = q.R[k];
+    }
+}
+
+static void *patch_stage(Engine *e, size_t bytes) {
+    if (e->patch_inflight) { // the previous batch may still be reading the staging buffer
+        OB_CUDA(cudaEventSynchronize(e->ev_patch));
+        e->patch_inflight = false;
+    }
+    if (bytes > e->cap_patch) {
+        if (e->h_patch) OB_CUDA(cudaFreeHost(e->h_patch));
+        if (e->d_patch) OB_CUDA(cudaFree(e->d_patch));
+        e->cap_patch = bytes * 2 + 4096;
+        OB_CUDA(cudaMallocHost(&e->h_patch, e->cap_patch));
+        OB_CUDA(cudaMalloc(&e->d_patch, e->cap_patch));
+    }
+    if (!e->ev_patch) OB_CUDA(cudaEventCreateWithFlags(&e->ev_patch, cudaEventDisableTiming));
+    return e->h_patch;
+}
+
+static inline float4 ld4(const std::vector<float> &v, size_t i) { return make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]); }
+
+// per-env body ranges: index of a body relative to the first body of its env makes the colouring priorities,
+// and with them the Gauss-Seidel order of a world, independent of which other worlds share the batch;
+// contiguous envs let the island solver stage body data in shared memory.  Bodies are only ever appended.
+static int env_note_body(Engine *e, int i, int en) {
+    if (en < 0 || en >= (int)e->env_first.size()) { e->env_contig = false; e->env_max_local = std::max(e->env_max_local, i); return i; }
+    if (e->env_cnt[en] == 0) e->env_first[en] = i;
+    else if (e->env_first[en] + e->env_cnt[en] != i) e->env_contig = false;
+    e->env_cnt[en]++;
+    const int local = i - e->env_first[en];
+    e->env_max_local = std::max(e->env_max_local, local);
+    return local;
+}
+
+static void env_upload_tables(Engine *e, cudaStream_t st) {
+    const size_t ne = e->env_first.size();
+    if ((int)ne > e->cap_env_bodies) {
+        dev_realloc(e->E.first_body, 0, ne + 1, st, false);
+        dev_realloc(e->E.n_body, 0, ne + 1, st, false);
+        e->cap_env_bodies = (int)ne;
+    }
+    e->E.max_bodies = e->env_max_local + 1;
+    e->E.contiguous = e->env_contig ? 1 : 0;
+    upload(e->E.first_body, e->env_first.data(), ne, st);
+    upload(e->E.n_body, e->env_cnt.data(), ne, st);
+}
+
+// per-env geom ranges of the all-pairs-per-env broadphase (same append-only bookkeeping)
+static void envg_note_geom(Engine *e, int i) {
+    const HostGeoms &g = e->hg;
+    const int ne = (int)e->envg_first.size();
+    if (ne == 1) { e->envg_cnt[0] = i + 1; e->envg_max = i + 1; return; }
+    const int en = g.env[i];
+    if (en < 0) { e->envg_shared.push_back(i); return; }
+    if (en >= ne) { e->envg_ok = false; return; }
+    if (e->envg_cnt[en] == 0) e->envg_first[en] = i;
+    else if (e->envg_first[en] + e->envg_cnt[en] != i) e->envg_ok = false; // not one contiguous range
+    e->envg_cnt[en]++;
+    e->envg_max = std::max(e->envg_max, e->envg_cnt[en]);
+}
+
+static void envg_upload_tables(Engine *e, cudaStream_t st) {
+    EnvBroad &eb = e->EB;
+    const int ne = (int)e->envg_first.size();
+    bool ok = e->broad_mode != 0 && e->hg.n > 0 && e->envg_ok;
+    if (ok && ne == 1) ok = e->hg.n <= (e->broad_mode == 1 ? 4096 : 1024);
+    else if (ok) ok = e->envg_max <= 2048 && e->envg_shared.size() <= 256;
+    eb.enabled = 0;
+    if (!ok) return;
+    if (ne > e->cap_eb_envs) {
+        dev_realloc(eb.first, 0, (size_t)ne, st, false); dev_realloc(eb.count, 0, (size_t)ne, st, false);
+        e->cap_eb_envs = ne;
+    }
+    if ((int)e->envg_shared.size() > e->cap_eb_shared) {
+        const size_t cap = e->envg_shared.size() + 64;
+        dev_realloc(eb.shared, 0, cap, st, false);
+        e->cap_eb_shared = (int)cap;
+    }
+    upload(eb.first, e->envg_first.data(), (size_t)ne, st); upload(eb.count, e->envg_cnt.data(), (size_t)ne, st);
+    upload(eb.shared, e->envg_shared.data(), e->envg_shared.size(), st);
+    eb.enabled = 1;
+    eb.single = ne == 1 ? 1 : 0;
+    eb.n_shared = (int)e->envg_shared.size();
+    eb.n_alive = e->envg_alive;
+}
+
+static void clear_dirty_bodies(Engine *e) {
+    for (int i : e->dirty_b) e->mask_b[i] = 0;
+    e->dirty_b.clear();
+}
+static void clear_dirty_geoms(Engine *e) {
+    for (int i : e->dirty_g) e->mask_g[i] = 0;
+    e->dirty_g.clear();
+}
+
+void eng_mark_body_fields(Engine *e, int i, int fields) {
+    if (fields & FLD_FORCE) { // accumulators are consumed by the next step: remember whose mirror to clear then
+        if ((int)e->inforce_b.size() < e->hb.n) e->inforce_b.resize((size_t)e->hb.n, 0);
+        if (!e->inforce_b[i]) { e->inforce_b[i] = 1; e->force_b.push_back(i); }
+    }
+    if (e->bodies_dirty) return; // a full upload is pending anyway
+    if ((int)e->mask_b.size() < e->hb.n) e->mask_b.resize((size_t)e->hb.n, 0);
+    if (!e->mask_b[i]) e->dirty_b.push_back(i);
+    e->mask_b[i] |= (unsigned char)fields;
+}
+void eng_mark_geom(Engine *e, int i) {
+    if (e->geoms_dirty) return;
+    if ((int)e->mask_g.size() < e->hg.n) e->mask_g.resize((size_t)e->hg.n, 0);
+    if (!e->mask_g[i]) e->dirty_g.push_back(i);
+    e->mask_g[i] = 1;
+}
+
 void eng_sync_to_device(Engine *e) {
     OB_CUDA(cudaSetDevice(e->device));
-    if (e->host_stale && (e->bodies_dirty)) {
-        // host wrote into stale mirrors: bring the device state back first so untouched bodies survive
-        // (callers that edit bodies call eng_sync_to_host before editing; this is a safety net)
+    // A full upload sends the host mirrors as they are, so it needs them coherent.  Setters queue field
+    // patches instead; only the bulk calls (and the very first sync) ask for a full upload, and they
+    // refresh the mirrors first (shim: fresh()).
+    if (e->bodies_dirty && e->host_stale && e->n_b_dev > 0) {
+        fprintf(stderr, "libode_b200: internal error: full upload requested over stale host mirrors\n");
+        abort();
     }
     engine_ensure_capacity(e);
     cudaStream_t st = e->st;
@@ -364,44 +542,53 @@ void eng_sync_to_device(Engine *e) {
         upload(e->B.invI, b.invI.data(), 3 * n, st); upload(e->B.facc, b.facc.data(), n, st);
         upload(e->B.tacc, b.tacc.data(), n, st); upload(e->B.flags, b.flags.data(), n, st);
         {
-            // index of a body relative to the first body of its env: makes the colouring priorities, and
-            // with them the Gauss-Seidel order of a world, independent of which other worlds share the batch
-            std::vector<int> first((size_t)std::max(e->n_envs, 1), INT32_MAX), local(n);
-            for (size_t i = 0; i < n; i++) {
-                const int en = b.env[i];
-                if (en >= 0 && en < (int)first.size() && (int)i < first[en]) first[en] = (int)i;
-            }
-            for (size_t i = 0; i < n; i++) {
-                const int en = b.env[i];
-                local[i] = (en >= 0 && en < (int)first.size()) ? (int)i - first[en] : (int)i;
-            }
-            int max_local = 0;
-            for (size_t i = 0; i < n; i++) max_local = std::max(max_local, local[i]);
-            e->E.max_bodies = max_local + 1;
-            // per-env body ranges; contiguous envs let the island solver stage body data in shared memory
-            std::vector<int> cnt(first.size(), 0);
-            for (size_t i = 0; i < n; i++) if (b.env[i] >= 0 && b.env[i] < (int)first.size()) cnt[b.env[i]]++;
-            bool contiguous = true;
-            for (size_t i = 0; i < n && contiguous; i++) {
-                const int en = b.env[i];
-                if (en < 0 || en >= (int)first.size() || local[i] >= cnt[en]) contiguous = false;
-            }
-            for (auto &f : first) if (f == INT32_MAX) f = 0;
-            e->E.contiguous = contiguous ? 1 : 0;
-            if ((int)first.size() > e->cap_env_bodies) {
-                dev_realloc(e->E.first_body, 0, first.size() + 1, st, false);
-                dev_realloc(e->E.n_body, 0, first.size() + 1, st, false);
-                e->cap_env_bodies = (int)first.size();
-            }
-            upload(e->E.first_body, first.data(), first.size(), st);
-            upload(e->E.n_body, cnt.data(), cnt.size(), st);
+            const size_t ne = (size_t)std::max(e->n_envs, 1);
+            e->env_first.assign(ne, 0); e->env_cnt.assign(ne, 0);
+            e->env_max_local = 0; e->env_contig = true;
+            std::vector<int> local(n);
+            for (size_t i = 0; i < n; i++) local[i] = env_note_body(e, (int)i, b.env[i]);
+            env_upload_tables(e, st);
             upload(e->B.local, local.data(), n, st);
             upload(e->B.env, b.env.data(), n, st);
             OB_CUDA(cudaStreamSynchronize(st)); // `local` is a temporary
         }
         e->bodies_dirty = false;
         e->forces_dirty = false;
-    } else if (e->forces_dirty) {
+        e->n_b_dev = b.n;
+        clear_dirty_bodies(e);
+    } else if (!e->dirty_b.empty()) {
+        const HostBodies &b = e->hb;
+        const size_t nd = e->dirty_b.size();
+        BodyPatch *hp = static_cast<BodyPatch *>(patch_stage(e, nd * sizeof(BodyPatch)));
+        std::sort(e->dirty_b.begin(), e->dirty_b.end()); // new bodies join their env ranges in index order
+        bool grew = false;
+        for (size_t k = 0; k < nd; k++) {
+            const int i = e->dirty_b[k];
+            BodyPatch &q = hp[k];
+            q.idx = i; q.mask = e->mask_b[i]; q.flags = b.flags[i]; q.env = b.env[i];
+            q.local = 0; q.pad0 = q.pad1 = q.pad2 = 0;
+            if (i >= e->n_b_dev) { // appended since the last sync
+                q.mask = FLD_ALL | 64;
+                q.local = env_note_body(e, i, b.env[i]);
+                grew = true;
+            }
+            q.pos = ld4(b.pos, i); q.quat = ld4(b.quat, i); q.lvel = ld4(b.lvel, i); q.avel = ld4(b.avel, i);
+            q.facc = ld4(b.facc, i); q.tacc = ld4(b.tacc, i);
+            for (int r = 0; r < 3; r++) {
+                q.R[r] = ld4(b.R, 3 * (size_t)i + r); q.I[r] = ld4(b.I, 3 * (size_t)i + r);
+                q.invI[r] = ld4(b.invI, 3 * (size_t)i + r);
+            }
+        }
+        OB_CUDA(cudaMemcpyAsync(e->d_patch, hp, nd * sizeof(BodyPatch), cudaMemcpyHostToDevice, st));
+        k_patch_bodies<<<(unsigned)((nd + 127) / 128), 128, 0, st>>>(e->B, static_cast<const BodyPatch *>(e->d_patch), (int)nd);
+        OB_CHECK_KERNEL("k_patch_bodies", st);
+        OB_CUDA(cudaEventRecord(e->ev_patch, st));
+        e->patch_inflight = true;
+        if (grew) env_upload_tables(e, st);
+        e->n_b_dev = b.n;
+        clear_dirty_bodies(e);
+    }
+    if (e->forces_dirty) { // bulk force upload (whole arrays)
         const HostBodies &b = e->hb;
         upload(e->B.facc, b.facc.data(), (size_t)b.n, st);
         upload(e->B.tacc, b.tacc.data(), (size_t)b.n, st);
@@ -418,56 +605,55 @@ void eng_sync_to_device(Engine *e) {
         upload(e->G.col, g.col.data(), n, st); upload(e->G.env, g.env.data(), n, st);
         upload(e->G.alive, g.alive.data(), n, st);
         upload(e->G.mesh, mesh.data(), n, st);
-        // all-pairs-per-env broadphase: usable when every env's geoms are one index range of modest size
         {
-            EnvBroad &eb = e->EB;
-            eb.enabled = 0;
-            const int ne = std::max(e->n_envs, 1);
-            std::vector<int> first((size_t)ne, 0), cnt((size_t)ne, 0), shared;
-            int n_alive = 0;
-            for (size_t i = 0; i < n; i++) n_alive += g.alive[i] ? 1 : 0;
-            bool ok = e->broad_mode != 0 && n > 0;
-            if (ok && ne == 1) {
-                ok = n <= (e->broad_mode == 1 ? 4096u : 1024u);
-                first[0] = 0; cnt[0] = (int)n;
-            } else if (ok) {
-                int maxc = 0;
-                for (size_t i = 0; i < n && ok; i++) {
-                    const int en = g.env[i];
-                    if (en < 0) { shared.push_back((int)i); continue; }
-                    if (en >= ne) { ok = false; break; }
-                    if (cnt[en] == 0) first[en] = (int)i;
-                    else if (first[en] + cnt[en] != (int)i) ok = false; // not one contiguous range
-                    cnt[en]++;
-                    maxc = std::max(maxc, cnt[en]);
-                }
-                ok = ok && maxc <= 2048 && shared.size() <= 256;
-            }
-            if (ok) {
-                if (ne > e->cap_eb_envs) {
-                    dev_realloc(eb.first, 0, (size_t)ne, st, false); dev_realloc(eb.count, 0, (size_t)ne, st, false);
-                    e->cap_eb_envs = ne;
-                }
-                if ((int)shared.size() > e->cap_eb_shared) {
-                    dev_realloc(eb.shared, 0, shared.size(), st, false);
-                    e->cap_eb_shared = (int)shared.size();
-                }
-                upload(eb.first, first.data(), (size_t)ne, st); upload(eb.count, cnt.data(), (size_t)ne, st);
-                upload(eb.shared, shared.data(), shared.size(), st);
-                eb.enabled = 1;
-                eb.single = ne == 1 ? 1 : 0;
-                eb.n_shared = (int)shared.size();
-                eb.n_alive = n_alive;
-            }
-            OB_CUDA(cudaStreamSynchronize(st)); // `mesh`, `first`, `cnt`, `shared` are temporaries
+            const size_t ne = (size_t)std::max(e->n_envs, 1);
+            e->envg_first.assign(ne, 0); e->envg_cnt.assign(ne, 0); e->envg_shared.clear();
+            e->envg_max = 0; e->envg_ok = true; e->envg_alive = 0;
+            for (size_t i = 0; i < n; i++) { envg_note_geom(e, (int)i); e->envg_alive += g.alive[i] ? 1 : 0; }
+            envg_upload_tables(e, st);
         }
+        OB_CUDA(cudaStreamSynchronize(st)); // `mesh` is a temporary
         e->geoms_dirty = false;
+        e->n_g_dev = g.n;
+        clear_dirty_geoms(e);
+    } else if (!e->dirty_g.empty()) {
+        const HostGeoms &g = e->hg;
+        const size_t nd = e->dirty_g.size();
+        // the body batch may still be in flight in the shared staging buffer: geoms get the second half
+        if (e->patch_inflight) { OB_CUDA(cudaEventSynchronize(e->ev_patch)); e->patch_inflight = false; }
+        GeomPatch *hp = static_cast<GeomPatch *>(patch_stage(e, nd * sizeof(GeomPatch)));
+        std::sort(e->dirty_g.begin(), e->dirty_g.end());
+        bool tables = false;
+        for (size_t k = 0; k < nd; k++) {
+            const int i = e->dirty_g[k];
+            GeomPatch &q = hp[k];
+            q.idx = i; q.type = g.type[i]; q.body = g.body[i]; q.env = g.env[i]; q.cat = g.cat[i]; q.col = g.col[i];
+            q.alive = g.alive[i]; q.mesh = g.type[i] == G_TRIMESH ? (int)g.dims[4 * (size_t)i] : 0;
+            q.dims = ld4(g.dims, i); q.pos = ld4(g.pos, i);
+            for (int r = 0; r < 3; r++) q.R[r] = ld4(g.R, 3 * (size_t)i + r);
+            if (i >= e->n_g_dev) { envg_note_geom(e, i); e->envg_alive += g.alive[i] ? 1 : 0; tables = true; }
+        }
+        OB_CUDA(cudaMemcpyAsync(e->d_patch, hp, nd * sizeof(GeomPatch), cudaMemcpyHostToDevice, st));
+        k_patch_geoms<<<(unsigned)((nd + 127) / 128), 128, 0, st>>>(e->G, static_cast<const GeomPatch *>(e->d_patch), (int)nd);
+        OB_CHECK_KERNEL("k_patch_geoms", st);
+        OB_CUDA(cudaEventRecord(e->ev_patch, st));
+        e->patch_inflight = true;
+        // alive flags or env ids of existing geoms changed: recount (the ranges themselves are append-only)
+        int alive = 0;
+        for (int i = 0; i < g.n; i++) alive += g.alive[i] ? 1 : 0;
+        if (alive != e->envg_alive) { e->envg_alive = alive; tables = true; }
+        if (tables) envg_upload_tables(e, st);
+        else e->EB.n_alive = e->envg_alive;
+        e->n_g_dev = g.n;
+        clear_dirty_geoms(e);
     }
 }
 
 void eng_sync_to_host(Engine *e) {
     if (!e->host_stale) return;
     OB_CUDA(cudaSetDevice(e->device));
+    // queued field edits live only in the mirrors: send them before the mirrors are overwritten
+    if (!e->dirty_b.empty() || !e->dirty_g.empty()) eng_sync_to_device(e);
     HostBodies &b = e->hb;
     const size_t n = (size_t)std::min(b.n, e->B.n);
     cudaStream_t st = e->st;
@@ -479,9 +665,6 @@ void eng_sync_to_host(Engine *e) {
         OB_CUDA(cudaMemcpyAsync(b.avel.data(), e->B.avel, n * 16, cudaMemcpyDeviceToHost, st));
     }
     OB_CUDA(cudaStreamSynchronize(st));
-    // accumulators were consumed by the step
-    std::fill(b.facc.begin(), b.facc.end(), 0.f);
-    std::fill(b.tacc.begin(), b.tacc.end(), 0.f);
     e->host_stale = false;
 }
 
@@ -561,8 +744,19 @@ HostPairs eng_fetch_pairs(Engine *e) {
     return hp;
 }
 
+// the step consumes the force accumulators (the device clears its copy in the integrate tail)
+static void consume_force_mirrors(Engine *e) {
+    HostBodies &b = e->hb;
+    for (int i : e->force_b) {
+        for (int k = 0; k < 4; k++) { b.facc[4 * (size_t)i + k] = 0.f; b.tacc[4 * (size_t)i + k] = 0.f; }
+        e->inforce_b[i] = 0;
+    }
+    e->force_b.clear();
+}
+
 void eng_step_device_contacts(Engine *e, float h, const Surface &surf) {
     eng_sync_to_device(e);
+    consume_force_mirrors(e);
     engine_ensure_pair_capacity(e);
     if (e->timing && !e->have_device_contacts) {
         OB_CUDA(cudaEventRecord(e->ev[0], e->st));
@@ -579,6 +773,7 @@ void eng_step_device_contacts(Engine *e, float h, const Surface &surf) {
 
 void eng_step_host_contacts(Engine *e, float h, const HostContact *contacts, int n) {
     eng_sync_to_device(e);
+    consume_force_mirrors(e);
     // group consecutive joints that attach the same ordered body pair into manifolds (<= 8 each)
     e->st_pd.clear(); e->st_ns.clear(); e->st_surf.clear(); e->st_mrec.clear();
     int cur_b1 = -2, cur_b2 = -2, cur_rev = 0;

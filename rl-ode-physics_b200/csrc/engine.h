@@ -155,6 +155,11 @@ void eng_mark_geoms_dirty(Engine *);
 void eng_mark_forces_dirty(Engine *);
 void eng_set_num_envs(Engine *, int n);
 void eng_set_capacity(Engine *, long max_pairs, long max_manifolds);
+// incremental edits: only the named fields of the named body / the named geom are sent to the device at the
+// next collide or step (one packed copy + one scatter kernel), the host mirrors need not be fresh
+enum BodyField { FLD_POS = 1, FLD_ROT = 2, FLD_LVEL = 4, FLD_AVEL = 8, FLD_MASS = 16, FLD_FORCE = 32, FLD_ALL = 63 };
+void eng_mark_body_fields(Engine *, int body, int fields);
+void eng_mark_geom(Engine *, int geom);
 void eng_set_big_extent(Engine *, float extent);
 void eng_set_broadphase(Engine *, int mode);
 void eng_set_solver_mode(Engine *, int mode, int env_group);

@@ -16,6 +16,17 @@ struct Engine {
     HostGeoms hg;
     bool bodies_dirty = false, geoms_dirty = false, forces_dirty = false;
     bool host_stale = false; // device state is newer than the host mirrors
+    // incremental ingestion (spawns, per-tick setters): dirty lists + per-entry field masks
+    std::vector<int> dirty_b, dirty_g, force_b;
+    std::vector<unsigned char> mask_b, mask_g, inforce_b;
+    int n_b_dev = 0, n_g_dev = 0;   // bodies / geoms the device already holds
+    std::vector<int> env_first, env_cnt, envg_first, envg_cnt, envg_shared; // persistent per-env ranges
+    int env_max_local = 0, envg_max = 0, envg_alive = 0;
+    bool env_contig = true, envg_ok = true;
+    void *h_patch = nullptr, *d_patch = nullptr;
+    size_t cap_patch = 0;
+    cudaEvent_t ev_patch = nullptr;
+    bool patch_inflight = false;
     int n_envs = 1;
     float big_extent = INFINITY;
 

@@ -344,6 +344,13 @@ extern "C" size_t dWorldPackMsgUpdateBodiesB200(dWorldID w, void *dst, int msg_t
     return eng_pack_msg(w->eng, dst, msg_type, blocking != 0);
 }
 extern "C" float dTestGridBarrierB200(dWorldID w, int iters) { return eng_barrier_bench(w->eng, iters); }
+// test hook: take the whole-array upload path (refresh the mirrors, then re-send everything) instead of
+// the queued field patches, so tests can check that the two are equivalent
+extern "C" void dTestForceFullSyncB200(dWorldID w) {
+    fresh(w);
+    eng_mark_bodies_dirty(w->eng);
+    eng_mark_geoms_dirty(w->eng);
+}
 extern "C" void dWorldEnableTimingB200(dWorldID w, int on) { eng_enable_timing(w->eng, on); }
 extern "C" void dWorldGetTimingsB200(dWorldID w, float out[4]) { eng_last_timings(w->eng, out); }
 extern "C" int dWorldGetNumBodiesB200(dWorldID w) { return eng_bodies(w->eng).n; }
@@ -363,7 +370,6 @@ static dxBody *new_body(dxWorld *w) {
 }
 
 extern "C" dBodyID dBodyCreate(dWorldID w) {
-    fresh(w);
     dxBody *b = new_body(w);
     eng_bodies(w->eng).flags[b->idx] = BF_GYRO; // ODE >= 0.13: gyroscopic mode on by default
     return b;
@@ -372,72 +378,70 @@ extern "C" dBodyID dBodyCreate(dWorldID w) {
 extern "C" void dBodyDestroy(dBodyID b) {
     if (!b || !b->alive) return;
     dxWorld *w = b->w;
-    fresh(w);
     // ODE detaches the body's geoms; the slot stays as an inert kinematic body
     for (dxGeom &g : w->geoms)
         if (g.alive && g.body == b) {
+            // the detached geom stays where the body was
+            const float *bp = dBodyGetPosition(b), *bR = dBodyGetRotation(b);
+            HostGeoms &hg = eng_geoms(w->eng);
+            memcpy(&hg.pos[4 * g.idx], bp, 3 * sizeof(float));
+            memcpy(&hg.R[12 * g.idx], bR, 12 * sizeof(float));
             g.body = nullptr;
-            eng_geoms(w->eng).body[g.idx] = -1;
-            eng_mark_geoms_dirty(w->eng);
+            hg.body[g.idx] = -1;
+            eng_mark_geom(w->eng, g.idx);
         }
     HostBodies &hb = eng_bodies(w->eng);
     hb.flags[b->idx] = BF_KINEMATIC | BF_NOGRAVITY;
     hb.pos[4 * b->idx + 3] = 0.f;
     for (int k = 0; k < 3; k++) { hb.lvel[4 * b->idx + k] = 0; hb.avel[4 * b->idx + k] = 0; }
     for (int k = 0; k < 12; k++) hb.invI[12 * b->idx + k] = 0;
-    eng_mark_bodies_dirty(w->eng);
+    eng_mark_body_fields(w->eng, b->idx, FLD_MASS | FLD_LVEL | FLD_AVEL);
     b->alive = false;
 }
 
 #define HB(b) eng_bodies((b)->w->eng)
 
 extern "C" void dBodySetPosition(dBodyID b, dReal x, dReal y, dReal z) {
-    fresh(b->w);
     float *p = &HB(b).pos[4 * b->idx];
     p[0] = x; p[1] = y; p[2] = z;
-    eng_mark_bodies_dirty(b->w->eng);
+    eng_mark_body_fields(b->w->eng, b->idx, FLD_POS);
 }
 extern "C" void dBodySetRotation(dBodyID b, const dMatrix3 R) {
-    fresh(b->w);
     float *r = &HB(b).R[12 * b->idx], *q = &HB(b).quat[4 * b->idx];
     memcpy(r, R, 12 * sizeof(float));
     r[3] = r[7] = r[11] = 0;
     dRtoQ(r, q);
     normalize4(q);
-    eng_mark_bodies_dirty(b->w->eng);
+    eng_mark_body_fields(b->w->eng, b->idx, FLD_ROT);
 }
 extern "C" void dBodySetQuaternion(dBodyID b, const dQuaternion qq) {
-    fresh(b->w);
     float *r = &HB(b).R[12 * b->idx], *q = &HB(b).quat[4 * b->idx];
     memcpy(q, qq, 4 * sizeof(float));
     normalize4(q);
     dQtoR(q, r);
-    eng_mark_bodies_dirty(b->w->eng);
+    eng_mark_body_fields(b->w->eng, b->idx, FLD_ROT);
 }
 extern "C" void dBodySetLinearVel(dBodyID b, dReal x, dReal y, dReal z) {
-    fresh(b->w);
     float *p = &HB(b).lvel[4 * b->idx];
     p[0] = x; p[1] = y; p[2] = z;
-    eng_mark_bodies_dirty(b->w->eng);
+    eng_mark_body_fields(b->w->eng, b->idx, FLD_LVEL);
 }
 extern "C" void dBodySetAngularVel(dBodyID b, dReal x, dReal y, dReal z) {
-    fresh(b->w);
     float *p = &HB(b).avel[4 * b->idx];
     p[0] = x; p[1] = y; p[2] = z;
-    eng_mark_bodies_dirty(b->w->eng);
+    eng_mark_body_fields(b->w->eng, b->idx, FLD_AVEL);
 }
 extern "C" const dReal *dBodyGetPosition(dBodyID b) { fresh(b->w); return &HB(b).pos[4 * b->idx]; }
 extern "C" const dReal *dBodyGetRotation(dBodyID b) { fresh(b->w); return &HB(b).R[12 * b->idx]; }
 extern "C" const dReal *dBodyGetQuaternion(dBodyID b) { fresh(b->w); return &HB(b).quat[4 * b->idx]; }
 extern "C" const dReal *dBodyGetLinearVel(dBodyID b) { fresh(b->w); return &HB(b).lvel[4 * b->idx]; }
 extern "C" const dReal *dBodyGetAngularVel(dBodyID b) { fresh(b->w); return &HB(b).avel[4 * b->idx]; }
-extern "C" const dReal *dBodyGetForce(dBodyID b) { fresh(b->w); return &HB(b).facc[4 * b->idx]; }
-extern "C" const dReal *dBodyGetTorque(dBodyID b) { fresh(b->w); return &HB(b).tacc[4 * b->idx]; }
+extern "C" const dReal *dBodyGetForce(dBodyID b) { return &HB(b).facc[4 * b->idx]; }
+extern "C" const dReal *dBodyGetTorque(dBodyID b) { return &HB(b).tacc[4 * b->idx]; }
 
 extern "C" void dBodySetMass(dBodyID b, const dMass *m) {
     if (!(m->mass > 0)) fatal("dBodySetMass: mass must be > 0");
     if (m->c[0] != 0 || m->c[1] != 0 || m->c[2] != 0) fatal("dBodySetMass: centre of mass must be at the origin");
-    fresh(b->w);
     HostBodies &hb = HB(b);
     hb.lvel[4 * b->idx + 3] = m->mass;
     memcpy(&hb.I[12 * b->idx], m->I, 12 * sizeof(float));
@@ -445,7 +449,7 @@ extern "C" void dBodySetMass(dBodyID b, const dMass *m) {
         hb.pos[4 * b->idx + 3] = 1.0f / m->mass;
         invert3(m->I, &hb.invI[12 * b->idx]);
     }
-    eng_mark_bodies_dirty(b->w->eng);
+    eng_mark_body_fields(b->w->eng, b->idx, FLD_MASS);
 }
 extern "C" void dBodyGetMass(dBodyID b, dMass *m) {
     HostBodies &hb = HB(b);
@@ -454,48 +458,48 @@ extern "C" void dBodyGetMass(dBodyID b, dMass *m) {
     memcpy(m->I, &hb.I[12 * b->idx], 12 * sizeof(float));
 }
 extern "C" void dBodySetKinematic(dBodyID b) {
-    fresh(b->w);
     HostBodies &hb = HB(b);
     hb.flags[b->idx] |= BF_KINEMATIC;
     hb.pos[4 * b->idx + 3] = 0.f; // invMass = 0, invI = 0
     for (int k = 0; k < 12; k++) hb.invI[12 * b->idx + k] = 0;
-    eng_mark_bodies_dirty(b->w->eng);
+    eng_mark_body_fields(b->w->eng, b->idx, FLD_MASS);
 }
 extern "C" void dBodySetDynamic(dBodyID b) {
-    fresh(b->w);
     HostBodies &hb = HB(b);
     hb.flags[b->idx] &= ~BF_KINEMATIC;
     hb.pos[4 * b->idx + 3] = 1.0f / hb.lvel[4 * b->idx + 3];
     invert3(&hb.I[12 * b->idx], &hb.invI[12 * b->idx]);
-    eng_mark_bodies_dirty(b->w->eng);
+    eng_mark_body_fields(b->w->eng, b->idx, FLD_MASS);
 }
 extern "C" int dBodyIsKinematic(dBodyID b) { return (HB(b).flags[b->idx] & BF_KINEMATIC) != 0; }
 static void set_flag(dBodyID b, int flag, bool on) {
-    fresh(b->w);
     int &f = HB(b).flags[b->idx];
     f = on ? (f | flag) : (f & ~flag);
-    eng_mark_bodies_dirty(b->w->eng);
+    eng_mark_body_fields(b->w->eng, b->idx, FLD_MASS);
 }
 extern "C" void dBodySetGravityMode(dBodyID b, int mode) { set_flag(b, BF_NOGRAVITY, mode == 0); }
 extern "C" int dBodyGetGravityMode(dBodyID b) { return (HB(b).flags[b->idx] & BF_NOGRAVITY) == 0; }
 extern "C" void dBodySetGyroscopicMode(dBodyID b, int on) { set_flag(b, BF_GYRO, on != 0); }
 extern "C" int dBodyGetGyroscopicMode(dBodyID b) { return (HB(b).flags[b->idx] & BF_GYRO) != 0; }
 extern "C" void dBodyAddForce(dBodyID b, dReal fx, dReal fy, dReal fz) {
-    fresh(b->w);
     float *f = &HB(b).facc[4 * b->idx];
     f[0] += fx; f[1] += fy; f[2] += fz;
-    eng_mark_forces_dirty(b->w->eng);
+    eng_mark_body_fields(b->w->eng, b->idx, FLD_FORCE);
 }
 extern "C" void dBodyAddTorque(dBodyID b, dReal fx, dReal fy, dReal fz) {
-    fresh(b->w);
     float *f = &HB(b).tacc[4 * b->idx];
     f[0] += fx; f[1] += fy; f[2] += fz;
-    eng_mark_forces_dirty(b->w->eng);
+    eng_mark_body_fields(b->w->eng, b->idx, FLD_FORCE);
 }
 extern "C" void dBodySetData(dBodyID b, void *d) { b->data = d; }
 extern "C" void *dBodyGetData(dBodyID b) { return b->data; }
 extern "C" dWorldID dBodyGetWorld(dBodyID b) { return b->w; }
-extern "C" void dBodySetEnvB200(dBodyID b, int env) { HB(b).env[b->idx] = env; }
+extern "C" void dBodySetEnvB200(dBodyID b, int env) {
+    if (HB(b).env[b->idx] == env) return;
+    fresh(b->w); // env membership shapes the per-env tables: full re-upload
+    HB(b).env[b->idx] = env;
+    eng_mark_bodies_dirty(b->w->eng);
+}
 extern "C" int dBodyGetIndexB200(dBodyID b) { return b->idx; }
 extern "C" dBodyID dWorldGetBodyB200(dWorldID w, int i) { return (i >= 0 && i < (int)w->bodies.size()) ? &w->bodies[i] : nullptr; }
 
@@ -565,7 +569,7 @@ extern "C" dGeomID dCreatePlane(dSpaceID s, dReal a, dReal b, dReal c, dReal d) 
 extern "C" void dGeomDestroy(dGeomID g) {
     if (!g || !g->alive) return;
     HG(g).alive[g->idx] = 0;
-    eng_mark_geoms_dirty(g->space->w->eng);
+    eng_mark_geom(g->space->w->eng, g->idx);
     g->alive = false;
 }
 extern "C" void dGeomSetBody(dGeomID g, dBodyID b) {
@@ -574,28 +578,28 @@ extern "C" void dGeomSetBody(dGeomID g, dBodyID b) {
     HostGeoms &hg = HG(g);
     hg.body[g->idx] = b ? b->idx : -1;
     if (b && hg.env[g->idx] < 0) hg.env[g->idx] = eng_bodies(b->w->eng).env[b->idx];
-    eng_mark_geoms_dirty(g->space->w->eng);
+    eng_mark_geom(g->space->w->eng, g->idx);
 }
 extern "C" dBodyID dGeomGetBody(dGeomID g) { return g->body; }
 extern "C" void dGeomSetPosition(dGeomID g, dReal x, dReal y, dReal z) {
     if (g->body) { dBodySetPosition(g->body, x, y, z); return; }
     float *p = &HG(g).pos[4 * g->idx];
     p[0] = x; p[1] = y; p[2] = z;
-    eng_mark_geoms_dirty(g->space->w->eng);
+    eng_mark_geom(g->space->w->eng, g->idx);
 }
 extern "C" void dGeomSetRotation(dGeomID g, const dMatrix3 R) {
     if (g->body) { dBodySetRotation(g->body, R); return; }
     float *r = &HG(g).R[12 * g->idx];
     memcpy(r, R, 12 * sizeof(float));
     r[3] = r[7] = r[11] = 0;
-    eng_mark_geoms_dirty(g->space->w->eng);
+    eng_mark_geom(g->space->w->eng, g->idx);
 }
 extern "C" void dGeomSetQuaternion(dGeomID g, const dQuaternion q) {
     if (g->body) { dBodySetQuaternion(g->body, q); return; }
     dQuaternion qq = {q[0], q[1], q[2], q[3]};
     normalize4(qq);
     dQtoR(qq, &HG(g).R[12 * g->idx]);
-    eng_mark_geoms_dirty(g->space->w->eng);
+    eng_mark_geom(g->space->w->eng, g->idx);
 }
 extern "C" const dReal *dGeomGetPosition(dGeomID g) {
     if (g->body) return dBodyGetPosition(g->body);
@@ -612,11 +616,11 @@ extern "C" void dGeomGetQuaternion(dGeomID g, dQuaternion q) {
 extern "C" int dGeomGetClass(dGeomID g) { return HG(g).type[g->idx]; }
 extern "C" void dGeomSetCategoryBits(dGeomID g, unsigned long bits) {
     HG(g).cat[g->idx] = (uint32_t)bits;
-    eng_mark_geoms_dirty(g->space->w->eng);
+    eng_mark_geom(g->space->w->eng, g->idx);
 }
 extern "C" void dGeomSetCollideBits(dGeomID g, unsigned long bits) {
     HG(g).col[g->idx] = (uint32_t)bits;
-    eng_mark_geoms_dirty(g->space->w->eng);
+    eng_mark_geom(g->space->w->eng, g->idx);
 }
 extern "C" unsigned long dGeomGetCategoryBits(dGeomID g) { return HG(g).cat[g->idx]; }
 extern "C" unsigned long dGeomGetCollideBits(dGeomID g) { return HG(g).col[g->idx]; }
@@ -626,7 +630,7 @@ extern "C" dSpaceID dGeomGetSpace(dGeomID g) { return g->space; }
 extern "C" dReal dGeomSphereGetRadius(dGeomID g) { return HG(g).dims[4 * g->idx]; }
 extern "C" void dGeomSphereSetRadius(dGeomID g, dReal r) {
     HG(g).dims[4 * g->idx] = r;
-    eng_mark_geoms_dirty(g->space->w->eng);
+    eng_mark_geom(g->space->w->eng, g->idx);
 }
 extern "C" void dGeomBoxGetLengths(dGeomID g, dVector3 out) {
     for (int k = 0; k < 3; k++) out[k] = HG(g).dims[4 * g->idx + k];
@@ -635,7 +639,7 @@ extern "C" void dGeomBoxGetLengths(dGeomID g, dVector3 out) {
 extern "C" void dGeomBoxSetLengths(dGeomID g, dReal lx, dReal ly, dReal lz) {
     float *d = &HG(g).dims[4 * g->idx];
     d[0] = lx; d[1] = ly; d[2] = lz;
-    eng_mark_geoms_dirty(g->space->w->eng);
+    eng_mark_geom(g->space->w->eng, g->idx);
 }
 extern "C" void dGeomPlaneGetParams(dGeomID g, dVector4 out) {
     for (int k = 0; k < 4; k++) out[k] = HG(g).dims[4 * g->idx + k];
@@ -644,11 +648,11 @@ extern "C" void dGeomPlaneSetParams(dGeomID g, dReal a, dReal b, dReal c, dReal 
     float p[4] = {a, b, c, d};
     plane_normalize(p);
     memcpy(&HG(g).dims[4 * g->idx], p, sizeof(p));
-    eng_mark_geoms_dirty(g->space->w->eng);
+    eng_mark_geom(g->space->w->eng, g->idx);
 }
 extern "C" void dGeomSetEnvB200(dGeomID g, int env) {
     HG(g).env[g->idx] = env;
-    eng_mark_geoms_dirty(g->space->w->eng);
+    eng_mark_geom(g->space->w->eng, g->idx);
 }
 extern "C" int dGeomGetIndexB200(dGeomID g) { return g->idx; }
 
@@ -709,7 +713,6 @@ extern "C" int dWorldAddTriMeshB200(dWorldID w, const float *verts, int nv, cons
 extern "C" int dWorldAddBodiesB200(dWorldID w, int n, const float *pos3, const float *quat4, const float *lvel3,
                                    const float *avel3, const float *mass, const float *inertia9, const int *flags,
                                    const int *env) {
-    fresh(w);
     HostBodies &hb = eng_bodies(w->eng);
     const int first = hb.n;
     for (int i = 0; i < n; i++) {
@@ -740,8 +743,7 @@ extern "C" int dWorldAddBodiesB200(dWorldID w, int n, const float *pos3, const f
             if (inertia9) invert3(&hb.I[12 * k], &hb.invI[12 * k]);
         }
     }
-    eng_mark_bodies_dirty(w->eng);
-    return first;
+    return first; // eng_add_body queued them (or asked for the first full upload)
 }
 
 extern "C" int dSpaceAddGeomsB200(dSpaceID s, dWorldID w, int n, const int *type, const float *dims4, const int *body,
@@ -772,7 +774,6 @@ extern "C" int dSpaceAddGeomsB200(dSpaceID s, dWorldID w, int n, const int *type
         if (col) hg.col[k] = col[i];
         hg.env[k] = env ? env[i] : (b >= 0 ? eng_bodies(w->eng).env[b] : -1);
     }
-    eng_mark_geoms_dirty(w->eng);
     return first;
 }
 

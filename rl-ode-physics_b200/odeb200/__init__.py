@@ -105,6 +105,7 @@ _SIGS = [
     ("dWorldAddBodiesB200", _i, [_vp, _i, _fp, _fp, _fp, _fp, _fp, _fp, _ip, _ip]),
     ("dSpaceAddGeomsB200", _i, [_vp, _vp, _i, _ip, _fp, _ip, _fp, _fp, _up, _up, _ip]),
     ("dWorldAddTriMeshB200", _i, [_vp, _fp, _i, _ip, _i]),
+    ("dTestForceFullSyncB200", None, [_vp]),
     ("dWorldGetBodyB200", _vp, [_vp, _i]), ("dSpaceGetGeomB200", _vp, [_vp, _i]),
     ("dWorldGetNumBodiesB200", _i, [_vp]),
     ("dBodyGetIndexB200", _i, [_vp]), ("dGeomGetIndexB200", _i, [_vp]),
@@ -224,6 +225,31 @@ class World:
                                       _p(ga[4], _fp), _p(ga[5], _up), _p(ga[6], _up), _p(ga[7], _ip))
         self.n_bodies += n
         self.n_geoms += ng
+
+    def spawn(self, pos, kind, dims, R=None, cat=2, col=3):
+        """The reference's AddBody (src/main.c:695-733) through the handle API: one body + one geom."""
+        L = self.L
+        b = C.c_void_p(L.dBodyCreate(self.w))
+        L.dBodySetPosition(b, float(pos[0]), float(pos[1]), float(pos[2]))
+        if R is not None:
+            r = np.ascontiguousarray(R, np.float32)
+            L.dBodySetRotation(b, _p(r, _fp))
+        if kind == "sphere":
+            g = C.c_void_p(L.dCreateSphere(self.space, float(dims[0])))
+        else:
+            g = C.c_void_p(L.dCreateBox(self.space, float(dims[0]), float(dims[1]), float(dims[2])))
+        L.dGeomSetBody(g, b)
+        L.dGeomSetCategoryBits(g, cat)
+        L.dGeomSetCollideBits(g, col)
+        self.n_bodies += 1
+        self.n_geoms += 1
+        return b, g
+
+    def body_handle(self, i):
+        return C.c_void_p(self.L.dWorldGetBodyB200(self.w, int(i)))
+
+    def force_full_sync(self):
+        self.L.dTestForceFullSyncB200(self.w)
 
     def set_surface(self, s):
         self.L.dWorldSetSurfaceB200(self.w, C.byref(s))

@@ -189,3 +189,71 @@ def test_kinematic_body_via_api_and_velocity_setters():
     assert s.pos(k)[1] == 1.0 and abs(s.pos(k)[0] - 10 * H) < 1e-5
     assert s.vel(d)[0] > 0.5
     s.close()
+
+
+def _identity_R12():
+    return np.float32([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0])
+
+
+@pytest.mark.parametrize("scene", ["soup", "batch"])
+def test_incremental_ingestion_equals_full_upload(scene):
+    """Spawns and setters on a running world are sent as queued field patches (one packed copy + one scatter
+    kernel, no mirror refresh).  The result must be bit-identical to refreshing the mirrors and re-uploading
+    every array after each edit (the path every world takes at its first sync)."""
+    outs = []
+    for full in (False, True):
+        if scene == "soup":
+            sc = scenes.random_soup(200, seed=7)
+        else:
+            sc = scenes.batched_worlds_scene(4, seed=4, spacing=0.7)
+        ew = util.engine_world(sc)
+        L = ew.L
+        rs = np.random.RandomState(3)
+        player = None
+        for step in range(30):
+            if step == 5 and scene == "soup":       # a kinematic "player" sphere appears (src/main.c:150-160)
+                player, _ = ew.spawn([0.0, 1.0, 0.0], "sphere", [0.5])
+                L.dBodySetKinematic(player)
+            if step >= 5 and step % 6 == 5 and scene == "soup":   # a client pressed M (src/main.c:502-522)
+                pos = [rs.uniform(-2, 2), rs.uniform(2, 4), rs.uniform(-2, 2)]
+                if rs.randint(2):
+                    ew.spawn(pos, "box", list(rs.uniform(0.2, 1.0, 3)), R=_identity_R12())
+                else:
+                    ew.spawn(pos, "sphere", [rs.uniform(0.1, 0.4)])
+            if player is not None:                   # MSGTYPE_S_PLAYER_UPDATE: the player body is teleported
+                L.dBodySetPosition(player, float(0.02 * step), 1.0, float(-0.01 * step))
+            if step % 4 == 1:                        # velocity / force setters on bodies that are mid-flight
+                b = ew.body_handle(3)
+                L.dBodyAddForce(b, 0.0, 30.0, 0.0)
+                L.dBodyAddForce(b, 5.0, 0.0, 0.0)
+                L.dBodySetAngularVel(ew.body_handle(7), 0.0, 2.0, 0.0)
+                L.dBodySetLinearVel(ew.body_handle(11), 1.0, 0.5, 0.0)
+            if full:
+                ew.force_full_sync()
+            ew.tick(sc["h"])
+        outs.append(ew.state())
+        assert ew.stats()["n_contacts"] > 10
+        ew.close()
+    a, b = outs
+    assert len(a["pos"]) == len(b["pos"]) and (scene != "soup" or len(a["pos"]) > 200)
+    for k in ("pos", "quat", "lvel", "avel"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_destroyed_body_leaves_its_geom_in_place_incrementally():
+    """dBodyDestroy on a running world: the geom stays where the body was (ODE detaches it), other bodies keep
+    colliding with it; done through queued patches, no full refresh."""
+    sc = scenes.random_soup(50, seed=2)
+    ew = util.engine_world(sc)
+    for _ in range(5):
+        ew.tick(sc["h"])
+    st = ew.state()
+    b = ew.body_handle(4)
+    ew.L.dBodyDestroy(b)
+    for _ in range(3):
+        ew.tick(sc["h"])
+    st2 = ew.state()
+    # the destroyed body's slot is inert now; everything else kept moving
+    assert np.array_equal(st2["pos"][4], st["pos"][4])
+    assert not np.array_equal(st2["pos"][5], st["pos"][5])
+    ew.close()
