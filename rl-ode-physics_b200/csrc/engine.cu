@@ -302,7 +302,9 @@ void engine_ensure_pair_capacity(Engine *e) {
         OB_CUDA(cudaMemsetAsync(bp.cell_start, 0, ((size_t)bp.cap_cells + 2) * sizeof(int), st));
         OB_CUDA(cudaMemsetAsync(bp.cell_end, 0, ((size_t)bp.cap_cells + 2) * sizeof(int), st));
     }
-    long wantp = e->want_pairs > 0 ? e->want_pairs : (long)e->hg.n * 8 + 1024;
+    // sized from the geom CAPACITY (which grows geometrically), so that a spawn does not re-allocate these
+    const long ng = std::max(e->cap_g, e->hg.n);
+    long wantp = e->want_pairs > 0 ? e->want_pairs : ng * 8 + 1024;
     if (wantp > bp.cap_pairs) {
         const size_t n = (size_t)wantp;
         dev_realloc(bp.pairs, 0, n, st, false);
@@ -316,7 +318,7 @@ void engine_ensure_pair_capacity(Engine *e) {
     }
     // solver units: manifolds (<= pairs) or, with per-contact units, contacts
     const bool per_contact = e->contact_units >= 0 ? e->contact_units == 1 : e->n_envs > 1;
-    long wantm = e->want_manifolds > 0 ? e->want_manifolds : (long)e->hg.n * (per_contact ? 8 : 6) + 1024;
+    long wantm = e->want_manifolds > 0 ? e->want_manifolds : ng * (per_contact ? 8 : 6) + 1024;
     if (!per_contact && wantm > bp.cap_pairs) wantm = bp.cap_pairs;
     if ((long)e->st_mrec.size() > wantm) wantm = (long)e->st_mrec.size();
     if (wantm > e->M.cap) {
