@@ -102,6 +102,11 @@ void dWorldSetSolverModeB200(dWorldID, int mode, int env_group);
 void dWorldSetContactUnitsB200(dWorldID, int per_contact);
 /* dynamic geoms whose AABB extent exceeds this are treated like static "big" geoms (default inf) */
 void dWorldSetBigExtentB200(dWorldID, float extent);
+/* dWorldStep parity mode (the reference calls dWorldStep, src/main.c:213; libode solves its LCP exactly): let
+ * dWorldStep run up to max_iters SOR/PGS sweeps and stop once the largest |delta lambda| of a sweep is below
+ * tol (tol 0: always max_iters).  max_iters 0 (default): dWorldStep == dWorldQuickStep.  dWorldQuickStep is
+ * not affected. */
+void dWorldSetStepSolverB200(dWorldID, int max_iters, float tol);
 /* broadphase layout: -1 automatic (default), 0 uniform grid (sort + cell sweep), 1 all pairs per env (batched
  * worlds whose geoms were added env by env, or one world of <= 4096 geoms; falls back to the grid
  * otherwise).  Both emit the same pair SET; the order inside the list differs. */
@@ -114,6 +119,7 @@ typedef struct dStepStatsB200 {
     int colour_rounds;
     float cell_size;
     int grid_dims[3];
+    int solver_iters; /* sweeps the last solve ran (fewer than the limit when residual-terminated) */
 } dStepStatsB200;
 void dWorldGetStatsB200(dWorldID, dStepStatsB200 *); /* blocking */
 void dWorldEnableTimingB200(dWorldID, int on);

@@ -11,6 +11,7 @@
 #include "ode_oracle.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -1204,6 +1205,77 @@ void orc_last_lambda(const orc_world *w, float *lambda, int n) {
     if (n > 0) memcpy(lambda, w->last_lambda, sizeof(float) * (size_t)n);
 }
 
+/* Exact box-constrained LCP for an SPD matrix: block principal pivoting (Judice & Pires) with the
+ * single-pivot fallback that guarantees termination.  F = free (w = 0), L = at lo (w >= 0), U = at hi
+ * (w <= 0), w = A x - b.  Dense Cholesky on the free block; sizes here are a few hundred rows. */
+static int solve_blcp(int m, const double *A, const double *b, const float *lo, const float *hi, double *x) {
+    char *st = (char *)calloc((size_t)m, 1); /* 0 F, 1 L, 2 U */
+    int *F = (int *)malloc(sizeof(int) * (size_t)m);
+    double *C = (double *)malloc(sizeof(double) * (size_t)m * (size_t)m);
+    double *r = (double *)malloc(sizeof(double) * (size_t)m);
+    double *wv = (double *)malloc(sizeof(double) * (size_t)m);
+    const double eps = 1e-11;
+    int best = m + 1, p = 10, ok = 0;
+    for (long iter = 0; iter < 200L * (m + 10); iter++) {
+        int nf = 0;
+        for (int i = 0; i < m; i++) {
+            if (st[i] == 0) F[nf++] = i;
+            else x[i] = st[i] == 1 ? (double)lo[i] : (double)hi[i];
+        }
+        for (int a = 0; a < nf; a++) {
+            int i = F[a];
+            double s = b[i];
+            for (int j = 0; j < m; j++) if (st[j]) s -= A[(size_t)i * m + j] * x[j];
+            r[a] = s;
+            for (int c = 0; c <= a; c++) C[(size_t)a * nf + c] = A[(size_t)i * m + F[c]];
+        }
+        /* Cholesky C = L L^T (lower), then two triangular solves */
+        for (int a = 0; a < nf; a++) {
+            for (int c = 0; c <= a; c++) {
+                double s = C[(size_t)a * nf + c];
+                for (int k = 0; k < c; k++) s -= C[(size_t)a * nf + k] * C[(size_t)c * nf + k];
+                if (a == c) { if (s <= 0) s = 1e-300; C[(size_t)a * nf + a] = sqrt(s); }
+                else C[(size_t)a * nf + c] = s / C[(size_t)c * nf + c];
+            }
+        }
+        for (int a = 0; a < nf; a++) {
+            double s = r[a];
+            for (int k = 0; k < a; k++) s -= C[(size_t)a * nf + k] * r[k];
+            r[a] = s / C[(size_t)a * nf + a];
+        }
+        for (int a = nf - 1; a >= 0; a--) {
+            double s = r[a];
+            for (int k = a + 1; k < nf; k++) s -= C[(size_t)k * nf + a] * r[k];
+            r[a] = s / C[(size_t)a * nf + a];
+        }
+        for (int a = 0; a < nf; a++) x[F[a]] = r[a];
+        int ninf = 0, last = -1;
+        for (int i = 0; i < m; i++) {
+            double s = -b[i];
+            for (int j = 0; j < m; j++) s += A[(size_t)i * m + j] * x[j];
+            wv[i] = s;
+            int bad = 0;
+            if (st[i] == 0) bad = (x[i] < (double)lo[i] - eps) || (x[i] > (double)hi[i] + eps);
+            else if (st[i] == 1) bad = wv[i] < -eps;
+            else bad = wv[i] > eps;
+            if (bad) { ninf++; last = i; }
+        }
+        if (ninf == 0) { ok = 1; break; }
+        int all = 0;
+        if (ninf < best) { best = ninf; p = 10; all = 1; }
+        else if (p > 0) { p--; all = 1; }
+        for (int i = 0; i < m; i++) {
+            if (!all && i != last) continue;
+            if (st[i] == 0) {
+                if (x[i] < (double)lo[i] - eps) st[i] = 1;
+                else if (x[i] > (double)hi[i] + eps) st[i] = 2;
+            } else if ((st[i] == 1 && wv[i] < -eps) || (st[i] == 2 && wv[i] > eps)) st[i] = 0;
+        }
+    }
+    free(st); free(F); free(C); free(r); free(wv);
+    return ok;
+}
+
 int orc_quickstep(orc_world *w, float h, int order_mode, const int *perm) {
     int nb = w->nb;
     float stepsize1 = 1.0f / h;
@@ -1352,7 +1424,7 @@ int orc_quickstep(orc_world *w, float h, int order_mode, const int *perm) {
         }
         free(tmp1);
 
-        /* SOR_LCP */
+        /* iMJ = invM * J^T (compute_invM_JT) */
         for (int i = 0; i < m; i++) {
             int b1 = jb[2 * i], b2 = jb[2 * i + 1];
             float *im = iMJ + 12 * i, *Ji = J + 12 * i;
@@ -1362,6 +1434,47 @@ int orc_quickstep(orc_world *w, float h, int order_mode, const int *perm) {
                 for (int k = 0; k < 3; k++) im[6 + k] = w->b[b2].invMass * Ji[6 + k];
                 mul0_331(im + 9, invI + 12 * b2, Ji + 9);
             }
+        }
+        float *fc = (float *)calloc(6 * (size_t)nb, sizeof(float));
+        if (order_mode == 3) {
+            /* dWorldStep's answer: the exact solution of  A lambda = rhs + w,  lo <= lambda <= hi,
+             * A = J invM J^T + cfm/h  (what libode's Dantzig solver dSolveLCP returns; A is SPD for
+             * cfm > 0 so the solution is unique and any exact method finds it).  Double precision. */
+            double *A = (double *)calloc((size_t)m * (size_t)m, sizeof(double));
+            double *bb = (double *)malloc(sizeof(double) * (size_t)m);
+            double *x = (double *)calloc((size_t)m, sizeof(double));
+            for (int i = 0; i < m; i++) {
+                const float *im = iMJ + 12 * i;
+                for (int j2 = 0; j2 < m; j2++) {
+                    const float *Jj = J + 12 * j2;
+                    double a = 0;
+                    for (int s1 = 0; s1 < 2; s1++) {
+                        int bi = jb[2 * i + s1];
+                        if (bi < 0) continue;
+                        for (int s2 = 0; s2 < 2; s2++)
+                            if (jb[2 * j2 + s2] == bi)
+                                for (int k = 0; k < 6; k++) a += (double)im[6 * s1 + k] * (double)Jj[6 * s2 + k];
+                    }
+                    A[(size_t)i * m + j2] = a;
+                }
+                A[(size_t)i * m + i] += (double)cfm[i];
+                bb[i] = (double)rhs[i];
+                if (findex[i] >= 0) { fprintf(stderr, "ode_oracle: exact mode does not take findex rows\n"); abort(); }
+            }
+            if (!solve_blcp(m, A, bb, lo, hi, x)) { fprintf(stderr, "ode_oracle: exact LCP did not terminate\n"); abort(); }
+            for (int i = 0; i < m; i++) {
+                lambda[i] = (float)x[i];
+                const float *im = iMJ + 12 * i;
+                int b1 = jb[2 * i], b2 = jb[2 * i + 1];
+                for (int k = 0; k < 6; k++) fc[6 * b1 + k] += (float)(x[i] * (double)im[k]);
+                if (b2 >= 0) for (int k = 0; k < 6; k++) fc[6 * b2 + k] += (float)(x[i] * (double)im[6 + k]);
+            }
+            free(A); free(bb); free(x);
+        }
+        /* SOR_LCP */
+        for (int i = 0; i < m && order_mode != 3; i++) {
+            int b2 = jb[2 * i + 1];
+            float *im = iMJ + 12 * i, *Ji = J + 12 * i;
             float sum = 0;
             for (int k = 0; k < 6; k++) sum += im[k] * Ji[k];
             if (b2 >= 0) for (int k = 0; k < 6; k++) sum += im[6 + k] * Ji[6 + k];
@@ -1370,7 +1483,6 @@ int orc_quickstep(orc_world *w, float h, int order_mode, const int *perm) {
             rhs[i] *= Ad[i];
             Adcfm[i] = Ad[i] * cfm[i];
         }
-        float *fc = (float *)calloc(6 * (size_t)nb, sizeof(float));
         int *order = (int *)malloc(sizeof(int) * (size_t)m);
         if (order_mode == 2 && perm) memcpy(order, perm, sizeof(int) * (size_t)m);
         else if (order_mode == 1) { for (int i = 0; i < m; i++) order[i] = i; }
@@ -1378,7 +1490,7 @@ int orc_quickstep(orc_world *w, float h, int order_mode, const int *perm) {
             int head = 0, tail = m - 1;
             for (int i = 0; i < m; i++) { if (findex[i] < 0) order[head++] = i; else order[tail--] = i; }
         }
-        for (int it = 0; it < w->iters; it++) {
+        for (int it = 0; it < w->iters && order_mode != 3; it++) {
             if (order_mode == 0 && (it & 7) == 0) {
                 for (int i = 1; i < m; i++) {
                     int t = order[i], sw = ode_rand_int(w, i + 1);

@@ -97,7 +97,9 @@ long orc_collide_all(orc_world *, int maxc, const orc_surface *surf);
 
 /* dWorldQuickStep. order_mode 0: ODE ordering (findex<0 first, reshuffle every 8 iterations with
  * ODE's LCG); 1: fixed order = rows in joint order every iteration (joint j -> rows 3j..);
- * 2: caller permutation `perm` of row indices (length = number of rows). */
+ * 2: caller permutation `perm` of row indices (length = number of rows);
+ * 3: no sweeps -- the exact solution of the step's LCP (what dWorldStep's Dantzig solver returns),
+ *    by principal pivoting in double precision; rows with findex (Approx1 friction) are not accepted. */
 int orc_quickstep(orc_world *, float h, int order_mode, const int *perm);
 int orc_num_rows(const orc_world *);
 /* diagnostics of the last step: max |delta lambda| of last iteration etc. */

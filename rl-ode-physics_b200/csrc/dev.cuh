@@ -156,6 +156,7 @@ struct StepConfig {
     float h, erp, cfm, sor_w, max_vel, min_depth;
     float gx, gy, gz;
     int iters;
+    float tol; // > 0: stop the sweeps when the largest |delta lambda| of a sweep falls below it (global solver)
 };
 
 void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_surface);

@@ -65,9 +65,9 @@ Engine *eng_create(int device) {
     for (int i = 0; i < 5; i++) OB_CUDA(cudaEventCreate(&e->ev[i]));
     OB_CUDA(cudaMalloc(&e->M.count, sizeof(int)));
     OB_CUDA(cudaMalloc(&e->M.colour_start, 72 * sizeof(int)));
-    OB_CUDA(cudaMalloc(&e->M.meta, 8 * sizeof(int)));
+    OB_CUDA(cudaMalloc(&e->M.meta, 12 * sizeof(int)));
     OB_CUDA(cudaMemset(e->M.count, 0, sizeof(int)));
-    OB_CUDA(cudaMemset(e->M.meta, 0, 8 * sizeof(int)));
+    OB_CUDA(cudaMemset(e->M.meta, 0, 12 * sizeof(int)));
     OB_CUDA(cudaMalloc(&e->bp.acc, 8 * sizeof(unsigned)));
     OB_CUDA(cudaMalloc(&e->bp.gp, sizeof(GridParams)));
     OB_CUDA(cudaMalloc(&e->bp.counters, sizeof(BroadCounters)));

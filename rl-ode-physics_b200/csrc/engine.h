@@ -100,6 +100,7 @@ struct StepStats {
     int colour_rounds;
     float cell_size;
     int grid_dims[3];
+    int solver_iters; // sweeps the last solve ran (< iterations when residual-terminated)
 };
 enum StatFlags { SF_PAIR_OVERFLOW = 1, SF_MANIFOLD_OVERFLOW = 2, SF_CAND_OVERFLOW = 4 };
 
@@ -107,6 +108,7 @@ struct WorldParams {
     float gravity[3] = {0, 0, 0};
     float erp = 0.2f, cfm = 1e-5f, sor_w = 1.3f;
     int iters = 20;
+    float tol = 0.f; // > 0: residual-terminated sweeps (dWorldStep parity mode)
     float max_vel = INFINITY, min_depth = 0.0f;
 };
 

@@ -65,6 +65,8 @@ struct dxWorld {
     std::vector<dxJointGroup *> groups; // groups that hold joints of this world
     dSurfaceParameters surface;
     int max_contacts = 8;
+    int step_iters = 0;   // dWorldStep parity mode (dWorldSetStepSolverB200)
+    float step_tol = 0.f;
     bool device_contacts_pending = false;
     // callback context
     bool in_callback = false;
@@ -313,7 +315,20 @@ extern "C" int dWorldQuickStep(dWorldID w, dReal h) {
     w->device_contacts_pending = false;
     return 1;
 }
-extern "C" int dWorldStep(dWorldID w, dReal h) { return dWorldQuickStep(w, h); }
+// dWorldStep is libode's exact (Dantzig) stepper; here it is the same SOR/PGS solver, by default with the
+// QuickStep iteration count.  dWorldSetStepSolverB200 makes it run up to `max_iters` sweeps and stop when the
+// largest |delta lambda| of a sweep falls below `tol` (0: always max_iters): the LCP solution in the limit.
+extern "C" int dWorldStep(dWorldID w, dReal h) {
+    if (!w) return 0;
+    WorldParams &p = eng_params(w->eng);
+    if (w->step_iters <= 0) return dWorldQuickStep(w, h);
+    const int iters = p.iters;
+    p.iters = w->step_iters; p.tol = w->step_tol;
+    const int r = dWorldQuickStep(w, h);
+    p.iters = iters; p.tol = 0.f;
+    return r;
+}
+extern "C" void dWorldSetStepSolverB200(dWorldID w, int max_iters, float tol) { w->step_iters = max_iters; w->step_tol = tol < 0 ? 0 : tol; }
 
 extern "C" void dWorldSetSurfaceB200(dWorldID w, const dSurfaceParameters *s) { w->surface = *s; }
 extern "C" void dWorldGetSurfaceB200(dWorldID w, dSurfaceParameters *s) { *s = w->surface; }

@@ -534,7 +534,7 @@ __device__ __forceinline__ void st_fc(float4 *p, float4 v) {
 // arrays (indexed by body) or, on the island path, the env's copy in shared memory (indexed by local body)
 template <bool L2ONLY, bool SINGLE = false>
 __device__ __forceinline__ void solve_manifold_core(int s, const int4 rec, RowRec cur, const SolverArrays &S, float4 *fcp,
-                                                    const float4 *invp, int fs = 2, int fo = 1) {
+                                                    const float4 *invp, int fs = 2, int fo = 1, float *maxd = nullptr) {
     const int b1 = rec.x, b2 = rec.y, nc = SINGLE ? 1 : rec.z; // SINGLE: per-contact units, no contact loop
     const bool two = b2 >= 0;
     FC f1, f2;
@@ -581,6 +581,8 @@ __device__ __forceinline__ void solve_manifold_core(int s, const int4 rec, RowRe
             }
         }
         S.lam[si] = lam;
+        if (maxd) // residual-terminated mode: largest |delta lambda| this thread produced in the sweep
+            *maxd = fmaxf(*maxd, fmaxf(fabsf(lam.x - cur.lam.x), fmaxf(fabsf(lam.y - cur.lam.y), fabsf(lam.z - cur.lam.z))));
         if (!SINGLE) cur = nxt;
     }
     st_fc<L2ONLY>(&fcp[fs * b1], make_float4(f1.l.x, f1.l.y, f1.l.z, 0.f));
@@ -593,9 +595,9 @@ __device__ __forceinline__ void solve_manifold_core(int s, const int4 rec, RowRe
 
 template <bool L2ONLY, bool SINGLE = false>
 __device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, float4 *fcp, const float4 *invp, int fs = 2,
-                                               int fo = 1) {
+                                               int fo = 1, float *maxd = nullptr) {
     const int4 rec = __ldg(&S.mrec[s]);
-    solve_manifold_core<L2ONLY, SINGLE>(s, rec, load_rows(S, (size_t)s), S, fcp, invp, fs, fo);
+    solve_manifold_core<L2ONLY, SINGLE>(s, rec, load_rows(S, (size_t)s), S, fcp, invp, fs, fo, maxd);
 }
 
 // grid-wide barrier of the persistent solver (all CTAs are co-resident: cooperative launch).  One
@@ -674,7 +676,13 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // next phase's rows with cp.async before the barrier, L2 evict-first hints on the rows and a persisting-L2
 // window on the body data, and fetching each thread's first record + rows of the next phase into registers
 // before the barrier, were all measured and did not help; they are not in the code.)
-__global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays S, BodyArrays B, StepConfig cfg) {
+// TOL: residual-terminated sweeps (the dWorldStep parity mode): every thread tracks the
+// largest |delta lambda| of its sweep, the grid max goes through one of three rotating slots (meta[8..10]:
+// a slot is re-zeroed only after every CTA has passed the barrier that follows its last read), and all CTAs
+// take the same exit decision after the sweep's last barrier.
+template <bool TOL>
+__global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays S, BodyArrays B, StepConfig cfg,
+                                                  StepStats *__restrict__ stats) {
     const int n = *M.count;
     const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
     unsigned *bar = reinterpret_cast<unsigned *>(&M.meta[6]);
@@ -688,10 +696,19 @@ __global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays
 #ifdef OB_ENV_PROFILE
         if (gt == 0) g_phase_t[0] = gtimer();
 #endif
-        for (int it = 0; it < cfg.iters; it++) {
+        unsigned *resid = reinterpret_cast<unsigned *>(&M.meta[8]);
+        int it = 0;
+        for (; it < cfg.iters; it++) {
+            float maxd = 0.f;
             for (int c = 0; c < ncol; c++) {
                 const int s0 = cs[c], s1 = cs[c + 1];
-                for (int s = s0 + gt; s < s1; s += gs) solve_manifold<true>(s, S, B.fc, B.inv);
+                for (int s = s0 + gt; s < s1; s += gs) solve_manifold<true>(s, S, B.fc, B.inv, 2, 1, TOL ? &maxd : nullptr);
+                if (TOL && c == ncol - 1 && ovf1 == ovf0) {
+                    maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, 16)); maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, 8));
+                    maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, 4)); maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, 2));
+                    maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, 1));
+                    if ((threadIdx.x & 31) == 0 && maxd > 0.f) atomicMax(&resid[it % 3], __float_as_uint(maxd));
+                }
                 grid_barrier(bar, target);
 #ifdef OB_ENV_PROFILE
                 if (gt == 0 && it * ncol + c < 255) { g_phase_t[it * ncol + c + 1] = gtimer(); g_phase_n[it * ncol + c + 1] = s1 - s0; }
@@ -700,10 +717,23 @@ __global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays
             if (ovf1 > ovf0) {
                 // manifolds that found no free colour (> 64 neighbours): one thread, in order
                 if (gt == 0)
-                    for (int s = ovf0; s < ovf1; s++) solve_manifold<true>(s, S, B.fc, B.inv);
+                    for (int s = ovf0; s < ovf1; s++) solve_manifold<true>(s, S, B.fc, B.inv, 2, 1, TOL ? &maxd : nullptr);
+                if (TOL) {
+                    maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, 16)); maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, 8));
+                    maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, 4)); maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, 2));
+                    maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, 1));
+                    if ((threadIdx.x & 31) == 0 && maxd > 0.f) atomicMax(&resid[it % 3], __float_as_uint(maxd));
+                }
                 grid_barrier(bar, target);
             }
+            if (TOL) {
+                unsigned r;
+                asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(r) : "l"(&resid[it % 3]) : "memory");
+                if (gt == 0) resid[(it + 2) % 3] = 0u; // last read before this sweep's barrier, next written two sweeps on
+                if (__uint_as_float(r) < cfg.tol) { it++; break; }
+            }
         }
+        if (gt == 0) stats->solver_iters = it;
     }
     for (int i = gt; i < B.n; i += gs) integrate_body(i, B, cfg.h, __ldcg(&B.fc[2 * i]), __ldcg(&B.fc[2 * i + 1]));
 }
@@ -1002,6 +1032,7 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
         }
         atomicMax(&stats->n_colours, max_col);
         atomicMax(&stats->colour_rounds, max_rounds);
+        if (blockIdx.x == 0 && threadIdx.x == 0) stats->solver_iters = cfg.iters;
     }
 }
 
@@ -1054,12 +1085,14 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
     cfg.max_vel = e->params.max_vel; cfg.min_depth = e->params.min_depth;
     cfg.gx = e->params.gravity[0]; cfg.gy = e->params.gravity[1]; cfg.gz = e->params.gravity[2];
     cfg.iters = e->params.iters;
+    cfg.tol = e->params.tol;
 
     k_stats_reset<<<1, 1, 0, st>>>(e->d_stats);
     OB_CHECK_KERNEL("k_stats_reset", st);
     // island path with contiguous envs: per-body preparation and the integrate/pack tail run inside
     // k_env_solve, env by env; otherwise they are separate passes over all bodies
-    const bool island = !host_contacts && e->have_device_contacts && e->n_envs > 1 && e->E.max_bodies <= 1024 && e->solver_mode != 1;
+    const bool island = !host_contacts && e->have_device_contacts && e->n_envs > 1 && e->E.max_bodies <= 1024 && e->solver_mode != 1 &&
+                        !(cfg.tol > 0.f); // residual termination is a grid-wide decision: global solver
     const int fused = (island && e->E.contiguous && e->env_fuse) ? 1 : 0;
     if (!fused) {
         k_body_prep<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(B, cfg);
@@ -1176,9 +1209,12 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
         SolverArrays S = e->S;
         OB_CUDA(cudaMemsetAsync(&M.meta[6], 0, sizeof(int), st)); // grid barrier counter
         long work = max_manifolds > nb ? max_manifolds : nb;
-        int grid = coop_grid(e, (const void *)k_solve, 256, work);
-        void *args[] = {(void *)&M, (void *)&S, (void *)&B, (void *)&cfg};
-        OB_CUDA(cudaLaunchCooperativeKernel((const void *)k_solve, dim3((unsigned)grid), dim3(256), args, 0, st));
+        const void *fn = cfg.tol > 0.f ? (const void *)k_solve<true> : (const void *)k_solve<false>;
+        if (cfg.tol > 0.f) OB_CUDA(cudaMemsetAsync(&M.meta[8], 0, 3 * sizeof(int), st)); // residual slots
+        int grid = coop_grid(e, fn, 256, work);
+        StepStats *d_stats = e->d_stats;
+        void *args[] = {(void *)&M, (void *)&S, (void *)&B, (void *)&cfg, (void *)&d_stats};
+        OB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(256), args, 0, st));
         OB_CHECK_KERNEL("k_solve", st);
     }
     if (e->timing) OB_CUDA(cudaEventRecord(e->ev[4], st));

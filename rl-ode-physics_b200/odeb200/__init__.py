@@ -43,7 +43,8 @@ class StepStats(C.Structure):
     _fields_ = [("n_geoms", C.c_int), ("n_big", C.c_int), ("n_pairs", C.c_int), ("n_contacts", C.c_int),
                 ("n_manifolds", C.c_int), ("n_colours", C.c_int), ("n_overflow", C.c_int), ("flags", C.c_int),
                 ("class_count", C.c_int * 7), ("n_rows", C.c_int), ("n_rows1", C.c_int), ("n_rows2", C.c_int),
-                ("colour_rounds", C.c_int), ("cell_size", C.c_float), ("grid_dims", C.c_int * 3)]
+                ("colour_rounds", C.c_int), ("cell_size", C.c_float), ("grid_dims", C.c_int * 3),
+                ("solver_iters", C.c_int)]
 
     def as_dict(self):
         d = {}
@@ -120,6 +121,7 @@ _SIGS = [
     ("dWorldSetCapacityB200", None, [_vp, C.c_long, C.c_long]),
     ("dWorldSetBigExtentB200", None, [_vp, _f]),
     ("dWorldSetBroadphaseB200", None, [_vp, _i]),
+    ("dWorldSetStepSolverB200", None, [_vp, _i, _f]),
     ("dWorldSetSolverModeB200", None, [_vp, _i, _i]),
     ("dWorldSetContactUnitsB200", None, [_vp, _i]),
     ("dWorldGetStatsB200", None, [_vp, C.POINTER(StepStats)]),
@@ -272,6 +274,14 @@ class World:
 
     def step(self, h):
         return self.L.dWorldQuickStep(self.w, float(h))
+
+    def set_step_solver(self, max_iters, tol=0.0):
+        """dWorldStep parity mode: dWorldStep runs up to max_iters sweeps, stopping below tol."""
+        self.L.dWorldSetStepSolverB200(self.w, int(max_iters), float(tol))
+
+    def world_step(self, h):
+        """dWorldStep (what the reference calls, src/main.c:213)."""
+        return self.L.dWorldStep(self.w, float(h))
 
     def tick(self, h, max_contacts=8):
         """One reference tick (src/main.c:212-214), device-resident."""

@@ -336,3 +336,27 @@ def test_one_step_tolerance_is_meaningful_under_fma_rounding(oracle_lib):
         d = np.abs(sa[k].astype(np.float64) - sb[k]) / np.maximum(np.abs(sa[k]), floor)
         assert d.max() < 1e-4, k
     assert np.abs(sa["lvel"] - sb["lvel"]).max() > 0          # ... but it is not bit-identical
+
+
+def test_exact_lcp_mode_is_the_limit_of_the_sweeps(oracle_lib):
+    """order_mode 3 (the dWorldStep restatement: exact LCP by principal pivoting, double precision) must be
+    what SOR/PGS converges to -- A = J invM J^T + cfm/h is SPD, so the bounded LCP has one solution -- and
+    20 sweeps must be measurably further from it than 2000."""
+    from odeb200 import scenes
+    sc = scenes.server_scene(seed=1, y_range=(1.0, 6.0))
+    dist = {}
+    ref = None
+    for iters, mode in ((0, 3), (20, 1), (200, 1), (5000, 1)):
+        ow = O.OracleWorld(iters=max(iters, 1))
+        ow.load_scene(sc)
+        nc = ow.collide_all(8, O.reference_surface())
+        assert nc > 20
+        ow.quickstep(sc["h"], order_mode=mode)
+        v = np.concatenate([ow.state()["lvel"], ow.state()["avel"]], axis=1).astype(np.float64)
+        if mode == 3:
+            ref = v
+        else:
+            dist[iters] = np.abs(v - ref).max()
+    assert dist[5000] < 2e-3, dist
+    assert dist[20] > 5 * dist[5000], dist
+    assert dist[200] < dist[20], dist

@@ -10,6 +10,7 @@ import os
 import numpy as np
 import pytest
 
+import oracle as O
 import util
 from odeb200 import scenes
 
@@ -440,3 +441,33 @@ def test_capacity_overflow_is_flagged_not_silent():
     s = ew.state()
     assert np.isfinite(s["pos"]).all()
     ew.close()
+
+
+def test_dworldstep_parity_mode_converges_to_the_exact_lcp():
+    """the reference calls dWorldStep (src/main.c:213), libode's exact Dantzig stepper.
+    With dWorldSetStepSolverB200 the engine's dWorldStep runs residual-terminated sweeps; its distance from the
+    oracle's exact LCP restatement (order_mode 3) must shrink with the sweep budget, and the tolerance must end
+    the sweeps early.  Distances are velocities after one C1 tick (m/s, rad/s)."""
+    sc = _scene("c1_low")
+    ow = util.oracle_world(sc)
+    ow.collide_all(8, O.reference_surface())
+    ow.quickstep(sc["h"], order_mode=3)
+    so = ow.state()
+    ref = np.concatenate([so["lvel"], so["avel"]], axis=1).astype(np.float64)
+    dist, used = {}, {}
+    for iters, tol in ((0, 0.0), (100, 0.0), (2000, 0.0), (20000, 1e-4)):
+        ew = util.engine_world(sc)
+        ew.set_step_solver(iters, tol)
+        ew.collide()
+        ew.world_step(sc["h"])
+        se = ew.state()
+        v = np.concatenate([se["lvel"], se["avel"]], axis=1).astype(np.float64)
+        dist[iters] = float(np.abs(v - ref).max())
+        used[iters] = ew.stats()["solver_iters"]
+        ew.close()
+    print("dWorldStep parity mode: max |v - v_exact| by sweep budget:", dist, "sweeps used:", used)
+    assert used[0] == 20 and used[100] == 100 and used[2000] == 2000
+    assert 20 < used[20000] < 20000                 # the tolerance ended the sweeps
+    assert dist[0] > 0.01                           # 20 QuickStep sweeps are visibly not the LCP solution
+    assert dist[100] < 0.2 * dist[0]
+    assert dist[2000] < 2e-3 and dist[20000] < 2e-3
