@@ -213,6 +213,25 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank (and first-touch its pinned staging buffers) on the CPUs nearest its GPU: at 8 ranks the
+    per-tick snapshot / force copies otherwise cross sockets.  Returns the previous affinity (restored for the
+    cpu_baseline leg, which uses every host thread)."""
+    try:
+        import pynvml
+        prev = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = {i for i in range(n) if (int(words[i // 64]) >> (i % 64)) & 1} & prev
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return prev
+    except Exception:
+        return None
+
+
 def main():
     args = parse_args()
     from odeb200 import sharding
@@ -226,6 +245,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libode_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
+    prev_affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         sharding.init_process_group("nccl")
     dev = "cuda:%d" % local_rank

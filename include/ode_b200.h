@@ -102,6 +102,10 @@ void dWorldSetSolverModeB200(dWorldID, int mode, int env_group);
 void dWorldSetContactUnitsB200(dWorldID, int per_contact);
 /* dynamic geoms whose AABB extent exceeds this are treated like static "big" geoms (default inf) */
 void dWorldSetBigExtentB200(dWorldID, float extent);
+/* Wavefront OBJ (v / f records, 1-based or negative indices, polygons fan-triangulated) into a trimesh data
+ * object, in place of dGeomTriMeshDataBuildSingle (the reference ships res/teapot.obj and res/grassPlane.obj;
+ * BASELINE config 2 uses the teapot as a static collision mesh).  Returns the triangle count or -1. */
+int dGeomTriMeshDataBuildFromOBJB200(dTriMeshDataID, const char *path);
 /* dWorldStep parity mode (the reference calls dWorldStep, src/main.c:213; libode solves its LCP exactly): let
  * dWorldStep run up to max_iters SOR/PGS sweeps and stop once the largest |delta lambda| of a sweep is below
  * tol (tol 0: always max_iters).  max_iters 0 (default): dWorldStep == dWorldQuickStep.  dWorldQuickStep is

@@ -711,6 +711,48 @@ extern "C" void dGeomTriMeshDataBuildSingle(dTriMeshDataID d, const void *Vertic
     d->bound_world = nullptr;
     d->mesh_id = -1;
 }
+// Wavefront OBJ -> trimesh data (res/teapot.obj, res/grassPlane.obj).  Reads `v x y z`
+// and `f` records (`a`, `a/b`, `a//c`, `a/b/c`; 1-based, negative = relative to the vertices read so far);
+// polygons are fan-triangulated; everything else is skipped.  Returns the triangle count, -1 if the file cannot
+// be read or holds no triangle.
+extern "C" int dGeomTriMeshDataBuildFromOBJB200(dTriMeshDataID d, const char *path) {
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    d->verts.clear(); d->tris.clear();
+    char line[4096];
+    while (fgets(line, sizeof(line), f)) {
+        const char *p = line;
+        while (*p == ' ' || *p == '\t') p++;
+        if (p[0] == 'v' && (p[1] == ' ' || p[1] == '\t')) {
+            float x, y, z;
+            if (sscanf(p + 1, "%f %f %f", &x, &y, &z) == 3) { d->verts.push_back(x); d->verts.push_back(y); d->verts.push_back(z); }
+        } else if (p[0] == 'f' && (p[1] == ' ' || p[1] == '\t')) {
+            const int nv = (int)d->verts.size() / 3;
+            int idx[64], n = 0;
+            p += 1;
+            while (n < 64) {
+                while (*p == ' ' || *p == '\t') p++;
+                if (*p == 0 || *p == '\n' || *p == '\r' || *p == '#') break;
+                char *end;
+                long v = strtol(p, &end, 10);
+                if (end == p) break;
+                if (v < 0) v = nv + v + 1;
+                idx[n++] = (int)v - 1;
+                p = end;
+                while (*p && *p != ' ' && *p != '\t' && *p != '\n' && *p != '\r') p++; // skip /vt/vn
+            }
+            bool ok = n >= 3;
+            for (int k = 0; k < n; k++) ok = ok && idx[k] >= 0 && idx[k] < nv;
+            if (ok)
+                for (int k = 1; k + 1 < n; k++) { d->tris.push_back(idx[0]); d->tris.push_back(idx[k]); d->tris.push_back(idx[k + 1]); }
+        }
+    }
+    fclose(f);
+    d->bound_world = nullptr;
+    d->mesh_id = -1;
+    const int nt = (int)d->tris.size() / 3;
+    return nt > 0 ? nt : -1;
+}
 extern "C" dGeomID dCreateTriMesh(dSpaceID s, dTriMeshDataID d, dTriCallback *, dTriArrayCallback *, dTriRayCallback *) {
     dxWorld *w = space_world(s);
     if (d->bound_world != w || d->mesh_id < 0) {

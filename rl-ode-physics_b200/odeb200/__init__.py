@@ -94,6 +94,7 @@ _SIGS = [
     ("dGeomTriMeshDataCreate", _vp, []), ("dGeomTriMeshDataDestroy", None, [_vp]),
     ("dGeomTriMeshDataBuildSingle", None, [_vp, _vp, _i, _i, _vp, _i, _i]),
     ("dCreateTriMesh", _vp, [_vp, _vp, _vp, _vp, _vp]),
+    ("dGeomTriMeshDataBuildFromOBJB200", _i, [_vp, C.c_char_p]),
     ("dJointGroupCreate", _vp, [_i]), ("dJointGroupEmpty", None, [_vp]), ("dJointGroupDestroy", None, [_vp]),
     ("dJointCreateContact", _vp, [_vp, _vp, C.POINTER(Contact)]), ("dJointAttach", None, [_vp, _vp, _vp]),
     # extensions

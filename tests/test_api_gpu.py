@@ -257,3 +257,41 @@ def test_destroyed_body_leaves_its_geom_in_place_incrementally():
     assert np.array_equal(st2["pos"][4], st["pos"][4])
     assert not np.array_equal(st2["pos"][5], st["pos"][5])
     ew.close()
+
+
+def test_obj_loader_builds_the_same_trimesh_as_buildsingle(tmp_path):
+    """SURVEY section 8 f4 (loader half): an OBJ with quads, `a/b/c` references, negative indices and noise lines
+    must give the same collision mesh -- hence bit-identical contacts -- as dGeomTriMeshDataBuildSingle fed
+    with the triangulation done here."""
+    verts = np.float32([[-2, 0, -2], [2, 0, -2], [2, 0, 2], [-2, 0, 2], [0, 1.0, 0]])
+    lines = ["# test mesh", "o pyramid", "mtllib none.mtl"]
+    lines += ["v %g %g %g" % tuple(v) for v in verts]
+    lines += ["vn 0 1 0", "vt 0 0", "usemtl m", "s off",
+              "f 1/1/1 2/1/1 3/1/1 4/1/1",        # quad -> fan: (0,1,2), (0,2,3)
+              "f 1//1 5//1 2//1",
+              "f -4 -1 -3",                         # relative: (1, 4, 2)
+              "f 3 5 4", "f 4 5 1"]
+    path = tmp_path / "pyramid.obj"
+    path.write_text("\n".join(lines) + "\n")
+    tris = np.int32([[0, 1, 2], [0, 2, 3], [0, 4, 1], [1, 4, 2], [2, 4, 3], [3, 4, 0]])
+    L = odeb200.lib()
+    results = []
+    for use_obj in (True, False):
+        s = Server()
+        d = C.c_void_p(L.dGeomTriMeshDataCreate())
+        if use_obj:
+            assert L.dGeomTriMeshDataBuildFromOBJB200(d, str(path).encode()) == len(tris)
+        else:
+            v = np.ascontiguousarray(verts); t = np.ascontiguousarray(tris)
+            L.dGeomTriMeshDataBuildSingle(d, v.ctypes.data, 12, len(v), t.ctypes.data, 3 * len(t), 12)
+        g = C.c_void_p(L.dCreateTriMesh(s.space, d, None, None, None))
+        s.geoms.append(g)
+        balls = [s.add_body(p, "sphere", (0.3,))[0] for p in ([0.5, 1.2, 0.3], [-1.0, 0.9, 0.2], [1.2, 0.5, -0.8], [0.0, 1.6, 0.0])]
+        for _ in range(40):
+            s.tick()
+        results.append(np.stack([s.pos(b) for b in balls]))
+        s.close()
+        L.dGeomTriMeshDataDestroy(d)
+    assert np.array_equal(results[0], results[1])
+    assert results[0][:, 1].min() > 0.2              # nobody fell through the mesh
+    assert L.dGeomTriMeshDataBuildFromOBJB200(C.c_void_p(L.dGeomTriMeshDataCreate()), b"/nonexistent.obj") == -1
