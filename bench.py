@@ -355,7 +355,7 @@ def main():
                 traffic = tj.get(args.workload, {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        kname = ("k_env_solve<G> + k_integrate (island solver: colouring, rows, 20 PGS iterations; integrate + snapshot pack)"
+        kname = ("k_env_solve<G> (island solver: body preparation, colouring, rows, 20 PGS iterations, integrate + snapshot pack in one kernel)"
                  if args.workload == "C4" else "k_solve (20 PGS iterations x colours, fused integrate + snapshot pack)")
         roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved,
                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
