@@ -74,6 +74,14 @@ void dWorldWaitB200(dWorldID);
  * send them GPU to GPU); asynchronous on the world's stream. */
 void dWorldPackStatesDeviceB200(dWorldID, const int *d_idx, int n, float *d_out16);
 void dWorldUnpackStatesDeviceB200(dWorldID, const int *d_idx, int n, const float *d_in16);
+/* impulse half of the halo exchange: the velocity change the last step's contacts
+ * gave each listed body -- 8 floats per body: h*fc linear xyz, pad, angular xyz, pad -- gathered into a DEVICE
+ * buffer; the receiving world adds such a buffer to the listed bodies' velocities (kinematic bodies are
+ * skipped).  A slab that solves a contact against a dynamic ghost sends the ghost's impulse to its owner.
+ * Batched worlds keep their accumulators on chip unless dWorldSetKeepImpulsesB200(world, 1). */
+void dWorldPackImpulsesDeviceB200(dWorldID, const int *d_idx, int n, float *d_out8);
+void dWorldAddImpulsesDeviceB200(dWorldID, const int *d_idx, int n, const float *d_in8);
+void dWorldSetKeepImpulsesB200(dWorldID, int on);
 /* CUDA-event timer on the world's stream: everything queued between start and stop */
 void dWorldTimerStartB200(dWorldID);
 void dWorldTimerStopB200(dWorldID);

@@ -934,6 +934,48 @@ void eng_pack_states_device(Engine *e, const int *d_idx, int n, float *d_out) {
     k_pack_states<<<(unsigned)((n + 255) / 256), 256, 0, e->st>>>(n, d_idx, e->B, reinterpret_cast<float4 *>(d_out));
     OB_CHECK_KERNEL("k_pack_states", e->st);
 }
+// Constraint impulses of the last step, per listed body: 8 floats = h * fc (linear xyz, pad, angular xyz, pad),
+// i.e. exactly the velocity change the step's contacts gave the body.  A slab that solves a cross-face contact
+// against a dynamic ghost sends these to the ghost's owner, which adds them.
+__global__ void __launch_bounds__(256) k_pack_impulses(int n, const int *__restrict__ idx, const float4 *__restrict__ fc, float h,
+                                                        float4 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = idx[i];
+    const float4 l = fc[2 * (size_t)b], a = fc[2 * (size_t)b + 1];
+    out[2 * (size_t)i] = make_float4(h * l.x, h * l.y, h * l.z, 0.f);
+    out[2 * (size_t)i + 1] = make_float4(h * a.x, h * a.y, h * a.z, 0.f);
+}
+__global__ void __launch_bounds__(256) k_add_impulses(int n, const int *__restrict__ idx, BodyArrays B, const float4 *__restrict__ in) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = idx[i];
+    if (!(B.pos[b].w > 0.f)) return; // kinematic / destroyed bodies take no impulse
+    const float4 l = in[2 * (size_t)i], a = in[2 * (size_t)i + 1];
+    float4 lv = B.lvel[b], av = B.avel[b];
+    lv.x += l.x; lv.y += l.y; lv.z += l.z;
+    av.x += a.x; av.y += a.y; av.z += a.z;
+    B.lvel[b] = lv;
+    B.avel[b] = av;
+}
+void eng_pack_impulses_device(Engine *e, const int *d_idx, int n, float *d_out) {
+    if (!e->fc_valid) {
+        fprintf(stderr, "libode_b200: dWorldPackImpulsesDeviceB200: no accumulators from the last step (call "
+                        "dWorldSetKeepImpulsesB200(world, 1) before stepping batched worlds)\n");
+        abort();
+    }
+    if (n <= 0) return;
+    k_pack_impulses<<<(unsigned)((n + 255) / 256), 256, 0, e->st>>>(n, d_idx, e->B.fc, e->last_h, reinterpret_cast<float4 *>(d_out));
+    OB_CHECK_KERNEL("k_pack_impulses", e->st);
+}
+void eng_add_impulses_device(Engine *e, const int *d_idx, int n, const float *d_in) {
+    eng_sync_to_device(e);
+    if (n <= 0) return;
+    k_add_impulses<<<(unsigned)((n + 255) / 256), 256, 0, e->st>>>(n, d_idx, e->B, reinterpret_cast<const float4 *>(d_in));
+    OB_CHECK_KERNEL("k_add_impulses", e->st);
+    e->host_stale = true;
+}
+void eng_set_keep_impulses(Engine *e, int on) { e->keep_fc = on != 0; }
 void eng_unpack_states_device(Engine *e, const int *d_idx, int n, const float *d_in) {
     eng_sync_to_device(e);
     if (n <= 0) return;

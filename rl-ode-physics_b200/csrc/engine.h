@@ -193,6 +193,9 @@ void eng_set_forces(Engine *, const float *f6, int n);
 // halo exchange: gather / scatter body states (16 floats each) through device buffers (async)
 void eng_pack_states_device(Engine *, const int *d_idx, int n, float *d_out);
 void eng_unpack_states_device(Engine *, const int *d_idx, int n, const float *d_in);
+void eng_pack_impulses_device(Engine *, const int *d_idx, int n, float *d_out);
+void eng_add_impulses_device(Engine *, const int *d_idx, int n, const float *d_in);
+void eng_set_keep_impulses(Engine *, int on);
 // wait for everything queued on the engine stream
 void eng_wait(Engine *);
 StepStats eng_stats(Engine *);                  // blocking: stats of the last collide/step

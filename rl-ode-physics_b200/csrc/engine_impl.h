@@ -16,6 +16,8 @@ struct Engine {
     HostGeoms hg;
     bool bodies_dirty = false, geoms_dirty = false, forces_dirty = false;
     bool host_stale = false; // device state is newer than the host mirrors
+    bool keep_fc = false, fc_valid = false; // the last step left the bodies' accumulators fc in global memory
+    float last_h = 0.f;
     // incremental ingestion (spawns, per-tick setters): dirty lists + per-entry field masks
     std::vector<int> dirty_b, dirty_g, force_b;
     std::vector<unsigned char> mask_b, mask_g, inforce_b;

@@ -341,6 +341,9 @@ extern "C" void dWorldSetSolverModeB200(dWorldID w, int mode, int env_group) { e
 extern "C" void dWorldSetContactUnitsB200(dWorldID w, int per_contact) { eng_set_contact_units(w->eng, per_contact); }
 extern "C" void dWorldWaitB200(dWorldID w) { eng_wait(w->eng); }
 extern "C" void dWorldPackStatesDeviceB200(dWorldID w, const int *d_idx, int n, float *d_out) { eng_pack_states_device(w->eng, d_idx, n, d_out); }
+extern "C" void dWorldPackImpulsesDeviceB200(dWorldID w, const int *d_idx, int n, float *d_out) { eng_pack_impulses_device(w->eng, d_idx, n, d_out); }
+extern "C" void dWorldAddImpulsesDeviceB200(dWorldID w, const int *d_idx, int n, const float *d_in) { eng_add_impulses_device(w->eng, d_idx, n, d_in); }
+extern "C" void dWorldSetKeepImpulsesB200(dWorldID w, int on) { eng_set_keep_impulses(w->eng, on); }
 extern "C" void dWorldUnpackStatesDeviceB200(dWorldID w, const int *d_idx, int n, const float *d_in) { eng_unpack_states_device(w->eng, d_idx, n, d_in); }
 extern "C" void dWorldTimerStartB200(dWorldID w) { eng_timer_start(w->eng); }
 extern "C" void dWorldTimerStopB200(dWorldID w) { eng_timer_stop(w->eng); }

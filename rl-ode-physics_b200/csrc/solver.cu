@@ -864,7 +864,11 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
         }
         if (trips == 0) { // no contacts in any env of this warp: free flight
             if (fused)
-                for (int i = g; i < nbod; i += G) integrate_body(fb + i, B, cfg.h, make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f));
+                for (int i = g; i < nbod; i += G) {
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    integrate_body(fb + i, B, cfg.h, z, z);
+                    if (fused == 2) { B.fc[2 * (size_t)(fb + i)] = z; B.fc[2 * (size_t)(fb + i) + 1] = z; }
+                }
             continue;
         }
         PROF_T(t0);
@@ -999,6 +1003,10 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
                 const float4 fl = stage ? sm_fc[i] : B.fc[2 * (size_t)(fb + i)];
                 const float4 fa = stage ? sm_fc[mb + i] : B.fc[2 * (size_t)(fb + i) + 1];
                 integrate_body(fb + i, B, cfg.h, fl, fa);
+                if (fused == 2) { // the caller wants the step's impulses (dWorldPackImpulsesDeviceB200)
+                    B.fc[2 * (size_t)(fb + i)] = fl;
+                    B.fc[2 * (size_t)(fb + i) + 1] = fa;
+                }
             }
             __syncwarp();
         } else if (stage) { // hand the accumulators to k_integrate
@@ -1093,7 +1101,9 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
     // k_env_solve, env by env; otherwise they are separate passes over all bodies
     const bool island = !host_contacts && e->have_device_contacts && e->n_envs > 1 && e->E.max_bodies <= 1024 && e->solver_mode != 1 &&
                         !(cfg.tol > 0.f); // residual termination is a grid-wide decision: global solver
-    const int fused = (island && e->E.contiguous && e->env_fuse) ? 1 : 0;
+    const int fused = (island && e->E.contiguous && e->env_fuse) ? (e->keep_fc ? 2 : 1) : 0;
+    e->last_h = h;
+    e->fc_valid = fused != 1; // the fused island path keeps the accumulators in shared memory only
     if (!fused) {
         k_body_prep<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(B, cfg);
         OB_CHECK_KERNEL("k_body_prep", st);

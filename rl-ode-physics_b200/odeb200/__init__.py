@@ -117,6 +117,8 @@ _SIGS = [
     ("dWorldGetSnapshotDeviceB200", _vp, [_vp]),
     ("dWorldWaitB200", None, [_vp]),
     ("dWorldPackStatesDeviceB200", None, [_vp, _vp, _i, _vp]), ("dWorldUnpackStatesDeviceB200", None, [_vp, _vp, _i, _vp]),
+    ("dWorldPackImpulsesDeviceB200", None, [_vp, _vp, _i, _vp]), ("dWorldAddImpulsesDeviceB200", None, [_vp, _vp, _i, _vp]),
+    ("dWorldSetKeepImpulsesB200", None, [_vp, _i]),
     ("dWorldTimerStartB200", None, [_vp]), ("dWorldTimerStopB200", None, [_vp]),
     ("dWorldTimerElapsedB200", C.c_float, [_vp]), ("dGetKernelLaunchCountB200", C.c_long, []),
     ("dWorldSetCapacityB200", None, [_vp, C.c_long, C.c_long]),
