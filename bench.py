@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--settle", type=int, default=-1)
     ap.add_argument("--slab-cols", type=int, default=128, help="C5: lattice columns (x) per GPU; z = 1024, y = 16")
+    ap.add_argument("--coupling", default="impulse", choices=["impulse", "ghost"],
+                    help="C5: impulse = lower slab owns cross-face contacts, impulses sent back to the owner; "
+                         "ghost = kinematic ghosts on both sides")
     return ap.parse_args()
 
 
@@ -255,9 +258,13 @@ def main():
     if args.workload == "C5":
         # one slab of the 1024(z) x 16(y) lattice per GPU, halo exchange of boundary bodies over NCCL
         from odeb200 import slabs
-        sc, halo = slabs.slab_scene(rank, world, nx_per_slab=args.slab_cols, nz=1024, ny=16, seed=5, margin_cols=4)
+        sc, halo = slabs.slab_scene(rank, world, nx_per_slab=args.slab_cols, nz=1024, ny=16, seed=5, margin_cols=4,
+                                     coupling=args.coupling)
         desc = ("C5: slab-decomposed single world, %d x 1024 x 16 lattice columns per GPU (%d bodies/GPU), NCCL halo exchange "
-                "of boundary-body states each tick, dt=1/60, QuickStep 20 iters" % (args.slab_cols, args.slab_cols * 1024 * 16))
+                "each tick (%s), dt=1/60, QuickStep 20 iters"
+                % (args.slab_cols, args.slab_cols * 1024 * 16,
+                   "boundary-body states to the lower slab, contact impulses back to the owner" if args.coupling == "impulse"
+                   else "boundary-body states both ways, kinematic ghosts"))
         n_bodies = sc["n_owned"]
     else:
         sc, desc = build_scene(args.workload, rank, args.worlds_per_gpu)
@@ -268,7 +275,7 @@ def main():
     h = sc["h"]
     if args.workload == "C5":
         slab = slabs.SlabWorld(ew, halo, dev)
-        exch = (lambda: slabs.exchange_nccl(slab, rank, world)) if world > 1 else (lambda: None)
+        exch = (lambda kind: slabs.exchange_nccl(slab, rank, world, kind)) if world > 1 else (lambda kind: None)
 
         def do_tick():
             slabs.tick(slab, exch, h)

@@ -7,7 +7,8 @@ from odeb200 import scenes, slabs
 
 def test_neighbouring_slabs_agree_on_the_halo():
     n_slabs, nx, nz, ny, mc = 3, 6, 5, 3, 2
-    built = [slabs.slab_scene(r, n_slabs, nx_per_slab=nx, nz=nz, ny=ny, seed=5, margin_cols=mc) for r in range(n_slabs)]
+    built = [slabs.slab_scene(r, n_slabs, nx_per_slab=nx, nz=nz, ny=ny, seed=5, margin_cols=mc, coupling="ghost")
+             for r in range(n_slabs)]
     for r, (sc, halo) in enumerate(built):
         n_own = sc["n_owned"]
         assert n_own == nx * nz * ny
@@ -18,8 +19,8 @@ def test_neighbouring_slabs_agree_on_the_halo():
         assert np.array_equal(g["body"][5:], np.arange(len(b["pos"])))
         assert (g["cat"][5:5 + n_own] == slabs.CAT_OBJ).all() and (g["cat"][5 + n_own:] == slabs.CAT_GHOST).all()
         if halo["right"] is not None:
-            send, _ = halo["right"]
-            _, recv = built[r + 1][1]["left"]
+            send = halo["right"]["send_state"]
+            recv = built[r + 1][1]["left"]["recv_state"]
             nb, ng = built[r + 1][0]["bodies"], built[r + 1][0]["geoms"]
             assert len(send) == len(recv) == mc * nz * ny
             # the neighbour's ghosts mirror exactly the bodies we send, in the same order
@@ -30,12 +31,39 @@ def test_neighbouring_slabs_agree_on_the_halo():
             face = 0.5 * (b["pos"][:n_own, 0].max() + nb["pos"][:built[r + 1][0]["n_owned"], 0].min())
             assert (np.abs(b["pos"][send, 0] - face) < (mc + 0.5) * 1.8).all()
         if halo["left"] is not None:
-            send, _ = halo["left"]
-            _, recv = built[r - 1][1]["right"]
+            send = halo["left"]["send_state"]
+            recv = built[r - 1][1]["right"]["recv_state"]
             assert np.array_equal(b["pos"][send], built[r - 1][0]["bodies"]["pos"][recv])
     # slabs tile x without gaps: owned x ranges are disjoint and ordered
     xs = [(sc["bodies"]["pos"][:sc["n_owned"], 0].min(), sc["bodies"]["pos"][:sc["n_owned"], 0].max()) for sc, _ in built]
     assert xs[0][1] < xs[1][0] and xs[1][1] < xs[2][0]
+
+
+def test_impulse_coupling_lower_slab_owns_the_face():
+    """a cross-slab contact is owned by the lower slab.  Rank r mirrors only rank r+1's
+    boundary columns, as dynamic bodies with the owners' masses; states travel down, impulses travel up, and
+    the index lists of the two ends of every message line up."""
+    n_slabs, nx, nz, ny, mc = 3, 6, 5, 3, 2
+    built = [slabs.slab_scene(r, n_slabs, nx_per_slab=nx, nz=nz, ny=ny, seed=5, margin_cols=mc) for r in range(n_slabs)]
+    for r, (sc, halo) in enumerate(built):
+        n_own = sc["n_owned"]
+        b, g = sc["bodies"], sc["geoms"]
+        n_ghost = len(b["pos"]) - n_own
+        assert n_ghost == (mc * nz * ny if r < n_slabs - 1 else 0)
+        assert (b["flags"] == 0).all()                              # ghosts are dynamic here
+        assert (g["cat"][5 + n_own:] == slabs.CAT_GHOST).all() and (g["col"][5 + n_own:] == 0).all()
+        if r > 0:
+            left, up = halo["left"], built[r - 1][1]["right"]
+            assert left["recv_state"] is None and left["send_imp"] is None
+            assert np.array_equal(left["send_state"], left["recv_imp"])
+            assert np.array_equal(up["recv_state"], up["send_imp"])
+            assert up["send_state"] is None and up["recv_imp"] is None
+            lower = built[r - 1][0]["bodies"]
+            # the lower rank's ghosts mirror exactly the bodies we send: same pose, same mass, same shape
+            assert np.array_equal(b["pos"][left["send_state"]], lower["pos"][up["recv_state"]])
+            assert np.array_equal(b["mass"][left["send_state"]], lower["mass"][up["recv_state"]])
+            assert np.array_equal(g["dims"][5 + left["send_state"]], built[r - 1][0]["geoms"]["dims"][5 + up["recv_state"]])
+    assert built[0][1]["left"] is None and built[-1][1]["right"] is None
 
 
 def test_ghosts_only_collide_with_owned_bodies():

@@ -21,16 +21,16 @@ def _build(n_slabs, **kw):
 
 
 def test_two_slab_pile_with_halo_exchange():
-    kw = dict(nx_per_slab=8, nz=32, ny=6, seed=5, spacing=0.8, margin_cols=3)
+    kw = dict(nx_per_slab=8, nz=32, ny=6, seed=5, spacing=0.8, margin_cols=3, coupling="ghost")
     built = _build(2, **kw)
     sl = [s for _, s in built]
     h = built[0][0]["h"]
     for step in range(150):
         for s in sl:
-            s.pack()
-        slabs.exchange_local(sl)
+            s.pack("state")
+        slabs.exchange_local(sl, "state")
         for s in sl:
-            s.unpack()
+            s.unpack("state")
         if step == 149:
             break
         for s in sl:
@@ -38,8 +38,8 @@ def test_two_slab_pile_with_halo_exchange():
     st = [s.w.state() for s in sl]
     n0, n1 = built[0][0]["n_owned"], built[1][0]["n_owned"]
     # after an exchange the ghosts carry exactly the owners' states
-    send0, recv0 = sl[0].sides["right"]["send_idx"].cpu().numpy(), sl[0].sides["right"]["recv_idx"].cpu().numpy()
-    send1, recv1 = sl[1].sides["left"]["send_idx"].cpu().numpy(), sl[1].sides["left"]["recv_idx"].cpu().numpy()
+    send0, recv0 = sl[0].sides["right"]["send_state_idx"].cpu().numpy(), sl[0].sides["right"]["recv_state_idx"].cpu().numpy()
+    send1, recv1 = sl[1].sides["left"]["send_state_idx"].cpu().numpy(), sl[1].sides["left"]["recv_state_idx"].cpu().numpy()
     for k in ("pos", "quat", "lvel", "avel"):
         assert np.array_equal(st[0][k][send0], st[1][k][recv1]), k
         assert np.array_equal(st[1][k][send1], st[0][k][recv0]), k
@@ -76,5 +76,133 @@ def test_two_slab_pile_with_halo_exchange():
     assert abs(y_dec.mean() - so["pos"][:, 1].mean()) < 0.05 * so["pos"][:, 1].mean()
     assert abs(y_dec.max() - so["pos"][:, 1].max()) < 0.35
     one.close()
+    for s in sl:
+        s.w.close()
+
+
+def _two_sphere_slabs(coupling, va, vb):
+    """Two unit-mass spheres on a collision course along x in free space, one per slab (face at x = 0)."""
+    import odeb200
+    CAT_OBJ, CAT_GHOST = slabs.CAT_OBJ, slabs.CAT_GHOST
+    pa, pb = (-0.45, 0.0, 0.0), (0.45, 0.0, 0.0)
+    worlds, halos = [], []
+    for r in range(2):
+        sc = scenes._empty_scene("pair%d" % r, gravity=(0.0, 0.0, 0.0))
+        own_p, own_v = (pa, va) if r == 0 else (pb, vb)
+        oth_p, oth_v = (pb, vb) if r == 0 else (pa, va)
+        b0 = scenes._add_body(sc, own_p, lvel=own_v, flags=0)
+        scenes._add_geom(sc, scenes.SPHERE, (0.5, 0, 0, 0), body=b0, cat=CAT_OBJ, col=CAT_OBJ | CAT_GHOST)
+        hs = {"send_state": None, "recv_state": None, "send_imp": None, "recv_imp": None}
+        mirror = coupling == "ghost" or r == 0
+        if mirror:
+            b1 = scenes._add_body(sc, oth_p, lvel=oth_v, flags=scenes.BODY_KINEMATIC if coupling == "ghost" else 0)
+            scenes._add_geom(sc, scenes.SPHERE, (0.5, 0, 0, 0), body=b1, cat=CAT_GHOST, col=0)
+            hs["recv_state"] = np.int32([b1])
+            if coupling == "impulse":
+                hs["send_imp"] = np.int32([b1])
+        if coupling == "ghost" or r == 1:
+            hs["send_state"] = np.int32([b0])
+        if coupling == "impulse" and r == 1:
+            hs["recv_imp"] = np.int32([b0])
+        sc = scenes.finalize(sc)
+        w = odeb200.World(gravity=sc["gravity"])
+        w.load_scene(sc)
+        halo = {"left": hs if r == 1 else None, "right": hs if r == 0 else None}
+        worlds.append(slabs.SlabWorld(w, halo, "cuda:0"))
+    return worlds
+
+
+def _run_pair(coupling, va, vb, ticks=12):
+    sl = _two_sphere_slabs(coupling, va, vb)
+    exch = lambda kind: slabs.exchange_local(sl, kind)   # noqa: E731
+    for _ in range(ticks):
+        # the same order bench.py runs per rank: states, tick, impulses -- here phase by phase over both slabs
+        for s in sl:
+            s.pack("state")
+        exch("state")
+        for s in sl:
+            s.unpack("state")
+        for s in sl:
+            s.w.tick(1.0 / 60.0)
+        if sl[0].has_imp:
+            for s in sl:
+                s.pack("imp")
+            exch("imp")
+            for s in sl:
+                s.unpack("imp")
+    v = [s.w.state()["lvel"][0].astype(np.float64) for s in sl]
+    for s in sl:
+        s.w.close()
+    return v
+
+
+def test_impulse_coupling_conserves_momentum_across_the_face():
+    """SURVEY.md section 8e step 3.  A moving sphere (slab 0) hits a resting one (slab 1).  With the impulse halo
+    the lower slab solves the two-body contact and the owner of the struck sphere receives the opposite impulse:
+    total momentum is conserved and the result matches the same two spheres in ONE world.  With kinematic ghosts
+    each side sees an immovable obstacle and over-corrects."""
+    va, vb = (2.0, 0.0, 0.0), (0.0, 0.0, 0.0)
+    v_imp = _run_pair("impulse", va, vb)
+    p_imp = v_imp[0][0] + v_imp[1][0]
+    assert abs(p_imp - 2.0) < 1e-4, v_imp
+    assert v_imp[1][0] > 0.5 and v_imp[0][0] < 1.5            # the struck sphere really moves off
+    # one world, no decomposition
+    sc = scenes._empty_scene("pair", gravity=(0.0, 0.0, 0.0))
+    for p, v in (((-0.45, 0, 0), va), ((0.45, 0, 0), vb)):
+        b = scenes._add_body(sc, p, lvel=v, flags=0)
+        scenes._add_geom(sc, scenes.SPHERE, (0.5, 0, 0, 0), body=b)
+    one = util.engine_world(scenes.finalize(sc))
+    for _ in range(12):
+        one.tick(1.0 / 60.0)
+    vo = one.state()["lvel"].astype(np.float64)
+    one.close()
+    assert abs(vo[0, 0] + vo[1, 0] - 2.0) < 1e-4
+    print("impulse halo:", v_imp, "one world:", vo[:, 0])
+    assert abs(v_imp[0][0] - vo[0, 0]) < 0.25 and abs(v_imp[1][0] - vo[1, 0]) < 0.25, (v_imp, vo)
+    v_gh = _run_pair("ghost", va, vb)
+    # each side resolves the whole relative velocity against an immovable obstacle: the pair flies apart much
+    # faster than physics allows (the impulse halo does not)
+    sep_one = vo[1, 0] - vo[0, 0]
+    assert (v_gh[1][0] - v_gh[0][0]) > 2.0 * sep_one and abs((v_imp[1][0] - v_imp[0][0]) - sep_one) < 0.3, (v_gh, v_imp, vo)
+
+
+def test_two_slab_pile_with_impulse_halo():
+    """the default coupling on a pile: states down, impulses up; the pile settles like the undecomposed one"""
+    kw = dict(nx_per_slab=8, nz=32, ny=6, seed=5, spacing=0.8, margin_cols=3, coupling="impulse")
+    built = _build(2, **kw)
+    sl = [s for _, s in built]
+    h = built[0][0]["h"]
+    exch = lambda kind: slabs.exchange_local(sl, kind)   # noqa: E731
+    for step in range(150):
+        for kind in ("state",):
+            for s in sl:
+                s.pack(kind)
+            exch(kind)
+            for s in sl:
+                s.unpack(kind)
+        for s in sl:
+            s.w.tick(h)
+        for s in sl:
+            s.pack("imp")
+        exch("imp")
+        for s in sl:
+            s.unpack("imp")
+    st = [s.w.state() for s in sl]
+    n0, n1 = built[0][0]["n_owned"], built[1][0]["n_owned"]
+    assert "left" not in sl[0].sides and "right" not in sl[1].sides
+    assert len(st[1]["pos"]) == n1                              # the upper slab holds no ghosts
+    for r, n in ((0, n0), (1, n1)):
+        assert np.isfinite(st[r]["pos"]).all()
+        assert st[r]["pos"][:n, 1].min() > 0.0
+        assert np.abs(st[r]["lvel"][:n]).max() < 9.0
+        assert sl[r].w.stats()["flags"] == 0
+    # cross-face contacts exist on the lower slab and stay shallow
+    sl[0].w.collide(8)
+    pr, cnt, pd, nrm, side = sl[0].w.contacts()
+    gb = built[0][0]["geoms"]["body"]
+    cross = np.repeat((gb[pr[:, 0]] >= n0) | (gb[pr[:, 1]] >= n0), cnt)
+    assert cross.sum() >= 4 and pd[cross, 3].max() < 0.15
+    y_dec = np.concatenate([st[0]["pos"][:n0, 1], st[1]["pos"][:n1, 1]])
+    assert 0.2 < y_dec.mean() < 3.0
     for s in sl:
         s.w.close()
