@@ -82,6 +82,19 @@ void dWorldUnpackStatesDeviceB200(dWorldID, const int *d_idx, int n, const float
 void dWorldPackImpulsesDeviceB200(dWorldID, const int *d_idx, int n, float *d_out8);
 void dWorldAddImpulsesDeviceB200(dWorldID, const int *d_idx, int n, const float *d_in8);
 void dWorldSetKeepImpulsesB200(dWorldID, int on);
+/* dynamic halo (bodies move, so the set near a slab face is rebuilt every tick, on the device):
+ *  - Select: indices of the bodies with mask[b] != 0 (mask may be NULL) and lo <= pos[axis] < hi, ascending, into
+ *    d_idx_out[0..cap); unused entries are -1; *d_count = number selected (may exceed cap: then truncated).
+ *  - PackBodies: 48 floats per list entry -- pos3 invM | quat4 | lvel3 mass | avel3 geom-type | geom dims4 |
+ *    I (3x4) | invI (3x4) | body flags, pad3 -- i.e. everything the other side needs to simulate the body;
+ *    d_body_geom maps a body to its geom; entries with index -1 are marked empty.
+ *  - UnpackBodies: slot i of the message goes into body d_ghost_body[i] / geom d_ghost_geom[i] (a pool of
+ *    cap ghost slots created once); empty entries switch the slot off (geom not alive, body inert).
+ * The impulse calls above skip -1 entries, so the same list drives the return path. */
+void dWorldSelectBodiesDeviceB200(dWorldID, int axis, float lo, float hi, const int *d_mask, int *d_idx_out, int cap,
+                                  int *d_count);
+void dWorldPackBodiesDeviceB200(dWorldID, const int *d_idx, int cap, const int *d_body_geom, float *d_out48);
+void dWorldUnpackBodiesDeviceB200(dWorldID, const int *d_ghost_body, const int *d_ghost_geom, int cap, const float *d_in48);
 /* CUDA-event timer on the world's stream: everything queued between start and stop */
 void dWorldTimerStartB200(dWorldID);
 void dWorldTimerStopB200(dWorldID);

@@ -99,6 +99,7 @@ void eng_destroy(Engine *e) {
     dev_free(G.col); dev_free(G.env); dev_free(G.mesh); dev_free(G.alive); dev_free(G.amin); dev_free(G.amax);
     BroadPhase &bp = e->bp;
     dev_free(e->EB.first); dev_free(e->EB.count); dev_free(e->EB.shared);
+    dev_free(e->sel_flag);
     if (e->h_patch) cudaFreeHost(e->h_patch);
     if (e->d_patch) cudaFree(e->d_patch);
     if (e->ev_patch) cudaEventDestroy(e->ev_patch);
@@ -942,6 +943,11 @@ __global__ void __launch_bounds__(256) k_pack_impulses(int n, const int *__restr
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int b = idx[i];
+    if (b < 0) { // empty slot of a counted list
+        out[2 * (size_t)i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        out[2 * (size_t)i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
     const float4 l = fc[2 * (size_t)b], a = fc[2 * (size_t)b + 1];
     out[2 * (size_t)i] = make_float4(h * l.x, h * l.y, h * l.z, 0.f);
     out[2 * (size_t)i + 1] = make_float4(h * a.x, h * a.y, h * a.z, 0.f);
@@ -950,7 +956,7 @@ __global__ void __launch_bounds__(256) k_add_impulses(int n, const int *__restri
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int b = idx[i];
-    if (!(B.pos[b].w > 0.f)) return; // kinematic / destroyed bodies take no impulse
+    if (b < 0 || !(B.pos[b].w > 0.f)) return; // empty slots, kinematic / destroyed bodies take no impulse
     const float4 l = in[2 * (size_t)i], a = in[2 * (size_t)i + 1];
     float4 lv = B.lvel[b], av = B.avel[b];
     lv.x += l.x; lv.y += l.y; lv.z += l.z;
@@ -976,6 +982,113 @@ void eng_add_impulses_device(Engine *e, const int *d_idx, int n, const float *d_
     e->host_stale = true;
 }
 void eng_set_keep_impulses(Engine *e, int on) { e->keep_fc = on != 0; }
+
+// ---- dynamic halo: which bodies sit near a slab face changes as the pile moves, so the list is rebuilt on the
+// device every tick (flag -> scan -> compact: ascending, deterministic), and the message carries whole bodies
+// (state + mass properties + the shape of the body's geom) into a pool of ghost slots on the other side.
+__global__ void __launch_bounds__(256) k_select_flag(BodyArrays B, int axis, float lo, float hi, const int *__restrict__ mask,
+                                                      int *__restrict__ flag) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B.n) return;
+    const float4 p = B.pos[b];
+    const float x = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+    flag[b] = ((!mask || mask[b]) && x >= lo && x < hi) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) k_select_write(int n, const int *__restrict__ off, const int *__restrict__ total, int cap,
+                                                       const float4 *__restrict__ pos, int axis, float lo, float hi,
+                                                       const int *__restrict__ mask, int *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float4 p = pos[i];
+        const float x = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+        if ((!mask || mask[i]) && x >= lo && x < hi && off[i] < cap) out[off[i]] = i;
+    }
+    if (i < cap && i >= *total) out[i] = -1;
+}
+void eng_select_bodies_device(Engine *e, int axis, float lo, float hi, const int *d_mask, int *d_idx_out, int cap, int *d_count) {
+    eng_sync_to_device(e);
+    const int n = e->B.n;
+    if (n + 1 > e->cap_sel) {
+        dev_realloc(e->sel_flag, 0, (size_t)n + (size_t)n / 4 + 65, e->st, false);
+        e->cap_sel = n + n / 4 + 64;
+    }
+    const int m = std::max(n, cap);
+    if (m <= 0) return;
+    if (n > 0) {
+        k_select_flag<<<(unsigned)((n + 255) / 256), 256, 0, e->st>>>(e->B, axis, lo, hi, d_mask, e->sel_flag);
+        OB_CHECK_KERNEL("k_select_flag", e->st);
+        scan_exclusive(e->sel_flag, e->sel_flag, n, nullptr, d_count, e->scan, e->st);
+    } else {
+        OB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), e->st));
+    }
+    k_select_write<<<(unsigned)((m + 255) / 256), 256, 0, e->st>>>(n, e->sel_flag, d_count, cap, e->B.pos, axis, lo, hi, d_mask, d_idx_out);
+    OB_CHECK_KERNEL("k_select_write", e->st);
+}
+
+// 12 float4 per body: pos+invM | quat | lvel+mass | avel+geom type (int bits, -1: empty slot) | geom dims |
+// I rows (3) | invI rows (3) | body flags (int bits)
+__global__ void __launch_bounds__(128) k_pack_bodies(int cap, const int *__restrict__ idx, const int *__restrict__ body_geom,
+                                                      BodyArrays B, GeomArrays G, float4 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    float4 *o = out + 12 * (size_t)i;
+    const int b = idx[i];
+    const int g = b >= 0 ? body_geom[b] : -1;
+    if (b < 0 || g < 0) {
+        o[3] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        return;
+    }
+    o[0] = B.pos[b]; o[1] = B.quat[b]; o[2] = B.lvel[b];
+    const float4 av = B.avel[b];
+    o[3] = make_float4(av.x, av.y, av.z, __int_as_float(G.type[g]));
+    o[4] = G.dims[g];
+    for (int k = 0; k < 3; k++) { o[5 + k] = B.I[3 * (size_t)b + k]; o[8 + k] = B.invI[3 * (size_t)b + k]; }
+    o[11] = make_float4(__int_as_float(B.flags[b]), 0.f, 0.f, 0.f);
+}
+__global__ void __launch_bounds__(128) k_unpack_bodies(int cap, const int *__restrict__ ghost_body, const int *__restrict__ ghost_geom,
+                                                        BodyArrays B, GeomArrays G, const float4 *__restrict__ in) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    const float4 *r = in + 12 * (size_t)i;
+    const int b = ghost_body[i], g = ghost_geom[i];
+    const float4 r3 = r[3];
+    const int type = __float_as_int(r3.w);
+    if (type < 0) { // unused slot: no geom, inert body
+        G.alive[g] = 0;
+        float4 p = B.pos[b];
+        p.w = 0.f;
+        B.pos[b] = p;
+        B.flags[b] = BF_KINEMATIC | BF_NOGRAVITY;
+        const float4 lv = B.lvel[b];
+        B.lvel[b] = make_float4(0.f, 0.f, 0.f, lv.w);
+        B.avel[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    B.pos[b] = r[0];
+    B.quat[b] = r[1];
+    store_m3(B.R, b, q_to_r(r[1]));
+    B.lvel[b] = r[2];
+    B.avel[b] = make_float4(r3.x, r3.y, r3.z, 0.f);
+    for (int k = 0; k < 3; k++) { B.I[3 * (size_t)b + k] = r[5 + k]; B.invI[3 * (size_t)b + k] = r[8 + k]; }
+    B.flags[b] = __float_as_int(r[11].x);
+    G.type[g] = type;
+    G.dims[g] = r[4];
+    G.alive[g] = 1;
+}
+void eng_pack_bodies_device(Engine *e, const int *d_idx, int cap, const int *d_body_geom, float *d_out) {
+    eng_sync_to_device(e);
+    if (cap <= 0) return;
+    k_pack_bodies<<<(unsigned)((cap + 127) / 128), 128, 0, e->st>>>(cap, d_idx, d_body_geom, e->B, e->G, reinterpret_cast<float4 *>(d_out));
+    OB_CHECK_KERNEL("k_pack_bodies", e->st);
+}
+void eng_unpack_bodies_device(Engine *e, const int *d_ghost_body, const int *d_ghost_geom, int cap, const float *d_in) {
+    eng_sync_to_device(e);
+    if (cap <= 0) return;
+    k_unpack_bodies<<<(unsigned)((cap + 127) / 128), 128, 0, e->st>>>(cap, d_ghost_body, d_ghost_geom, e->B, e->G,
+                                                                     reinterpret_cast<const float4 *>(d_in));
+    OB_CHECK_KERNEL("k_unpack_bodies", e->st);
+    e->host_stale = true;
+}
 void eng_unpack_states_device(Engine *e, const int *d_idx, int n, const float *d_in) {
     eng_sync_to_device(e);
     if (n <= 0) return;

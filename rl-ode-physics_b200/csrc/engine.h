@@ -196,6 +196,9 @@ void eng_unpack_states_device(Engine *, const int *d_idx, int n, const float *d_
 void eng_pack_impulses_device(Engine *, const int *d_idx, int n, float *d_out);
 void eng_add_impulses_device(Engine *, const int *d_idx, int n, const float *d_in);
 void eng_set_keep_impulses(Engine *, int on);
+void eng_select_bodies_device(Engine *, int axis, float lo, float hi, const int *d_mask, int *d_idx_out, int cap, int *d_count);
+void eng_pack_bodies_device(Engine *, const int *d_idx, int cap, const int *d_body_geom, float *d_out);
+void eng_unpack_bodies_device(Engine *, const int *d_ghost_body, const int *d_ghost_geom, int cap, const float *d_in);
 // wait for everything queued on the engine stream
 void eng_wait(Engine *);
 StepStats eng_stats(Engine *);                  // blocking: stats of the last collide/step

@@ -18,6 +18,8 @@ struct Engine {
     bool host_stale = false; // device state is newer than the host mirrors
     bool keep_fc = false, fc_valid = false; // the last step left the bodies' accumulators fc in global memory
     float last_h = 0.f;
+    int *sel_flag = nullptr; // scratch of eng_select_bodies_device
+    int cap_sel = 0;
     // incremental ingestion (spawns, per-tick setters): dirty lists + per-entry field masks
     std::vector<int> dirty_b, dirty_g, force_b;
     std::vector<unsigned char> mask_b, mask_g, inforce_b;

@@ -344,6 +344,15 @@ extern "C" void dWorldPackStatesDeviceB200(dWorldID w, const int *d_idx, int n, 
 extern "C" void dWorldPackImpulsesDeviceB200(dWorldID w, const int *d_idx, int n, float *d_out) { eng_pack_impulses_device(w->eng, d_idx, n, d_out); }
 extern "C" void dWorldAddImpulsesDeviceB200(dWorldID w, const int *d_idx, int n, const float *d_in) { eng_add_impulses_device(w->eng, d_idx, n, d_in); }
 extern "C" void dWorldSetKeepImpulsesB200(dWorldID w, int on) { eng_set_keep_impulses(w->eng, on); }
+extern "C" void dWorldSelectBodiesDeviceB200(dWorldID w, int axis, float lo, float hi, const int *d_mask, int *d_idx_out, int cap, int *d_count) {
+    eng_select_bodies_device(w->eng, axis, lo, hi, d_mask, d_idx_out, cap, d_count);
+}
+extern "C" void dWorldPackBodiesDeviceB200(dWorldID w, const int *d_idx, int cap, const int *d_body_geom, float *d_out48) {
+    eng_pack_bodies_device(w->eng, d_idx, cap, d_body_geom, d_out48);
+}
+extern "C" void dWorldUnpackBodiesDeviceB200(dWorldID w, const int *d_ghost_body, const int *d_ghost_geom, int cap, const float *d_in48) {
+    eng_unpack_bodies_device(w->eng, d_ghost_body, d_ghost_geom, cap, d_in48);
+}
 extern "C" void dWorldUnpackStatesDeviceB200(dWorldID w, const int *d_idx, int n, const float *d_in) { eng_unpack_states_device(w->eng, d_idx, n, d_in); }
 extern "C" void dWorldTimerStartB200(dWorldID w) { eng_timer_start(w->eng); }
 extern "C" void dWorldTimerStopB200(dWorldID w) { eng_timer_stop(w->eng); }

@@ -119,6 +119,9 @@ _SIGS = [
     ("dWorldPackStatesDeviceB200", None, [_vp, _vp, _i, _vp]), ("dWorldUnpackStatesDeviceB200", None, [_vp, _vp, _i, _vp]),
     ("dWorldPackImpulsesDeviceB200", None, [_vp, _vp, _i, _vp]), ("dWorldAddImpulsesDeviceB200", None, [_vp, _vp, _i, _vp]),
     ("dWorldSetKeepImpulsesB200", None, [_vp, _i]),
+    ("dWorldSelectBodiesDeviceB200", None, [_vp, _i, _f, _f, _vp, _vp, _i, _vp]),
+    ("dWorldPackBodiesDeviceB200", None, [_vp, _vp, _i, _vp, _vp]),
+    ("dWorldUnpackBodiesDeviceB200", None, [_vp, _vp, _vp, _i, _vp]),
     ("dWorldTimerStartB200", None, [_vp]), ("dWorldTimerStopB200", None, [_vp]),
     ("dWorldTimerElapsedB200", C.c_float, [_vp]), ("dGetKernelLaunchCountB200", C.c_long, []),
     ("dWorldSetCapacityB200", None, [_vp, C.c_long, C.c_long]),

@@ -197,3 +197,215 @@ def tick(slab, exchange, h, max_contacts=8):
         slab.pack("imp")
         exchange("imp")
         slab.unpack("imp")
+
+
+# ------------------------------------------------------------------ dynamic halo + migration
+#
+# The lists above are fixed at set-up, which is only right while bodies stay in their lattice columns.  The
+# dynamic variant rebuilds everything from the bodies' CURRENT positions (impulse coupling only):
+#   * every tick rank r selects, on the device, its own bodies with x < face_left + margin and sends them whole
+#     (state + mass properties + geom shape, 48 floats) to rank r-1, which unpacks them into a POOL of ghost
+#     slots (unused slots are switched off); impulses return along the same list;
+#   * every `migrate_every` ticks bodies whose centre crossed a face by more than `hyst` change owner: the old
+#     owner selects and packs them on the device, the records travel like a halo message, the new owner spawns
+#     them through the handle API (queued patches: no re-upload of the world) and the old owner destroys them.
+
+REC = 48  # floats per body record (dWorldPackBodiesDeviceB200)
+
+
+def dynamic_slab_scene(rank, n_slabs, nx_per_slab=128, nz=1024, ny=16, seed=5, spacing=1.8, margin_cols=4, h=1.0 / 60.0,
+                       pool_factor=1.5, mig_cap=4096):
+    """One rank's scene for the dynamic halo: its own lattice slab + (unless it is the last rank) a pool of ghost
+    slots for the right neighbour's boundary bodies.  Returns (scene, info)."""
+    nx_total = nx_per_slab * n_slabs
+    x0 = -0.5 * (nx_total - 1) * spacing
+    z0 = -0.5 * (nz - 1) * spacing
+    own_b, own_g, _ = _slab_lattice(rank, nx_per_slab, nz, ny, seed, spacing, x0, z0)
+    n_own = len(own_b["pos"])
+    own_g["cat"][:] = CAT_OBJ
+    own_g["col"][:] = CAT_OBJ | CAT_MAP | CAT_GHOST
+    pool = int(pool_factor * margin_cols * nz * ny) + 64
+    bparts, gparts = [own_b], [own_g]
+    has_pool = rank < n_slabs - 1
+    if has_pool:
+        pb = {
+            "pos": np.stack([np.zeros(pool), -1000.0 - np.arange(pool), np.zeros(pool)], axis=1).astype(np.float32),
+            "quat": np.tile(np.array([1, 0, 0, 0], np.float32), (pool, 1)),
+            "lvel": np.zeros((pool, 3), np.float32), "avel": np.zeros((pool, 3), np.float32),
+            "mass": np.ones(pool, np.float32),
+            "inertia": np.tile(np.array([1, 0, 0, 0, 1, 0, 0, 0, 1], np.float32), (pool, 1)),
+            "flags": np.full(pool, scenes.BODY_KINEMATIC, np.int32), "env": np.zeros(pool, np.int32),
+        }
+        pg = {
+            "type": np.full(pool, scenes.SPHERE, np.int32), "dims": np.tile(np.float32([0.1, 0, 0, 0]), (pool, 1)),
+            "body": np.arange(n_own, n_own + pool, dtype=np.int32), "pos": np.zeros((pool, 3), np.float32),
+            "R": np.tile(np.array(scenes.IDENT_R, np.float32), (pool, 1)),
+            "cat": np.full(pool, CAT_GHOST, np.uint32), "col": np.zeros(pool, np.uint32), "env": np.zeros(pool, np.int32),
+        }
+        bparts.append(pb)
+        gparts.append(pg)
+    half_x = 0.5 * nx_total * spacing + 1.0
+    half_z = 0.5 * nz * spacing + 1.0
+    st = scenes._static_geoms([(scenes.PLANE, (0, 1, 0, 0.0), (0, 0, 0), scenes.IDENT_R, -1),
+                               (scenes.PLANE, (1, 0, 0, -half_x), (0, 0, 0), scenes.IDENT_R, -1),
+                               (scenes.PLANE, (-1, 0, 0, -half_x), (0, 0, 0), scenes.IDENT_R, -1),
+                               (scenes.PLANE, (0, 0, 1, -half_z), (0, 0, 0), scenes.IDENT_R, -1),
+                               (scenes.PLANE, (0, 0, -1, -half_z), (0, 0, 0), scenes.IDENT_R, -1)])
+    st["cat"][:] = CAT_MAP
+    st["col"][:] = CAT_OBJ
+    sc = scenes.from_arrays("C5-dyn-slab%d" % rank, scenes._concat(bparts), scenes._concat([st] + gparts), h=h)
+    sc["n_owned"] = n_own
+    face_left = x0 + (rank * nx_per_slab - 0.5) * spacing
+    info = {
+        "rank": rank, "n_slabs": n_slabs, "n_own": n_own, "n_static": 5, "pool": pool, "has_pool": has_pool,
+        "pool_first_body": n_own, "pool_first_geom": 5 + n_own,
+        "face_left": face_left, "face_right": face_left + nx_per_slab * spacing,
+        "margin": margin_cols * spacing, "hyst": 0.25 * margin_cols * spacing, "mig_cap": mig_cap,
+    }
+    return sc, info
+
+
+class DynamicSlabWorld:
+    """Slab with a device-selected halo and host-driven migration.  Buffer names follow SlabWorld, so
+    exchange_nccl / exchange_local move kinds "state", "imp" and "mig" unchanged."""
+
+    def __init__(self, world, info, device):
+        import torch
+        self.w, self.torch, self.dev, self.info = world, torch, device, info
+        self.rank, self.n_slabs = info["rank"], info["n_slabs"]
+        n_bodies = world.n_bodies
+        cap = n_bodies + 16 * info["mig_cap"]
+        self.own_mask = torch.zeros(cap, dtype=torch.int32, device=device)
+        self.own_mask[:info["n_own"]] = 1
+        self.body_geom = torch.full((cap,), -1, dtype=torch.int32, device=device)
+        self.body_geom[:n_bodies] = torch.arange(info["n_static"], info["n_static"] + n_bodies, dtype=torch.int32, device=device)
+        self.n_owned = info["n_own"]
+        self.count = torch.zeros(4, dtype=torch.int32, device=device)
+        P, M = info["pool"], info["mig_cap"]
+        f32 = dict(dtype=torch.float32, device=device)
+        i32 = dict(dtype=torch.int32, device=device)
+        self.sides = {}
+        if self.rank > 0:
+            self.sides["left"] = {
+                "send_state_idx": torch.full((P,), -1, **i32), "send_state_buf": torch.zeros((P, REC), **f32),
+                "recv_imp_buf": torch.zeros((P, 8), **f32),
+                "send_mig_idx": torch.full((M,), -1, **i32), "send_mig_buf": torch.zeros((M, REC), **f32),
+                "recv_mig_buf": torch.zeros((M, REC), **f32),
+            }
+        if self.rank < self.n_slabs - 1:
+            self.sides["right"] = {
+                "ghost_body": torch.arange(info["pool_first_body"], info["pool_first_body"] + P, **i32),
+                "ghost_geom": torch.arange(info["pool_first_geom"], info["pool_first_geom"] + P, **i32),
+                "recv_state_buf": torch.zeros((P, REC), **f32), "send_imp_buf": torch.zeros((P, 8), **f32),
+                "send_mig_idx": torch.full((M,), -1, **i32), "send_mig_buf": torch.zeros((M, REC), **f32),
+                "recv_mig_buf": torch.zeros((M, REC), **f32),
+            }
+        self.has_imp = True
+        self.migrated_in = self.migrated_out = 0
+
+    # -- per tick
+    def pack(self, kind="state"):
+        L, w = self.w.L, self.w.w
+        inf = float("inf")
+        if kind == "state" and "left" in self.sides:
+            s = self.sides["left"]
+            L.dWorldSelectBodiesDeviceB200(w, 0, -inf, self.info["face_left"] + self.info["margin"], self.own_mask.data_ptr(),
+                                           s["send_state_idx"].data_ptr(), s["send_state_idx"].numel(), self.count.data_ptr())
+            L.dWorldPackBodiesDeviceB200(w, s["send_state_idx"].data_ptr(), s["send_state_idx"].numel(), self.body_geom.data_ptr(),
+                                         s["send_state_buf"].data_ptr())
+        if kind == "imp" and "right" in self.sides:
+            s = self.sides["right"]
+            L.dWorldPackImpulsesDeviceB200(w, s["ghost_body"].data_ptr(), s["ghost_body"].numel(), s["send_imp_buf"].data_ptr())
+        if kind == "mig":
+            for side, s in self.sides.items():
+                lo, hi = (-inf, self.info["face_left"] - self.info["hyst"]) if side == "left" else (self.info["face_right"] + self.info["hyst"], inf)
+                L.dWorldSelectBodiesDeviceB200(w, 0, lo, hi, self.own_mask.data_ptr(), s["send_mig_idx"].data_ptr(),
+                                               s["send_mig_idx"].numel(), self.count.data_ptr() + (4 if side == "left" else 8))
+                L.dWorldPackBodiesDeviceB200(w, s["send_mig_idx"].data_ptr(), s["send_mig_idx"].numel(), self.body_geom.data_ptr(),
+                                             s["send_mig_buf"].data_ptr())
+        self.w.wait()
+
+    def unpack(self, kind="state"):
+        L, w = self.w.L, self.w.w
+        if kind == "state" and "right" in self.sides:
+            s = self.sides["right"]
+            L.dWorldUnpackBodiesDeviceB200(w, s["ghost_body"].data_ptr(), s["ghost_geom"].data_ptr(), s["ghost_body"].numel(),
+                                           s["recv_state_buf"].data_ptr())
+        if kind == "imp" and "left" in self.sides:
+            s = self.sides["left"]
+            L.dWorldAddImpulsesDeviceB200(w, s["send_state_idx"].data_ptr(), s["send_state_idx"].numel(), s["recv_imp_buf"].data_ptr())
+        if kind == "mig":
+            self._apply_migration()
+
+    # -- migration (host side; the exchange of kind "mig" has completed)
+    def _apply_migration(self):
+        import ctypes as C
+        from . import Mass
+        L, w, space = self.w.L, self.w.w, self.w.space
+        for side, s in self.sides.items():
+            # leaving: destroy what we sent
+            out_idx = s["send_mig_idx"].cpu().numpy()
+            out_idx = out_idx[out_idx >= 0]
+            if len(out_idx):
+                geoms = self.body_geom[self.torch.as_tensor(out_idx, dtype=self.torch.long, device=self.dev)].cpu().numpy()
+                for b, g in zip(out_idx.tolist(), geoms.tolist()):
+                    L.dGeomDestroy(C.c_void_p(L.dSpaceGetGeomB200(space, int(g))))
+                    L.dBodyDestroy(C.c_void_p(L.dWorldGetBodyB200(w, int(b))))
+                self.own_mask[self.torch.as_tensor(out_idx, dtype=self.torch.long, device=self.dev)] = 0
+                self.n_owned -= len(out_idx)
+                self.migrated_out += len(out_idx)
+            # arriving: spawn through the handle API (queued as patches, sent with the next collide)
+            rec = s["recv_mig_buf"].cpu().numpy()
+            types = rec[:, 15].view(np.int32)
+            new_b, new_g = [], []
+            for r in rec[types >= 0]:
+                t = int(r[15:16].view(np.int32)[0])
+                b = C.c_void_p(L.dBodyCreate(w))
+                L.dBodySetPosition(b, float(r[0]), float(r[1]), float(r[2]))
+                q = np.ascontiguousarray(r[4:8], np.float32)
+                L.dBodySetQuaternion(b, q.ctypes.data_as(C.POINTER(C.c_float)))
+                L.dBodySetLinearVel(b, float(r[8]), float(r[9]), float(r[10]))
+                L.dBodySetAngularVel(b, float(r[12]), float(r[13]), float(r[14]))
+                m = Mass()
+                m.mass = float(r[11])
+                for k in range(12):
+                    m.I[k] = float(r[20 + k])
+                L.dBodySetMass(b, C.byref(m))
+                flags = int(r[44:45].view(np.int32)[0])
+                L.dBodySetGyroscopicMode(b, 1 if flags & scenes.BODY_GYRO else 0)
+                if t == scenes.SPHERE:
+                    g = C.c_void_p(L.dCreateSphere(space, float(r[16])))
+                else:
+                    g = C.c_void_p(L.dCreateBox(space, float(r[16]), float(r[17]), float(r[18])))
+                L.dGeomSetBody(g, b)
+                L.dGeomSetCategoryBits(g, CAT_OBJ)
+                L.dGeomSetCollideBits(g, CAT_OBJ | CAT_MAP | CAT_GHOST)
+                new_b.append(L.dBodyGetIndexB200(b))
+                new_g.append(L.dGeomGetIndexB200(g))
+            if new_b:
+                if max(new_b) >= self.own_mask.numel():
+                    raise RuntimeError("DynamicSlabWorld: body capacity exhausted by migration")
+                ib = self.torch.as_tensor(new_b, dtype=self.torch.long, device=self.dev)
+                self.own_mask[ib] = 1
+                self.body_geom[ib] = self.torch.as_tensor(new_g, dtype=self.torch.int32, device=self.dev)
+                self.w.n_bodies += len(new_b)
+                self.w.n_geoms += len(new_b)
+                self.n_owned += len(new_b)
+                self.migrated_in += len(new_b)
+
+    def halo_bytes(self):
+        n = 0
+        for s in self.sides.values():
+            for k in ("send_state_buf", "send_imp_buf"):
+                if k in s:
+                    n += s[k].numel() * 4
+        return n
+
+
+def tick_dynamic(slab, exchange, h, step, migrate_every=16, max_contacts=8):
+    """one tick of a dynamic slab; every `migrate_every` ticks ownership follows the bodies first"""
+    if migrate_every > 0 and step % migrate_every == 0 and step > 0:
+        slab.pack("mig")
+        exchange("mig")
+        slab.unpack("mig")
+    tick(slab, exchange, h, max_contacts)

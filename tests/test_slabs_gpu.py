@@ -206,3 +206,72 @@ def test_two_slab_pile_with_impulse_halo():
     assert 0.2 < y_dec.mean() < 3.0
     for s in sl:
         s.w.close()
+
+
+def _build_dynamic(n_slabs, **kw):
+    import odeb200
+    out = []
+    for r in range(n_slabs):
+        sc, info = slabs.dynamic_slab_scene(r, n_slabs, **kw)
+        w = odeb200.World(gravity=sc["gravity"])
+        w.load_scene(sc)
+        out.append((sc, slabs.DynamicSlabWorld(w, info, "cuda:0")))
+    return out
+
+
+def _phase(sl, kind):
+    for s in sl:
+        s.pack(kind)
+    slabs.exchange_local(sl, kind)
+    for s in sl:
+        s.unpack(kind)
+
+
+def test_dynamic_halo_selects_by_position_and_migrates_bodies():
+    """Dynamic halo: the boundary set is re-selected on the device from the bodies' current x each tick and sent
+    as whole bodies into the lower slab's ghost pool; bodies whose centre crossed a face change owner (destroyed on
+    one side, spawned through the handle API on the other).  A fast sphere is shot from slab 0 into slab 1."""
+    kw = dict(nx_per_slab=6, nz=8, ny=3, seed=5, spacing=1.0, margin_cols=2, mig_cap=256)
+    built = _build_dynamic(2, **kw)
+    sl = [s for _, s in built]
+    h = built[0][0]["h"]
+    n0, n1 = sl[0].n_owned, sl[1].n_owned
+    # the projectile: body 0 of slab 0, lifted above the pile and thrown along +x
+    L = sl[0].w.L
+    shot = sl[0].w.body_handle(0)
+    L.dBodySetPosition(shot, -1.0, 6.0, 0.0)
+    L.dBodySetLinearVel(shot, 6.0, 0.0, 0.0)
+    owner_history = []
+    for step in range(60):
+        if step % 4 == 0 and step > 0:
+            _phase(sl, "mig")
+        _phase(sl, "state")
+        if step == 1:
+            # ghosts on slab 0 are exactly slab 1's current boundary bodies, whole (state, mass, shape)
+            st0, st1 = sl[0].w.state(), sl[1].w.state()
+            idx = sl[1].sides["left"]["send_state_idx"].cpu().numpy()
+            k = int((idx >= 0).sum())
+            assert 0 < k < len(idx) and (idx[k:] == -1).all()
+            sel = np.nonzero(st1["pos"][:n1, 0] < sl[1].info["face_left"] + sl[1].info["margin"])[0]
+            assert np.array_equal(idx[:k], sel)                       # selection = positions, ascending
+            gb = sl[0].sides["right"]["ghost_body"].cpu().numpy()[:k]
+            for key in ("pos", "quat", "lvel", "avel"):
+                assert np.array_equal(st0[key][gb], st1[key][idx[:k]]), key
+        for s in sl:
+            s.w.tick(h)
+        _phase(sl, "imp")
+        owner_history.append((sl[0].n_owned, sl[1].n_owned))
+    assert owner_history[0] == (n0, n1)
+    assert sl[0].migrated_out >= 1 and sl[1].migrated_in == sl[0].migrated_out   # the shot (at least) changed owner
+    assert sl[0].n_owned + sl[1].n_owned == n0 + n1                               # nobody lost, nobody duplicated
+    st0, st1 = sl[0].w.state(), sl[1].w.state()
+    m0 = sl[0].own_mask.cpu().numpy()[:len(st0["pos"])].astype(bool)
+    m1 = sl[1].own_mask.cpu().numpy()[:len(st1["pos"])].astype(bool)
+    assert m0.sum() == sl[0].n_owned and m1.sum() == sl[1].n_owned and not m0[0]  # body 0 of slab 0 is gone ...
+    xs1 = st1["pos"][m1]
+    assert (xs1[:, 0] > sl[1].info["face_left"] + 2.0).any()                       # ... and flies on inside slab 1
+    for st, m in ((st0, m0), (st1, m1)):
+        assert np.isfinite(st["pos"][m]).all() and st["pos"][m, 1].min() > 0.0
+    for s in sl:
+        assert s.w.stats()["flags"] == 0
+        s.w.close()
