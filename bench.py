@@ -43,6 +43,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--settle", type=int, default=-1)
     ap.add_argument("--slab-cols", type=int, default=128, help="C5: lattice columns (x) per GPU; z = 1024, y = 16")
+    ap.add_argument("--halo", default="dynamic", choices=["dynamic", "static"],
+                    help="C5: dynamic = boundary set re-selected on the device each tick + migration between slabs; "
+                         "static = boundary set fixed by the initial lattice column")
+    ap.add_argument("--migrate-every", type=int, default=16, help="C5 dynamic halo: ticks between ownership updates")
     ap.add_argument("--coupling", default="impulse", choices=["impulse", "ghost"],
                     help="C5: impulse = lower slab owns cross-face contacts, impulses sent back to the owner; "
                          "ghost = kinematic ghosts on both sides")
@@ -258,11 +262,18 @@ def main():
     if args.workload == "C5":
         # one slab of the 1024(z) x 16(y) lattice per GPU, halo exchange of boundary bodies over NCCL
         from odeb200 import slabs
-        sc, halo = slabs.slab_scene(rank, world, nx_per_slab=args.slab_cols, nz=1024, ny=16, seed=5, margin_cols=4,
-                                     coupling=args.coupling)
+        if args.halo == "dynamic":
+            sc, halo = slabs.dynamic_slab_scene(rank, world, nx_per_slab=args.slab_cols, nz=1024, ny=16, seed=5, margin_cols=4)
+            args.coupling = "impulse"
+        else:
+            sc, halo = slabs.slab_scene(rank, world, nx_per_slab=args.slab_cols, nz=1024, ny=16, seed=5, margin_cols=4,
+                                         coupling=args.coupling)
         desc = ("C5: slab-decomposed single world, %d x 1024 x 16 lattice columns per GPU (%d bodies/GPU), NCCL halo exchange "
-                "each tick (%s), dt=1/60, QuickStep 20 iters"
+                "each tick (%s; %s), dt=1/60, QuickStep 20 iters"
                 % (args.slab_cols, args.slab_cols * 1024 * 16,
+                   ("boundary set selected on the device from current positions, whole-body records into a ghost pool, "
+                    "ownership migrates every %d ticks" % args.migrate_every) if args.halo == "dynamic"
+                   else "boundary set fixed by the initial lattice column",
                    "boundary-body states to the lower slab, contact impulses back to the owner" if args.coupling == "impulse"
                    else "boundary-body states both ways, kinematic ghosts"))
         n_bodies = sc["n_owned"]
@@ -274,11 +285,16 @@ def main():
     ew.load_scene(sc)
     h = sc["h"]
     if args.workload == "C5":
-        slab = slabs.SlabWorld(ew, halo, dev)
+        slab = slabs.DynamicSlabWorld(ew, halo, dev) if args.halo == "dynamic" else slabs.SlabWorld(ew, halo, dev)
         exch = (lambda kind: slabs.exchange_nccl(slab, rank, world, kind)) if world > 1 else (lambda kind: None)
+        tick_no = [0]
 
         def do_tick():
-            slabs.tick(slab, exch, h)
+            if args.halo == "dynamic":
+                slabs.tick_dynamic(slab, exch, h, tick_no[0], args.migrate_every)
+            else:
+                slabs.tick(slab, exch, h)
+            tick_no[0] += 1
     else:
         def do_tick():
             ew.tick(h)
@@ -385,6 +401,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": desc, "bodies_per_gpu": n_bodies, "settle_steps": settle,
                        "halo_bytes_per_tick_per_gpu": (slab.halo_bytes() if slab else 0),
+                       "migrated_out_rank0": (getattr(slab, "migrated_out", 0) if slab else 0),
                        "l2": "inputs larger than L2: ~%.0f MB of body, contact and row arrays are streamed per tick (126 MB L2)"
                              % ((sum(ab.values()) / 20 + 200 * n_bodies) / 1e6),
                        "counts": {k: st[k] for k in ("n_pairs", "n_contacts", "n_manifolds", "n_rows1", "n_rows2", "n_colours")}},

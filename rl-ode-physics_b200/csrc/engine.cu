@@ -612,7 +612,12 @@ void eng_sync_to_device(Engine *e) {
             const size_t ne = (size_t)std::max(e->n_envs, 1);
             e->envg_first.assign(ne, 0); e->envg_cnt.assign(ne, 0); e->envg_shared.clear();
             e->envg_max = 0; e->envg_ok = true; e->envg_alive = 0;
-            for (size_t i = 0; i < n; i++) { envg_note_geom(e, (int)i); e->envg_alive += g.alive[i] ? 1 : 0; }
+            e->alive_dev.assign(n, 0);
+            for (size_t i = 0; i < n; i++) {
+                envg_note_geom(e, (int)i);
+                e->alive_dev[i] = g.alive[i] ? 1 : 0;
+                e->envg_alive += e->alive_dev[i];
+            }
             envg_upload_tables(e, st);
         }
         OB_CUDA(cudaStreamSynchronize(st)); // `mesh` is a temporary
@@ -634,17 +639,18 @@ void eng_sync_to_device(Engine *e) {
             q.alive = g.alive[i]; q.mesh = g.type[i] == G_TRIMESH ? (int)g.dims[4 * (size_t)i] : 0;
             q.dims = ld4(g.dims, i); q.pos = ld4(g.pos, i);
             for (int r = 0; r < 3; r++) q.R[r] = ld4(g.R, 3 * (size_t)i + r);
-            if (i >= e->n_g_dev) { envg_note_geom(e, i); e->envg_alive += g.alive[i] ? 1 : 0; tables = true; }
+            if ((int)e->alive_dev.size() < g.n) e->alive_dev.resize((size_t)g.n, 0);
+            const unsigned char now = g.alive[i] ? 1 : 0;
+            if (i >= e->n_g_dev) { envg_note_geom(e, i); e->envg_alive += now; tables = true; }
+            else if (now != e->alive_dev[i]) e->envg_alive += (int)now - (int)e->alive_dev[i];
+            e->alive_dev[i] = now;
         }
         OB_CUDA(cudaMemcpyAsync(e->d_patch, hp, nd * sizeof(GeomPatch), cudaMemcpyHostToDevice, st));
         k_patch_geoms<<<(unsigned)((nd + 127) / 128), 128, 0, st>>>(e->G, static_cast<const GeomPatch *>(e->d_patch), (int)nd);
         OB_CHECK_KERNEL("k_patch_geoms", st);
         OB_CUDA(cudaEventRecord(e->ev_patch, st));
         e->patch_inflight = true;
-        // alive flags or env ids of existing geoms changed: recount (the ranges themselves are append-only)
-        int alive = 0;
-        for (int i = 0; i < g.n; i++) alive += g.alive[i] ? 1 : 0;
-        if (alive != e->envg_alive) { e->envg_alive = alive; tables = true; }
+        // (the per-env ranges are append-only; the alive count follows the patches)
         if (tables) envg_upload_tables(e, st);
         else e->EB.n_alive = e->envg_alive;
         e->n_g_dev = g.n;

@@ -22,7 +22,7 @@ struct Engine {
     int cap_sel = 0;
     // incremental ingestion (spawns, per-tick setters): dirty lists + per-entry field masks
     std::vector<int> dirty_b, dirty_g, force_b;
-    std::vector<unsigned char> mask_b, mask_g, inforce_b;
+    std::vector<unsigned char> mask_b, mask_g, inforce_b, alive_dev;
     int n_b_dev = 0, n_g_dev = 0;   // bodies / geoms the device already holds
     std::vector<int> env_first, env_cnt, envg_first, envg_cnt, envg_shared; // persistent per-env ranges
     int env_max_local = 0, envg_max = 0, envg_alive = 0;

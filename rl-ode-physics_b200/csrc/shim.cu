@@ -8,6 +8,7 @@
 // conversions (dRtoQ, dMass helpers).
 #include <string.h>
 
+#include <algorithm>
 #include <deque>
 #include <vector>
 
@@ -19,11 +20,13 @@ using namespace ob;
 
 struct dxJointGroup;
 
+struct dxGeom;
 struct dxBody {
     dxWorld *w;
     int idx;
     void *data;
     bool alive;
+    std::vector<dxGeom *> geoms; // geoms attached with dGeomSetBody (so destroying a body is not a scan of the space)
 };
 
 struct dxGeom {
@@ -392,7 +395,7 @@ extern "C" void dWorldGetStatsB200(dWorldID w, dStepStatsB200 *out) {
 
 static dxBody *new_body(dxWorld *w) {
     const int idx = eng_add_body(w->eng);
-    w->bodies.push_back(dxBody{w, idx, nullptr, true});
+    w->bodies.push_back(dxBody{w, idx, nullptr, true, {}});
     return &w->bodies.back();
 }
 
@@ -406,7 +409,8 @@ extern "C" void dBodyDestroy(dBodyID b) {
     if (!b || !b->alive) return;
     dxWorld *w = b->w;
     // ODE detaches the body's geoms; the slot stays as an inert kinematic body
-    for (dxGeom &g : w->geoms)
+    for (dxGeom *gp : b->geoms) {
+        dxGeom &g = *gp;
         if (g.alive && g.body == b) {
             // the detached geom stays where the body was
             const float *bp = dBodyGetPosition(b), *bR = dBodyGetRotation(b);
@@ -417,6 +421,8 @@ extern "C" void dBodyDestroy(dBodyID b) {
             hg.body[g.idx] = -1;
             eng_mark_geom(w->eng, g.idx);
         }
+    }
+    b->geoms.clear();
     HostBodies &hb = eng_bodies(w->eng);
     hb.flags[b->idx] = BF_KINEMATIC | BF_NOGRAVITY;
     hb.pos[4 * b->idx + 3] = 0.f;
@@ -595,12 +601,21 @@ extern "C" dGeomID dCreatePlane(dSpaceID s, dReal a, dReal b, dReal c, dReal d) 
 }
 extern "C" void dGeomDestroy(dGeomID g) {
     if (!g || !g->alive) return;
+    if (g->body) {
+        std::vector<dxGeom *> &v = g->body->geoms;
+        v.erase(std::remove(v.begin(), v.end(), g), v.end());
+    }
     HG(g).alive[g->idx] = 0;
     eng_mark_geom(g->space->w->eng, g->idx);
     g->alive = false;
 }
 extern "C" void dGeomSetBody(dGeomID g, dBodyID b) {
     if (b && b->w != g->space->w) fatal("dGeomSetBody: the body belongs to a different world than the geom's space");
+    if (g->body && g->body != b) {
+        std::vector<dxGeom *> &v = g->body->geoms;
+        v.erase(std::remove(v.begin(), v.end(), g), v.end());
+    }
+    if (b && g->body != b) b->geoms.push_back(g);
     g->body = b;
     HostGeoms &hg = HG(g);
     hg.body[g->idx] = b ? b->idx : -1;
@@ -831,6 +846,7 @@ extern "C" int dSpaceAddGeomsB200(dSpaceID s, dWorldID w, int n, const int *type
         if (b >= 0) {
             if (b >= (int)w->bodies.size()) fatal("dSpaceAddGeomsB200: body index out of range");
             g->body = &w->bodies[b];
+            g->body->geoms.push_back(g);
             hg.body[k] = b;
         } else {
             if (pos3) for (int c = 0; c < 3; c++) hg.pos[4 * k + c] = pos3[3 * i + c];

@@ -76,3 +76,27 @@ def test_ghosts_only_collide_with_owned_bodies():
     plane, owned, ghost = 0, 5, 5 + n_own
     assert passes(owned, owned + 1) and passes(owned, ghost) and passes(owned, plane)
     assert not passes(ghost, ghost + 1) and not passes(ghost, plane) and not passes(plane, plane + 1)
+
+
+def test_dynamic_slab_scene_layout():
+    """dynamic halo: every rank but the last carries a pool of switched-off ghost slots behind its own bodies;
+    pools have one size (a message fills the receiver's pool slot for slot); faces tile the x axis; geom index =
+    5 static planes + body index (the body->geom map DynamicSlabWorld starts from)."""
+    n_slabs = 3
+    built = [slabs.dynamic_slab_scene(r, n_slabs, nx_per_slab=6, nz=5, ny=3, margin_cols=2, spacing=1.8) for r in range(n_slabs)]
+    pools = {info["pool"] for _, info in built}
+    assert len(pools) == 1
+    for r, (sc, info) in enumerate(built):
+        b, g = sc["bodies"], sc["geoms"]
+        n_own, pool = info["n_own"], info["pool"]
+        assert info["has_pool"] == (r < n_slabs - 1)
+        assert len(b["pos"]) == n_own + (pool if info["has_pool"] else 0)
+        assert np.array_equal(g["body"][5:], np.arange(len(b["pos"])))
+        assert (b["flags"][:n_own] == 0).all() and (b["flags"][n_own:] == scenes.BODY_KINEMATIC).all()
+        assert (g["cat"][5 + n_own:] == slabs.CAT_GHOST).all() and (g["col"][5 + n_own:] == 0).all()
+        assert (b["pos"][n_own:, 1] < -100).all()                       # parked far below the ground plane
+        xs = b["pos"][:n_own, 0]
+        assert info["face_left"] < xs.min() and xs.max() < info["face_right"]
+        if r > 0:
+            assert abs(info["face_left"] - built[r - 1][1]["face_right"]) < 1e-9
+        assert 0 < info["hyst"] < info["margin"]
