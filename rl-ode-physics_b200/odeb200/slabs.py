@@ -15,8 +15,9 @@ device copy when several slabs are emulated on one GPU).  Two couplings:
   face pushes only the owned body on each side (each side sees an immovable obstacle).  One exchange per tick.
 
 Ghost geoms collide with owned bodies only (category bits), never with each other or with static geoms.
-Boundary membership is fixed by the initial lattice column: bodies do not migrate between slabs (DESIGN.md
-section 6).
+`slab_scene` / `SlabWorld` fix the boundary membership by the initial lattice column; `dynamic_slab_scene` /
+`DynamicSlabWorld` (further down) re-select it from the current positions every tick and migrate bodies between
+slabs.
 """
 import numpy as np
 
