@@ -79,6 +79,7 @@ Engine *eng_create(int device) {
     if (const char *g = getenv("ODE_B200_ENV_STAGE")) e->env_stage = atoi(g);
     if (const char *g = getenv("ODE_B200_L2_PERSIST")) e->l2_persist = atoi(g);
     if (const char *g = getenv("ODE_B200_ENV_FUSE")) e->env_fuse = atoi(g);
+    if (const char *g = getenv("ODE_B200_TINY_SOLVER")) e->tiny_solver = atoi(g);
     if (const char *g = getenv("ODE_B200_BROADPHASE")) e->broad_mode = !strcmp(g, "grid") ? 0 : !strcmp(g, "env") ? 1 : -1;
     return e;
 }

@@ -509,8 +509,14 @@ __device__ __forceinline__ void solve_row(V3 dir, V3 c1, V3 c2, bool two, float 
 struct RowRec {
     float4 q0, q1, q2, q3, q4, lam;
 };
+template <bool NC = true>
 __device__ __forceinline__ RowRec load_rows(const SolverArrays &S, size_t si) {
     RowRec r;
+    if (!NC) { // the arrays may live in shared memory (small-world solver): generic loads
+        r.q0 = S.q0[si]; r.q1 = S.q1[si]; r.q2 = S.q2[si]; r.q3 = S.q3[si]; r.q4 = S.q4[si];
+        r.lam = S.lam[si];
+        return r;
+    }
     // rows are written by k_rows before this kernel starts: read-only path; lambda is thread-private
     r.q0 = __ldg(&S.q0[si]); r.q1 = __ldg(&S.q1[si]); r.q2 = __ldg(&S.q2[si]);
     r.q3 = __ldg(&S.q3[si]); r.q4 = __ldg(&S.q4[si]);
@@ -532,7 +538,7 @@ __device__ __forceinline__ void st_fc(float4 *p, float4 v) {
 
 // fcp / invp: where the accumulators and world inverse inertias of the unit's bodies live -- the global
 // arrays (indexed by body) or, on the island path, the env's copy in shared memory (indexed by local body)
-template <bool L2ONLY, bool SINGLE = false>
+template <bool L2ONLY, bool SINGLE = false, bool NC = true>
 __device__ __forceinline__ void solve_manifold_core(int s, const int4 rec, RowRec cur, const SolverArrays &S, float4 *fcp,
                                                     const float4 *invp, int fs = 2, int fo = 1, float *maxd = nullptr) {
     const int b1 = rec.x, b2 = rec.y, nc = SINGLE ? 1 : rec.z; // SINGLE: per-contact units, no contact loop
@@ -558,7 +564,7 @@ __device__ __forceinline__ void solve_manifold_core(int s, const int4 rec, RowRe
     for (int k = 0; k < nc; k++) {
         const size_t si = (size_t)k * S.cap + s;
         RowRec nxt = cur;
-        if (!SINGLE && k + 1 < nc) nxt = load_rows(S, si + S.cap);
+        if (!SINGLE && k + 1 < nc) nxt = load_rows<NC>(S, si + S.cap);
         float4 lam = cur.lam;
         const int lflags = __float_as_int(lam.w);
         const int the_m = lflags & 0xf;
@@ -593,11 +599,11 @@ __device__ __forceinline__ void solve_manifold_core(int s, const int4 rec, RowRe
     }
 }
 
-template <bool L2ONLY, bool SINGLE = false>
+template <bool L2ONLY, bool SINGLE = false, bool NC = true>
 __device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, float4 *fcp, const float4 *invp, int fs = 2,
                                                int fo = 1, float *maxd = nullptr) {
-    const int4 rec = __ldg(&S.mrec[s]);
-    solve_manifold_core<L2ONLY, SINGLE>(s, rec, load_rows(S, (size_t)s), S, fcp, invp, fs, fo, maxd);
+    const int4 rec = NC ? __ldg(&S.mrec[s]) : S.mrec[s];
+    solve_manifold_core<L2ONLY, SINGLE, NC>(s, rec, load_rows<NC>(S, (size_t)s), S, fcp, invp, fs, fo, maxd);
 }
 
 // grid-wide barrier of the persistent solver (all CTAs are co-resident: cooperative launch).  One
@@ -682,7 +688,8 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // take the same exit decision after the sweep's last barrier.
 template <bool TOL>
 __global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays S, BodyArrays B, StepConfig cfg,
-                                                  StepStats *__restrict__ stats) {
+                                                  StepStats *__restrict__ stats, const int *__restrict__ done_flag) {
+    if (done_flag && *done_flag) return; // the small-world solver already did the whole solve + tail
     const int n = *M.count;
     const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
     unsigned *bar = reinterpret_cast<unsigned *>(&M.meta[6]);
@@ -736,6 +743,67 @@ __global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays
         if (gt == 0) stats->solver_iters = it;
     }
     for (int i = gt; i < B.n; i += gs) integrate_body(i, B, cfg.h, __ldcg(&B.fc[2 * i]), __ldcg(&B.fc[2 * i + 1]));
+}
+
+// Small single worlds (the reference's own scene: 68 bodies, ~80 manifolds): the colour phases of k_solve are
+// ~2 us each -- a grid barrier plus a chain of L2 round trips -- for a handful of manifolds.  One CTA with the
+// rows, the manifold records, the accumulators and the world inverse inertias in shared memory runs the same
+// phases (same colours, same order inside a manifold: bit-identical results) separated by __syncthreads only.
+// Falls through (flag stays 0) when the world does not fit; k_solve then does the work.
+constexpr int TINY_MANIFOLDS = 160, TINY_BODIES = 256, TINY_THREADS = 256;
+__global__ void __launch_bounds__(TINY_THREADS) k_tiny_solve(ManifoldArrays M, SolverArrays S, BodyArrays B, StepConfig cfg,
+                                                              StepStats *__restrict__ stats, int *__restrict__ done_flag) {
+    extern __shared__ __align__(16) unsigned char tiny_smem[];
+    const int n = *M.count, nb = B.n, tid = threadIdx.x;
+    if (n > TINY_MANIFOLDS || nb > TINY_BODIES) {
+        if (tid == 0) *done_flag = 0;
+        return;
+    }
+    __shared__ int cs[OVERFLOW_COLOUR + 2];
+    SolverArrays T;
+    T.cap = n;
+    float4 *p = reinterpret_cast<float4 *>(tiny_smem);
+    T.q0 = p; p += 8 * n; T.q1 = p; p += 8 * n; T.q2 = p; p += 8 * n; T.q3 = p; p += 8 * n;
+    T.q4 = p; p += 8 * n; T.q5 = p; p += 8 * n; T.lam = p; p += 8 * n;
+    T.mrec = reinterpret_cast<int4 *>(p); p += n;
+    float4 *fc = p; p += 2 * nb;
+    float4 *inv = p;
+    if (tid < OVERFLOW_COLOUR + 2) cs[tid] = M.colour_start[tid];
+    for (int s = tid; s < n; s += TINY_THREADS) {
+        const int4 rec = S.mrec[s];
+        T.mrec[s] = rec;
+        for (int k = 0; k < rec.z; k++) {
+            const size_t g = (size_t)k * S.cap + s;
+            const int t = k * n + s;
+            T.q0[t] = S.q0[g]; T.q1[t] = S.q1[g]; T.q2[t] = S.q2[g]; T.q3[t] = S.q3[g]; T.q4[t] = S.q4[g];
+            const float4 lam = S.lam[g];
+            T.lam[t] = lam;
+            if (__float_as_int(lam.w) & 0x40) T.q5[t] = S.q5[g];
+        }
+    }
+    for (int i = tid; i < 2 * nb; i += TINY_THREADS) fc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < 3 * nb; i += TINY_THREADS) inv[i] = B.inv[i];
+    __syncthreads();
+    if (n > 0) {
+        const int ncol = M.meta[0];
+        const int ovf0 = cs[OVERFLOW_COLOUR], ovf1 = cs[OVERFLOW_COLOUR + 1];
+        for (int it = 0; it < cfg.iters; it++) {
+            for (int c = 0; c < ncol; c++) {
+                for (int s = cs[c] + tid; s < cs[c + 1]; s += TINY_THREADS) solve_manifold<false, false, false>(s, T, fc, inv);
+                __syncthreads();
+            }
+            if (ovf1 > ovf0) {
+                if (tid == 0)
+                    for (int s = ovf0; s < ovf1; s++) solve_manifold<false, false, false>(s, T, fc, inv);
+                __syncthreads();
+            }
+        }
+    }
+    for (int i = tid; i < nb; i += TINY_THREADS) {
+        B.fc[2 * i] = fc[2 * i]; B.fc[2 * i + 1] = fc[2 * i + 1]; // dWorldPackImpulsesDeviceB200 reads them
+        integrate_body(i, B, cfg.h, fc[2 * i], fc[2 * i + 1]);
+    }
+    if (tid == 0) { *done_flag = 1; stats->solver_iters = cfg.iters; }
 }
 
 // micro-benchmark hook: cost of one grid barrier at the solver's launch shape
@@ -1221,9 +1289,21 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
         long work = max_manifolds > nb ? max_manifolds : nb;
         const void *fn = cfg.tol > 0.f ? (const void *)k_solve<true> : (const void *)k_solve<false>;
         if (cfg.tol > 0.f) OB_CUDA(cudaMemsetAsync(&M.meta[8], 0, 3 * sizeof(int), st)); // residual slots
-        int grid = coop_grid(e, fn, 256, work);
         StepStats *d_stats = e->d_stats;
-        void *args[] = {(void *)&M, (void *)&S, (void *)&B, (void *)&cfg, (void *)&d_stats};
+        const int *done_flag = nullptr;
+        if (nb <= TINY_BODIES && !(cfg.tol > 0.f) && e->tiny_solver) {
+            const size_t smem = (size_t)TINY_MANIFOLDS * (7 * 8 + 1) * 16 + (size_t)nb * 5 * 16;
+            static bool attr_set = false;
+            if (!attr_set) {
+                OB_CUDA(cudaFuncSetAttribute(k_tiny_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_set = true;
+            }
+            k_tiny_solve<<<1, TINY_THREADS, smem, st>>>(M, S, B, cfg, d_stats, &M.meta[11]);
+            OB_CHECK_KERNEL("k_tiny_solve", st);
+            done_flag = &M.meta[11];
+        }
+        int grid = coop_grid(e, fn, 256, work);
+        void *args[] = {(void *)&M, (void *)&S, (void *)&B, (void *)&cfg, (void *)&d_stats, (void *)&done_flag};
         OB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(256), args, 0, st));
         OB_CHECK_KERNEL("k_solve", st);
     }
