@@ -111,7 +111,8 @@ dReal dWorldGetContactMaxCorrectingVel(dWorldID);
 void dWorldSetContactSurfaceLayer(dWorldID, dReal depth);
 dReal dWorldGetContactSurfaceLayer(dWorldID);
 /* Both steppers run the same graph-coloured SOR/PGS solver (src/main.c:213 calls dWorldStep;
- * north_star names dWorldQuickStep).  Return 1 on success, 0 on failure. */
+ * north_star names dWorldQuickStep).  dWorldStep can be told to iterate towards libode's exact LCP answer:
+ * dWorldSetStepSolverB200 in ode_b200.h.  Return 1 on success, 0 on failure. */
 int dWorldStep(dWorldID, dReal stepsize);                      /* src/main.c:213 */
 int dWorldQuickStep(dWorldID, dReal stepsize);
 
