@@ -252,7 +252,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libode_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
-    prev_affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    prev_affinity = bind_to_gpu_numa_node(local_rank) if (world > 1 and not os.environ.get("ODE_B200_NO_BIND")) else None
     if world > 1:
         sharding.init_process_group("nccl")
     dev = "cuda:%d" % local_rank

@@ -502,6 +502,33 @@ __global__ void k_pairs_finish(int n, const int *__restrict__ off, int cap_pairs
     stats->grid_dims[0] = gp->dx; stats->grid_dims[1] = gp->dy; stats->grid_dims[2] = gp->dz;
 }
 
+// dCollide(o1, o2) outside a space traversal: refresh the poses, then hand the narrowphase a one-pair list
+__global__ void k_single_pair(GeomArrays g, int g1, int g2, int2 *__restrict__ pairs, BroadCounters *__restrict__ bc,
+                              StepStats *__restrict__ stats) {
+    int ta = g.type[g1], tb = g.type[g2];
+    int ga = g1, gb = g2;
+    if (ta > tb || (ta == tb && ga > gb)) { int t = ga; ga = gb; gb = t; t = ta; ta = tb; tb = t; }
+    const int cls = (g.alive[g1] && g.alive[g2]) ? pair_class(ta, tb) : PC_NONE;
+    pairs[0] = make_int2(ga, gb);
+    bc->n_pairs = 1;
+    bc->first_big = bc->first_dead = g.n;
+    for (int c = 0; c <= PC_COUNT; c++) bc->class_start[c] = c <= cls ? 0 : 1;
+    stats->n_pairs = 1;
+    stats->flags = 0;
+    for (int c = 0; c < PC_COUNT; c++) stats->class_count[c] = c == cls ? 1 : 0;
+}
+
+void broadphase_single_pair(BroadPhase &bp, GeomArrays g, const float4 *b_pos, const float4 *b_R, MeshTable meshes, float big_extent,
+                            int g1, int g2, StepStats *d_stats, cudaStream_t st) {
+    const unsigned nb = (unsigned)((g.n + 255) / 256);
+    static const unsigned acc_init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
+    OB_CUDA(cudaMemcpyAsync(bp.acc, acc_init, sizeof(acc_init), cudaMemcpyHostToDevice, st));
+    k_geom_update<<<nb, 256, 0, st>>>(g, b_pos, b_R, meshes, big_extent, bp.acc);
+    OB_CHECK_KERNEL("k_geom_update", st);
+    k_single_pair<<<1, 1, 0, st>>>(g, g1, g2, bp.pairs, bp.counters, d_stats);
+    OB_CHECK_KERNEL("k_single_pair", st);
+}
+
 void broadphase_run(BroadPhase &bp, GeomArrays g, const float4 *b_pos, const float4 *b_R, MeshTable meshes,
                     int n_envs, float big_extent, const EnvBroad &eb, StepStats *d_stats, cudaStream_t st) {
     const int n = g.n;

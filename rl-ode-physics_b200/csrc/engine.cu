@@ -705,6 +705,25 @@ __global__ void __launch_bounds__(256) k_compact_contacts(const BroadCounters *_
     }
 }
 
+// dCollide outside a space traversal: one pair through the same narrowphase kernels
+HostPairs eng_collide_pair(Engine *e, int g1, int g2, int max_contacts) {
+    if (e->have_device_contacts) {
+        fprintf(stderr, "libode_b200: dCollide between dSpaceCollideDeviceB200 and the step would discard the world's "
+                        "contacts; call it before the collide or after the step\n");
+        abort();
+    }
+    eng_sync_to_device(e);
+    engine_ensure_pair_capacity(e);
+    if (max_contacts < 1) max_contacts = 1;
+    if (max_contacts > 8) max_contacts = 8;
+    broadphase_single_pair(e->bp, e->G, e->B.pos, e->B.R, e->meshes, e->big_extent, g1, g2, e->d_stats, e->st);
+    narrowphase_run(e->bp, e->G, e->meshes, e->hmeshes, e->cs, max_contacts, e->d_stats, e->num_sms, e->st);
+    e->have_device_contacts = true;
+    HostPairs hp = eng_fetch_pairs(e);
+    e->have_device_contacts = false;
+    return hp;
+}
+
 HostPairs eng_fetch_pairs(Engine *e) {
     HostPairs hp;
     OB_CUDA(cudaSetDevice(e->device));

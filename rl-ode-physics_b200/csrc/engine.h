@@ -181,6 +181,7 @@ struct HostPairs {
     const float *normal_side = nullptr;         // 4 per contact (w = bitcast int side2 / triangle)
 };
 HostPairs eng_fetch_pairs(Engine *);
+HostPairs eng_collide_pair(Engine *, int g1, int g2, int max_contacts);
 // step with device-resident contacts of the last eng_collide and one surface for every contact
 void eng_step_device_contacts(Engine *, float h, const Surface &surf);
 // step with host-provided contact joints (compat mode)

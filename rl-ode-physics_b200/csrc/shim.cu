@@ -937,8 +937,15 @@ extern "C" int dCollide(dGeomID o1, dGeomID o2, int flags, dContactGeom *contact
         // answer needs the pair re-collided with that limit (set dWorldSetMaxContactsB200 to avoid)
         fatal("dCollide: max contacts smaller than the world's precomputed limit; call dWorldSetMaxContactsB200 first");
     }
-    fatal("dCollide outside dSpaceCollide's callback is not supported by this build");
-    return 0;
+    if (w->in_callback) fatal("dCollide inside the callback is served for the callback's own pair only");
+    // anywhere else: the pair goes through the narrowphase kernels on its own (a GPU round trip per call)
+    HostPairs hp = eng_collide_pair(w->eng, o1->idx, o2->idx, maxc);
+    if (hp.n_pairs != 1 || hp.count[0] == 0) return 0;
+    const HostPairs saved = w->cb_pairs;
+    w->cb_pairs = hp;
+    const int n = copy_contacts(w, hp.first[0], hp.count[0], hp.g1[0] != o1->idx, o1, o2, maxc, contact, skip);
+    w->cb_pairs = saved;
+    return n;
 }
 
 extern "C" int dSpaceGetPairsB200(dSpaceID s, int *pairs2, int cap) {

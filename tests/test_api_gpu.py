@@ -295,3 +295,32 @@ def test_obj_loader_builds_the_same_trimesh_as_buildsingle(tmp_path):
     assert np.array_equal(results[0], results[1])
     assert results[0][:, 1].min() > 0.2              # nobody fell through the mesh
     assert L.dGeomTriMeshDataBuildFromOBJB200(C.c_void_p(L.dGeomTriMeshDataCreate()), b"/nonexistent.obj") == -1
+
+
+def test_dcollide_outside_the_space_traversal_matches_the_oracle():
+    """dCollide(o1, o2) called directly (not from dSpaceCollide's callback) runs the one pair through the same
+    narrowphase kernels: contacts bit-equal to the oracle's dCollide, in either argument order."""
+    s = Server()
+    L = s.L
+    ow = O.OracleWorld()
+    floor = s.add_static_box((0, 0, 0), (10, 1, 10)); ow.add_geom(O.BOX, [10, 1, 10], pos=[0, 0, 0])
+    b1, g1 = s.add_body((0.1, 0.9, 0.0), "box", (1.0, 1.0, 1.0))
+    o1 = ow.add_body(np.float32([0.1, 0.9, 0.0]), flags=O.BODY_GYRO); ow.add_geom(O.BOX, [1, 1, 1], body=o1)
+    b2, g2 = s.add_body((0.6, 1.5, 0.2), "sphere", (0.45,))
+    o2 = ow.add_body(np.float32([0.6, 1.5, 0.2]), flags=O.BODY_GYRO); ow.add_geom(O.SPHERE, [0.45], body=o2)
+    contacts = (odeb200.Contact * 8)()
+    geom0 = C.cast(C.addressof(contacts) + odeb200.Contact.geom.offset, C.POINTER(odeb200.ContactGeom))
+    for (ga, gb, ia, ib) in ((floor, g1, 0, 1), (g1, g2, 1, 2), (g2, g1, 2, 1), (floor, g2, 0, 2)):
+        n = L.dCollide(ga, gb, 8, geom0, C.sizeof(odeb200.Contact))
+        ref = ow.collide(ia, ib, 8)
+        assert n == len(ref), (ia, ib, n, len(ref))
+        for k in range(n):
+            cg = contacts[k].geom
+            assert np.array_equal(np.float32(list(cg.pos)[:3]), np.float32(list(ref[k].pos)[:3])), (ia, ib, k)
+            assert np.array_equal(np.float32(list(cg.normal)[:3]), np.float32(list(ref[k].normal)[:3])), (ia, ib, k)
+            assert np.float32(cg.depth) == np.float32(ref[k].depth)
+    # the world still ticks normally afterwards
+    for _ in range(3):
+        s.tick()
+    assert s.pos(b1)[1] > 0.9
+    s.close()
