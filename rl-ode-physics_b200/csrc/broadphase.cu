@@ -250,7 +250,8 @@ __device__ __forceinline__ int test_pair(const float4 &lo1, const float4 &hi1, c
 
 // The count pass also parks each thread's first SWEEP_TCAP hits (k-major, coalesced) so that the fill
 // pass is a pure compaction for almost every thread instead of a second traversal of the grid.
-constexpr int SWEEP_TCAP = 8;
+// (16: in a settled pile a geom emits 4-7 pairs on average and a third of them more than 8; one such lane makes
+// its whole warp wait for a second traversal -- C3: fill pass 253 us at 8)
 
 struct PairSink {
     int cnt[PC_COUNT];

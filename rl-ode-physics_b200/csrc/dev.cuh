@@ -69,6 +69,8 @@ struct BroadCounters {
     int class_start[PC_COUNT + 1];
 };
 
+constexpr int SWEEP_TCAP = 16; // hits a sweep thread can park in the count pass (broadphase.cu)
+
 struct BroadPhase {
     int cap_geoms = 0, cap_cells = 0, key_bits = 0, cap_pairs = 0;
     unsigned *acc = nullptr;

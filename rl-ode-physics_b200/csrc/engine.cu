@@ -282,7 +282,7 @@ void engine_ensure_capacity(Engine *e) {
         dev_realloc(bp.s_min, 0, n, st, false); dev_realloc(bp.s_max, 0, n, st, false);
         dev_realloc(bp.s_flt, 0, n, st, false);
         dev_realloc(bp.cnt, 0, (size_t)PC_COUNT * n + 1, st, false);
-        dev_realloc(bp.sweep_tmp, 0, (size_t)8 * n, st, false);
+        dev_realloc(bp.sweep_tmp, 0, (size_t)SWEEP_TCAP * n, st, false);
         dev_realloc(bp.sweep_tot, 0, n, st, false);
         bp.cap_geoms = (int)n;
         e->cap_g = (int)n;

@@ -151,6 +151,22 @@ __global__ void __launch_bounds__(256) k_manifold_dynbits(ManifoldArrays M, cons
     }
 }
 
+// grid-wide barrier of the persistent solver (all CTAs are co-resident: cooperative launch).  One
+// release-add per CTA on a monotone counter, thread 0 spins with acquire loads.
+__device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
 // ------------------------------------------------------------------ edge colouring
 
 __device__ __forceinline__ unsigned long long manifold_prio(int tie, int lb1, int lb2) {
@@ -184,6 +200,8 @@ __device__ __forceinline__ int pick_colour(unsigned long long mask, unsigned lon
 // the smallest hashed priority among the uncoloured manifolds at both of its dynamic bodies; a
 // winner takes the lowest colour free at both bodies.  Only kinematic/static ends never conflict.
 __global__ void __launch_bounds__(256) k_colour(ManifoldArrays M, BodyArrays B, int spread) {
+    // (cg's grid sync, not the solver's own barrier: at this kernel's ~1200 CTAs one spinning thread per CTA on a
+    // single counter is slower -- measured on C3: prepare 1.02 -> 1.25 ms)
     cg::grid_group grid = cg::this_grid();
     const int n = *M.count;
     const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
@@ -604,22 +622,6 @@ __device__ __forceinline__ void solve_manifold(int s, const SolverArrays &S, flo
                                                int fo = 1, float *maxd = nullptr) {
     const int4 rec = NC ? __ldg(&S.mrec[s]) : S.mrec[s];
     solve_manifold_core<L2ONLY, SINGLE, NC>(s, rec, load_rows<NC>(S, (size_t)s), S, fcp, invp, fs, fo, maxd);
-}
-
-// grid-wide barrier of the persistent solver (all CTAs are co-resident: cooperative launch).  One
-// release-add per CTA on a monotone counter, thread 0 spins with acquire loads.
-__device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        target += gridDim.x;
-        __threadfence();
-        atomicAdd(ctr, 1u);
-        unsigned v;
-        do {
-            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-        } while (v < target);
-    }
-    __syncthreads();
 }
 
 // velocity update, dxStepBody (semi-implicit Euler + quaternion renormalisation + dQtoR) and the
