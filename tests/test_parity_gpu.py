@@ -247,6 +247,35 @@ def test_full_size_pile_properties():
     ew.close()
 
 
+def test_full_size_batched_worlds_copies_agree_bit_for_bit():
+    """BASELINE config 4 at full size (8192 worlds x 128 bodies = 1,048,576 bodies): the batch is 128 tiles of
+    the same 64 worlds, so after 60 ticks every tile must equal tile 0 bit for bit -- each world's result
+    depends on nothing but that world, whichever CTA, warp and L2 slice happened to process it."""
+    base = scenes.batched_worlds_scene(64, seed=4)
+    tiles, per_world, nw = 128, 128, 64
+    nb = nw * per_world
+    b, g = base["bodies"], base["geoms"]
+    bodies = {k: np.concatenate([v] * tiles) for k, v in b.items()}
+    bodies["env"] = (np.arange(tiles * nb) // per_world).astype(np.int32)
+    dyn = {k: v[1:] for k, v in g.items()}                      # geom 0 is the shared plane
+    geoms = {k: np.concatenate([g[k][:1]] + [dyn[k]] * tiles) for k in g}
+    geoms["body"] = np.concatenate([[-1], np.arange(tiles * nb)]).astype(np.int32)
+    geoms["env"] = np.concatenate([[-1], np.arange(tiles * nb) // per_world]).astype(np.int32)
+    sc = scenes.from_arrays("C4-tiled", bodies, geoms, h=base["h"])
+    ew = util.engine_world(sc)
+    for _ in range(60):
+        ew.tick(sc["h"])
+    st = ew.stats()
+    assert st["flags"] == 0 and st["n_overflow"] == 0 and st["n_contacts"] > 500000
+    s = ew.state()
+    ew.close()
+    for k in ("pos", "quat", "lvel", "avel"):
+        a = s[k].reshape(tiles, nb, -1)
+        assert np.isfinite(a).all()
+        assert (a == a[0:1]).all(), k
+    assert s["pos"][:, 1].min() > -0.05
+
+
 def test_mass_and_inertia_parity():
     """dMassSetBox-style inertia (non-identity, gyroscopic term active) against the oracle."""
     rs = np.random.RandomState(3)
