@@ -1095,6 +1095,117 @@ static int collide_sphere_trimesh(const orc_world *w, const ogeom *s, const ogeo
     return nout;
 }
 
+/* box vs trimesh.  libode's collision_trimesh_box.cpp (SAT + clipping per triangle) is not restated; like
+ * sphere-trimesh the engine defines an order-independent vertex/face rule, restated here (mesh-local frame):
+ *   per triangle with unit normal n (skipped when degenerate or when its box misses the box's AABB):
+ *     (a) each of the 8 box vertices pv with signed distance d = n.(pv - a) in [-maxdepth, 0) whose
+ *         projection lies inside the triangle (three edge tests, boundary included): contact at pv,
+ *         direction n, depth -d; maxdepth = the box's smallest side length;
+ *     (b) each triangle vertex inside the box: contact at the vertex, direction = minus the outward normal
+ *         of the box face it is nearest to (lowest axis on ties), depth = distance to that face.
+ *   selection as for spheres: (depth desc, triangle*16 + sub-index asc), duplicates within 1e-3 * the
+ *   smallest half side dropped, at most maxc (<= 8).  Edge-edge contacts are not generated.
+ * Output (box = g1, trimesh = g2): normal from the mesh into the box, side2 = triangle index. */
+static int collide_box_trimesh(const orc_world *w, const ogeom *bx, const ogeom *tm, int maxc, orc_contact_geom *out) {
+    const omesh *m = &w->m[tm->mesh];
+    float cb[3], d[3], A[3][3], h[3], ext[3], pv[8][3];
+    for (int k = 0; k < 3; k++) d[k] = bx->pos[k] - tm->pos[k];
+    mul1_331(cb, tm->R, d);
+    for (int k = 0; k < 3; k++) {
+        float col[3] = {bx->R[k], bx->R[4 + k], bx->R[8 + k]};
+        mul1_331(A[k], tm->R, col);
+        h[k] = 0.5f * bx->dims[k];
+    }
+    for (int j = 0; j < 3; j++) ext[j] = fabsf(A[0][j]) * h[0] + fabsf(A[1][j]) * h[1] + fabsf(A[2][j]) * h[2];
+    for (int v = 0; v < 8; v++)
+        for (int j = 0; j < 3; j++) {
+            float s0 = (v & 1) ? h[0] : -h[0], s1 = (v & 2) ? h[1] : -h[1], s2 = (v & 4) ? h[2] : -h[2];
+            pv[v][j] = ((cb[j] + s0 * A[0][j]) + s1 * A[1][j]) + s2 * A[2][j];
+        }
+    const float hmin = fminf(h[0], fminf(h[1], h[2]));
+    const float maxdepth = 2.0f * hmin;
+    if (maxc > 8) maxc = 8;
+    tri_cand *cand = 0;
+    int nc = 0, capc = 0;
+    for (int t = 0; t < m->nt; t++) {
+        const float *a = m->v + 3 * m->t[3 * t], *b = m->v + 3 * m->t[3 * t + 1], *c = m->v + 3 * m->t[3 * t + 2];
+        int skip = 0;
+        for (int k = 0; k < 3; k++) {
+            float lo = fminf(a[k], fminf(b[k], c[k])), hi = fmaxf(a[k], fmaxf(b[k], c[k]));
+            if (cb[k] - ext[k] > hi || cb[k] + ext[k] < lo) skip = 1;
+        }
+        if (skip) continue;
+        float e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]}, nr[3], n[3];
+        cross3(nr, e1, e2);
+        float l2 = dot3(nr, nr);
+        if (!(l2 > 0)) continue;
+        float inv = 1.0f / sqrtf(l2);
+        n[0] = nr[0] * inv; n[1] = nr[1] * inv; n[2] = nr[2] * inv;
+        for (int sub = 0; sub < 11; sub++) {
+            float depth, q[3], dir[3];
+            if (sub < 8) {
+                float e[3] = {pv[sub][0] - a[0], pv[sub][1] - a[1], pv[sub][2] - a[2]};
+                float dd = dot3(n, e);
+                if (!(dd < 0 && dd >= -maxdepth)) continue;
+                float pr[3] = {pv[sub][0] - dd * n[0], pv[sub][1] - dd * n[1], pv[sub][2] - dd * n[2]};
+                const float *tv[3] = {a, b, c};
+                int inside = 1;
+                for (int j = 0; j < 3; j++) {
+                    const float *p0 = tv[j], *p1 = tv[(j + 1) % 3];
+                    float ed[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, rq[3] = {pr[0] - p0[0], pr[1] - p0[1], pr[2] - p0[2]}, cr[3];
+                    cross3(cr, ed, rq);
+                    if (!(dot3(cr, nr) >= 0)) inside = 0;
+                }
+                if (!inside) continue;
+                depth = -dd;
+                memcpy(q, pv[sub], 12); memcpy(dir, n, 12);
+            } else {
+                const float *tv = sub == 8 ? a : (sub == 9 ? b : c);
+                float e[3] = {tv[0] - cb[0], tv[1] - cb[1], tv[2] - cb[2]}, loc[3];
+                int inside = 1, ks = 0;
+                float best = 0;
+                for (int k = 0; k < 3; k++) {
+                    loc[k] = dot3(A[k], e);
+                    if (!(fabsf(loc[k]) <= h[k])) inside = 0;
+                    float pen = h[k] - fabsf(loc[k]);
+                    if (k == 0 || pen < best) { best = pen; ks = k; }
+                }
+                if (!inside) continue;
+                float sg = loc[ks] < 0 ? 1.0f : -1.0f; /* minus the outward normal of the nearest face */
+                depth = best;
+                memcpy(q, tv, 12);
+                dir[0] = sg * A[ks][0]; dir[1] = sg * A[ks][1]; dir[2] = sg * A[ks][2];
+            }
+            if (nc == capc) { capc = capc ? capc * 2 : 32; cand = (tri_cand *)realloc(cand, sizeof(tri_cand) * (size_t)capc); }
+            cand[nc].depth = depth; cand[nc].tri = t * 16 + sub;
+            memcpy(cand[nc].q, q, 12); memcpy(cand[nc].n, dir, 12);
+            nc++;
+        }
+    }
+    qsort(cand, (size_t)nc, sizeof(tri_cand), cmp_cand);
+    int nout = 0;
+    float tol2 = (1e-3f * hmin) * (1e-3f * hmin);
+    float accq[8][3];
+    for (int i = 0; i < nc && nout < maxc; i++) {
+        int dup = 0;
+        for (int j = 0; j < nout; j++) {
+            float e[3] = {cand[i].q[0] - accq[j][0], cand[i].q[1] - accq[j][1], cand[i].q[2] - accq[j][2]};
+            if (dot3(e, e) <= tol2) { dup = 1; break; }
+        }
+        if (dup) continue;
+        memcpy(accq[nout], cand[i].q, 12);
+        float pw[3], nw[3];
+        mul0_331(pw, tm->R, cand[i].q);
+        mul0_331(nw, tm->R, cand[i].n);
+        for (int k = 0; k < 3; k++) { out[nout].pos[k] = pw[k] + tm->pos[k]; out[nout].normal[k] = nw[k]; }
+        out[nout].depth = cand[i].depth;
+        out[nout].side1 = -1; out[nout].side2 = cand[i].tri >> 4;
+        nout++;
+    }
+    free(cand);
+    return nout;
+}
+
 /* dCollide (collision_kernel.cpp): colliders are registered for (lower class, higher class);
  * called the other way round, the result is computed swapped and then normals are negated and
  * g1/g2, side1/side2 exchanged. */
@@ -1113,7 +1224,8 @@ int orc_collide(orc_world *w, int i1, int i2, int maxc, orc_contact_geom *out) {
     else if (a->type == ORC_BOX && b->type == ORC_BOX) n = collide_box_box(a, b, maxc, out);
     else if (a->type == ORC_BOX && b->type == ORC_PLANE) n = collide_box_plane(a, b, maxc, out);
     else if (a->type == ORC_SPHERE && b->type == ORC_TRIMESH) n = collide_sphere_trimesh(w, a, b, maxc, out);
-    else n = 0; /* plane-plane, box-trimesh, ...: no collider */
+    else if (a->type == ORC_BOX && b->type == ORC_TRIMESH) n = collide_box_trimesh(w, a, b, maxc, out);
+    else n = 0; /* plane-plane, plane-trimesh, ...: no collider */
     for (int i = 0; i < n; i++) {
         if (swap) {
             out[i].normal[0] = -out[i].normal[0]; out[i].normal[1] = -out[i].normal[1]; out[i].normal[2] = -out[i].normal[2];

@@ -229,6 +229,7 @@ __device__ __forceinline__ int pair_class(int ta, int tb) { // ta <= tb
     } else if (ta == G_BOX) {
         if (tb == G_BOX) return PC_BOX_BOX;
         if (tb == G_PLANE) return PC_BOX_PLANE;
+        if (tb == G_TRIMESH) return PC_SPHERE_TRIMESH; // the trimesh kernel takes spheres and boxes
     }
     return PC_NONE;
 }

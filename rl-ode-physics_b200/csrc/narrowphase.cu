@@ -612,11 +612,106 @@ __global__ void __launch_bounds__(TM_WARPS * 32) k_np_sphere_trimesh(const Broad
         const int2 pr = pairs[pi];
         if (g.mesh[pr.y] != mesh_id) continue;
         const V3 ps = v3(g.pos[pr.x]);
-        const float r = g.dims[pr.x].x;
         const V3 mp = v3(g.pos[pr.y]);
         const M3 mR = load_m3(g.R, pr.y);
         const V3 c = mulT(mR, ps - mp);
+        const bool is_box = g.type[pr.x] == G_BOX;   // warp-uniform: one pair per warp
+        float r = g.dims[pr.x].x;                     // sphere radius, or (box) the smallest half side
         int ncand = 0;
+        if (is_box) {
+            // box vs trimesh: vertex/face rule of DESIGN.md "box-trimesh" (restated by the oracle).  Lane = triangle;
+            // the 8 box vertices and the 3 triangle vertices are tried as sub-items in lockstep.
+            const float4 dm = g.dims[pr.x];
+            const float h[3] = {0.5f * dm.x, 0.5f * dm.y, 0.5f * dm.z};
+            const M3 bR = load_m3(g.R, pr.x);
+            const V3 A[3] = {mulT(mR, v3(bR.r0.x, bR.r1.x, bR.r2.x)), mulT(mR, v3(bR.r0.y, bR.r1.y, bR.r2.y)),
+                             mulT(mR, v3(bR.r0.z, bR.r1.z, bR.r2.z))};
+            const V3 ext = v3(fabsf(A[0].x) * h[0] + fabsf(A[1].x) * h[1] + fabsf(A[2].x) * h[2],
+                              fabsf(A[0].y) * h[0] + fabsf(A[1].y) * h[1] + fabsf(A[2].y) * h[2],
+                              fabsf(A[0].z) * h[0] + fabsf(A[1].z) * h[1] + fabsf(A[2].z) * h[2]);
+            const float hmin = fminf(h[0], fminf(h[1], h[2]));
+            const float maxdepth = 2.0f * hmin;
+            r = hmin;
+            for (int t0 = 0; t0 < mesh.nt; t0 += 32) {
+                const int t = t0 + lane;
+                bool live = false;
+                V3 a, b, cc, nr, n;
+                a = b = cc = nr = n = v3(0.f, 0.f, 0.f);
+                if (t < mesh.nt) {
+                    const int i0 = tris[3 * t], i1 = tris[3 * t + 1], i2 = tris[3 * t + 2];
+                    a = v3(verts[3 * i0], verts[3 * i0 + 1], verts[3 * i0 + 2]);
+                    b = v3(verts[3 * i1], verts[3 * i1 + 1], verts[3 * i1 + 2]);
+                    cc = v3(verts[3 * i2], verts[3 * i2 + 1], verts[3 * i2 + 2]);
+                    bool skip = false;
+                    skip |= (c.x - ext.x > fmaxf(a.x, fmaxf(b.x, cc.x))) || (c.x + ext.x < fminf(a.x, fminf(b.x, cc.x)));
+                    skip |= (c.y - ext.y > fmaxf(a.y, fmaxf(b.y, cc.y))) || (c.y + ext.y < fminf(a.y, fminf(b.y, cc.y)));
+                    skip |= (c.z - ext.z > fmaxf(a.z, fmaxf(b.z, cc.z))) || (c.z + ext.z < fminf(a.z, fminf(b.z, cc.z)));
+                    if (!skip) {
+                        nr = cross(b - a, cc - a);
+                        const float l2 = dot(nr, nr);
+                        if (l2 > 0) {
+                            const float inv = 1.0f / sqrtf(l2);
+                            n = v3(nr.x * inv, nr.y * inv, nr.z * inv);
+                            live = true;
+                        }
+                    }
+                }
+                if (!__any_sync(0xffffffffu, live)) continue;
+                for (int sub = 0; sub < 11; sub++) {
+                    bool hit = false;
+                    TriCand cd;
+                    if (live) {
+                        if (sub < 8) {
+                            const float s0 = (sub & 1) ? h[0] : -h[0], s1 = (sub & 2) ? h[1] : -h[1], s2 = (sub & 4) ? h[2] : -h[2];
+                            const V3 pv = v3(((c.x + s0 * A[0].x) + s1 * A[1].x) + s2 * A[2].x,
+                                             ((c.y + s0 * A[0].y) + s1 * A[1].y) + s2 * A[2].y,
+                                             ((c.z + s0 * A[0].z) + s1 * A[1].z) + s2 * A[2].z);
+                            const float dd = dot(n, pv - a);
+                            if (dd < 0 && dd >= -maxdepth) {
+                                const V3 pq = v3(pv.x - dd * n.x, pv.y - dd * n.y, pv.z - dd * n.z);
+                                bool inside = true;
+                                inside = inside && (dot(cross(b - a, pq - a), nr) >= 0);
+                                inside = inside && (dot(cross(cc - b, pq - b), nr) >= 0);
+                                inside = inside && (dot(cross(a - cc, pq - cc), nr) >= 0);
+                                if (inside) {
+                                    hit = true;
+                                    cd.depth = -dd; cd.tri = t * 16 + sub;
+                                    cd.qx = pv.x; cd.qy = pv.y; cd.qz = pv.z;
+                                    cd.nx = n.x; cd.ny = n.y; cd.nz = n.z;
+                                }
+                            }
+                        } else {
+                            const V3 tv = sub == 8 ? a : (sub == 9 ? b : cc);
+                            const V3 e = tv - c;
+                            const float loc[3] = {dot(A[0], e), dot(A[1], e), dot(A[2], e)};
+                            bool inside = true;
+                            int ks = 0;
+                            float best = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 3; k++) {
+                                if (!(fabsf(loc[k]) <= h[k])) inside = false;
+                                const float pen = h[k] - fabsf(loc[k]);
+                                if (k == 0 || pen < best) { best = pen; ks = k; }
+                            }
+                            if (inside) {
+                                const float sg = loc[ks] < 0 ? 1.0f : -1.0f;
+                                const V3 ax = ks == 0 ? A[0] : (ks == 1 ? A[1] : A[2]);
+                                hit = true;
+                                cd.depth = best; cd.tri = t * 16 + sub;
+                                cd.qx = tv.x; cd.qy = tv.y; cd.qz = tv.z;
+                                cd.nx = sg * ax.x; cd.ny = sg * ax.y; cd.nz = sg * ax.z;
+                            }
+                        }
+                    }
+                    const unsigned hm = __ballot_sync(0xffffffffu, hit);
+                    if (hit) {
+                        const int slot = ncand + __popc(hm & lt);
+                        if (slot < TM_CAND) mine[slot] = cd;
+                    }
+                    ncand += __popc(hm);
+                }
+            }
+        } else
         for (int t0 = 0; t0 < mesh.nt; t0 += 32) {
             const int t = t0 + lane;
             bool hit = false;
@@ -653,7 +748,7 @@ __global__ void __launch_bounds__(TM_WARPS * 32) k_np_sphere_trimesh(const Broad
                             }
                             if (ok) {
                                 hit = true;
-                                cd.depth = r - dist; cd.tri = t;
+                                cd.depth = r - dist; cd.tri = t * 16;
                                 cd.qx = q.x; cd.qy = q.y; cd.qz = q.z;
                                 cd.nx = n.x; cd.ny = n.y; cd.nz = n.z;
                             }
@@ -697,7 +792,7 @@ __global__ void __launch_bounds__(TM_WARPS * 32) k_np_sphere_trimesh(const Broad
             if (lane == 0) {
                 const V3 pw = mul(mR, v3(w.qx, w.qy, w.qz));
                 const V3 nw = mul(mR, v3(w.nx, w.ny, w.nz));
-                put_contact(cs, pi, nout, pw + mp, w.depth, nw, w.tri);
+                put_contact(cs, pi, nout, pw + mp, w.depth, nw, w.tri >> 4);
             }
             for (int i = lane; i < ncand; i += 32) {
                 if (mine[i].depth >= 0.f) {

@@ -304,9 +304,10 @@ def trimesh_scene(n_side=100, seed=2, sphere_scale=5.0, h=1.0 / 60.0, mesh=None,
     return from_arrays("C2", bodies, _concat([sg, geoms]), meshes=[(verts, tris)], h=h)
 
 
-def trimesh_contact_scene(n=256, seed=11, sphere_scale=5.0, mesh=None, h=1.0 / 60.0):
+def trimesh_contact_scene(n=256, seed=11, sphere_scale=5.0, mesh=None, h=1.0 / 60.0, box_fraction=0.0):
     """Spheres placed in touch with a static trimesh (centre = triangle centroid + 0.8 r along the
-    face normal): exercises sphere-vs-trimesh contacts from step 0."""
+    face normal): exercises sphere-vs-trimesh contacts from step 0.  With box_fraction > 0 that share of
+    the bodies are randomly rotated boxes (sides 0.4..1.6 r) instead: box-vs-trimesh contacts."""
     verts, tris = mesh if mesh is not None else teapot_mesh()
     rs = np.random.RandomState(seed)
     pick = rs.choice(len(tris), size=n, replace=False)
@@ -326,8 +327,17 @@ def trimesh_contact_scene(n=256, seed=11, sphere_scale=5.0, mesh=None, h=1.0 / 6
     }
     dims = np.zeros((n, 4), np.float32)
     dims[:, 0] = rad
+    gtype = np.full(n, SPHERE, np.int32)
+    if box_fraction > 0:
+        is_box = rs.uniform(size=n) < box_fraction
+        sides = rs.uniform(0.4, 1.6, size=(n, 3)) * rad[:, None]
+        q = rs.normal(size=(n, 4))
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+        gtype[is_box] = BOX
+        dims[is_box, :3] = sides[is_box]
+        bodies["quat"][is_box] = q[is_box].astype(np.float32)
     geoms = {
-        "type": np.full(n, SPHERE, np.int32), "dims": dims, "body": np.arange(n, dtype=np.int32),
+        "type": gtype, "dims": dims, "body": np.arange(n, dtype=np.int32),
         "pos": np.zeros((n, 3), np.float32), "R": np.tile(np.array(IDENT_R, np.float32), (n, 1)),
         "cat": np.full(n, CMASK_OBJ, np.uint32), "col": np.full(n, CMASK_OBJ | CMASK_MAP, np.uint32),
         "env": np.zeros(n, np.int32),

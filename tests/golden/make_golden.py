@@ -27,6 +27,7 @@ def golden_scenes():
         "soup_axis": scenes.random_soup(150, seed=9, rotated=False),
         "teapot256": scenes.trimesh_contact_scene(256, seed=11),
         "batch8": scenes.batched_worlds_scene(8, seed=4, spacing=0.7),
+        "teapot_boxes": scenes.trimesh_contact_scene(192, seed=13, box_fraction=0.6),
     }
 
 
@@ -59,7 +60,10 @@ def oracle_record(sc):
 
 if __name__ == "__main__":
     O.build()
+    only = sys.argv[1:]
     for name, sc in golden_scenes().items():
+        if only and name not in only:
+            continue
         rec = oracle_record(sc)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
         print(name, "pairs", len(rec["pairs"]), "contacts", int(rec["count"].sum()))

@@ -360,3 +360,55 @@ def test_exact_lcp_mode_is_the_limit_of_the_sweeps(oracle_lib):
     assert dist[5000] < 2e-3, dist
     assert dist[20] > 5 * dist[5000], dist
     assert dist[200] < dist[20], dist
+
+
+def _quad_mesh(size=4.0):
+    v = np.float32([[-size, 0, -size], [size, 0, -size], [size, 0, size], [-size, 0, size]])
+    t = np.int32([[0, 2, 1], [0, 3, 2]])          # normals +y
+    return v, t
+
+
+def test_box_trimesh_vertex_face_rule(oracle_lib):
+    """box-trimesh (engine-defined rule): a box sunk 0.05 into a flat two-triangle floor gets its four
+    lower vertices as contacts, normal +y (from the mesh into the box), depth 0.05; tilted so that one vertex is
+    lowest, that vertex comes first (deepest)."""
+    w = O.OracleWorld()
+    v, t = _quad_mesh()
+    m = w.add_mesh(v, t)
+    gm = w.add_geom(O.TRIMESH, [m])
+    b = w.add_body([0.3, 0.45, -0.2])
+    gb = w.add_geom(O.BOX, [1.0, 1.0, 1.0], body=b)
+    cs = w.collide(gb, gm, 8)
+    assert len(cs) == 4
+    for c in cs:
+        assert tuple(c.normal)[:3] == (0.0, 1.0, 0.0)
+        assert c.depth == pytest.approx(0.05, abs=1e-6)
+        assert c.pos[1] == pytest.approx(-0.05, abs=1e-6) and abs(abs(c.pos[0] - 0.3) - 0.5) < 1e-6
+        assert c.side2 in (0, 1) and c.side1 == -1
+    # argument order swapped: normals negated, sides exchanged (dCollide's contract)
+    cs2 = w.collide(gm, gb, 8)
+    assert len(cs2) == 4 and tuple(cs2[0].normal)[:3] == (0.0, -1.0, 0.0) and cs2[0].side1 in (0, 1)
+    # a box high above the floor: nothing
+    w2 = O.OracleWorld()
+    m2 = w2.add_mesh(v, t)
+    gm2 = w2.add_geom(O.TRIMESH, [m2])
+    b2 = w2.add_body([0.0, 0.51, 0.0])
+    gb2 = w2.add_geom(O.BOX, [1.0, 1.0, 1.0], body=b2)
+    assert len(w2.collide(gb2, gm2, 8)) == 0
+
+
+def test_box_trimesh_mesh_vertex_inside_box(oracle_lib):
+    """a spike of the mesh poking into the bottom face of a box: contact at the spike's tip, pushing the box up
+    by the tip's distance to the bottom face"""
+    w = O.OracleWorld()
+    v = np.float32([[-1, 0, -1], [1, 0, -1], [0, 0, 1], [0, 1.0, 0]])
+    t = np.int32([[0, 3, 1], [1, 3, 2], [2, 3, 0]])
+    m = w.add_mesh(v, t)
+    gm = w.add_geom(O.TRIMESH, [m])
+    b = w.add_body([0.0, 1.4, 0.0])
+    gb = w.add_geom(O.BOX, [3.0, 1.0, 3.0], body=b)          # bottom face at y = 0.9: the tip is 0.1 inside
+    cs = w.collide(gb, gm, 8)
+    assert len(cs) == 1
+    c = cs[0]
+    assert tuple(c.pos)[:3] == (0.0, 1.0, 0.0) and tuple(c.normal)[:3] == (0.0, 1.0, 0.0)
+    assert c.depth == pytest.approx(0.1, abs=1e-6)

@@ -27,12 +27,13 @@ def _scene(name):
         "soup_axis": lambda: scenes.random_soup(150, seed=9, rotated=False),
         "teapot256": lambda: scenes.trimesh_contact_scene(256, seed=11),
         "batch8": lambda: scenes.batched_worlds_scene(8, seed=4, spacing=0.7),
+        "teapot_boxes": lambda: scenes.trimesh_contact_scene(192, seed=13, box_fraction=0.6),
         "soup1500": lambda: scenes.random_soup(1500, seed=21, extent=7.0),
         "pile_dense": lambda: scenes.pile_scene(12, 12, 6, seed=5, spacing=0.6),
     }[name]()
 
 
-GOLDEN = ["c1_low", "c1p_low", "soup200", "soup_axis", "teapot256", "batch8"]
+GOLDEN = ["c1_low", "c1p_low", "soup200", "soup_axis", "teapot256", "batch8", "teapot_boxes"]
 ALL = GOLDEN + ["soup1500", "pile_dense"]
 
 
@@ -500,3 +501,31 @@ def test_dworldstep_parity_mode_converges_to_the_exact_lcp():
     assert dist[0] > 0.01                           # 20 QuickStep sweeps are visibly not the LCP solution
     assert dist[100] < 0.2 * dist[0]
     assert dist[2000] < 2e-3 and dist[20000] < 2e-3
+
+
+def test_boxes_rest_on_a_trimesh_floor():
+    """box-trimesh end to end: boxes dropped on a two-triangle floor mesh come to rest on it (as they would on
+    dCreatePlane), none tunnels through, and the class counter shows the trimesh kernel took the pairs."""
+    sc = scenes._empty_scene("boxes-on-mesh")
+    v = np.float32([[-8, 0, -8], [8, 0, -8], [8, 0, 8], [-8, 0, 8]])
+    t = np.int32([[0, 2, 1], [0, 3, 2]])
+    scenes._add_geom(sc, scenes.TRIMESH, (0.0, 0, 0, 0))
+    rs = np.random.RandomState(4)
+    sizes = []
+    for i in range(12):
+        s = rs.uniform(0.4, 1.0, 3)
+        sizes.append(s)
+        b = scenes._add_body(sc, (float(-5 + 2.5 * (i % 4)), 1.5 + 0.2 * i, float(-3 + 3.0 * (i // 4))), flags=0)
+        scenes._add_geom(sc, scenes.BOX, (s[0], s[1], s[2], 0), body=b)
+    sc = scenes.finalize(sc)
+    sc["meshes"] = [(v, t)]
+    ow, ew = util.load_both(sc)
+    for step in range(240):
+        ew.tick(sc["h"])
+    st = ew.stats()
+    assert st["flags"] == 0 and st["class_count"][5] == 12          # every box is in touch with the mesh
+    s = ew.state()
+    half_y = np.array([x[1] for x in sizes]) * 0.5
+    assert np.abs(s["lvel"]).max() < 0.05
+    assert (s["pos"][:, 1] > half_y - 0.03).all() and (s["pos"][:, 1] < half_y + 0.03).all()
+    ew.close()
