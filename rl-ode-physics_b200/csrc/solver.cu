@@ -945,12 +945,85 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
         // ---- colouring (rule of k_colour, at group scope)
         for (int i = g; i < mb; i += G) { masks[i] = 0ull; prio[i] = ~0ull; }
         for (int i = g; i < 68; i += G) { cstart[i] = 0; cursor[i] = 0; }
+        // With staging, 64 of the region's 80 bytes per body are idle until the iterations: they cache each unit's
+        // priority, env-local body ids, dynamic bits and colour, so the rounds below touch shared memory only
+        // (measured: the rounds were 20 % of the kernel, one L2 round trip after another).
+        const int nun = me - ms;
+        const bool fastc = stage && __all_sync(FULL, nun <= 4 * mb);
+        uint4 *uc = reinterpret_cast<uint4 *>(env_smem + (size_t)grp * region + 16 * (size_t)mb);
+        constexpr unsigned UC_D1 = 1u << 24, UC_D2 = 1u << 25;
         for (int j = 0; j < trips; j++) {
             const int m = ms + g + j * G;
-            if (m < me) E.col[m] = 255;
+            if (m < me) {
+                if (fastc) {
+                    const int4 r = E.rec[m];
+                    const int l1 = B.local[r.x], l2 = r.y >= 0 ? B.local[r.y] : -1;
+                    const unsigned long long pr = manifold_prio(r.z, l1, l2);
+                    uc[m - ms] = make_uint4((unsigned)pr, (unsigned)(pr >> 32),
+                                            ((unsigned)l1 & 0xfffu) | (((unsigned)l2 & 0xfffu) << 12) |
+                                                ((r.w & REC_DYN1) ? UC_D1 : 0u) | ((r.w & REC_DYN2) ? UC_D2 : 0u),
+                                            255u);
+                } else {
+                    E.col[m] = 255;
+                }
+            }
         }
         __syncwarp();
         int rounds = 0;
+        if (fastc) {
+            for (;; rounds++) {
+                for (int j = 0; j < trips; j++) {
+                    const int u = g + j * G;
+                    if (u < nun) {
+                        const uint4 q = uc[u];
+                        if (q.w == 255u) {
+                            const unsigned long long pr = (unsigned long long)q.x | ((unsigned long long)q.y << 32);
+                            if (q.z & UC_D1) atomicMin(&prio[q.z & 0xfffu], pr);
+                            if (q.z & UC_D2) atomicMin(&prio[(q.z >> 12) & 0xfffu], pr);
+                        }
+                    }
+                }
+                __syncwarp();
+                bool left = false;
+                for (int j = 0; j < trips; j++) {
+                    const int u = g + j * G;
+                    if (u < nun) {
+                        const uint4 q = uc[u];
+                        if (q.w == 255u) {
+                            const unsigned long long pr = (unsigned long long)q.x | ((unsigned long long)q.y << 32);
+                            const int l1 = (int)(q.z & 0xfffu), l2 = (int)((q.z >> 12) & 0xfffu);
+                            const bool d1 = q.z & UC_D1, d2 = q.z & UC_D2;
+                            if ((!d1 || prio[l1] == pr) && (!d2 || prio[l2] == pr)) {
+                                unsigned long long mask = 0ull;
+                                if (d1) mask |= masks[l1];
+                                if (d2) mask |= masks[l2];
+                                const int c = pick_colour(mask, pr, spread);
+                                if (c != OVERFLOW_COLOUR) {
+                                    const unsigned long long bit = 1ull << c;
+                                    if (d1) masks[l1] |= bit;
+                                    if (d2) masks[l2] |= bit;
+                                }
+                                uc[u].w = (unsigned)c;
+                                atomicAdd(&cstart[c + 1], 1);
+                            } else left = true;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (!__any_sync(FULL, left)) break;
+                for (int j = 0; j < trips; j++) {
+                    const int u = g + j * G;
+                    if (u < nun) {
+                        const uint4 q = uc[u];
+                        if (q.w == 255u) {
+                            if (q.z & UC_D1) prio[q.z & 0xfffu] = ~0ull;
+                            if (q.z & UC_D2) prio[(q.z >> 12) & 0xfffu] = ~0ull;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        } else
         for (;; rounds++) {
             for (int j = 0; j < trips; j++) {
                 const int m = ms + g + j * G;
@@ -1009,7 +1082,7 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
         for (int j = 0; j < trips; j++) {
             const int m = ms + g + j * G;
             if (m < me) {
-                const int c = E.col[m];
+                const int c = fastc ? (int)uc[m - ms].w : (int)E.col[m];
                 const int r = atomicAdd(&cursor[c], 1);
                 E.perm[ms + cstart[c] + r] = m;
                 if (c < OVERFLOW_COLOUR && c + 1 > ncol) ncol = c + 1;
