@@ -952,32 +952,52 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
         const bool fastc = stage && __all_sync(FULL, nun <= 4 * mb);
         uint4 *uc = reinterpret_cast<uint4 *>(env_smem + (size_t)grp * region + 16 * (size_t)mb);
         constexpr unsigned UC_D1 = 1u << 24, UC_D2 = 1u << 25;
-        for (int j = 0; j < trips; j++) {
-            const int m = ms + g + j * G;
-            if (m < me) {
-                if (fastc) {
-                    const int4 r = E.rec[m];
-                    const int l1 = B.local[r.x], l2 = r.y >= 0 ? B.local[r.y] : -1;
-                    const unsigned long long pr = manifold_prio(r.z, l1, l2);
-                    uc[m - ms] = make_uint4((unsigned)pr, (unsigned)(pr >> 32),
-                                            ((unsigned)l1 & 0xfffu) | (((unsigned)l2 & 0xfffu) << 12) |
-                                                ((r.w & REC_DYN1) ? UC_D1 : 0u) | ((r.w & REC_DYN2) ? UC_D2 : 0u),
-                                            255u);
-                } else {
-                    E.col[m] = 255;
+        if (fastc) {
+            // all loads of a stage are issued before the first use (two dependent L2 round trips in total, not per trip)
+            constexpr int TB = 6;
+            for (int j0 = 0; j0 < trips; j0 += TB) {
+                int4 r[TB];
+                int l1[TB], l2[TB];
+#pragma unroll
+                for (int k = 0; k < TB; k++) {
+                    const int m = ms + g + (j0 + k) * G;
+                    r[k] = (j0 + k < trips && m < me) ? E.rec[m] : make_int4(-1, -1, 0, 0);
                 }
+#pragma unroll
+                for (int k = 0; k < TB; k++) {
+                    l1[k] = r[k].x >= 0 ? B.local[r[k].x] : -1;
+                    l2[k] = r[k].y >= 0 ? B.local[r[k].y] : -1;
+                }
+#pragma unroll
+                for (int k = 0; k < TB; k++) {
+                    if (r[k].x < 0) continue;
+                    const unsigned long long pr = manifold_prio(r[k].z, l1[k], l2[k]);
+                    uc[g + (j0 + k) * G] = make_uint4((unsigned)pr, (unsigned)(pr >> 32),
+                                                       ((unsigned)l1[k] & 0xfffu) | (((unsigned)l2[k] & 0xfffu) << 12) |
+                                                           ((r[k].w & REC_DYN1) ? UC_D1 : 0u) | ((r[k].w & REC_DYN2) ? UC_D2 : 0u),
+                                                       255u);
+                }
+            }
+        } else {
+            for (int j = 0; j < trips; j++) {
+                const int m = ms + g + j * G;
+                if (m < me) E.col[m] = 255;
             }
         }
         __syncwarp();
         int rounds = 0;
         if (fastc) {
             for (;; rounds++) {
+                // later rounds stamp their priorities with a smaller top byte (as k_colour does): atomicMin then
+                // prefers them over what earlier rounds left behind and the losers need no reset pass
+                const bool stamped = rounds < 254;
+                const unsigned long long stamp = stamped ? ((unsigned long long)(254 - rounds) << 56) : 0ull;
                 for (int j = 0; j < trips; j++) {
                     const int u = g + j * G;
                     if (u < nun) {
                         const uint4 q = uc[u];
                         if (q.w == 255u) {
-                            const unsigned long long pr = (unsigned long long)q.x | ((unsigned long long)q.y << 32);
+                            const unsigned long long pr = stamp | (unsigned long long)q.x | ((unsigned long long)q.y << 32);
                             if (q.z & UC_D1) atomicMin(&prio[q.z & 0xfffu], pr);
                             if (q.z & UC_D2) atomicMin(&prio[(q.z >> 12) & 0xfffu], pr);
                         }
@@ -990,14 +1010,15 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
                     if (u < nun) {
                         const uint4 q = uc[u];
                         if (q.w == 255u) {
-                            const unsigned long long pr = (unsigned long long)q.x | ((unsigned long long)q.y << 32);
+                            const unsigned long long base = (unsigned long long)q.x | ((unsigned long long)q.y << 32);
+                            const unsigned long long pr = stamp | base;
                             const int l1 = (int)(q.z & 0xfffu), l2 = (int)((q.z >> 12) & 0xfffu);
                             const bool d1 = q.z & UC_D1, d2 = q.z & UC_D2;
                             if ((!d1 || prio[l1] == pr) && (!d2 || prio[l2] == pr)) {
                                 unsigned long long mask = 0ull;
                                 if (d1) mask |= masks[l1];
                                 if (d2) mask |= masks[l2];
-                                const int c = pick_colour(mask, pr, spread);
+                                const int c = pick_colour(mask, base, spread);
                                 if (c != OVERFLOW_COLOUR) {
                                     const unsigned long long bit = 1ull << c;
                                     if (d1) masks[l1] |= bit;
@@ -1011,17 +1032,19 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
                 }
                 __syncwarp();
                 if (!__any_sync(FULL, left)) break;
-                for (int j = 0; j < trips; j++) {
-                    const int u = g + j * G;
-                    if (u < nun) {
-                        const uint4 q = uc[u];
-                        if (q.w == 255u) {
-                            if (q.z & UC_D1) prio[q.z & 0xfffu] = ~0ull;
-                            if (q.z & UC_D2) prio[(q.z >> 12) & 0xfffu] = ~0ull;
+                if (!stamped) { // out of stamps: reset the losers' bodies
+                    for (int j = 0; j < trips; j++) {
+                        const int u = g + j * G;
+                        if (u < nun) {
+                            const uint4 q = uc[u];
+                            if (q.w == 255u) {
+                                if (q.z & UC_D1) prio[q.z & 0xfffu] = ~0ull;
+                                if (q.z & UC_D2) prio[(q.z >> 12) & 0xfffu] = ~0ull;
+                            }
                         }
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         } else
         for (;; rounds++) {
