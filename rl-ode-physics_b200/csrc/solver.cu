@@ -1118,13 +1118,21 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
         for (int j = 0; j < trips; j++) {
             const int s = ms + g + j * G;
             if (s < me) {
-                const int4 r = E.rec[E.perm[s]];
+                const int m = E.perm[s];
+                const int4 r = E.rec[m];
                 build_manifold_rows(s, r, B, src, usurf, S, cfg, rows1, rows2, ncont);
                 if (stage) { // the iterations index the shared-memory copies by env-local body
-                    int4 mr = S.mrec[s];
-                    mr.x = B.local[r.x];
-                    mr.y = r.y >= 0 ? B.local[r.y] : -1;
-                    S.mrec[s] = mr;
+                    int l1, l2;
+                    if (fastc) { // the colouring cache still holds the unit's local body ids
+                        const unsigned q = uc[m - ms].z;
+                        l1 = (int)(q & 0xfffu);
+                        l2 = (int)((q >> 12) & 0xfffu);
+                        if (l2 == 0xfff) l2 = -1;
+                    } else {
+                        l1 = B.local[r.x];
+                        l2 = r.y >= 0 ? B.local[r.y] : -1;
+                    }
+                    S.mrec[s] = make_int4(l1, l2, r.w & 0xff, r.z);
                 }
             }
         }
