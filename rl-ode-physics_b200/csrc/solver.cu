@@ -951,7 +951,7 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
         const int nun = me - ms;
         const bool fastc = stage && __all_sync(FULL, nun <= 4 * mb);
         uint4 *uc = reinterpret_cast<uint4 *>(env_smem + (size_t)grp * region + 16 * (size_t)mb);
-        constexpr unsigned UC_D1 = 1u << 24, UC_D2 = 1u << 25;
+        constexpr unsigned UC_D1 = 1u << 24, UC_D2 = 1u << 25, UC_REV = 1u << 26; // bits 27..30: contacts of the unit
         if (fastc) {
             // all loads of a stage are issued before the first use (two dependent L2 round trips in total, not per trip)
             constexpr int TB = 6;
@@ -974,7 +974,8 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
                     const unsigned long long pr = manifold_prio(r[k].z, l1[k], l2[k]);
                     uc[g + (j0 + k) * G] = make_uint4((unsigned)pr, (unsigned)(pr >> 32),
                                                        ((unsigned)l1[k] & 0xfffu) | (((unsigned)l2[k] & 0xfffu) << 12) |
-                                                           ((r[k].w & REC_DYN1) ? UC_D1 : 0u) | ((r[k].w & REC_DYN2) ? UC_D2 : 0u),
+                                                           ((r[k].w & REC_DYN1) ? UC_D1 : 0u) | ((r[k].w & REC_DYN2) ? UC_D2 : 0u) |
+                                                           ((r[k].w & REC_REV) ? UC_REV : 0u) | (((unsigned)r[k].w & 0xfu) << 27),
                                                        255u);
                 }
             }
@@ -1107,7 +1108,9 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
             if (m < me) {
                 const int c = fastc ? (int)uc[m - ms].w : (int)E.col[m];
                 const int r = atomicAdd(&cursor[c], 1);
-                E.perm[ms + cstart[c] + r] = m;
+                // sorted position -> unit: in the cache's (now dead) high priority word, else in global memory
+                if (fastc) uc[cstart[c] + r].y = (unsigned)(m - ms);
+                else E.perm[ms + cstart[c] + r] = m;
                 if (c < OVERFLOW_COLOUR && c + 1 > ncol) ncol = c + 1;
             }
         }
@@ -1118,22 +1121,24 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
         for (int j = 0; j < trips; j++) {
             const int s = ms + g + j * G;
             if (s < me) {
-                const int m = E.perm[s];
-                const int4 r = E.rec[m];
-                build_manifold_rows(s, r, B, src, usurf, S, cfg, rows1, rows2, ncont);
-                if (stage) { // the iterations index the shared-memory copies by env-local body
-                    int l1, l2;
-                    if (fastc) { // the colouring cache still holds the unit's local body ids
-                        const unsigned q = uc[m - ms].z;
-                        l1 = (int)(q & 0xfffu);
-                        l2 = (int)((q >> 12) & 0xfffu);
-                        if (l2 == 0xfff) l2 = -1;
-                    } else {
-                        l1 = B.local[r.x];
-                        l2 = r.y >= 0 ? B.local[r.y] : -1;
-                    }
-                    S.mrec[s] = make_int4(l1, l2, r.w & 0xff, r.z);
+                int4 r;
+                int l1 = 0, l2 = -1;
+                if (fastc) {
+                    // the whole record comes out of the cache: unit id, contact slot (= the priority's tie word),
+                    // local body ids (bodies of an env are one index range), flags -- no global reads before the rows
+                    const uint4 q = uc[uc[s - ms].y];
+                    l1 = (int)(q.z & 0xfffu);
+                    l2 = (int)((q.z >> 12) & 0xfffu);
+                    if (l2 == 0xfff) l2 = -1;
+                    const int w = (int)((q.z >> 27) & 0xfu) | ((q.z & UC_REV) ? REC_REV : 0) | ((q.z & UC_D1) ? REC_DYN1 : 0) |
+                                  ((q.z & UC_D2) ? REC_DYN2 : 0);
+                    r = make_int4(fb + l1, l2 >= 0 ? fb + l2 : -1, (int)q.x, w);
+                } else {
+                    r = E.rec[E.perm[s]];
+                    if (stage) { l1 = B.local[r.x]; l2 = r.y >= 0 ? B.local[r.y] : -1; }
                 }
+                build_manifold_rows(s, r, B, src, usurf, S, cfg, rows1, rows2, ncont);
+                if (stage) S.mrec[s] = make_int4(l1, l2, r.w & 0xff, r.z); // the iterations index the shared-memory copies by local body
             }
         }
         __syncwarp();
