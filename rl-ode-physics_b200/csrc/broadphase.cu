@@ -259,6 +259,53 @@ struct PairSink {
     int total;
 };
 
+// Pair positions without a scan over 7 counters per geom: the count pass also reduces each class over its
+// 128-thread block (7 sums per block); only those sums are scanned; the fill pass re-derives each thread's
+// offsets as (scanned base of its block and class) + (prefix of the per-thread counts inside the block).
+constexpr int SWEEP_THREADS = 128;
+
+__device__ __forceinline__ void block_class_sums(const int (&v)[PC_COUNT], int *__restrict__ blk, int nblk) {
+    __shared__ int wsum[PC_COUNT][SWEEP_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < PC_COUNT; c++) {
+        const int t = __reduce_add_sync(0xffffffffu, v[c]);
+        if (lane == 0) wsum[c][wid] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < PC_COUNT) {
+        int t = 0;
+        for (int w = 0; w < SWEEP_THREADS / 32; w++) t += wsum[threadIdx.x][w];
+        blk[threadIdx.x * nblk + blockIdx.x] = t;
+    }
+}
+
+__device__ __forceinline__ void block_offsets(const int *__restrict__ cnt, const int *__restrict__ blkoff, int n, int i, int nblk,
+                                              int (&off)[PC_COUNT]) {
+    __shared__ int wsum[PC_COUNT][SWEEP_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int v[PC_COUNT], inc[PC_COUNT];
+#pragma unroll
+    for (int c = 0; c < PC_COUNT; c++) {
+        v[c] = i < n ? cnt[c * n + i] : 0;
+        int x = v[c];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += t;
+        }
+        inc[c] = x;
+        if (lane == 31) wsum[c][wid] = x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < PC_COUNT; c++) {
+        int base = blkoff[c * nblk + blockIdx.x];
+        for (int w = 0; w < wid; w++) base += wsum[c][w];
+        off[c] = base + inc[c] - v[c];
+    }
+}
+
 template <bool FILL>
 __device__ __forceinline__ void emit(int cls, int i, int n, const float4 &lo1, const uint4 &f1, const float4 &lo2,
                                      const uint4 &f2, PairSink &sink, const int *__restrict__ off,
@@ -268,7 +315,7 @@ __device__ __forceinline__ void emit(int cls, int i, int n, const float4 &lo1, c
     // canonical callback order: lower class first, then lower geom id
     if (ta > tb || (ta == tb && ga > gb)) { int t = ga; ga = gb; gb = t; }
     if (FILL) {
-        const int pos = off[cls * n + i] + sink.cnt[cls];
+        const int pos = off[cls] + sink.cnt[cls]; // off: this thread's offsets (block_offsets)
         if (pos < cap_pairs) pairs[pos] = make_int2(ga, gb);
     } else if (sink.total < SWEEP_TCAP) {
         tmp[(size_t)sink.total * n + i] = make_int2(ga | (cls << 28), gb);
@@ -281,33 +328,39 @@ __device__ __forceinline__ void emit(int cls, int i, int n, const float4 &lo1, c
 // the rest of its own cell row (cells x, x+1) and the rows (dy,dz) in {(1,0),(-1,1),(0,1),(1,1)},
 // each a contiguous run of up to three cells; then the big list.
 template <bool FILL>
-__global__ void __launch_bounds__(128) k_sweep(int n, const uint32_t *__restrict__ keys,
+__global__ void __launch_bounds__(SWEEP_THREADS) k_sweep(int n, const uint32_t *__restrict__ keys,
                                                 const float4 *__restrict__ s_min, const float4 *__restrict__ s_max,
                                                 const uint4 *__restrict__ s_flt, const int *__restrict__ cell_start,
                                                 const int *__restrict__ cell_end, const GridParams *__restrict__ gpp,
                                                 const BroadCounters *__restrict__ bc, int *__restrict__ cnt,
-                                                const int *__restrict__ off, int2 *__restrict__ pairs, int cap_pairs,
-                                                int2 *__restrict__ tmp, int *__restrict__ tot) {
+                                                int *__restrict__ blk, const int *__restrict__ blkoff,
+                                                int2 *__restrict__ pairs, int cap_pairs, int2 *__restrict__ tmp,
+                                                int *__restrict__ tot) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int nblk = gridDim.x;
     const int first_big = bc->first_big, first_dead = bc->first_dead;
     PairSink sink;
 #pragma unroll
     for (int c = 0; c < PC_COUNT; c++) sink.cnt[c] = 0;
     sink.total = 0;
+    int off[PC_COUNT];
+    bool traverse = i < n;
     if (FILL) {
-        const int t = tot[i];
-        if (t <= SWEEP_TCAP) { // every hit of this thread was parked by the count pass: compact, in order
-            for (int k = 0; k < t; k++) {
-                const int2 e = tmp[(size_t)k * n + i];
-                const int cls = e.x >> 28;
-                const int pos = off[cls * n + i] + sink.cnt[cls]++;
-                if (pos < cap_pairs) pairs[pos] = make_int2(e.x & 0x0fffffff, e.y);
+        block_offsets(cnt, blkoff, n, i, nblk, off); // every thread of the block takes part
+        if (i < n) {
+            const int t = tot[i];
+            if (t <= SWEEP_TCAP) { // every hit of this thread was parked by the count pass: compact, in order
+                for (int k = 0; k < t; k++) {
+                    const int2 e = tmp[(size_t)k * n + i];
+                    const int cls = e.x >> 28;
+                    const int pos = off[cls] + sink.cnt[cls]++;
+                    if (pos < cap_pairs) pairs[pos] = make_int2(e.x & 0x0fffffff, e.y);
+                }
+                traverse = false;
             }
-            return;
         }
     }
-    if (i < first_dead) {
+    if (traverse && i < first_dead) {
         const float4 lo1 = s_min[i], hi1 = s_max[i];
         const uint4 f1 = s_flt[i];
         if (i < first_big) {
@@ -369,9 +422,12 @@ __global__ void __launch_bounds__(128) k_sweep(int n, const uint32_t *__restrict
         }
     }
     if (!FILL) {
+        if (i < n) {
 #pragma unroll
-        for (int c = 0; c < PC_COUNT; c++) cnt[c * n + i] = sink.cnt[c];
-        tot[i] = sink.total;
+            for (int c = 0; c < PC_COUNT; c++) cnt[c * n + i] = sink.cnt[c];
+            tot[i] = sink.total;
+        }
+        block_class_sums(sink.cnt, blk, nblk);
     }
 }
 
@@ -409,32 +465,37 @@ __device__ __forceinline__ GeomRec load_rec(const GeomArrays &g, int j, bool sin
 }
 
 template <bool FILL>
-__global__ void __launch_bounds__(128) k_env_sweep(GeomArrays g, const float4 *__restrict__ cr,
+__global__ void __launch_bounds__(SWEEP_THREADS) k_env_sweep(GeomArrays g, const float4 *__restrict__ cr,
                                                     const int *__restrict__ efirst, const int *__restrict__ ecount,
                                                     const int *__restrict__ shared, int n_shared, int single,
-                                                    int *__restrict__ cnt, const int *__restrict__ off,
+                                                    int *__restrict__ cnt, int *__restrict__ blk, const int *__restrict__ blkoff,
                                                     int2 *__restrict__ pairs, int cap_pairs, int2 *__restrict__ tmp,
                                                     int *__restrict__ tot) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = g.n;
-    if (i >= n) return;
+    const int nblk = gridDim.x;
     PairSink sink;
 #pragma unroll
     for (int c = 0; c < PC_COUNT; c++) sink.cnt[c] = 0;
     sink.total = 0;
+    int off[PC_COUNT];
+    bool traverse = i < n;
     if (FILL) {
-        const int t = tot[i];
-        if (t <= SWEEP_TCAP) {
-            for (int k = 0; k < t; k++) {
-                const int2 e = tmp[(size_t)k * n + i];
-                const int cls = e.x >> 28;
-                const int pos = off[cls * n + i] + sink.cnt[cls]++;
-                if (pos < cap_pairs) pairs[pos] = make_int2(e.x & 0x0fffffff, e.y);
+        block_offsets(cnt, blkoff, n, i, nblk, off);
+        if (i < n) {
+            const int t = tot[i];
+            if (t <= SWEEP_TCAP) {
+                for (int k = 0; k < t; k++) {
+                    const int2 e = tmp[(size_t)k * n + i];
+                    const int cls = e.x >> 28;
+                    const int pos = off[cls] + sink.cnt[cls]++;
+                    if (pos < cap_pairs) pairs[pos] = make_int2(e.x & 0x0fffffff, e.y);
+                }
+                traverse = false;
             }
-            return;
         }
     }
-    if (g.alive[i]) {
+    if (traverse && g.alive[i]) {
         const GeomRec me = load_rec(g, i, single != 0);
         const float4 c1 = cr[i];
         const int env = (int)me.f.z;
@@ -469,9 +530,12 @@ __global__ void __launch_bounds__(128) k_env_sweep(GeomArrays g, const float4 *_
         }
     }
     if (!FILL) {
+        if (i < n) {
 #pragma unroll
-        for (int c = 0; c < PC_COUNT; c++) cnt[c * n + i] = sink.cnt[c];
-        tot[i] = sink.total;
+            for (int c = 0; c < PC_COUNT; c++) cnt[c * n + i] = sink.cnt[c];
+            tot[i] = sink.total;
+        }
+        block_class_sums(sink.cnt, blk, nblk);
     }
 }
 
@@ -483,14 +547,14 @@ __global__ void k_env_counters(BroadCounters *__restrict__ bc, GridParams *__res
     gp->cell = 0.f; gp->dx = gp->dy = gp->dz = 0; gp->n_envs = n_envs;
 }
 
-__global__ void k_pairs_finish(int n, const int *__restrict__ off, int cap_pairs, BroadCounters *__restrict__ bc,
+__global__ void k_pairs_finish(int nblk, const int *__restrict__ off, int cap_pairs, BroadCounters *__restrict__ bc,
                                StepStats *__restrict__ stats, const GridParams *__restrict__ gp) {
-    int total = off[PC_COUNT * n];
+    int total = off[PC_COUNT * nblk]; // off: exclusive scan of the per-block class sums
     int flags = 0;
     if (total > cap_pairs) { total = cap_pairs; flags |= SF_PAIR_OVERFLOW; }
     bc->n_pairs = total;
     for (int c = 0; c < PC_COUNT; c++) {
-        int s = off[c * n];
+        int s = off[c * nblk];
         if (s > cap_pairs) s = cap_pairs;
         bc->class_start[c] = s;
     }
@@ -545,21 +609,21 @@ void broadphase_run(BroadPhase &bp, GeomArrays g, const float4 *b_pos, const flo
     k_geom_update<<<nb, 256, 0, st>>>(g, b_pos, b_R, meshes, big_extent, bp.acc);
     OB_CHECK_KERNEL("k_geom_update", st);
     if (eb.enabled) {
-        const unsigned nb2 = (unsigned)((n + 127) / 128);
+        const unsigned nb2 = (unsigned)((n + SWEEP_THREADS - 1) / SWEEP_THREADS);
         float4 *cr = bp.s_min;
         k_env_bounds<<<nb, 256, 0, st>>>(g, cr);
         OB_CHECK_KERNEL("k_env_bounds", st);
         k_env_counters<<<1, 1, 0, st>>>(bp.counters, bp.gp, eb.n_alive, eb.n_shared, n_envs);
         OB_CHECK_KERNEL("k_env_counters", st);
-        k_env_sweep<false><<<nb2, 128, 0, st>>>(g, cr, eb.first, eb.count, eb.shared, eb.n_shared, eb.single, bp.cnt,
-                                                nullptr, nullptr, 0, bp.sweep_tmp, bp.sweep_tot);
+        k_env_sweep<false><<<nb2, SWEEP_THREADS, 0, st>>>(g, cr, eb.first, eb.count, eb.shared, eb.n_shared, eb.single, bp.cnt,
+                                                          bp.blk, nullptr, nullptr, 0, bp.sweep_tmp, bp.sweep_tot);
         OB_CHECK_KERNEL("k_env_sweep", st);
-        OB_CUDA(cudaMemsetAsync(bp.cnt + (size_t)PC_COUNT * n, 0, sizeof(int), st));
-        scan_exclusive(bp.cnt, bp.cnt, (long)PC_COUNT * n + 1, nullptr, nullptr, bp.scan, st);
-        k_env_sweep<true><<<nb2, 128, 0, st>>>(g, cr, eb.first, eb.count, eb.shared, eb.n_shared, eb.single, nullptr,
-                                               bp.cnt, bp.pairs, bp.cap_pairs, bp.sweep_tmp, bp.sweep_tot);
+        OB_CUDA(cudaMemsetAsync(bp.blk + (size_t)PC_COUNT * nb2, 0, sizeof(int), st));
+        scan_exclusive(bp.blk, bp.blk, (long)PC_COUNT * nb2 + 1, nullptr, nullptr, bp.scan, st);
+        k_env_sweep<true><<<nb2, SWEEP_THREADS, 0, st>>>(g, cr, eb.first, eb.count, eb.shared, eb.n_shared, eb.single, bp.cnt,
+                                                         nullptr, bp.blk, bp.pairs, bp.cap_pairs, bp.sweep_tmp, bp.sweep_tot);
         OB_CHECK_KERNEL("k_env_sweep", st);
-        k_pairs_finish<<<1, 1, 0, st>>>(n, bp.cnt, bp.cap_pairs, bp.counters, d_stats, bp.gp);
+        k_pairs_finish<<<1, 1, 0, st>>>((int)nb2, bp.blk, bp.cap_pairs, bp.counters, d_stats, bp.gp);
         OB_CHECK_KERNEL("k_pairs_finish", st);
         return;
     }
@@ -571,16 +635,17 @@ void broadphase_run(BroadPhase &bp, GeomArrays g, const float4 *b_pos, const flo
     k_sorted_records<<<nb, 256, 0, st>>>(g, bp.keys, bp.idx, bp.cap_cells, bp.s_min, bp.s_max, bp.s_flt, bp.cell_start,
                                          bp.cell_end, bp.counters);
     OB_CHECK_KERNEL("k_sorted_records", st);
-    const unsigned nb2 = (unsigned)((n + 127) / 128);
-    k_sweep<false><<<nb2, 128, 0, st>>>(n, bp.keys, bp.s_min, bp.s_max, bp.s_flt, bp.cell_start, bp.cell_end, bp.gp,
-                                        bp.counters, bp.cnt, nullptr, nullptr, 0, bp.sweep_tmp, bp.sweep_tot);
+    const unsigned nb2 = (unsigned)((n + SWEEP_THREADS - 1) / SWEEP_THREADS);
+    k_sweep<false><<<nb2, SWEEP_THREADS, 0, st>>>(n, bp.keys, bp.s_min, bp.s_max, bp.s_flt, bp.cell_start, bp.cell_end, bp.gp,
+                                                  bp.counters, bp.cnt, bp.blk, nullptr, nullptr, 0, bp.sweep_tmp, bp.sweep_tot);
     OB_CHECK_KERNEL("k_sweep", st);
-    OB_CUDA(cudaMemsetAsync(bp.cnt + (size_t)PC_COUNT * n, 0, sizeof(int), st));
-    scan_exclusive(bp.cnt, bp.cnt, (long)PC_COUNT * n + 1, nullptr, nullptr, bp.scan, st);
-    k_sweep<true><<<nb2, 128, 0, st>>>(n, bp.keys, bp.s_min, bp.s_max, bp.s_flt, bp.cell_start, bp.cell_end, bp.gp,
-                                       bp.counters, nullptr, bp.cnt, bp.pairs, bp.cap_pairs, bp.sweep_tmp, bp.sweep_tot);
+    OB_CUDA(cudaMemsetAsync(bp.blk + (size_t)PC_COUNT * nb2, 0, sizeof(int), st));
+    scan_exclusive(bp.blk, bp.blk, (long)PC_COUNT * nb2 + 1, nullptr, nullptr, bp.scan, st);
+    k_sweep<true><<<nb2, SWEEP_THREADS, 0, st>>>(n, bp.keys, bp.s_min, bp.s_max, bp.s_flt, bp.cell_start, bp.cell_end, bp.gp,
+                                                 bp.counters, bp.cnt, nullptr, bp.blk, bp.pairs, bp.cap_pairs, bp.sweep_tmp,
+                                                 bp.sweep_tot);
     OB_CHECK_KERNEL("k_sweep", st);
-    k_pairs_finish<<<1, 1, 0, st>>>(n, bp.cnt, bp.cap_pairs, bp.counters, d_stats, bp.gp);
+    k_pairs_finish<<<1, 1, 0, st>>>((int)nb2, bp.blk, bp.cap_pairs, bp.counters, d_stats, bp.gp);
     OB_CHECK_KERNEL("k_pairs_finish", st);
     k_cell_clear<<<nb, 256, 0, st>>>(n, bp.keys, bp.cap_cells, bp.cell_end);
     OB_CHECK_KERNEL("k_cell_clear", st);

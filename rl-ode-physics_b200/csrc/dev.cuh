@@ -81,7 +81,8 @@ struct BroadPhase {
     float4 *s_min = nullptr, *s_max = nullptr;
     uint4 *s_flt = nullptr;
     int *cell_start = nullptr, *cell_end = nullptr;
-    int *cnt = nullptr; // PC_COUNT * n + 1
+    int *cnt = nullptr; // PC_COUNT * n: pairs per sweep thread and class
+    int *blk = nullptr; // PC_COUNT * (sweep blocks) + 1: per-block class sums, scanned in place
     int2 *sweep_tmp = nullptr; // SWEEP_TCAP layers of n parked hits
     int *sweep_tot = nullptr;  // hits per sweep thread
     int2 *pairs = nullptr;

@@ -104,6 +104,7 @@ void eng_destroy(Engine *e) {
     if (e->h_patch) cudaFreeHost(e->h_patch);
     if (e->d_patch) cudaFree(e->d_patch);
     if (e->ev_patch) cudaEventDestroy(e->ev_patch);
+    dev_free(bp.blk);
     dev_free(bp.acc); dev_free(bp.gp); dev_free(bp.counters); dev_free(bp.keys); dev_free(bp.idx);
     dev_free(bp.s_min); dev_free(bp.s_max); dev_free(bp.s_flt); dev_free(bp.cell_start); dev_free(bp.cell_end);
     dev_free(bp.cnt); dev_free(bp.pairs); dev_free(bp.sweep_tmp); dev_free(bp.sweep_tot);
@@ -282,6 +283,7 @@ void engine_ensure_capacity(Engine *e) {
         dev_realloc(bp.s_min, 0, n, st, false); dev_realloc(bp.s_max, 0, n, st, false);
         dev_realloc(bp.s_flt, 0, n, st, false);
         dev_realloc(bp.cnt, 0, (size_t)PC_COUNT * n + 1, st, false);
+        dev_realloc(bp.blk, 0, (size_t)PC_COUNT * (n / 128 + 2) + 1, st, false);
         dev_realloc(bp.sweep_tmp, 0, (size_t)SWEEP_TCAP * n, st, false);
         dev_realloc(bp.sweep_tot, 0, n, st, false);
         bp.cap_geoms = (int)n;
