@@ -529,3 +529,34 @@ def test_boxes_rest_on_a_trimesh_floor():
     assert np.abs(s["lvel"]).max() < 0.05
     assert (s["pos"][:, 1] > half_y - 0.03).all() and (s["pos"][:, 1] < half_y + 0.03).all()
     ew.close()
+
+
+@pytest.mark.parametrize("seed", [101, 102, 103, 104, 105, 106])
+def test_random_soups_pairs_and_contacts(seed):
+    """more seeds of the dense random soup (rotated boxes + spheres + plane + static box), both broadphase layouts:
+    pair sets equal to the oracle's hash space, contacts equal bit for bit, one tick within the tolerance"""
+    sc = scenes.random_soup(260 + 7 * (seed % 5), seed=seed, extent=3.0 + 0.5 * (seed % 3), rotated=(seed % 2 == 0))
+    ow, ew0 = util.load_both(sc)
+    ew0.close()
+    op = util.sorted_pair_set(ow.broadphase(0))
+    ref = util.oracle_contacts(ow)
+    for mode in (0, 1):
+        ew = util.engine_world(sc)
+        ew.set_broadphase(mode)
+        ew.collide(8)
+        assert np.array_equal(util.sorted_pair_set(ew.pairs()), op), mode
+        got = _engine_contacts_by_pair(ew)
+        assert set(got) == set(ref)
+        for key, cs in ref.items():
+            pd, nrm, side = got[key]
+            assert len(pd) == len(cs), (mode, key)
+            for k, c in enumerate(cs):
+                assert np.array_equal(pd[k], np.array(list(c.pos) + [c.depth], np.float32)), (mode, key, k)
+                assert np.array_equal(nrm[k], np.array(list(c.normal), np.float32)), (mode, key, k)
+        if mode == 0:
+            ew.step(sc["h"])
+            util.oracle_tick_in_engine_order(ow, ew, sc["h"])
+            es, os_ = ew.state(), ow.state()
+            for k in ("pos", "quat", "lvel", "avel"):
+                assert util.rel_err(es[k], os_[k]).max() <= STATE_RTOL, k
+        ew.close()
