@@ -921,9 +921,17 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
     int *cstart = reinterpret_cast<int *>(env_smem + (size_t)GROUPS * region) + grp * 136;
     int *cursor = cstart + 68;
     int rows1 = 0, rows2 = 0, ncont = 0, max_col = 0, max_rounds = 0;
-    const int n_env_rounds = (E.n_envs + gridDim.x * GROUPS - 1) / (gridDim.x * GROUPS);
-    for (int er = 0; er < n_env_rounds; er++) {
-        const int env = (er * gridDim.x + blockIdx.x) * GROUPS + grp;
+    // Persistent warps: a warp takes the next block of 32/G envs from a counter when it is done, instead of a
+    // CTA of four warps waiting for its slowest env before the next CTA can start (envs differ by +-15 % in
+    // contacts and by a few colours).
+    constexpr int W = 32 / G; // envs per warp
+    int *next_item = &E.fill[E.n_envs];
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(next_item, 1);
+        item = __shfl_sync(FULL, item, 0);
+        if (item * W >= E.n_envs) break;
+        const int env = item * W + lane / G;
         const bool have = env < E.n_envs;
         const int ms = have ? E.start[env] : 0, me = have ? E.start[env + 1] : 0;
         const int trips = (__reduce_max_sync(FULL, me - ms) + G - 1) / G; // warp-uniform
@@ -1324,12 +1332,16 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
         // stage the env's body data in shared memory when its bodies are one index range and it fits
         const int stage = (E.contiguous && mb <= 160 && e->env_stage != 0) ? 1 : 0;
         const size_t smem = (size_t)groups * ((size_t)mb * (stage ? 80 : 16) + 136 * sizeof(int));
-        const unsigned grid = (unsigned)((ne + groups - 1) / groups);
+        unsigned grid = (unsigned)((ne + groups - 1) / groups);
         SolverArrays S = e->S;
+        // one resident wave of CTAs: their warps pull env blocks from the counter E.fill[ne] (zeroed above)
 #define OB_LAUNCH_ENV(GG, SS)                                                                                        \
     do {                                                                                                             \
         if (smem > 48 * 1024)                                                                                        \
             OB_CUDA(cudaFuncSetAttribute(k_env_solve<GG, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        int per_sm = 0;                                                                                              \
+        OB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_env_solve<GG, SS>, 128, smem));             \
+        if (per_sm > 0) grid = std::min(grid, (unsigned)(per_sm * e->num_sms));                                      \
         k_env_solve<GG, SS><<<grid, 128, smem, st>>>(E, B, src, usurf, S, cfg, e->colour_spread, stage, fused, e->d_stats);        \
     } while (0)
         if (per_contact) {
