@@ -499,8 +499,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_env_sweep(GeomArrays g, const
         const GeomRec me = load_rec(g, i, single != 0);
         const float4 c1 = cr[i];
         const int env = (int)me.f.z;
-        auto visit = [&](int j) {
-            const float4 c2 = cr[j];
+        auto visit2 = [&](int j, const float4 c2) {
             const float dx = c1.x - c2.x, dy = c1.y - c2.y, dz = c1.z - c2.z, rr = c1.w + c2.w;
             if (dx * dx + dy * dy + dz * dz > rr * rr) return; // NaN/inf (planes) fall through to the AABB test
             const float4 lo2 = g.amin[j], hi2 = g.amax[j];
@@ -512,13 +511,24 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_env_sweep(GeomArrays g, const
             const int cls = test_pair(me.lo, me.hi, me.f, o.lo, o.hi, o.f);
             if (cls >= 0) emit<FILL>(cls, i, n, me.lo, me.f, o.lo, o.f, sink, off, pairs, cap_pairs, tmp);
         };
+        auto visit = [&](int j) { visit2(j, cr[j]); };
         if (env >= 0) {
             const int first = efirst[env], c = ecount[env], li = i - first;
             const int half = (c - 1) >> 1;
-            int lj = li;
-            for (int d = 1; d <= half; d++) {
-                lj = (lj + 1 == c) ? 0 : lj + 1;
-                visit(first + lj);
+            // four bounding-sphere records in flight per step (the loads are independent; the tests keep their order)
+            for (int d = 1; d <= half; d += 4) {
+                int jj[4];
+                float4 cc[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    int lj = li + d + k;
+                    if (lj >= c) lj -= c;
+                    jj[k] = first + lj;
+                    cc[k] = (d + k <= half) ? cr[jj[k]] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (d + k <= half) visit2(jj[k], cc[k]);
             }
             if (!(c & 1) && li < (c >> 1)) visit(first + li + (c >> 1));
             for (int s = 0; s < n_shared; s++) visit(shared[s]);
