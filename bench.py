@@ -386,6 +386,15 @@ def main():
                     "algorithmic_bytes_per_launch": solver_alg, "layout_bytes_per_launch": layout_bytes(st, n_bodies),
                     "kernel_ms": t_solve * 1e3, "whole_tick_GBps": sum(ab.values()) / (tm["tick_ms"] * 1e-3) / 1e9,
                     "stage_ms": tm}
+        if traffic and t_solve > 0:
+            # what actually crossed the HBM interface (ncu capture of the same kernel, profiles/solver_traffic.json)
+            roofline["dram_GBps"] = traffic / t_solve / 1e9
+            roofline["dram_frac"] = roofline["dram_GBps"] / peak
+        roofline["note"] = ("achieved = SURVEY 8(d) algorithmic bytes of a row-streaming QuickStep / kernel time; this engine "
+                            "rebuilds J and iMJ from 96 B per contact and (island solver) re-reads rows from L2 / shared "
+                            "memory, so frac can exceed 1; dram_GBps is the measured HBM traffic rate; the kernel is "
+                            "issue-bound (profiles/README.md)" if args.workload == "C4" else
+                            "achieved = SURVEY 8(d) algorithmic bytes / kernel time; dram_GBps = measured HBM traffic rate")
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             import oracle as O
