@@ -662,10 +662,11 @@ __device__ __forceinline__ void integrate_body(int i, const BodyArrays &B, float
     B.tacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     // snapshot: column-major 4x4 = transpose of R, translation in 12..14 (src/main.c:602-622)
     float4 *sn = reinterpret_cast<float4 *>(B.snap + 16 * (size_t)i);
-    sn[0] = make_float4(R.r0.x, R.r1.x, R.r2.x, 0.f);
-    sn[1] = make_float4(R.r0.y, R.r1.y, R.r2.y, 0.f);
-    sn[2] = make_float4(R.r0.z, R.r1.z, R.r2.z, 0.f);
-    sn[3] = make_float4(p.x, p.y, p.z, 1.f);
+    // streaming stores: no kernel reads the snapshot back, it should not displace the solver's rows in L2
+    __stcs(&sn[0], make_float4(R.r0.x, R.r1.x, R.r2.x, 0.f));
+    __stcs(&sn[1], make_float4(R.r0.y, R.r1.y, R.r2.y, 0.f));
+    __stcs(&sn[2], make_float4(R.r0.z, R.r1.z, R.r2.z, 0.f));
+    __stcs(&sn[3], make_float4(p.x, p.y, p.z, 1.f));
 }
 
 #ifdef OB_ENV_PROFILE
