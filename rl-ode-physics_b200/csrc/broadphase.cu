@@ -115,8 +115,17 @@ __global__ void __launch_bounds__(256) k_geom_update(GeomArrays g, const float4 
     }
 }
 
+// The reduction slots are re-armed on the device by whichever one-thread kernel follows k_geom_update (no
+// host-to-device copy on the tick path: copy-engine work of the compute stream queues behind the application's
+// own snapshot / force transfers -- measured: collide 0.33 -> 0.52 ms while a 64 MB D2H copy was in flight).
+__device__ __forceinline__ void acc_rearm(unsigned *acc) {
+    acc[0] = acc[1] = acc[2] = 0xffffffffu;
+    acc[3] = acc[4] = acc[5] = acc[6] = acc[7] = 0u;
+}
+__global__ void k_acc_init(unsigned *acc) { acc_rearm(acc); }
+
 // one thread: turn the reductions into grid parameters, shrink the grid until it fits the table
-__global__ void k_grid_params(const unsigned *__restrict__ acc, GridParams *__restrict__ gp, int n_envs,
+__global__ void k_grid_params(unsigned *__restrict__ acc, GridParams *__restrict__ gp, int n_envs,
                               int cap_cells, int n_geoms, BroadCounters *__restrict__ bc) {
     float ext = ord2f(acc[6]);
     float lo[3], hi[3];
@@ -147,6 +156,7 @@ __global__ void k_grid_params(const unsigned *__restrict__ acc, GridParams *__re
     bc->first_big = n_geoms;
     bc->first_dead = n_geoms;
     bc->n_pairs = 0;
+    acc_rearm(acc);
 }
 
 // K2: grid key per geom (BIG / DEAD sentinels sort to the tail)
@@ -278,6 +288,7 @@ __device__ __forceinline__ void block_class_sums(const int (&v)[PC_COUNT], int *
         for (int w = 0; w < SWEEP_THREADS / 32; w++) t += wsum[threadIdx.x][w];
         blk[threadIdx.x * nblk + blockIdx.x] = t;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) blk[PC_COUNT * nblk] = 0; // the scan's total slot
 }
 
 __device__ __forceinline__ void block_offsets(const int *__restrict__ cnt, const int *__restrict__ blkoff, int n, int i, int nblk,
@@ -550,7 +561,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_env_sweep(GeomArrays g, const
 }
 
 __global__ void k_env_counters(BroadCounters *__restrict__ bc, GridParams *__restrict__ gp, int n_alive, int n_shared,
-                               int n_envs) {
+                               int n_envs, unsigned *__restrict__ acc) {
+    acc_rearm(acc);
     bc->first_dead = n_alive;
     bc->first_big = n_alive - n_shared;
     bc->n_pairs = 0;
@@ -580,7 +592,8 @@ __global__ void k_pairs_finish(int nblk, const int *__restrict__ off, int cap_pa
 
 // dCollide(o1, o2) outside a space traversal: refresh the poses, then hand the narrowphase a one-pair list
 __global__ void k_single_pair(GeomArrays g, int g1, int g2, int2 *__restrict__ pairs, BroadCounters *__restrict__ bc,
-                              StepStats *__restrict__ stats) {
+                              StepStats *__restrict__ stats, unsigned *__restrict__ acc) {
+    acc_rearm(acc);
     int ta = g.type[g1], tb = g.type[g2];
     int ga = g1, gb = g2;
     if (ta > tb || (ta == tb && ga > gb)) { int t = ga; ga = gb; gb = t; t = ta; ta = tb; tb = t; }
@@ -594,14 +607,17 @@ __global__ void k_single_pair(GeomArrays g, int g1, int g2, int2 *__restrict__ p
     for (int c = 0; c < PC_COUNT; c++) stats->class_count[c] = c == cls ? 1 : 0;
 }
 
+void broadphase_acc_init(BroadPhase &bp, cudaStream_t st) {
+    k_acc_init<<<1, 1, 0, st>>>(bp.acc);
+    OB_CHECK_KERNEL("k_acc_init", st);
+}
+
 void broadphase_single_pair(BroadPhase &bp, GeomArrays g, const float4 *b_pos, const float4 *b_R, MeshTable meshes, float big_extent,
                             int g1, int g2, StepStats *d_stats, cudaStream_t st) {
     const unsigned nb = (unsigned)((g.n + 255) / 256);
-    static const unsigned acc_init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
-    OB_CUDA(cudaMemcpyAsync(bp.acc, acc_init, sizeof(acc_init), cudaMemcpyHostToDevice, st));
     k_geom_update<<<nb, 256, 0, st>>>(g, b_pos, b_R, meshes, big_extent, bp.acc);
     OB_CHECK_KERNEL("k_geom_update", st);
-    k_single_pair<<<1, 1, 0, st>>>(g, g1, g2, bp.pairs, bp.counters, d_stats);
+    k_single_pair<<<1, 1, 0, st>>>(g, g1, g2, bp.pairs, bp.counters, d_stats, bp.acc);
     OB_CHECK_KERNEL("k_single_pair", st);
 }
 
@@ -614,8 +630,6 @@ void broadphase_run(BroadPhase &bp, GeomArrays g, const float4 *b_pos, const flo
         return;
     }
     const unsigned nb = (unsigned)((n + 255) / 256);
-    static const unsigned acc_init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
-    OB_CUDA(cudaMemcpyAsync(bp.acc, acc_init, sizeof(acc_init), cudaMemcpyHostToDevice, st));
     k_geom_update<<<nb, 256, 0, st>>>(g, b_pos, b_R, meshes, big_extent, bp.acc);
     OB_CHECK_KERNEL("k_geom_update", st);
     if (eb.enabled) {
@@ -623,12 +637,11 @@ void broadphase_run(BroadPhase &bp, GeomArrays g, const float4 *b_pos, const flo
         float4 *cr = bp.s_min;
         k_env_bounds<<<nb, 256, 0, st>>>(g, cr);
         OB_CHECK_KERNEL("k_env_bounds", st);
-        k_env_counters<<<1, 1, 0, st>>>(bp.counters, bp.gp, eb.n_alive, eb.n_shared, n_envs);
+        k_env_counters<<<1, 1, 0, st>>>(bp.counters, bp.gp, eb.n_alive, eb.n_shared, n_envs, bp.acc);
         OB_CHECK_KERNEL("k_env_counters", st);
         k_env_sweep<false><<<nb2, SWEEP_THREADS, 0, st>>>(g, cr, eb.first, eb.count, eb.shared, eb.n_shared, eb.single, bp.cnt,
                                                           bp.blk, nullptr, nullptr, 0, bp.sweep_tmp, bp.sweep_tot);
         OB_CHECK_KERNEL("k_env_sweep", st);
-        OB_CUDA(cudaMemsetAsync(bp.blk + (size_t)PC_COUNT * nb2, 0, sizeof(int), st));
         scan_exclusive(bp.blk, bp.blk, (long)PC_COUNT * nb2 + 1, nullptr, nullptr, bp.scan, st);
         k_env_sweep<true><<<nb2, SWEEP_THREADS, 0, st>>>(g, cr, eb.first, eb.count, eb.shared, eb.n_shared, eb.single, bp.cnt,
                                                          nullptr, bp.blk, bp.pairs, bp.cap_pairs, bp.sweep_tmp, bp.sweep_tot);
@@ -649,7 +662,6 @@ void broadphase_run(BroadPhase &bp, GeomArrays g, const float4 *b_pos, const flo
     k_sweep<false><<<nb2, SWEEP_THREADS, 0, st>>>(n, bp.keys, bp.s_min, bp.s_max, bp.s_flt, bp.cell_start, bp.cell_end, bp.gp,
                                                   bp.counters, bp.cnt, bp.blk, nullptr, nullptr, 0, bp.sweep_tmp, bp.sweep_tot);
     OB_CHECK_KERNEL("k_sweep", st);
-    OB_CUDA(cudaMemsetAsync(bp.blk + (size_t)PC_COUNT * nb2, 0, sizeof(int), st));
     scan_exclusive(bp.blk, bp.blk, (long)PC_COUNT * nb2 + 1, nullptr, nullptr, bp.scan, st);
     k_sweep<true><<<nb2, SWEEP_THREADS, 0, st>>>(n, bp.keys, bp.s_min, bp.s_max, bp.s_flt, bp.cell_start, bp.cell_end, bp.gp,
                                                  bp.counters, bp.cnt, nullptr, bp.blk, bp.pairs, bp.cap_pairs, bp.sweep_tmp,

@@ -102,6 +102,7 @@ struct EnvBroad {
 void broadphase_run(BroadPhase &bp, GeomArrays g, const float4 *b_pos, const float4 *b_R, MeshTable meshes,
                     int n_envs, float big_extent, const EnvBroad &eb, StepStats *d_stats, cudaStream_t st);
 
+void broadphase_acc_init(BroadPhase &bp, cudaStream_t st);
 void broadphase_single_pair(BroadPhase &bp, GeomArrays g, const float4 *b_pos, const float4 *b_R, MeshTable meshes, float big_extent,
                             int g1, int g2, StepStats *d_stats, cudaStream_t st);
 

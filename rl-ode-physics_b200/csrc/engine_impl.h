@@ -57,6 +57,15 @@ struct Engine {
     unsigned *msg_col = nullptr, *msg_out = nullptr;
     float4 *body_hot = nullptr; // fc (2 per body) followed by inv (3 per body)
     int l2_persist = 0;        // measured: the persisting carve-out costs more than it gives (profiles/README.md)        // keep body_hot resident in L2 through an access-policy window
+    // CUDA graphs of the device-resident tick of batched worlds (collide; step, one per snapshot buffer)
+    struct TickGraph {
+        cudaGraphExec_t exec = nullptr;
+        unsigned long long key = 0, warm_key = 0; // configuration captured / seen on the last ticks
+        int warm = 0, kernels = 0;
+        bool fc_valid = false;
+    };
+    TickGraph g_collide, g_step[2];
+    int graphs = 1;
     int tiny_solver = 1; // small single worlds: one-CTA shared-memory solver (k_tiny_solve) before k_solve
     int env_fuse = 1;  // island solver: run body preparation and the integrate/pack tail inside k_env_solve
     int env_stage = 1; // island solver: stage body data in shared memory when possible

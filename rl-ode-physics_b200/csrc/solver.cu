@@ -84,9 +84,16 @@ __device__ __forceinline__ void body_prep(int i, const BodyArrays &B, const Step
     B.prio[i] = ~0ull;
 }
 
-__global__ void k_stats_reset(StepStats *__restrict__ stats) {
-    stats->n_rows = 0; stats->n_rows1 = 0; stats->n_rows2 = 0; stats->n_contacts = 0;
-    stats->n_manifolds = 0; stats->n_colours = 0; stats->n_overflow = 0; stats->colour_rounds = 0;
+// start-of-step resets in one launch: statistics and, for batched worlds, the per-env counters (kernels, not
+// memsets/copies: copy-engine work on the compute stream queues behind the application's own transfers)
+__global__ void __launch_bounds__(256) k_stats_reset(StepStats *__restrict__ stats, int *__restrict__ env_cnt, int *__restrict__ env_fill,
+                                                      int n_env_slots) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        stats->n_rows = 0; stats->n_rows1 = 0; stats->n_rows2 = 0; stats->n_contacts = 0;
+        stats->n_manifolds = 0; stats->n_colours = 0; stats->n_overflow = 0; stats->colour_rounds = 0;
+    }
+    for (int k = i; k < n_env_slots; k += gridDim.x * blockDim.x) { env_cnt[k] = 0; env_fill[k] = 0; }
 }
 
 __global__ void __launch_bounds__(256) k_body_prep(BodyArrays B, StepConfig cfg) {
@@ -865,7 +872,8 @@ __global__ void __launch_bounds__(256) k_env_count(const BroadCounters *__restri
 __global__ void __launch_bounds__(256) k_env_bucket(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
                                                      const int *__restrict__ g_body, const int *__restrict__ nc,
                                                      const float4 *__restrict__ b_pos, const int *__restrict__ b_env,
-                                                     EnvArrays E, StepStats *__restrict__ stats, int per_contact, int kstride) {
+                                                     EnvArrays E, StepStats *__restrict__ stats, int per_contact, int kstride,
+                                                     int *__restrict__ m_count) {
     const int n = bc->n_pairs;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         const int2 pr = pairs[p];
@@ -881,7 +889,7 @@ __global__ void __launch_bounds__(256) k_env_bucket(const BroadCounters *__restr
         const int slot = E.start[e] + atomicAdd(&E.fill[e], units);
         for (int u = 0; u < units; u++) E.rec[slot + u] = make_int4(b1, b2, p + u * kstride, w);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) stats->n_manifolds = E.start[E.n_envs];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { stats->n_manifolds = E.start[E.n_envs]; *m_count = E.start[E.n_envs]; }
 }
 
 #ifdef OB_ENV_PROFILE
@@ -1283,13 +1291,16 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
     cfg.iters = e->params.iters;
     cfg.tol = e->params.tol;
 
-    k_stats_reset<<<1, 1, 0, st>>>(e->d_stats);
-    OB_CHECK_KERNEL("k_stats_reset", st);
     // island path with contiguous envs: per-body preparation and the integrate/pack tail run inside
     // k_env_solve, env by env; otherwise they are separate passes over all bodies
     const bool island = !host_contacts && e->have_device_contacts && e->n_envs > 1 && e->E.max_bodies <= 1024 && e->solver_mode != 1 &&
                         !(cfg.tol > 0.f); // residual termination is a grid-wide decision: global solver
     const int fused = (island && e->E.contiguous && e->env_fuse) ? (e->keep_fc ? 2 : 1) : 0;
+    {
+        const int slots = island ? e->n_envs + 1 : 0;
+        k_stats_reset<<<(unsigned)std::max(1, (slots + 255) / 256), 256, 0, st>>>(e->d_stats, e->E.cnt, e->E.fill, slots);
+        OB_CHECK_KERNEL("k_stats_reset", st);
+    }
     e->last_h = h;
     e->fc_valid = fused != 1; // the fused island path keeps the accumulators in shared memory only
     if (!fused) {
@@ -1312,15 +1323,12 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
         src.pd = e->cs.pd; src.ns = e->cs.ns; src.surf = nullptr; src.kstride = e->cs.stride;
         EnvArrays E = e->E;
         const int ne = E.n_envs;
-        OB_CUDA(cudaMemsetAsync(E.cnt, 0, ((size_t)ne + 1) * sizeof(int), st));
-        OB_CUDA(cudaMemsetAsync(E.fill, 0, ((size_t)ne + 1) * sizeof(int), st));
         k_env_count<<<pgrid, 256, 0, st>>>(e->bp.counters, e->bp.pairs, e->G.body, e->cs.nc, B.env, E.cnt, per_contact);
         OB_CHECK_KERNEL("k_env_count", st);
         scan_exclusive(E.cnt, E.start, (long)ne + 1, nullptr, nullptr, e->scan, st);
         k_env_bucket<<<pgrid, 256, 0, st>>>(e->bp.counters, e->bp.pairs, e->G.body, e->cs.nc, B.pos, B.env, E, e->d_stats,
-                                            per_contact, e->cs.stride);
+                                            per_contact, e->cs.stride, M.count);
         OB_CHECK_KERNEL("k_env_bucket", st);
-        OB_CUDA(cudaMemcpyAsync(M.count, E.start + ne, sizeof(int), cudaMemcpyDeviceToDevice, st));
         if (e->timing) {
             OB_CUDA(cudaEventRecord(e->ev[2], st));
             OB_CUDA(cudaEventRecord(e->ev[3], st));
