@@ -718,8 +718,9 @@ static unsigned long long graph_key(Engine *e, bool step) {
     return h;
 }
 static bool graphs_usable(Engine *e) {
-    return e->graphs && !e->timing && !ob_debug_sync() && e->n_envs > 1 && e->EB.enabled && e->meshes.n == 0 && e->solver_mode != 1 &&
-           e->E.max_bodies <= 1024 && !(e->params.tol > 0.f);
+    // batched worlds (island solver) and small single worlds (all-pairs broadphase, cooperative colouring + solver)
+    return e->graphs && !e->timing && !ob_debug_sync() && e->EB.enabled && e->meshes.n == 0 && !(e->params.tol > 0.f) &&
+           (e->n_envs == 1 || (e->solver_mode != 1 && e->E.max_bodies <= 1024));
 }
 template <typename F>
 static void run_graphed(Engine *e, Engine::TickGraph &g, unsigned long long key, F &&enqueue) {
