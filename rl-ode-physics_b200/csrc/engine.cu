@@ -708,6 +708,11 @@ static unsigned long long graph_key(Engine *e, bool step) {
                           e->cs.pd, e->cs.nc, e->M.rec, e->M.flag, e->S.q0, e->S.mrec, e->E.rec, e->E.cnt, e->E.start, e->E.fill,
                           e->E.first_body, e->EB.first, e->EB.count, e->EB.shared, e->d_stats};
     for (const void *p : ptrs) h = gk_ptr(h, p);
+    const void *sorts[] = {e->bp.sort.hist, e->bp.sort.keys_tmp, e->bp.sort.vals_tmp, e->bp.sort.scan.sums[0], e->bp.sort.scan.sums[1],
+                           e->sort.hist, e->sort.keys_tmp, e->sort.vals_tmp, e->sort.scan.sums[0], e->sort.scan.sums[1],
+                           e->bp.cell_start, e->bp.s_min, e->M.skey, e->M.sidx, e->M.colour};
+    for (const void *p : sorts) h = gk_ptr(h, p);
+    for (int m = 0; m < e->meshes.n; m++) { h = gk_ptr(h, e->meshes.m[m].verts); h = gk_mix(h, (unsigned long long)e->meshes.m[m].nt); }
     const int ints[] = {e->B.n, e->G.n, e->cap_b, e->cap_g, e->bp.cap_pairs, e->cs.stride, e->M.cap, e->S.cap, e->n_envs, e->max_contacts,
                         e->env_group, e->contact_units, e->solver_mode, e->env_stage, e->env_fuse, e->colour_spread, e->broad_mode,
                         e->tiny_solver, (int)e->keep_fc, e->EB.enabled, e->EB.single, e->EB.n_shared, e->EB.n_alive, e->E.contiguous,
@@ -718,9 +723,8 @@ static unsigned long long graph_key(Engine *e, bool step) {
     return h;
 }
 static bool graphs_usable(Engine *e) {
-    // batched worlds (island solver) and small single worlds (all-pairs broadphase, cooperative colouring + solver)
-    return e->graphs && !e->timing && !ob_debug_sync() && e->EB.enabled && e->meshes.n == 0 && !(e->params.tol > 0.f) &&
-           (e->n_envs == 1 || (e->solver_mode != 1 && e->E.max_bodies <= 1024));
+    // every device-resident tick: batched worlds (island solver) and single worlds (cooperative colouring + solver)
+    return e->graphs && !e->timing && !ob_debug_sync() && !(e->params.tol > 0.f);
 }
 template <typename F>
 static void run_graphed(Engine *e, Engine::TickGraph &g, unsigned long long key, F &&enqueue) {
