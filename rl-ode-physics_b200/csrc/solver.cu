@@ -907,7 +907,7 @@ __device__ unsigned long long g_env_prof[8];
 
 // The W = 32/G envs that share a warp run in LOCKSTEP: every loop bound is made warp-uniform (the
 // maximum over the warp's groups) and lanes without work are predicated off, so the groups never
-// diverge into serialised code paths.  The solver is issue-bound (ncu: 67 % issue-active, DRAM 8 %),
+// diverge into serialised code paths.  The solver is issue-bound (ncu: 64 % issue-active, DRAM 10 %),
 // so what matters is how many lanes of each issued instruction do useful work.
 template <int G, bool SINGLE>
 __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, BodyArrays B, ContactSource src, Surface usurf,
