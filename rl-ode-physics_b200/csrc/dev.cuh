@@ -141,6 +141,7 @@ struct EnvArrays {
     int *cnt;        // manifolds per env (n_envs + 1 for the scan)
     int *start;      // exclusive scan of cnt, [n_envs] = total
     int *fill;       // bucket cursors
+    int *order;      // envs by decreasing unit count (the island solver's work queue)
     int4 *rec;       // manifold records bucketed by env
     int *perm;       // per env: bucket slots ordered by colour
     unsigned char *col; // colour per bucket slot

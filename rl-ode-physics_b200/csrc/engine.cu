@@ -120,7 +120,7 @@ void eng_destroy(Engine *e) {
     SolverArrays &S = e->S;
     dev_free(S.q0); dev_free(S.q1); dev_free(S.q2); dev_free(S.q3); dev_free(S.q4); dev_free(S.q5); dev_free(S.lam); dev_free(S.mrec);
     sort_workspace_free(e->sort); scan_workspace_free(e->scan);
-    dev_free(e->E.first_body); dev_free(e->E.n_body); dev_free(e->E.cnt); dev_free(e->E.start); dev_free(e->E.fill); dev_free(e->E.rec); dev_free(e->E.perm); dev_free(e->E.col);
+    dev_free(e->E.first_body); dev_free(e->E.n_body); dev_free(e->E.cnt); dev_free(e->E.start); dev_free(e->E.fill); dev_free(e->E.order); dev_free(e->E.rec); dev_free(e->E.perm); dev_free(e->E.col);
     dev_free(e->hc_pd); dev_free(e->hc_ns); dev_free(e->hc_surf); dev_free(e->hc_mrec);
     dev_free(e->dl_first); dev_free(e->dl_pd); dev_free(e->dl_ns);
     for (auto &m : e->hmeshes) { dev_free(m.d_verts); dev_free(m.d_tris); }
@@ -354,6 +354,7 @@ void engine_ensure_pair_capacity(Engine *e) {
             const size_t n = (size_t)e->n_envs + 1;
             dev_realloc(e->E.cnt, 0, n, st, false); dev_realloc(e->E.start, 0, n, st, false);
             dev_realloc(e->E.fill, 0, n, st, false);
+            dev_realloc(e->E.order, 0, n, st, false);
             e->cap_envs = (int)n;
         }
     }

@@ -892,6 +892,23 @@ __global__ void __launch_bounds__(256) k_env_bucket(const BroadCounters *__restr
     if (blockIdx.x == 0 && threadIdx.x == 0) { stats->n_manifolds = E.start[E.n_envs]; *m_count = E.start[E.n_envs]; }
 }
 
+// Work queue order of the island solver: envs by decreasing unit count (64 size classes), so the warps' last
+// envs are the small ones and the kernel's tail is short.  The order inside a class is arbitrary; it does not
+// affect any result (envs are independent).
+__global__ void __launch_bounds__(1024) k_env_order(const int *__restrict__ cnt, int n_envs, int *__restrict__ order) {
+    __shared__ int hist[64], start[64];
+    if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int e = threadIdx.x; e < n_envs; e += blockDim.x) atomicAdd(&hist[63 - min(cnt[e] >> 3, 63)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < 64; b++) { start[b] = acc; acc += hist[b]; }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n_envs; e += blockDim.x) order[atomicAdd(&start[63 - min(cnt[e] >> 3, 63)], 1)] = e;
+}
+
 #ifdef OB_ENV_PROFILE
 __device__ unsigned long long g_env_prof[8];
 #define PROF_T(var) const long long var = clock64()
@@ -940,8 +957,9 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
         if (lane == 0) item = atomicAdd(next_item, 1);
         item = __shfl_sync(FULL, item, 0);
         if (item * W >= E.n_envs) break;
-        const int env = item * W + lane / G;
-        const bool have = env < E.n_envs;
+        const int qi = item * W + lane / G;
+        const bool have = qi < E.n_envs;
+        const int env = have ? E.order[qi] : E.n_envs;
         const int ms = have ? E.start[env] : 0, me = have ? E.start[env + 1] : 0;
         const int trips = (__reduce_max_sync(FULL, me - ms) + G - 1) / G; // warp-uniform
         const int fb = have ? E.first_body[env] : 0, nbod = have ? E.n_body[env] : 0;
@@ -1326,6 +1344,8 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
         k_env_count<<<pgrid, 256, 0, st>>>(e->bp.counters, e->bp.pairs, e->G.body, e->cs.nc, B.env, E.cnt, per_contact);
         OB_CHECK_KERNEL("k_env_count", st);
         scan_exclusive(E.cnt, E.start, (long)ne + 1, nullptr, nullptr, e->scan, st);
+        k_env_order<<<1, 1024, 0, st>>>(E.cnt, ne, E.order);
+        OB_CHECK_KERNEL("k_env_order", st);
         k_env_bucket<<<pgrid, 256, 0, st>>>(e->bp.counters, e->bp.pairs, e->G.body, e->cs.nc, B.pos, B.env, E, e->d_stats,
                                             per_contact, e->cs.stride, M.count);
         OB_CHECK_KERNEL("k_env_bucket", st);
