@@ -813,18 +813,50 @@ void narrowphase_run(const BroadPhase &bp, GeomArrays g, MeshTable meshes, const
     if (g.n == 0) return;
     // persistent grids: a multiple of the SM count, grid-stride over the class slice
     const unsigned grid = (unsigned)(num_sms * 8);
-    k_np_sphere_sphere<<<grid, 256, 0, st>>>(bp.counters, bp.pairs, g, cs);
-    OB_CHECK_KERNEL("k_np_sphere_sphere", st);
-    k_np_sphere_box<<<grid, 256, 0, st>>>(bp.counters, bp.pairs, g, cs);
-    OB_CHECK_KERNEL("k_np_sphere_box", st);
+    // The class kernels work on disjoint slices of the pair list.  While the tick is being captured into a CUDA
+    // graph they are forked onto side streams, so the graph runs them as parallel branches next to the long
+    // box-box kernel; plain launches stay on the one stream (the fork/join events would cost more than they buy).
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    OB_CUDA(cudaStreamIsCapturing(st, &cap));
+    struct Fork { cudaStream_t side[5]; cudaEvent_t fork_ev, join_ev[5]; };
+    static Fork forks[16] = {}; // per device (a process may hold worlds on several GPUs)
+    int dev = 0;
+    OB_CUDA(cudaGetDevice(&dev));
+    const bool forked = cap == cudaStreamCaptureStatusActive && dev < 16;
+    Fork &fk = forks[dev < 16 ? dev : 0];
+    cudaStream_t *side = fk.side;
+    cudaEvent_t &fork_ev = fk.fork_ev;
+    cudaEvent_t *join_ev = fk.join_ev;
+    if (forked && !fork_ev) {
+        OB_CUDA(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+        for (int i = 0; i < 5; i++) {
+            OB_CUDA(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+            OB_CUDA(cudaEventCreateWithFlags(&join_ev[i], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t s1 = st, s2 = st, s3 = st, s4 = st, s5 = st;
+    if (forked) {
+        OB_CUDA(cudaEventRecord(fork_ev, st));
+        for (int i = 0; i < 5; i++) OB_CUDA(cudaStreamWaitEvent(side[i], fork_ev, 0));
+        s1 = side[0]; s2 = side[1]; s3 = side[2]; s4 = side[3]; s5 = side[4];
+    }
     k_np_box_box<<<grid, 128, 0, st>>>(bp.counters, bp.pairs, g, cs, max_contacts);
     OB_CHECK_KERNEL("k_np_box_box", st);
-    k_np_sphere_plane<<<grid, 256, 0, st>>>(bp.counters, bp.pairs, g, cs);
-    OB_CHECK_KERNEL("k_np_sphere_plane", st);
-    k_np_box_plane<<<grid, 256, 0, st>>>(bp.counters, bp.pairs, g, cs, max_contacts);
-    OB_CHECK_KERNEL("k_np_box_plane", st);
-    k_np_none<<<grid, 256, 0, st>>>(bp.counters, cs);
-    OB_CHECK_KERNEL("k_np_none", st);
+    k_np_sphere_sphere<<<grid, 256, 0, s1>>>(bp.counters, bp.pairs, g, cs);
+    OB_CHECK_KERNEL("k_np_sphere_sphere", s1);
+    k_np_sphere_box<<<grid, 256, 0, s2>>>(bp.counters, bp.pairs, g, cs);
+    OB_CHECK_KERNEL("k_np_sphere_box", s2);
+    k_np_sphere_plane<<<grid, 256, 0, s3>>>(bp.counters, bp.pairs, g, cs);
+    OB_CHECK_KERNEL("k_np_sphere_plane", s3);
+    k_np_box_plane<<<grid, 256, 0, s4>>>(bp.counters, bp.pairs, g, cs, max_contacts);
+    OB_CHECK_KERNEL("k_np_box_plane", s4);
+    k_np_none<<<grid, 256, 0, s5>>>(bp.counters, cs);
+    OB_CHECK_KERNEL("k_np_none", s5);
+    if (forked)
+        for (int i = 0; i < 5; i++) {
+            OB_CUDA(cudaEventRecord(join_ev[i], side[i]));
+            OB_CUDA(cudaStreamWaitEvent(st, join_ev[i], 0));
+        }
     for (int m = 0; m < meshes.n; m++) {
         const TriMesh &hm = host_meshes[m];
         int bv = ((hm.nv * 3 * (int)sizeof(float) + 15) / 16) * 16;
