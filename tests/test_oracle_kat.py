@@ -437,3 +437,22 @@ def test_exact_lcp_single_contact_closed_form(oracle_lib):
     w2.collide_all(8, O.reference_surface())
     w2.quickstep(H, order_mode=1)
     assert abs(w2.body(b2)[3][1] - expect) < 1e-3
+
+
+def test_exact_lcp_head_on_bounce_closed_form(oracle_lib):
+    """two unit spheres (mass 1) head-on at +-1 m/s, 0.02 deep, no gravity, reference surface (bounce 0.2): the row
+    target is c = max(erp*depth/h, bounce * closing speed) = 0.4, A = 1/m1 + 1/m2 + cfm/h, so the separation speed
+    after the exact step is v_rel + 2 (c - v_rel) / A with v_rel = -2; momentum stays zero."""
+    w = O.OracleWorld(gravity=(0.0, 0.0, 0.0))
+    b1 = w.add_body([-0.49, 0, 0], lvel=[1.0, 0, 0])
+    w.add_geom(O.SPHERE, [0.5], body=b1)
+    b2 = w.add_body([0.49, 0, 0], lvel=[-1.0, 0, 0])
+    w.add_geom(O.SPHERE, [0.5], body=b2)
+    assert w.collide_all(8, O.reference_surface()) == 1
+    w.quickstep(H, order_mode=3)
+    v1, v2 = w.body(b1)[3], w.body(b2)[3]
+    A = 2.0 + 1e-5 / H
+    sep = -2.0 + 2.0 * (0.4 + 2.0) / A
+    assert (v2[0] - v1[0]) == pytest.approx(sep, rel=1e-5)
+    assert v1[0] + v2[0] == pytest.approx(0.0, abs=1e-6)
+    assert np.abs(np.concatenate([v1[1:], v2[1:]])).max() < 1e-7
