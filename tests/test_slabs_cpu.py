@@ -100,3 +100,60 @@ def test_dynamic_slab_scene_layout():
         if r > 0:
             assert abs(info["face_left"] - built[r - 1][1]["face_right"]) < 1e-9
         assert 0 < info["hyst"] < info["margin"]
+
+
+class _HostSlab:
+    """stand-in for SlabWorld / DynamicSlabWorld on the CPU: the same `sides` buffer naming, no engine behind it"""
+
+    def __init__(self, rank, n_slabs, sizes):
+        import torch
+        self.torch = torch
+        self.sides = {}
+        mk = lambda n, w, v: torch.full((n, w), float(v))   # noqa: E731
+        if rank > 0:        # impulse coupling: states go down (to rank-1), impulses come up from it; migrants both ways
+            self.sides["left"] = {"send_state_buf": mk(sizes["state"], 4, 100 + rank), "recv_imp_buf": mk(sizes["imp"], 2, -1),
+                                  "send_mig_buf": mk(sizes["mig"], 3, 300 + rank), "recv_mig_buf": mk(sizes["mig"], 3, -1)}
+        if rank < n_slabs - 1:
+            self.sides["right"] = {"recv_state_buf": mk(sizes["state"], 4, -1), "send_imp_buf": mk(sizes["imp"], 2, 200 + rank),
+                                   "send_mig_buf": mk(sizes["mig"], 3, 400 + rank), "recv_mig_buf": mk(sizes["mig"], 3, -1)}
+
+
+def _halo_worker(rank, world_size, port, q):
+    import os
+    import torch.distributed as dist
+    from odeb200 import sharding
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world_size), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    sharding.init_process_group("gloo")
+    slab = _HostSlab(rank, world_size, {"state": 5, "imp": 5, "mig": 3})
+    slab.torch.cuda.synchronize = lambda: None            # exchange_nccl ends with a device sync; nothing to sync here
+    for kind in ("state", "imp", "mig"):
+        slabs.exchange_nccl(slab, rank, world_size, kind)
+    out = {side: {k: float(v[0, 0]) for k, v in s.items() if k.startswith("recv_")} for side, s in slab.sides.items()}
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_halo_messages_route_between_three_ranks_gloo():
+    """the exchange the C5 bench runs over NCCL, on gloo with CPU tensors and world_size 3: states travel to the lower
+    neighbour, impulses back up, migrants both ways, and the middle rank talks to both sides in one batch"""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ws = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_halo_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in range(ws))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(ws):
+        if r < ws - 1:      # from the right neighbour: its states and its left-going migrants
+            assert res[r]["right"]["recv_state_buf"] == 100 + (r + 1)
+            assert res[r]["right"]["recv_mig_buf"] == 300 + (r + 1)
+        if r > 0:           # from the left neighbour: impulses for our boundary bodies and its right-going migrants
+            assert res[r]["left"]["recv_imp_buf"] == 200 + (r - 1)
+            assert res[r]["left"]["recv_mig_buf"] == 400 + (r - 1)
