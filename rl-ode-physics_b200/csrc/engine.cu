@@ -713,7 +713,11 @@ static unsigned long long graph_key(Engine *e, bool step) {
                            e->sort.hist, e->sort.keys_tmp, e->sort.vals_tmp, e->sort.scan.sums[0], e->sort.scan.sums[1],
                            e->bp.cell_start, e->bp.s_min, e->M.skey, e->M.sidx, e->M.colour};
     for (const void *p : sorts) h = gk_ptr(h, p);
-    for (int m = 0; m < e->meshes.n; m++) { h = gk_ptr(h, e->meshes.m[m].verts); h = gk_mix(h, (unsigned long long)e->meshes.m[m].nt); }
+    for (int m = 0; m < e->meshes.n; m++) {
+        h = gk_ptr(h, e->meshes.m[m].verts);
+        h = gk_ptr(h, e->meshes.m[m].tris);
+        h = gk_mix(h, ((unsigned long long)e->meshes.m[m].nt << 32) | (unsigned)e->meshes.m[m].nv);
+    }
     const int ints[] = {e->B.n, e->G.n, e->cap_b, e->cap_g, e->bp.cap_pairs, e->cs.stride, e->M.cap, e->S.cap, e->n_envs, e->max_contacts,
                         e->env_group, e->contact_units, e->solver_mode, e->env_stage, e->env_fuse, e->colour_spread, e->broad_mode,
                         e->tiny_solver, (int)e->keep_fc, e->EB.enabled, e->EB.single, e->EB.n_shared, e->EB.n_alive, e->E.contiguous,
