@@ -202,6 +202,9 @@ struct orc_world {
     unsigned long lcg_seed; /* ODE dRand state */
     int perturb_fma;        /* experiment: FMA-contracted solver arithmetic (not ODE's rounding) */
     float *last_lambda; int nrows;
+    /* diagnostics kept for the tests (orc_set_keep_rows): the last step's rows before Ad scaling */
+    int keep_rows;
+    float *dbg_J, *dbg_c, *dbg_cfm, *dbg_lo, *dbg_hi, *dbg_rhs; int *dbg_jb; int dbg_m;
 };
 
 orc_world *orc_create(void) {
@@ -211,8 +214,13 @@ orc_world *orc_create(void) {
     w->max_vel = ORC_INF; w->min_depth = 0;
     return w;
 }
+static void dbg_free(orc_world *w) {
+    free(w->dbg_J); free(w->dbg_c); free(w->dbg_cfm); free(w->dbg_lo); free(w->dbg_hi); free(w->dbg_rhs); free(w->dbg_jb);
+    w->dbg_J = w->dbg_c = w->dbg_cfm = w->dbg_lo = w->dbg_hi = w->dbg_rhs = 0; w->dbg_jb = 0; w->dbg_m = 0;
+}
 void orc_destroy(orc_world *w) {
     if (!w) return;
+    dbg_free(w);
     for (int i = 0; i < w->nm; i++) { free(w->m[i].v); free(w->m[i].t); }
     free(w->b); free(w->g); free(w->m); free(w->j); free(w->last_lambda); free(w);
 }
@@ -1312,6 +1320,22 @@ static int joint_rows(const ojoint *j) {
 }
 
 int orc_num_rows(const orc_world *w) { return w->nrows; }
+void orc_set_keep_rows(orc_world *w, int on) { w->keep_rows = on; if (!on) dbg_free(w); }
+/* rows of the last step as dxJointContact::getInfo2 + QuickStep built them, BEFORE SOR_LCP's Ad scaling:
+ * J (12 per row), c (the row's target velocity), cfm (already divided by h), lo, hi, rhs, body pair */
+int orc_last_rows(const orc_world *w, float *J, float *c, float *cfm, float *lo, float *hi, float *rhs, int *jb, int n) {
+    if (n > w->dbg_m) n = w->dbg_m;
+    if (n > 0) {
+        if (J) memcpy(J, w->dbg_J, sizeof(float) * 12 * (size_t)n);
+        if (c) memcpy(c, w->dbg_c, sizeof(float) * (size_t)n);
+        if (cfm) memcpy(cfm, w->dbg_cfm, sizeof(float) * (size_t)n);
+        if (lo) memcpy(lo, w->dbg_lo, sizeof(float) * (size_t)n);
+        if (hi) memcpy(hi, w->dbg_hi, sizeof(float) * (size_t)n);
+        if (rhs) memcpy(rhs, w->dbg_rhs, sizeof(float) * (size_t)n);
+        if (jb) memcpy(jb, w->dbg_jb, sizeof(int) * 2 * (size_t)n);
+    }
+    return w->dbg_m;
+}
 void orc_last_lambda(const orc_world *w, float *lambda, int n) {
     if (n > w->nrows) n = w->nrows;
     if (n > 0) memcpy(lambda, w->last_lambda, sizeof(float) * (size_t)n);
@@ -1422,6 +1446,7 @@ int orc_quickstep(orc_world *w, float h, int order_mode, const int *perm) {
     free(w->last_lambda);
     w->last_lambda = (float *)calloc((size_t)(m ? m : 1), sizeof(float));
     w->nrows = m;
+    if (w->keep_rows && m == 0) dbg_free(w);
 
     if (m > 0) {
         float *J = (float *)calloc((size_t)m * 12, sizeof(float));
@@ -1546,6 +1571,17 @@ int orc_quickstep(orc_world *w, float h, int order_mode, const int *perm) {
                 for (int k = 0; k < 3; k++) im[6 + k] = w->b[b2].invMass * Ji[6 + k];
                 mul0_331(im + 9, invI + 12 * b2, Ji + 9);
             }
+        }
+        if (w->keep_rows) {
+            dbg_free(w);
+            w->dbg_m = m;
+            w->dbg_J = (float *)malloc(sizeof(float) * 12 * (size_t)m); memcpy(w->dbg_J, J, sizeof(float) * 12 * (size_t)m);
+            w->dbg_c = (float *)malloc(sizeof(float) * (size_t)m); memcpy(w->dbg_c, c, sizeof(float) * (size_t)m);
+            w->dbg_cfm = (float *)malloc(sizeof(float) * (size_t)m); memcpy(w->dbg_cfm, cfm, sizeof(float) * (size_t)m);
+            w->dbg_lo = (float *)malloc(sizeof(float) * (size_t)m); memcpy(w->dbg_lo, lo, sizeof(float) * (size_t)m);
+            w->dbg_hi = (float *)malloc(sizeof(float) * (size_t)m); memcpy(w->dbg_hi, hi, sizeof(float) * (size_t)m);
+            w->dbg_rhs = (float *)malloc(sizeof(float) * (size_t)m); memcpy(w->dbg_rhs, rhs, sizeof(float) * (size_t)m);
+            w->dbg_jb = (int *)malloc(sizeof(int) * 2 * (size_t)m); memcpy(w->dbg_jb, jb, sizeof(int) * 2 * (size_t)m);
         }
         float *fc = (float *)calloc(6 * (size_t)nb, sizeof(float));
         if (order_mode == 3) {

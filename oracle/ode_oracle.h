@@ -104,6 +104,11 @@ int orc_quickstep(orc_world *, float h, int order_mode, const int *perm);
 int orc_num_rows(const orc_world *);
 /* diagnostics of the last step: max |delta lambda| of last iteration etc. */
 void orc_last_lambda(const orc_world *, float *lambda, int n);
+/* test diagnostics: keep the rows of each step (J 12 floats, c, cfm/h, lo, hi, rhs, body pair per row,
+ * before SOR_LCP scales them by Ad) so that tests can evaluate constraint residuals and re-solve the
+ * same LCP with an independently written solver.  Returns the number of rows of the last step. */
+void orc_set_keep_rows(orc_world *, int on);
+int orc_last_rows(const orc_world *, float *J, float *c, float *cfm, float *lo, float *hi, float *rhs, int *jb, int n);
 
 /* reference's snapshot pack: GetTransformMat (src/main.c:602-622) per body/geom */
 void orc_pack_body_transform(const orc_world *, int b, float out16[16]);

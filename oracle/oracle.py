@@ -79,6 +79,8 @@ def lib():
     L.orc_quickstep.argtypes = [C.c_void_p, C.c_float, C.c_int, ip]
     L.orc_num_rows.argtypes = [C.c_void_p]
     L.orc_last_lambda.argtypes = [C.c_void_p, fp, C.c_int]
+    L.orc_set_keep_rows.argtypes = [C.c_void_p, C.c_int]
+    L.orc_last_rows.argtypes = [C.c_void_p, fp, fp, fp, fp, fp, fp, ip, C.c_int]
     L.orc_pack_body_transform.argtypes = [C.c_void_p, C.c_int, fp]
     L.orc_pack_geom_transform.argtypes = [C.c_void_p, C.c_int, fp]
     L.orc_q_to_r.argtypes = [fp, fp]
@@ -241,6 +243,20 @@ class OracleWorld:
         out = np.zeros(max(n, 1), np.float32)
         self.L.orc_last_lambda(self.w, _ptr(out), n)
         return out[:n]
+
+    def keep_rows(self, on=True):
+        self.L.orc_set_keep_rows(self.w, 1 if on else 0)
+
+    def last_rows(self):
+        """Rows of the last step (before SOR_LCP's Ad scaling): dict of J[m,12], c, cfm (= cfm/h), lo, hi, rhs,
+        jb[m,2] (body pair, -1 = none) and lam (the lambda the step ended with)."""
+        m = self.L.orc_last_rows(self.w, None, None, None, None, None, None, None, 0)
+        J = np.zeros((max(m, 1), 12), np.float32)
+        v = [np.zeros(max(m, 1), np.float32) for _ in range(5)]
+        jb = np.zeros((max(m, 1), 2), np.int32)
+        self.L.orc_last_rows(self.w, _ptr(J), *[_ptr(x) for x in v], jb.ctypes.data_as(C.POINTER(C.c_int)), m)
+        return {"J": J[:m], "c": v[0][:m], "cfm": v[1][:m], "lo": v[2][:m], "hi": v[3][:m], "rhs": v[4][:m], "jb": jb[:m],
+                "lam": self.last_lambda()[:m]}
 
     def body_transform(self, b):
         out = np.zeros(16, np.float32)
