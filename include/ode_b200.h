@@ -67,6 +67,16 @@ void dWorldSetForcesB200(dWorldID, const float *force_torque6, int n);
  * (src/main.c:602-622), written by the solver-tail kernel. Copies bodies [first, first+count). */
 void dWorldGetSnapshotB200(dWorldID, float *dst16, int first, int count, int blocking);
 const float *dWorldGetSnapshotDeviceB200(dWorldID);
+/* Snapshot record format.  0 (default): the 16 floats of GetTransformMat.  1: the same without its four constant
+ * floats -- columns 0..2 of the 4x4 (3 floats each), then the translation: 12 floats.  2: position (x y z 1) and the
+ * quaternion (w x y z): 8 floats.  dWorldGetSnapshotB200 then delivers count * {16, 12, 8} floats: the formats cut
+ * the per-tick device-to-host traffic to 3/4 and 1/2 (at 8 GPUs the host's PCIe complex, not the GPUs, bounds the
+ * end-to-end tick rate).  dSnapshotExpandB200 turns `count` compact records into the 16-float layout on the host,
+ * with `threads` worker threads, bit-identical to format 0 (format 2 re-evaluates dQtoR in the solver tail's own
+ * arithmetic).  Bodies spawned or moved since the last step are included with their current pose. */
+void dWorldSetSnapshotFormatB200(dWorldID, int format);
+int dWorldGetSnapshotFormatB200(dWorldID);
+void dSnapshotExpandB200(const float *compact, int format, int count, float *dst16, int threads);
 void dWorldWaitB200(dWorldID);
 /* halo exchange of a slab-decomposed world: gather the states of the listed
  * bodies into a DEVICE buffer / scatter received states into the listed (ghost) bodies.  16 floats per
@@ -127,6 +137,9 @@ void dWorldSetBigExtentB200(dWorldID, float extent);
  * object, in place of dGeomTriMeshDataBuildSingle (the reference ships res/teapot.obj and res/grassPlane.obj;
  * BASELINE config 2 uses the teapot as a static collision mesh).  Returns the triangle count or -1. */
 int dGeomTriMeshDataBuildFromOBJB200(dTriMeshDataID, const char *path);
+/* read a trimesh data object back: copies up to cap_verts vertices (3 floats each) and cap_tris triangles (3 ints
+ * each); returns the triangle count and stores the vertex count in *n_verts (either buffer may be NULL) */
+int dGeomTriMeshDataGetB200(dTriMeshDataID, float *verts3, int cap_verts, int *tris3, int cap_tris, int *n_verts);
 /* dWorldStep parity mode (the reference calls dWorldStep, src/main.c:213; libode solves its LCP exactly): let
  * dWorldStep run up to max_iters SOR/PGS sweeps and stop once the largest |delta lambda| of a sweep is below
  * tol (tol 0: always max_iters).  max_iters 0 (default): dWorldStep == dWorldQuickStep.  dWorldQuickStep is
@@ -151,6 +164,8 @@ void dWorldEnableTimingB200(dWorldID, int on);
 /* CUDA-event times of the last tick, ms: collide, prepare (manifolds+colouring+rows), solve (PGS
  * iterations + integrate + pack), whole tick */
 void dWorldGetTimingsB200(dWorldID, float out_ms[4]);
+/* the same tick split further: broadphase, narrowphase, prepare, solve, whole tick */
+void dWorldGetStageTimingsB200(dWorldID, float out_ms[5]);
 
 /* parity-test hooks: the broadphase pair list and the contacts of the last collide (blocking).
  * pairs2: (g1,g2) per pair in device order; returns the number of pairs (may exceed cap). */

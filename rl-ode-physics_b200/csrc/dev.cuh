@@ -27,7 +27,8 @@ struct BodyArrays {
     float4 *inv;   // 3 per body: rows of the world-frame inverse inertia; row 0 .w = invMass
     float4 *tmp;   // 2 per body: v/h + invM*f, w/h + invI*t
     float4 *fc;    // 2 per body: constraint acceleration accumulators (lin, ang)
-    float *snap;   // 16 per body: GetTransformMat layout
+    float *snap;   // snapshot records, 16 / 12 / 8 floats each by snap_fmt: GetTransformMat layout or its compact forms
+    int snap_fmt;  // 0: 16 floats; 1: the 12 non-constant ones; 2: pos + quaternion (8 floats)
     // colouring scratch
     unsigned long long *colmask;
     unsigned long long *prio;

@@ -5,7 +5,7 @@
 
 #include <algorithm>
 
-#include "engine_impl.h"
+#include "solver_dev.cuh"
 
 namespace ob {
 
@@ -63,6 +63,7 @@ Engine *eng_create(int device) {
     OB_CUDA(cudaMallocHost(&e->h_stats, sizeof(StepStats)));
     memset(e->h_stats, 0, sizeof(StepStats));
     for (int i = 0; i < 5; i++) OB_CUDA(cudaEventCreate(&e->ev[i]));
+    OB_CUDA(cudaEventCreate(&e->ev_bp));
     OB_CUDA(cudaMalloc(&e->M.count, sizeof(int)));
     OB_CUDA(cudaMalloc(&e->M.colour_start, 72 * sizeof(int)));
     OB_CUDA(cudaMalloc(&e->M.meta, 12 * sizeof(int)));
@@ -78,6 +79,8 @@ Engine *eng_create(int device) {
     if (const char *g = getenv("ODE_B200_COLOUR_SPREAD")) eng_set_colour_spread(e, atoi(g));
     if (const char *g = getenv("ODE_B200_CONTACT_UNITS")) e->contact_units = atoi(g);
     if (const char *g = getenv("ODE_B200_ENV_STAGE")) e->env_stage = atoi(g);
+    if (const char *g = getenv("ODE_B200_ENV_PAIR")) e->env_pair = atoi(g);
+    if (const char *g = getenv("ODE_B200_ENV_PAIR_ROWS")) e->env_pair_rows = atoi(g);
     if (const char *g = getenv("ODE_B200_L2_PERSIST")) e->l2_persist = atoi(g);
     if (const char *g = getenv("ODE_B200_ENV_FUSE")) e->env_fuse = atoi(g);
     if (const char *g = getenv("ODE_B200_TINY_SOLVER")) e->tiny_solver = atoi(g);
@@ -130,6 +133,7 @@ void eng_destroy(Engine *e) {
     if (e->tev[0]) { cudaEventDestroy(e->tev[0]); cudaEventDestroy(e->tev[1]); }
     if (e->h_stats) cudaFreeHost(e->h_stats);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    if (e->ev_bp) cudaEventDestroy(e->ev_bp);
     cudaStreamDestroy(e->st);
     cudaStreamDestroy(e->copy_st);
     cudaStreamDestroy(e->h2d_st);
@@ -271,6 +275,7 @@ void engine_ensure_capacity(Engine *e) {
         OB_CUDA(cudaStreamSynchronize(e->copy_st));
         dev_realloc(e->snap_buf[0], 16 * o, 16 * n, st); dev_realloc(e->snap_buf[1], 16 * o, 16 * n, st);
         B.snap = e->snap_buf[e->snap_cur];
+        B.snap_fmt = e->snap_fmt;
         dev_realloc(B.colmask, o, n, st, false);
         dev_realloc(B.prio, o, n, st, false);
         e->cap_b = (int)n;
@@ -566,6 +571,7 @@ void eng_sync_to_device(Engine *e) {
         e->bodies_dirty = false;
         e->forces_dirty = false;
         e->n_b_dev = b.n;
+        e->snap_stale = true;
         clear_dirty_bodies(e);
     } else if (!e->dirty_b.empty()) {
         const HostBodies &b = e->hb;
@@ -597,6 +603,7 @@ void eng_sync_to_device(Engine *e) {
         e->patch_inflight = true;
         if (grew) env_upload_tables(e, st);
         e->n_b_dev = b.n;
+        e->snap_stale = true; // spawned or moved bodies: their snapshot records are rebuilt on demand
         clear_dirty_bodies(e);
     }
     if (e->forces_dirty) { // bulk force upload (whole arrays)
@@ -719,9 +726,9 @@ static unsigned long long graph_key(Engine *e, bool step) {
         h = gk_mix(h, ((unsigned long long)e->meshes.m[m].nt << 32) | (unsigned)e->meshes.m[m].nv);
     }
     const int ints[] = {e->B.n, e->G.n, e->cap_b, e->cap_g, e->bp.cap_pairs, e->cs.stride, e->M.cap, e->S.cap, e->n_envs, e->max_contacts,
-                        e->env_group, e->contact_units, e->solver_mode, e->env_stage, e->env_fuse, e->colour_spread, e->broad_mode,
+                        e->env_group, e->contact_units, e->solver_mode, e->env_stage, e->env_pair, e->env_pair_rows, e->env_fuse, e->colour_spread, e->broad_mode,
                         e->tiny_solver, (int)e->keep_fc, e->EB.enabled, e->EB.single, e->EB.n_shared, e->EB.n_alive, e->E.contiguous,
-                        e->E.max_bodies, e->meshes.n, (int)e->have_device_contacts};
+                        e->E.max_bodies, e->meshes.n, (int)e->have_device_contacts, e->snap_fmt};
     h = gk_bytes(h, ints, sizeof(ints));
     h = gk_bytes(h, &e->params, sizeof(e->params));
     h = gk_bytes(h, &e->big_extent, sizeof(float));
@@ -769,6 +776,7 @@ void eng_collide(Engine *e, int max_contacts) {
     if (e->timing) OB_CUDA(cudaEventRecord(e->ev[0], e->st));
     auto enqueue = [&]() {
         broadphase_run(e->bp, e->G, e->B.pos, e->B.R, e->meshes, e->n_envs, e->big_extent, e->EB, e->d_stats, e->st);
+        if (e->timing) OB_CUDA(cudaEventRecord(e->ev_bp, e->st)); // (timing on: plain launches, never captured)
         narrowphase_run(e->bp, e->G, e->meshes, e->hmeshes, e->cs, max_contacts, e->d_stats, e->num_sms, e->st);
     };
     if (graphs_usable(e)) run_graphed(e, e->g_collide, graph_key(e, false), enqueue);
@@ -946,7 +954,12 @@ void eng_step_host_contacts(Engine *e, float h, const HostContact *contacts, int
     e->ev_valid = e->timing;
 }
 
-const float *eng_snapshot_device(Engine *e) { return e->snap_buf[e->snap_cur]; }
+static void snapshot_refresh_if_stale(Engine *e);
+const float *eng_snapshot_device(Engine *e) {
+    eng_sync_to_device(e);
+    snapshot_refresh_if_stale(e);
+    return e->snap_buf[e->snap_cur];
+}
 
 // called by both step entry points around solver_step: flip the snapshot buffer, make the kernel that
 // will overwrite it wait for a still-draining copy, apply pending force uploads
@@ -958,17 +971,51 @@ static void step_begin(Engine *e) {
     }
     e->snap_cur = next;
     e->B.snap = e->snap_buf[next];
+    e->B.snap_fmt = e->snap_fmt;
+    e->snap_stale = false; // the step's tail writes every body's record
 }
 static void step_end(Engine *e) { OB_CUDA(cudaEventRecord(e->ev_step_done, e->st)); }
+
+// Snapshot records straight from the body state: for bodies spawned or moved by the host since the last step
+// (the reference's broadcast loop reads dBodyGetPosition/Rotation of a freshly added body without a step in
+// between, src/main.c:178-182 then :221-242) and after a change of the snapshot format.
+__global__ void __launch_bounds__(256) k_snapshot_refresh(BodyArrays B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B.n) return;
+    snapshot_store(B, i, B.pos[i], B.quat[i], load_m3(B.R, i));
+}
+static void snapshot_refresh_if_stale(Engine *e) {
+    if (!e->snap_stale || e->B.n == 0) return;
+    e->B.snap = e->snap_buf[e->snap_cur];
+    e->B.snap_fmt = e->snap_fmt;
+    if (e->snap_copy_pending[e->snap_cur]) { // a copy of this buffer may still be draining
+        OB_CUDA(cudaStreamWaitEvent(e->st, e->ev_snap_copied[e->snap_cur], 0));
+        e->snap_copy_pending[e->snap_cur] = false;
+    }
+    k_snapshot_refresh<<<(unsigned)((e->B.n + 255) / 256), 256, 0, e->st>>>(e->B);
+    OB_CHECK_KERNEL("k_snapshot_refresh", e->st);
+    e->snap_stale = false;
+}
+void eng_set_snapshot_format(Engine *e, int fmt) {
+    if (fmt < 0 || fmt > 2) { fprintf(stderr, "libode_b200: snapshot format %d does not exist (0, 1, 2)\n", fmt); abort(); }
+    if (fmt == e->snap_fmt) return;
+    e->snap_fmt = fmt;
+    e->snap_stale = true;
+}
+int eng_snapshot_format(Engine *e) { return e->snap_fmt; }
 
 void eng_snapshot_to_host(Engine *e, float *dst, int first, int count, bool blocking) {
     OB_CUDA(cudaSetDevice(e->device));
     if (count <= 0) return;
+    eng_sync_to_device(e);
+    snapshot_refresh_if_stale(e);
+    const size_t stride = e->snap_fmt == 0 ? 16 : (e->snap_fmt == 1 ? 12 : 8); // floats per record
     // the copy runs on the copy stream, after the step that produced the snapshot, and overlaps later ticks
     const int cur = e->snap_cur;
     OB_CUDA(cudaEventRecord(e->ev_step_done, e->st));
     OB_CUDA(cudaStreamWaitEvent(e->copy_st, e->ev_step_done, 0));
-    OB_CUDA(cudaMemcpyAsync(dst, e->snap_buf[cur] + 16 * (size_t)first, (size_t)count * 64, cudaMemcpyDeviceToHost, e->copy_st));
+    OB_CUDA(cudaMemcpyAsync(dst, e->snap_buf[cur] + stride * (size_t)first, (size_t)count * stride * sizeof(float),
+                            cudaMemcpyDeviceToHost, e->copy_st));
     OB_CUDA(cudaEventRecord(e->ev_snap_copied[cur], e->copy_st));
     e->snap_copy_pending[cur] = true;
     if (blocking) OB_CUDA(cudaStreamSynchronize(e->copy_st));
@@ -1222,8 +1269,8 @@ void eng_unpack_states_device(Engine *e, const int *d_idx, int n, const float *d
 // Slot -> body (transform from the fused snapshot) or static geom (GetTransformMat of its pose).
 __global__ void __launch_bounds__(256) k_pack_msg(int n_slots, const int *__restrict__ slot_body, const int *__restrict__ slot_geom,
                                                    const int *__restrict__ slot_type, const float *__restrict__ slot_size,
-                                                   const unsigned *__restrict__ slot_col, const float *__restrict__ snap,
-                                                   const float4 *__restrict__ g_pos, const float4 *__restrict__ g_R, int msg_type,
+                                                   const unsigned *__restrict__ slot_col, const float4 *__restrict__ b_pos,
+                                                   const float4 *__restrict__ b_R, const float4 *__restrict__ g_pos, const float4 *__restrict__ g_R, int msg_type,
                                                    unsigned *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) out[0] = (unsigned)msg_type;
@@ -1235,10 +1282,12 @@ __global__ void __launch_bounds__(256) k_pack_msg(int n_slots, const int *__rest
     for (int k = 0; k < 16; k++) t[k] = 0.f;
     if (type != 0) {
         const int b = slot_body[i], g = slot_geom[i];
-        if (b >= 0) {
-            for (int k = 0; k < 16; k++) t[k] = snap[16 * (size_t)b + k];
-        } else if (g >= 0) { // GetTransformMat(pos, rot): columns of the result = rows of ODE's R
-            const float4 p = g_pos[g], r0 = g_R[3 * g], r1 = g_R[3 * g + 1], r2 = g_R[3 * g + 2];
+        if (b >= 0 || g >= 0) { // GetTransformMat(pos, rot): columns of the result = rows of ODE's R
+            // (from the body state itself, not the snapshot buffer: valid for bodies spawned since the last step and
+            // whatever the snapshot format)
+            const float4 p = b >= 0 ? b_pos[b] : g_pos[g];
+            const float4 r0 = b >= 0 ? b_R[3 * b] : g_R[3 * g], r1 = b >= 0 ? b_R[3 * b + 1] : g_R[3 * g + 1],
+                         r2 = b >= 0 ? b_R[3 * b + 2] : g_R[3 * g + 2];
             t[0] = r0.x; t[1] = r1.x; t[2] = r2.x;
             t[4] = r0.y; t[5] = r1.y; t[6] = r2.y;
             t[8] = r0.z; t[9] = r1.z; t[10] = r2.z;
@@ -1275,7 +1324,7 @@ size_t eng_pack_msg(Engine *e, void *dst, int msg_type, bool blocking) {
     eng_sync_to_device(e);
     const size_t bytes = 4 + (size_t)e->msg_slots * 84;
     k_pack_msg<<<(unsigned)((e->msg_slots + 255) / 256), 256, 0, e->st>>>(e->msg_slots, e->msg_body, e->msg_geom, e->msg_type,
-                                                                       e->msg_size, e->msg_col, e->snap_buf[e->snap_cur], e->G.pos,
+                                                                       e->msg_size, e->msg_col, e->B.pos, e->B.R, e->G.pos,
                                                                        e->G.R, msg_type, e->msg_out);
     OB_CHECK_KERNEL("k_pack_msg", e->st);
     OB_CUDA(cudaMemcpyAsync(dst, e->msg_out, bytes, cudaMemcpyDeviceToHost, e->st));
@@ -1324,6 +1373,19 @@ void eng_last_timings(Engine *e, float out[4]) {
     cudaEventElapsedTime(&out[1], e->ev[1], e->ev[3]); // prep + manifolds + colouring + rows
     cudaEventElapsedTime(&out[2], e->ev[3], e->ev[4]); // solve + integrate + pack
     cudaEventElapsedTime(&out[3], e->ev[0], e->ev[4]); // whole tick
+}
+
+// broadphase, narrowphase, prepare, solve, whole tick (ms) of the last tick run with timing on
+void eng_stage_timings(Engine *e, float out[5]) {
+    for (int i = 0; i < 5; i++) out[i] = 0.f;
+    if (!e->ev_valid) return;
+    OB_CUDA(cudaSetDevice(e->device));
+    OB_CUDA(cudaEventSynchronize(e->ev[4]));
+    if (cudaEventElapsedTime(&out[0], e->ev[0], e->ev_bp) != cudaSuccess) { out[0] = 0.f; (void)cudaGetLastError(); }
+    if (cudaEventElapsedTime(&out[1], e->ev_bp, e->ev[1]) != cudaSuccess) { out[1] = 0.f; (void)cudaGetLastError(); }
+    cudaEventElapsedTime(&out[2], e->ev[1], e->ev[3]);
+    cudaEventElapsedTime(&out[3], e->ev[3], e->ev[4]);
+    cudaEventElapsedTime(&out[4], e->ev[0], e->ev[4]);
 }
 
 int eng_export_solver_order(Engine *e, int *pair_g1, int *pair_g2, int *pair_k, int cap) {

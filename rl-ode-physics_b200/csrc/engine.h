@@ -188,6 +188,8 @@ void eng_step_device_contacts(Engine *, float h, const Surface &surf);
 void eng_step_host_contacts(Engine *, float h, const HostContact *contacts, int n);
 // snapshot: 16 floats per body in the reference's GetTransformMat layout (src/main.c:602-622)
 const float *eng_snapshot_device(Engine *);
+void eng_set_snapshot_format(Engine *, int fmt); // 0: 16 floats, 1: 12 floats, 2: pos + quaternion
+int eng_snapshot_format(Engine *);
 void eng_snapshot_to_host(Engine *, float *dst, int first, int count, bool blocking);
 // upload per-body external force/torque (6 floats per body) for the next step
 void eng_set_forces(Engine *, const float *f6, int n);
@@ -218,5 +220,6 @@ float eng_barrier_bench(Engine *, int iters); // microseconds per grid barrier (
 // event-timed sections of the last step, milliseconds (collide, prep+colour+rows, solve+tail)
 void eng_last_timings(Engine *, float out[4]);
 void eng_enable_timing(Engine *, int on);
+void eng_stage_timings(Engine *, float out[5]); // broadphase, narrowphase, prepare, solve, whole tick
 
 } // namespace ob

@@ -66,9 +66,12 @@ struct Engine {
     };
     TickGraph g_collide, g_step[2];
     int graphs = 1;
+    bool tiny_attr_set = false; // k_tiny_solve's dynamic shared memory limit raised on this engine's device
     int tiny_solver = 1; // small single worlds: one-CTA shared-memory solver (k_tiny_solve) before k_solve
     int env_fuse = 1;  // island solver: run body preparation and the integrate/pack tail inside k_env_solve
     int env_stage = 1; // island solver: stage body data in shared memory when possible
+    int env_pair = 1;      // island solver: lane-pair kernel (solver_env.cu) for per-contact units on contiguous envs
+    int env_pair_rows = 0; // ... with the first N row records of an env in shared memory (0: rows stay in global memory / L2)
     int solver_mode = 0; // 0 automatic, 1 force the global (grid-barrier) solver
     int contact_units = -1; // -1 automatic (per contact for batched worlds), 0 manifold units, 1 contact units
     int broad_mode = -1;   // -1 auto, 0 uniform grid, 1 all pairs per env
@@ -99,6 +102,7 @@ struct Engine {
     StepStats *d_stats = nullptr;
     StepStats *h_stats = nullptr; // pinned
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_bp = nullptr; // end of the broadphase inside the collide stage
     bool timing = false;
     float last_ms[4] = {0, 0, 0, 0};
     bool ev_valid = false;
@@ -110,6 +114,8 @@ struct Engine {
     cudaStream_t h2d_st = nullptr;
     float *snap_buf[2] = {nullptr, nullptr};
     int snap_cur = 0;                 // buffer the last step wrote (B.snap points at it)
+    int snap_fmt = 0;                 // record format (dWorldSetSnapshotFormatB200)
+    bool snap_stale = false;          // bodies were spawned / moved by the host since the records were written
     cudaEvent_t ev_step_done = nullptr;
     cudaEvent_t ev_snap_copied[2] = {nullptr, nullptr};
     bool snap_copy_pending[2] = {false, false};

@@ -862,12 +862,14 @@ void narrowphase_run(const BroadPhase &bp, GeomArrays g, MeshTable meshes, const
         int bv = ((hm.nv * 3 * (int)sizeof(float) + 15) / 16) * 16;
         int bt = ((hm.nt * 3 * (int)sizeof(int) + 15) / 16) * 16;
         int dyn = bv + bt;
-        static bool attr_set = false;
+        static bool attr_set[64] = {false}; // per device: function attributes live in the device's context
+        int dev = 0;
+        OB_CUDA(cudaGetDevice(&dev));
         const int max_dyn = 200 * 1024;
         if (dyn > max_dyn) { bv = 0; bt = 0; dyn = 0; } // mesh too large to stage: read through L2
-        if (!attr_set) {
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
             OB_CUDA(cudaFuncSetAttribute(k_np_sphere_trimesh, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
-            attr_set = true;
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
         }
         k_np_sphere_trimesh<<<(unsigned)num_sms, TM_WARPS * 32, dyn, st>>>(bp.counters, bp.pairs, g, meshes.m[m], m, cs,
                                                                           max_contacts, bv, bt, d_stats);

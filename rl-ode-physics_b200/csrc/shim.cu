@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <deque>
+#include <thread>
 #include <vector>
 
 #include "dmath.cuh"
@@ -383,6 +384,7 @@ extern "C" void dTestForceFullSyncB200(dWorldID w) {
 }
 extern "C" void dWorldEnableTimingB200(dWorldID w, int on) { eng_enable_timing(w->eng, on); }
 extern "C" void dWorldGetTimingsB200(dWorldID w, float out[4]) { eng_last_timings(w->eng, out); }
+extern "C" void dWorldGetStageTimingsB200(dWorldID w, float out[5]) { eng_stage_timings(w->eng, out); }
 extern "C" int dWorldGetNumBodiesB200(dWorldID w) { return eng_bodies(w->eng).n; }
 
 extern "C" void dWorldGetStatsB200(dWorldID w, dStepStatsB200 *out) {
@@ -780,6 +782,13 @@ extern "C" int dGeomTriMeshDataBuildFromOBJB200(dTriMeshDataID d, const char *pa
     const int nt = (int)d->tris.size() / 3;
     return nt > 0 ? nt : -1;
 }
+extern "C" int dGeomTriMeshDataGetB200(dTriMeshDataID d, float *verts3, int cap_verts, int *tris3, int cap_tris, int *n_verts) {
+    const int nv = (int)d->verts.size() / 3, nt = (int)d->tris.size() / 3;
+    if (n_verts) *n_verts = nv;
+    if (verts3 && cap_verts > 0) memcpy(verts3, d->verts.data(), sizeof(float) * 3 * (size_t)std::min(nv, cap_verts));
+    if (tris3 && cap_tris > 0) memcpy(tris3, d->tris.data(), sizeof(int) * 3 * (size_t)std::min(nt, cap_tris));
+    return nt;
+}
 extern "C" dGeomID dCreateTriMesh(dSpaceID s, dTriMeshDataID d, dTriCallback *, dTriArrayCallback *, dTriRayCallback *) {
     dxWorld *w = space_world(s);
     if (d->bound_world != w || d->mesh_id < 0) {
@@ -879,6 +888,49 @@ extern "C" void dWorldGetSnapshotB200(dWorldID w, float *dst, int first, int cou
     eng_snapshot_to_host(w->eng, dst, first, count, blocking != 0);
 }
 extern "C" const float *dWorldGetSnapshotDeviceB200(dWorldID w) { return eng_snapshot_device(w->eng); }
+extern "C" void dWorldSetSnapshotFormatB200(dWorldID w, int fmt) { eng_set_snapshot_format(w->eng, fmt); }
+extern "C" int dWorldGetSnapshotFormatB200(dWorldID w) { return eng_snapshot_format(w->eng); }
+
+// Host-side expansion of compact snapshot records into the reference's GetTransformMat layout (src/main.c:602-622).
+// Format 2 rebuilds R with dQtoR in the arithmetic the solver tail uses (dmath.cuh q_to_r, no FMA contraction in
+// either build), so the result equals the format-0 snapshot bit for bit (tests/test_api_gpu.py).
+static void expand_range(const float *src, int fmt, long i0, long i1, float *dst) {
+    if (fmt == 1) {
+        for (long i = i0; i < i1; i++) {
+            const float *s = src + 12 * i;
+            float *d = dst + 16 * i;
+            d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = 0.f;
+            d[4] = s[3]; d[5] = s[4]; d[6] = s[5]; d[7] = 0.f;
+            d[8] = s[6]; d[9] = s[7]; d[10] = s[8]; d[11] = 0.f;
+            d[12] = s[9]; d[13] = s[10]; d[14] = s[11]; d[15] = 1.f;
+        }
+    } else if (fmt == 2) {
+        for (long i = i0; i < i1; i++) {
+            const float *s = src + 8 * i;
+            float *d = dst + 16 * i;
+            const ob::M3 R = ob::q_to_r(make_float4(s[4], s[5], s[6], s[7]));
+            d[0] = R.r0.x; d[1] = R.r1.x; d[2] = R.r2.x; d[3] = 0.f;
+            d[4] = R.r0.y; d[5] = R.r1.y; d[6] = R.r2.y; d[7] = 0.f;
+            d[8] = R.r0.z; d[9] = R.r1.z; d[10] = R.r2.z; d[11] = 0.f;
+            d[12] = s[0]; d[13] = s[1]; d[14] = s[2]; d[15] = 1.f;
+        }
+    } else {
+        memcpy(dst + 16 * i0, src + 16 * i0, (size_t)(i1 - i0) * 64);
+    }
+}
+extern "C" void dSnapshotExpandB200(const float *src, int fmt, int count, float *dst16, int threads) {
+    if (count <= 0) return;
+    if (threads <= 1 || count < 4096) { expand_range(src, fmt, 0, count, dst16); return; }
+    if (threads > 64) threads = 64;
+    std::vector<std::thread> pool;
+    const long chunk = ((long)count + threads - 1) / threads;
+    for (int t = 1; t < threads; t++) {
+        const long a = t * chunk, b = std::min<long>((long)count, a + chunk);
+        if (a < b) pool.emplace_back(expand_range, src, fmt, a, b, dst16);
+    }
+    expand_range(src, fmt, 0, std::min<long>(count, chunk), dst16);
+    for (auto &th : pool) th.join();
+}
 
 // ------------------------------------------------------------------ collision
 

@@ -115,6 +115,10 @@ _SIGS = [
     ("dWorldSetForcesB200", None, [_vp, _fp, _i]),
     ("dWorldGetSnapshotB200", None, [_vp, _vp, _i, _i, _i]),
     ("dWorldGetSnapshotDeviceB200", _vp, [_vp]),
+    ("dWorldSetSnapshotFormatB200", None, [_vp, _i]), ("dWorldGetSnapshotFormatB200", _i, [_vp]),
+    ("dSnapshotExpandB200", None, [_vp, _i, _i, _vp, _i]),
+    ("dWorldGetStageTimingsB200", None, [_vp, _fp]),
+    ("dGeomTriMeshDataGetB200", _i, [_vp, _fp, _i, _ip, _i, _ip]),
     ("dWorldWaitB200", None, [_vp]),
     ("dWorldPackStatesDeviceB200", None, [_vp, _vp, _i, _vp]), ("dWorldUnpackStatesDeviceB200", None, [_vp, _vp, _i, _vp]),
     ("dWorldPackImpulsesDeviceB200", None, [_vp, _vp, _i, _vp]), ("dWorldAddImpulsesDeviceB200", None, [_vp, _vp, _i, _vp]),
@@ -305,11 +309,25 @@ class World:
         self.L.dWorldGetStateB200(self.w, _p(pos, _fp), _p(q, _fp), _p(lv, _fp), _p(av, _fp), _p(R, _fp))
         return {"pos": pos, "quat": q, "lvel": lv, "avel": av, "R": R}
 
+    SNAP_FLOATS = {0: 16, 1: 12, 2: 8}
+
+    def set_snapshot_format(self, fmt):
+        """0: GetTransformMat's 16 floats; 1: its 12 non-constant floats; 2: position + quaternion (8 floats)."""
+        self.L.dWorldSetSnapshotFormatB200(self.w, int(fmt))
+
     def snapshot(self, first=0, count=None):
+        """Snapshot records of bodies [first, first + count) in the world's current snapshot format."""
         n = self.L.dWorldGetNumBodiesB200(self.w)
         count = n - first if count is None else count
-        out = np.zeros((count, 16), np.float32)
+        out = np.zeros((count, self.SNAP_FLOATS[self.L.dWorldGetSnapshotFormatB200(self.w)]), np.float32)
         self.L.dWorldGetSnapshotB200(self.w, out.ctypes.data_as(C.c_void_p), first, count, 1)
+        return out
+
+    def expand_snapshot(self, compact, fmt, threads=4):
+        """dSnapshotExpandB200: compact records -> the reference's 16-float transforms (host side)."""
+        compact = np.ascontiguousarray(compact, np.float32)
+        out = np.zeros((len(compact), 16), np.float32)
+        self.L.dSnapshotExpandB200(compact.ctypes.data_as(C.c_void_p), int(fmt), len(compact), out.ctypes.data_as(C.c_void_p), threads)
         return out
 
     def stats(self):
@@ -319,6 +337,12 @@ class World:
 
     def enable_timing(self, on=True):
         self.L.dWorldEnableTimingB200(self.w, 1 if on else 0)
+
+    def stage_timings(self):
+        t = np.zeros(5, np.float32)
+        self.L.dWorldGetStageTimingsB200(self.w, _p(t, _fp))
+        return {"broadphase_ms": float(t[0]), "narrowphase_ms": float(t[1]), "prepare_ms": float(t[2]), "solve_ms": float(t[3]),
+                "tick_ms": float(t[4])}
 
     def timings(self):
         t = np.zeros(4, np.float32)

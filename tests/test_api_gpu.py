@@ -324,3 +324,109 @@ def test_dcollide_outside_the_space_traversal_matches_the_oracle():
         s.tick()
     assert s.pos(b1)[1] > 0.9
     s.close()
+
+
+@pytest.mark.parametrize("scene", ["soup", "batch"])
+def test_compact_snapshot_formats_expand_to_the_reference_layout_bit_for_bit(scene):
+    """dWorldSetSnapshotFormatB200: format 1 (the 12 non-constant floats) and format 2 (position + quaternion),
+    expanded on the host by dSnapshotExpandB200, must equal the 16-float GetTransformMat records (src/main.c:602-622)
+    byte for byte -- on the global solver's tail (soup) and on the island solver's fused tail (batch)."""
+    sc = scenes.random_soup(300, seed=5) if scene == "soup" else scenes.batched_worlds_scene(40, seed=4, spacing=0.7)
+    snaps = {}
+    for fmt in (0, 1, 2):
+        ew = util.engine_world(sc)
+        ew.set_snapshot_format(fmt)
+        for _ in range(12):
+            ew.tick(sc["h"])
+        raw = ew.snapshot()
+        assert raw.shape[1] == {0: 16, 1: 12, 2: 8}[fmt]
+        snaps[fmt] = ew.expand_snapshot(raw, fmt, threads=3)
+        if fmt == 2:                      # the window copy honours the record size
+            assert np.array_equal(ew.snapshot(first=7, count=9), raw[7:16])
+            st = ew.state()
+            assert np.array_equal(raw[:, :3], st["pos"]) and np.array_equal(raw[:, 4:], st["quat"])
+        ew.close()
+    assert np.array_equal(snaps[0].view(np.uint32), snaps[1].view(np.uint32))
+    assert np.array_equal(snaps[0].view(np.uint32), snaps[2].view(np.uint32))
+    assert (snaps[0][:, 15] == 1).all() and np.abs(snaps[0][:, :3]).max() <= 1.0 + 1e-6
+    # switching the format between ticks re-derives the records from the state, without a step
+    ew = util.engine_world(sc)
+    for _ in range(3):
+        ew.tick(sc["h"])
+    full = ew.snapshot()
+    ew.set_snapshot_format(2)
+    assert np.array_equal(ew.expand_snapshot(ew.snapshot(), 2), full)
+    ew.close()
+
+
+def test_snapshot_of_a_body_spawned_since_the_last_step():
+    """The reference's broadcast loop (src/main.c:221-242) may run right after MSGTYPE_S_NEW_BODY -> AddBody
+    (src/main.c:178-182) with no physics step in between: the snapshot and the MsgUpdateBodies wire image must
+    carry the spawn pose, not whatever the snapshot buffer held."""
+    sc = scenes.server_scene(seed=1, y_range=(1.0, 6.0))
+    ew = util.engine_world(sc)
+    for _ in range(5):
+        ew.tick(sc["h"])
+    n0 = ew.L.dWorldGetNumBodiesB200(ew.w)
+    R = np.float32([0, 0, 1, 0, 0, 1, 0, 0, -1, 0, 0, 0])          # a quarter turn about y
+    ew.spawn((1.5, 7.0, -2.0), "box", (0.4, 0.5, 0.6), R=R)
+    snap = ew.snapshot()
+    assert len(snap) == n0 + 1
+    want = np.float32([0, 0, -1, 0, 0, 1, 0, 0, 1, 0, 0, 0, 1.5, 7.0, -2.0, 1.0])   # GetTransformMat: transpose of R, then pos
+    assert np.array_equal(snap[n0], want)
+    # the other bodies keep the records of the last step
+    st = ew.state()
+    assert np.array_equal(snap[:n0, 12:15], st["pos"][:n0])
+    # moving an existing body without stepping is reflected too
+    b3 = ew.body_handle(3)
+    ew.L.dBodySetPosition(b3, 9.0, 8.0, 7.0)
+    assert np.array_equal(ew.snapshot()[3, 12:15], np.float32([9, 8, 7]))
+    ew.close()
+
+
+def test_boxes_settle_on_the_reference_terrain_mesh_loaded_from_obj(tmp_path):
+    """res/grassPlane.obj (266 triangles; committed as tests/golden/grassplane_mesh.npz) goes
+    through dGeomTriMeshDataBuildFromOBJB200 in Blender's OBJ dialect and serves as the static terrain: spheres and
+    boxes dropped on it come to rest on it, and the contacts equal those of the same mesh passed as arrays."""
+    import os
+    m = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grassplane_mesh.npz"))
+    verts, tris = m["verts"], m["tris"]
+    lines = ["# Blender", "o Plane"] + ["v %.6f %.6f %.6f" % tuple(v) for v in verts] + ["vn 0 1 0", "vt 0 0", "s off", "l 100 113"]
+    lines += ["f %d/1/1 %d/1/1 %d/1/1" % tuple(t + 1) for t in tris]
+    path = tmp_path / "grassPlane.obj"
+    path.write_text("\n".join(lines) + "\n")
+    L = odeb200.lib()
+    rs = np.random.RandomState(2)
+    spots = rs.uniform(-25, 25, size=(24, 2))
+    finals = []
+    for use_obj in (True, False):
+        s = Server()
+        d = C.c_void_p(L.dGeomTriMeshDataCreate())
+        if use_obj:
+            assert L.dGeomTriMeshDataBuildFromOBJB200(d, str(path).encode()) == 266
+            # %.6f text round trip: parse what the loader parsed so that both runs use the same floats
+            nv = C.c_int(0)
+            L.dGeomTriMeshDataGetB200(d, None, 0, None, 0, C.byref(nv))
+            v = np.zeros((nv.value, 3), np.float32)
+            L.dGeomTriMeshDataGetB200(d, v.ctypes.data_as(fp), nv.value, None, 0, C.byref(nv))
+            verts = v
+        else:
+            v = np.ascontiguousarray(verts); t = np.ascontiguousarray(tris)
+            L.dGeomTriMeshDataBuildSingle(d, v.ctypes.data, 12, len(v), t.ctypes.data, 3 * len(t), 12)
+        g = C.c_void_p(L.dCreateTriMesh(s.space, d, None, None, None))
+        s.geoms.append(g)
+        bodies = []
+        for i, (x, z) in enumerate(spots):
+            if i % 2:
+                bodies.append(s.add_body((x, 12.0, z), "sphere", (0.8,))[0])
+            else:
+                bodies.append(s.add_body((x, 12.0, z), "box", (1.2, 0.9, 1.5))[0])
+        for _ in range(360):
+            s.tick()
+        finals.append(np.stack([np.concatenate([s.pos(b), s.vel(b)]) for b in bodies]))
+        s.close()
+        L.dGeomTriMeshDataDestroy(d)
+    assert np.array_equal(finals[0], finals[1])
+    y = finals[0][:, 1]
+    assert y.min() > verts[:, 1].min() - 0.5 and y.max() < verts[:, 1].max() + 2.0      # on the terrain, not through it
+    assert np.abs(finals[0][::2, 3:]).max() < 1.0                                         # the boxes came to rest (spheres may still roll)

@@ -455,3 +455,38 @@ def test_exact_mode_satisfies_the_kkt_conditions_of_the_dense_lcp(oracle_lib):
     viol20, _ = lcp_residual(w.last_rows(), np.concatenate([s2["lvel"], s2["avel"]], axis=1).astype(np.float64), h)
     assert viol20.max() > 100 * viol.max()
     w.close()
+
+
+@pytest.mark.parametrize("h", [1.0 / 60.0, 1.0 / 120.0])
+def test_c1_600_ticks_oracle_residual_penetration_energy(oracle_lib, h):
+    """SURVEY 4(4) on the oracle alone (the GPU runs the same check alongside it in test_baseline_configs_gpu.py):
+    reference server scene, spawn heights y in [20, 50], h = 1/60 and the reference's 1/120 (src/main.c:208)."""
+    sc = scenes.server_scene(seed=1, h=h)
+    w = O.OracleWorld(gravity=sc["gravity"])
+    w.load_scene(sc)
+    w.keep_rows()
+    nd = 64
+
+    def energy(s):
+        return float(0.5 * (s["lvel"][:nd].astype(np.float64) ** 2).sum() + 0.5 * (s["avel"][:nd].astype(np.float64) ** 2).sum() +
+                     9.8 * s["pos"][:nd, 1].astype(np.float64).sum())
+    E0 = Eprev = energy(w.state())
+    max_inc = max_res = late_res = 0.0
+    vmax = np.sqrt(2 * 9.8 * 50.0) + 0.5
+    for step in range(600):
+        w.collide_all(8)
+        w.quickstep(h, order_mode=1)
+        rows = w.last_rows()
+        w.clear_contacts()
+        s = w.state()
+        E = energy(s)
+        max_inc, Eprev = max(max_inc, E - Eprev), E
+        if len(rows["c"]):
+            viol, _ = lcp_residual(rows, np.concatenate([s["lvel"], s["avel"]], axis=1).astype(np.float64), h)
+            max_res = max(max_res, float(viol.max()))
+            if step >= 450:
+                late_res = max(late_res, float(viol.max()))
+    assert max_res < 0.5 * vmax and late_res < 1.5
+    assert max_inc <= 1e-3 * E0 and Eprev < 0.1 * E0
+    assert s["pos"][:nd, 1].min() > 0.5
+    w.close()

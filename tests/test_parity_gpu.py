@@ -183,31 +183,6 @@ def _max_penetration(ew, sc):
     return float(d.max()) if len(d) else 0.0
 
 
-def test_c1_600_steps_bounded_residual():
-    sc = scenes.server_scene(seed=1)
-    ew = util.engine_world(sc)
-    n_dyn = 64
-    ke_peak, pen_max = 0.0, 0.0
-    for step in range(600):
-        ew.collide(8)
-        if step % 20 == 0:
-            pen_max = max(pen_max, _max_penetration(ew, sc))
-        ew.step(sc["h"])
-        if step % 50 == 49:
-            s = ew.state()
-            assert np.isfinite(s["pos"]).all()
-            ke_peak = max(ke_peak, float((s["lvel"][:n_dyn] ** 2).sum()))
-    s = ew.state()
-    # dropped from y in [20,50]: impact speed <= sqrt(2 g 50) ~ 31 m/s; nothing may exceed it
-    assert np.abs(s["lvel"]).max() < 35.0
-    assert pen_max < 0.6                         # fast impacts penetrate, but stay bounded
-    # everything ends inside the arena, above the floor (top at y = 0.5), the kinematic spheres untouched
-    assert s["pos"][:n_dyn, 1].min() > 0.5 and s["pos"][:n_dyn, 1].max() < 12.0
-    assert np.array_equal(s["pos"][n_dyn:, 1], np.full(4, 2.0, np.float32))
-    assert np.allclose(np.linalg.norm(s["quat"], axis=1), 1.0, atol=1e-5)
-    ew.close()
-
-
 def test_c1_at_rest_constraint_residual():
     """After settling, the solved velocities satisfy the contact rows: normal relative velocity at
     every active contact stays within the ERP push-out bound and bodies stop moving."""
@@ -341,20 +316,27 @@ def _surface(mode=0, **kw):
     return so, se
 
 
-@pytest.mark.parametrize("case", ["mu0", "mu_finite", "mu2", "approx1", "soft", "slip_motion"])
+def _surface_case(case):
+    B, MU2, SOFT_ERP, SOFT_CFM = 0x004, 0x001, 0x008, 0x010
+    M1, M2, MN, S1, S2, A1 = 0x020, 0x040, 0x080, 0x100, 0x200, 0x3000
+    return {
+        "mu0": lambda: _surface(B, mu=0.0, bounce=0.1, bounce_vel=0.05),
+        "mu_finite": lambda: _surface(B, mu=0.7, bounce=0.3, bounce_vel=0.2),
+        "mu2": lambda: _surface(MU2, mu=0.9, mu2=0.2),
+        "approx1": lambda: _surface(A1 | B, mu=0.5, bounce=0.2, bounce_vel=0.1),
+        "soft": lambda: _surface(SOFT_ERP | SOFT_CFM | B, mu=float("inf"), soft_erp=0.5, soft_cfm=1e-3, bounce=0.2, bounce_vel=0.1),
+        "slip_motion": lambda: _surface(S1 | S2 | M1 | M2 | MN, mu=2.0, slip1=0.01, slip2=0.02, motion1=0.1, motion2=-0.2, motionN=0.05),
+    }[case]()
+
+
+SURFACE_CASES = ["mu0", "mu_finite", "mu2", "approx1", "soft", "slip_motion"]
+
+
+@pytest.mark.parametrize("case", SURFACE_CASES)
 def test_surface_modes_parity(case):
     """dSurfaceParameters variants beyond the reference's (bounce, mu=inf): frictionless (1 row),
     box friction, mu2, friction pyramid approximation (findex), soft ERP/CFM, slip and motion."""
-    B, MU2, SOFT_ERP, SOFT_CFM = 0x004, 0x001, 0x008, 0x010
-    M1, M2, MN, S1, S2, A1 = 0x020, 0x040, 0x080, 0x100, 0x200, 0x3000
-    so, se = {
-        "mu0": _surface(B, mu=0.0, bounce=0.1, bounce_vel=0.05),
-        "mu_finite": _surface(B, mu=0.7, bounce=0.3, bounce_vel=0.2),
-        "mu2": _surface(MU2, mu=0.9, mu2=0.2),
-        "approx1": _surface(A1 | B, mu=0.5, bounce=0.2, bounce_vel=0.1),
-        "soft": _surface(SOFT_ERP | SOFT_CFM | B, mu=float("inf"), soft_erp=0.5, soft_cfm=1e-3, bounce=0.2, bounce_vel=0.1),
-        "slip_motion": _surface(S1 | S2 | M1 | M2 | MN, mu=2.0, slip1=0.01, slip2=0.02, motion1=0.1, motion2=-0.2, motionN=0.05),
-    }[case]
+    so, se = _surface_case(case)
     sc = scenes.random_soup(160, seed=13)
     ow, ew = util.load_both(sc)
     ew.set_surface(se)
@@ -364,6 +346,25 @@ def test_surface_modes_parity(case):
         es, os_ = ew.state(), ow.state()
         for k in ("pos", "quat", "lvel", "avel"):
             assert util.rel_err(es[k], os_[k]).max() <= STATE_RTOL, (case, step, k)
+    ew.close()
+
+
+@pytest.mark.parametrize("case", SURFACE_CASES)
+def test_surface_modes_parity_on_the_island_path(case):
+    """the same surfaces on batched worlds: the lane-pair island solver (solver_env.cu) bakes the world's one surface
+    into its row records (rows per contact, the three CFMs, friction limits) -- against the oracle, world by world"""
+    so, se = _surface_case(case)
+    sc = scenes.batched_worlds_scene(6, seed=4, spacing=0.7)
+    ow, ew = util.load_both(sc)
+    ew.set_surface(se)
+    for step in range(12):
+        ew.tick(sc["h"])
+        util.oracle_tick_in_engine_order(ow, ew, sc["h"], surf=so, rows_per_contact=1 if case == "mu0" else 3)
+        es, os_ = ew.state(), ow.state()
+        for k in ("pos", "quat", "lvel", "avel"):
+            assert util.rel_err(es[k], os_[k]).max() <= STATE_RTOL, (case, step, k)
+    st = ew.stats()
+    assert st["n_contacts"] > 30 and st["flags"] == 0
     ew.close()
 
 
@@ -444,12 +445,13 @@ def _crowded_scene(n_small=90, batched=False):
     return scenes.finalize(sc)
 
 
-@pytest.mark.parametrize("batched", [False, True])
+@pytest.mark.parametrize("batched", [False, True, "contacts"])
 def test_more_than_64_neighbours_overflow_class(batched):
-    sc = _crowded_scene(90, batched)
+    sc = _crowded_scene(90, bool(batched))
     ow, ew = util.load_both(sc)
-    if batched:
+    if batched is True:
         ew.set_contact_units(0)          # manifold units on the island path too: 90 + 4 manifolds on the slab
+    # "contacts": the batched default -- per-contact units, the lane-pair island solver's serial overflow class
     for step in range(3):
         ew.tick(sc["h"])
         st = ew.stats()

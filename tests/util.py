@@ -51,9 +51,13 @@ def load_both(sc, iters=20):
     return ow, ew
 
 
-def oracle_tick_in_engine_order(ow, ew, h, maxc=8, surf=None, rows_per_contact=3):
+def oracle_tick_in_engine_order(ow, ew, h, maxc=8, surf=None, rows_per_contact=3, geom_map=None, order=None):
     """Run the oracle's collide + QuickStep with the row order the engine used for its last step.
-    Returns the number of oracle contacts."""
+    Returns the number of oracle contacts.
+
+    geom_map: when the oracle world is a PART of the engine's world (one env of a batch), an int array
+    engine geom id -> oracle geom id (-1: not in the oracle world); the engine's solver order is then
+    restricted to the units whose geoms are all in the oracle world.  order: a solver order fetched earlier."""
     surf = surf or O.reference_surface()
     ow.clear_contacts()
     nc = ow.collide_all(maxc, surf)
@@ -77,7 +81,12 @@ def oracle_tick_in_engine_order(ow, ew, h, maxc=8, surf=None, rows_per_contact=3
                 rows += rows_per_contact
             j += 1
     assert j == nc
-    eg1, eg2, ek = ew.solver_order()
+    eg1, eg2, ek = order if order is not None else ew.solver_order()
+    if geom_map is not None:
+        gm = np.asarray(geom_map)
+        m1, m2 = gm[eg1], gm[eg2]
+        keep = (m1 >= 0) & (m2 >= 0)
+        eg1, eg2, ek = m1[keep], m2[keep], ek[keep]
     perm = []
     for a, b, k in zip(eg1, eg2, ek):
         jj = joint_of[(int(a), int(b), int(k))]
