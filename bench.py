@@ -41,6 +41,10 @@ def parse_args():
     ap.add_argument("--worlds-per-gpu", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary blocks (C3 roofline at N=1; strong scaling and C5 at N>1)")
+    ap.add_argument("--snapshot-format", type=int, default=2, choices=[0, 1, 2],
+                    help="record format of the end-to-end leg's per-tick snapshot copy: 0 = 16 floats (GetTransformMat), "
+                         "1 = its 12 non-constant floats, 2 = position + quaternion (8 floats)")
     ap.add_argument("--settle", type=int, default=-1)
     ap.add_argument("--slab-cols", type=int, default=128, help="C5: lattice columns (x) per GPU; z = 1024, y = 16")
     ap.add_argument("--halo", default="dynamic", choices=["dynamic", "static"],
@@ -58,7 +62,7 @@ def build_scene(workload, rank, worlds_per_gpu):
     if workload == "C4":
         first = rank * worlds_per_gpu
         sc = scenes.batched_worlds_scene(worlds_per_gpu, seed=4, first_world=first)
-        desc = "C4: %d independent 128-body worlds (plane + 8x4x4 lattice) per GPU, dt=1/60, QuickStep 20 iters" % worlds_per_gpu
+        desc = C4_DESC % worlds_per_gpu
     elif workload == "C3":
         sc = scenes.pile_scene(256, 256, 16, seed=3)
         desc = "C3: 1,048,576-body random box/sphere pile on a plane + 4 wall planes, dt=1/60, QuickStep 20 iters"
@@ -148,36 +152,33 @@ def algorithmic_bytes(st, n_geoms, iters=20):
     }
 
 
-def layout_bytes(st, n_bodies, iters=20):
-    """Minimum traffic of THIS engine's solver layout: 112 B per contact-iteration (5 float4
-    row records + lambda read/write) and per manifold-iteration 16 B record + per body end 80 B read (fc, world
-    inverse inertia) + 32 B fc write; the fused tail moves 312 B per body."""
-    C, M = st["n_contacts"], st["n_manifolds"]
-    two = st["n_rows2"] / max(1, st["n_rows"])
-    return iters * (112 * C + M * (16 + (1 + two) * 112)) + 312 * n_bodies
+def compulsory_bytes(st, n_bodies, workload):
+    """Once-through HBM bytes of the dominant kernel (what an ideal kernel that keeps every row on chip would still have
+    to move).  Island solver (C4, one fused kernel per solve): per body the state in and out + snapshot (SURVEY 8d:
+    312 B), per contact the narrowphase record (pos/depth + normal: 32 B) and the unit record (16 B).  Global solver
+    (C3): the same plus the row records, which it cannot keep on chip: 96 B written by k_rows is not its traffic, but
+    each of the 20 sweeps reads 96 B and writes 16 B per contact."""
+    C = st["n_contacts"]
+    base = 312 * n_bodies + 48 * C
+    if workload == "C4":
+        return base
+    return base + 20 * 112 * C
 
 
-def cpu_port_sample(n_worlds, settle, ticks):
-    """Single-thread oracle (CPU restatement of libode's QuickStep path, not libode) on n_worlds C4 worlds."""
-    import oracle as O
-    from odeb200 import scenes
-    sc = scenes.batched_worlds_scene(n_worlds, seed=4)
-    w = O.OracleWorld(gravity=sc["gravity"])
-    w.load_scene(sc)
-    for _ in range(settle):
-        w.tick(sc["h"])
-    t0 = time.perf_counter()
-    for _ in range(ticks):
-        w.tick(sc["h"])
-    dt = time.perf_counter() - t0
-    w.close()
-    return n_worlds * 128 * ticks / dt
+def kernel_counters(workload):
+    """ncu counters of the dominant kernel from the committed capture (profiles/kernel_counters.json), stamped with the
+    commit and the contact count they were measured at; never re-measured inside a bench run (a number taken under a
+    profiler is not a bench value, and ncu is not run by bench.py)."""
+    path = os.path.join(ROOT, "profiles", "kernel_counters.json")
+    try:
+        return json.load(open(path)).get(workload)
+    except Exception:
+        return None
 
 
-def run_reference(args, rank):
-    """--impl reference: the CPU port on all host threads, one block of worlds per thread."""
-    if rank != 0:
-        return
+def cpu_port_all_cores(steps, warmup, settle):
+    """The CPU oracle port (restatement of libode's QuickStep path, not libode) on every host thread: one block of 16
+    C4 worlds per thread, each thread stepping its own OracleWorld (ctypes releases the GIL inside the C call)."""
     import oracle as O
     from odeb200 import scenes
     O.build()
@@ -193,27 +194,43 @@ def run_reference(args, rank):
     def run(n):
         def work(w, h):
             for _ in range(n):
-                w.tick(h)      # ctypes releases the GIL inside the C call
+                w.tick(h)
         ths = [threading.Thread(target=work, args=wh) for wh in worlds]
         for th in ths:
             th.start()
         for th in ths:
             th.join()
 
-    run(SETTLE["C4"] if args.settle < 0 else args.settle)
-    run(max(args.warmup, 0))
+    run(settle)
+    run(max(warmup, 0))
     t0 = time.perf_counter()
-    run(args.steps)
+    run(steps)
     dt = time.perf_counter() - t0
+    for w, _ in worlds:
+        w.close()
     bodies = cores * wpt * 128
-    value = bodies * args.steps / dt
-    sample = "%d threads x %d C4 worlds (%d bodies), %d ticks after %d settle ticks" % (cores, wpt, bodies, args.steps, SETTLE["C4"])
+    sample = ("%d host threads x %d C4 worlds (%d bodies = a sample of the %d-world workload; worlds are independent, so "
+              "per-body throughput carries over), %d ticks after %d settle ticks; CPU restatement of libode's QuickStep path "
+              "(oracle port), not libode" % (cores, wpt, bodies, 8192, steps, settle))
+    return bodies * steps / dt, dt / steps * 1e3, cores, sample
+
+
+C4_DESC = "C4: %d independent 128-body worlds (plane + 8x4x4 lattice) per GPU, dt=1/60, QuickStep 20 iters"
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU port on all host threads, on a bounded sample of the GPU arm's workload."""
+    if rank != 0:
+        return
+    settle = SETTLE["C4"] if args.settle < 0 else args.settle
+    value, ms, cores, sample = cpu_port_all_cores(args.steps, args.warmup, settle)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C4 sample: " + sample, "note": "CPU restatement of libode's QuickStep path (oracle port), not libode: "
-                   "libode is an un-vendored, un-versioned dependency of the reference and is not installable here"},
+        "config": {"workload": C4_DESC % args.worlds_per_gpu, "sample": sample,
+                   "note": "libode is an un-vendored, un-versioned dependency of the reference and is not installable here: the "
+                           "reference arm is the oracle port; each step advances the sample, not the whole workload"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -237,6 +254,115 @@ def bind_to_gpu_numa_node(local_rank):
         return prev
     except Exception:
         return None
+
+
+def timed_device_ticks(L, ew, do_tick, steps, sharding, torch):
+    """exactly `steps` ticks between a barrier + synchronize on both sides; CUDA events on the engine's stream"""
+    ew.wait()
+    sharding.barrier()
+    torch.cuda.synchronize()
+    L.dWorldTimerStartB200(ew.w)
+    for _ in range(steps):
+        do_tick()
+    L.dWorldTimerStopB200(ew.w)
+    ew.wait()
+    torch.cuda.synchronize()
+    sharding.barrier()
+    return float(L.dWorldTimerElapsedB200(ew.w))
+
+
+def timed_e2e(L, ew, do_tick, n_bodies, steps, fmt, expand, sharding, torch, odeb200):
+    """The same ticks through the C ABI with HOST buffers: per tick the H2D copy of the per-body force/torque input
+    (24 B/body, pinned) and the D2H copy of the step's snapshot (64 / 48 / 32 B per body by format), both inside the
+    timed region; `expand` additionally rebuilds the reference's 16-float transforms on the host (dSnapshotExpandB200)."""
+    C = odeb200.C
+    floats = {0: 16, 1: 12, 2: 8}[fmt]
+    L.dWorldSetSnapshotFormatB200(ew.w, fmt)
+    f6 = torch.zeros((n_bodies, 6), dtype=torch.float32).pin_memory()
+    snap = [torch.empty((n_bodies, floats), dtype=torch.float32).pin_memory() for _ in range(2)]
+    full = torch.empty((n_bodies, 16), dtype=torch.float32) if expand else None
+    fp = C.cast(f6.data_ptr(), C.POINTER(C.c_float))
+    threads = max(1, (os.cpu_count() or 1) // max(1, sharding.dist_env()[2]))
+
+    def step(i):
+        L.dWorldSetForcesB200(ew.w, fp, n_bodies)
+        do_tick()
+        L.dWorldGetSnapshotB200(ew.w, snap[i & 1].data_ptr(), 0, n_bodies, 0)
+        if expand and i > 0:      # expand tick i-1's records (already on the host) while tick i runs on the GPU
+            L.dSnapshotExpandB200(snap[(i - 1) & 1].data_ptr(), fmt, n_bodies, full.data_ptr(), threads)
+
+    for i in range(3):
+        step(i)
+    ew.wait()
+    sharding.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    ew.wait()
+    if expand:
+        L.dSnapshotExpandB200(snap[(steps - 1) & 1].data_ptr(), fmt, n_bodies, full.data_ptr(), threads)
+    torch.cuda.synchronize()
+    dt_ms = (time.perf_counter() - t0) * 1e3
+    sharding.barrier()
+    ok = float(snap[0][0, 3 if fmt == 2 else floats - 1]) == 1.0 if fmt != 1 else True
+    assert ok and (not expand or float(full[n_bodies - 1, 15]) == 1.0)
+    L.dWorldSetSnapshotFormatB200(ew.w, 0)
+    return dt_ms
+
+
+def secondary_c3(L, odeb200, local_rank, peak):
+    """The HBM-bound config (BASELINE config 3, the one north_star's ">= 50 % of HBM" is about) on this rank's GPU:
+    20 timed ticks + per-stage CUDA-event times -> solver and broadphase fractions of the measured HBM peak."""
+    sc, desc = build_scene("C3", 0, 0)
+    nb, ng = len(sc["bodies"]["pos"]), len(sc["geoms"]["type"])
+    ew = odeb200.World(gravity=sc["gravity"], device=local_rank)
+    ew.load_scene(sc)
+    h = sc["h"]
+    for _ in range(SETTLE["C3"] + 5):
+        ew.tick(h)
+    ew.wait()
+    L.dWorldTimerStartB200(ew.w)
+    for _ in range(20):
+        ew.tick(h)
+    L.dWorldTimerStopB200(ew.w)
+    ms = float(L.dWorldTimerElapsedB200(ew.w)) / 20
+    st = ew.stats()
+    ew.enable_timing(True)
+    tm = []
+    for _ in range(6):
+        ew.tick(h)
+        ew.wait()
+        tm.append(ew.stage_timings())
+    ew.enable_timing(False)
+    ew.close()
+    tmean = {k: float(np.mean([t[k] for t in tm])) for k in tm[0]}
+    ab = algorithmic_bytes(st, ng)
+    solver_alg = ab["solver"] + ab["integrate_pack"]
+    kc = kernel_counters("C3") or {}
+    out = {
+        "workload": desc, "ms_per_step": ms, "value": nb / (ms * 1e-3), "unit": UNIT, "stage_ms": tmean,
+        "counts": {k: st[k] for k in ("n_pairs", "n_contacts", "n_manifolds", "n_rows1", "n_rows2", "n_colours")},
+        "solver": {"kernel": "k_solve (20 PGS sweeps x colour phases separated by grid barriers, fused integrate + snapshot pack)",
+                   "bound": "hbm", "algorithmic_bytes_per_launch": solver_alg, "compulsory_bytes_per_launch": compulsory_bytes(st, nb, "C3"),
+                   "kernel_ms": tmean["solve_ms"],
+                   "achieved": solver_alg / (tmean["solve_ms"] * 1e-3) / 1e9, "unit": "GB/s",
+                   "frac": solver_alg / (tmean["solve_ms"] * 1e-3) / 1e9 / peak,
+                   "compulsory_frac": compulsory_bytes(st, nb, "C3") / (tmean["solve_ms"] * 1e-3) / 1e9 / peak,
+                   "note": "achieved = SURVEY 8(d) algorithmic bytes (a row-streaming QuickStep: 228 / 132 B per row-sweep) / event-timed "
+                           "kernel time; compulsory = this engine's own layout (96 B read + 16 B written per contact-sweep, 312 B per "
+                           "body, 48 B per contact once); ncu DRAM bytes of the committed capture in `ncu`",
+                   "ncu": kc.get("k_solve")},
+        "broadphase": {"kernels": "k_geom_update, k_cell_keys, radix sort, k_sorted_records, k_sweep<count>, scan, k_sweep<fill>",
+                       "bound": "issue / latency (ncu: lanes per instruction, L1-served candidate reads)",
+                       "algorithmic_bytes": ab["broadphase"], "stage_ms": tmean["broadphase_ms"],
+                       "achieved": ab["broadphase"] / (tmean["broadphase_ms"] * 1e-3) / 1e9, "unit": "GB/s",
+                       "frac": ab["broadphase"] / (tmean["broadphase_ms"] * 1e-3) / 1e9 / peak,
+                       "ncu": kc.get("k_sweep")},
+        "narrowphase": {"algorithmic_bytes": ab["narrowphase"], "stage_ms": tmean["narrowphase_ms"],
+                        "frac": ab["narrowphase"] / (tmean["narrowphase_ms"] * 1e-3) / 1e9 / peak},
+    }
+    return out
 
 
 def main():
@@ -306,22 +432,13 @@ def main():
     # ---------------- device-resident throughput: W warm-up ticks, then exactly K timed ticks
     sampler = ClockSampler(local_rank)
     sampler.start()                  # nvidia-smi needs ~1 s to start; only samples taken under load are kept
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
         do_tick()
     ew.wait()
     sampler.mark()
-    sharding.barrier()
-    torch.cuda.synchronize()
     launches0 = L.dGetKernelLaunchCountB200()
-    solve_ms = []
-    L.dWorldTimerStartB200(ew.w)
-    for _ in range(args.steps):
-        do_tick()
-    L.dWorldTimerStopB200(ew.w)
-    ew.wait()
-    torch.cuda.synchronize()
-    sharding.barrier()
-    elapsed_ms = float(L.dWorldTimerElapsedB200(ew.w))
+    elapsed_ms = timed_device_ticks(L, ew, do_tick, args.steps, sharding, torch)
     launches = L.dGetKernelLaunchCountB200() - launches0
     clocks = sampler.stop()
     st = ew.stats()
@@ -329,98 +446,123 @@ def main():
     # eight more live ticks right behind the timed ones (stage events are off inside the timed region: with them
     # the engine does not replay the tick as a CUDA graph)
     ew.enable_timing(True)
+    stage = []
     for _ in range(8):
         do_tick()
         ew.wait()
-        solve_ms.append(ew.timings()["solve_ms"])
-    tm = ew.timings()
+        stage.append(ew.stage_timings())
     ew.enable_timing(False)
+    tm = {k: float(np.mean([t[k] for t in stage])) for k in stage[0]}
     t_max = sharding.all_reduce_max(elapsed_ms, dev)
     total_bodies = sharding.all_reduce_sum(n_bodies, dev)
     value = total_bodies * args.steps / (t_max * 1e-3)
 
-    # ---------------- end to end through the C ABI with HOST buffers (pinned): per tick H2D of the per-body
-    # force/torque input and D2H of the fused snapshot, both inside the timed region
+    # ---------------- end to end through the C ABI with HOST buffers (pinned)
     e2e = None
     if not args.no_e2e:
-        f6 = torch.zeros((n_bodies, 6), dtype=torch.float32).pin_memory()
-        snap = [torch.empty((n_bodies, 16), dtype=torch.float32).pin_memory() for _ in range(2)]
-        fp = odeb200.C.cast(f6.data_ptr(), odeb200.C.POINTER(odeb200.C.c_float))
-        for i in range(3):
-            L.dWorldSetForcesB200(ew.w, fp, n_bodies)
-            do_tick()
-            L.dWorldGetSnapshotB200(ew.w, snap[i & 1].data_ptr(), 0, n_bodies, 0)
-        ew.wait()
-        sharding.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            L.dWorldSetForcesB200(ew.w, fp, n_bodies)
-            do_tick()
-            L.dWorldGetSnapshotB200(ew.w, snap[i & 1].data_ptr(), 0, n_bodies, 0)
-        ew.wait()
-        torch.cuda.synchronize()
-        dt_ms = (time.perf_counter() - t0) * 1e3
-        sharding.barrier()
-        dt_max = sharding.all_reduce_max(dt_ms, dev)
-        assert float(snap[0][0, 15]) == 1.0 and float(snap[1][n_bodies - 1, 15]) == 1.0
-        e2e = {"value": total_bodies * args.steps / (dt_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n_bodies * 24 * world),
-               "d2h_bytes_per_step": int(n_bodies * 64 * world), "ms_per_step": dt_max / args.steps}
+        fmt = args.snapshot_format
+        rec = {0: 64, 1: 48, 2: 32}
+        dt = sharding.all_reduce_max(timed_e2e(L, ew, do_tick, n_bodies, args.steps, fmt, False, sharding, torch, odeb200), dev)
+        e2e = {"value": total_bodies * args.steps / (dt * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n_bodies * 24 * world),
+               "d2h_bytes_per_step": int(n_bodies * rec[fmt] * world), "ms_per_step": dt / args.steps,
+               "snapshot_format": {0: "16 floats per body: the reference's GetTransformMat layout (src/main.c:602-622)",
+                                   1: "12 floats per body: GetTransformMat without its four constant floats",
+                                   2: "8 floats per body: position + quaternion (dBodyGetPosition / dBodyGetQuaternion)"}[fmt]}
+        if fmt != 0 and not args.no_secondary:
+            # the same loop with the full 64 B records, and with the compact records expanded to them on the host
+            d0 = sharding.all_reduce_max(timed_e2e(L, ew, do_tick, n_bodies, args.steps, 0, False, sharding, torch, odeb200), dev)
+            dx = sharding.all_reduce_max(timed_e2e(L, ew, do_tick, n_bodies, args.steps, fmt, True, sharding, torch, odeb200), dev)
+            e2e["variants"] = {
+                "format0_64B_per_body": {"value": total_bodies * args.steps / (d0 * 1e-3), "ms_per_step": d0 / args.steps,
+                                         "d2h_bytes_per_step": int(n_bodies * 64 * world)},
+                "compact_then_expanded_on_host": {"value": total_bodies * args.steps / (dx * 1e-3), "ms_per_step": dx / args.steps,
+                                                  "note": "dSnapshotExpandB200 rebuilds the 16-float transforms of tick t-1 on "
+                                                          "the host's threads while tick t runs"}}
+
+    # ---------------- BASELINE config 4 as written: 8192 worlds in TOTAL, sharded over the GPUs (strong scaling)
+    strong = None
+    if world > 1 and args.workload == "C4" and not args.no_secondary:
+        first, cnt = sharding.shard_range(args.worlds_per_gpu, rank, world)
+        from odeb200 import scenes
+        sc2 = scenes.batched_worlds_scene(cnt, seed=4, first_world=first)
+        nb2 = len(sc2["bodies"]["pos"])
+        ew2 = odeb200.World(gravity=sc2["gravity"], device=local_rank)
+        ew2.load_scene(sc2)
+        tick2 = lambda: ew2.tick(h)  # noqa: E731
+        for _ in range(settle + warmup):
+            tick2()
+        ms2 = sharding.all_reduce_max(timed_device_ticks(L, ew2, tick2, args.steps, sharding, torch), dev)
+        tot2 = sharding.all_reduce_sum(nb2, dev)
+        strong = {"scaling": "strong", "workload": "BASELINE config 4 as written: %d worlds in total, %d per GPU" % (args.worlds_per_gpu, cnt),
+                  "value": tot2 * args.steps / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / args.steps}
+        if not args.no_e2e:
+            dt2 = sharding.all_reduce_max(timed_e2e(L, ew2, tick2, nb2, args.steps, args.snapshot_format, False, sharding, torch, odeb200), dev)
+            strong["e2e"] = {"value": tot2 * args.steps / (dt2 * 1e-3), "ms_per_step": dt2 / args.steps}
+        ew2.close()
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         ab = algorithmic_bytes(st, n_geoms)
-        t_solve = float(np.mean(solve_ms)) * 1e-3
+        t_solve = tm["solve_ms"] * 1e-3
+        island = args.workload == "C4"
+        comp = compulsory_bytes(st, n_bodies, "C4" if island else "C3")
         solver_alg = ab["solver"] + ab["integrate_pack"]
-        achieved = solver_alg / t_solve / 1e9 if t_solve > 0 else 0.0
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "solver_traffic.json")
-        if os.path.exists(tpath):
-            try:
-                tj = json.load(open(tpath))
-                traffic = tj.get(args.workload, {}).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        kname = ("k_env_solve<G> (island solver: body preparation, colouring, rows, 20 PGS iterations, integrate + snapshot pack in one kernel)"
-                 if args.workload == "C4" else "k_solve (20 PGS iterations x colours, fused integrate + snapshot pack)")
-        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved,
-                    "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                    "frac_of_8TBps_spec": achieved / 8000.0, "traffic": traffic,
-                    "algorithmic_bytes_per_launch": solver_alg, "layout_bytes_per_launch": layout_bytes(st, n_bodies),
-                    "kernel_ms": t_solve * 1e3, "whole_tick_GBps": sum(ab.values()) / (tm["tick_ms"] * 1e-3) / 1e9,
-                    "stage_ms": tm}
-        if traffic and t_solve > 0:
-            # what actually crossed the HBM interface (ncu capture of the same kernel, profiles/solver_traffic.json)
-            roofline["dram_GBps"] = traffic / t_solve / 1e9
-            roofline["dram_frac"] = roofline["dram_GBps"] / peak
-        roofline["note"] = ("achieved = SURVEY 8(d) algorithmic bytes of a row-streaming QuickStep / kernel time; this engine "
-                            "rebuilds J and iMJ from 96 B per contact and (island solver) re-reads rows from L2 / shared "
-                            "memory, so frac can exceed 1; dram_GBps is the measured HBM traffic rate; the kernel is "
-                            "issue-bound (profiles/README.md)" if args.workload == "C4" else
-                            "achieved = SURVEY 8(d) algorithmic bytes / kernel time; dram_GBps = measured HBM traffic rate")
+        kc = (kernel_counters(args.workload) or {}).get("k_env_solve2" if island else "k_solve")
+        if island:
+            # The island solver keeps an env's rows in L2 / shared memory for its 20 sweeps, so SURVEY 8(d)'s row-streaming byte
+            # model does not describe it (it would read 1.8x the HBM peak): the kernel is bound by instruction issue.  frac =
+            # once-through compulsory bytes / kernel time / peak says how far from an HBM-bound kernel it is.
+            roofline = {"bound": "issue", "kernel": "k_env_solve2 (lane-pair island solver: body preparation, colouring, rows, 20 PGS "
+                        "sweeps, integrate + snapshot pack of one world per warp, one launch per solve)",
+                        "achieved": comp / t_solve / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                        "frac": comp / t_solve / 1e9 / peak, "compulsory_bytes_per_launch": comp,
+                        "row_streaming_model_bytes_per_launch": solver_alg, "row_streaming_model_GBps": solver_alg / t_solve / 1e9}
+        else:
+            roofline = {"bound": "hbm", "kernel": "k_solve (20 PGS sweeps x colour phases, fused integrate + snapshot pack)",
+                        "achieved": solver_alg / t_solve / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                        "frac": solver_alg / t_solve / 1e9 / peak, "algorithmic_bytes_per_launch": solver_alg,
+                        "compulsory_bytes_per_launch": comp, "compulsory_frac": comp / t_solve / 1e9 / peak}
+        roofline.update({"frac_of_8TBps_spec": roofline["achieved"] / 8000.0, "kernel_ms": t_solve * 1e3, "stage_ms": tm,
+                         "whole_tick_algorithmic_GBps": sum(ab.values()) / (tm["tick_ms"] * 1e-3) / 1e9})
+        roofline["traffic"] = None
+        if kc:
+            # ncu --set full capture of the same kernel (per launch), committed under profiles/ and stamped with its commit:
+            # not re-measured by this run
+            roofline["traffic"] = kc.get("dram_bytes_per_launch")
+            roofline["ncu"] = kc
+            if kc.get("dram_bytes_per_launch"):
+                roofline["dram_GBps"] = kc["dram_bytes_per_launch"] / t_solve / 1e9
+                roofline["dram_frac"] = roofline["dram_GBps"] / peak
         cpu = None
+        secondary = None
         if world == 1 and not args.no_cpu_baseline:
-            import oracle as O
-            O.build()
-            nw = 64
-            v = cpu_port_sample(nw, SETTLE["C4"], 120)
-            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": "%d C4 worlds (%d bodies), 120 ticks after %d settle ticks, single thread; CPU restatement of "
-                             "libode's QuickStep path, not libode" % (nw, nw * 128, SETTLE["C4"])}
+            if prev_affinity:
+                os.sched_setaffinity(0, prev_affinity)
+            v, ms, cores, sample = cpu_port_all_cores(20, 3, SETTLE["C4"])
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        if world == 1 and args.workload == "C4" and not args.no_secondary:
+            ew.close()
+            ew = None
+            secondary = {"C3": secondary_c3(L, odeb200, local_rank, peak)}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": desc, "bodies_per_gpu": n_bodies, "settle_steps": settle,
                        "halo_bytes_per_tick_per_gpu": (slab.halo_bytes() if slab else 0),
                        "migrated_out_rank0": (getattr(slab, "migrated_out", 0) if slab else 0),
-                       "l2": "inputs larger than L2: ~%.0f MB of body, contact and row arrays are streamed per tick (126 MB L2)"
+                       "l2": "inputs larger than L2: ~%.0f MB of body, contact and row arrays are touched per tick (126 MB L2)"
                              % ((sum(ab.values()) / 20 + 200 * n_bodies) / 1e6),
                        "counts": {k: st[k] for k in ("n_pairs", "n_contacts", "n_manifolds", "n_rows1", "n_rows2", "n_colours")}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
+        if secondary:
+            line["secondary"] = secondary
+        if strong:
+            line["strong_scaling"] = strong
         print(json.dumps(line), flush=True)
-    ew.close()
+    if ew is not None:
+        ew.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -140,10 +140,17 @@ int dGeomTriMeshDataBuildFromOBJB200(dTriMeshDataID, const char *path);
 /* read a trimesh data object back: copies up to cap_verts vertices (3 floats each) and cap_tris triangles (3 ints
  * each); returns the triangle count and stores the vertex count in *n_verts (either buffer may be NULL) */
 int dGeomTriMeshDataGetB200(dTriMeshDataID, float *verts3, int cap_verts, int *tris3, int cap_tris, int *n_verts);
-/* dWorldStep parity mode (the reference calls dWorldStep, src/main.c:213; libode solves its LCP exactly): let
- * dWorldStep run up to max_iters SOR/PGS sweeps and stop once the largest |delta lambda| of a sweep is below
- * tol (tol 0: always max_iters).  max_iters 0 (default): dWorldStep == dWorldQuickStep.  dWorldQuickStep is
- * not affected. */
+/* What dWorldStep runs (the reference calls dWorldStep, src/main.c:213; libode's dWorldStep solves the step's LCP
+ * exactly, island by island, with a Dantzig solver).
+ *   max_iters == 0 (default): the exact solution too -- islands on the device, A = J M^-1 J^T + cfm/h per island,
+ *     block principal pivoting with a dense double-precision Cholesky, one CTA per island -- for worlds of at most
+ *     1024 bodies / 4096 contact manifolds whose islands have at most 384 rows (the reference's scene: 68 bodies);
+ *     larger worlds, larger islands and dContactApprox1 contacts fall back to dWorldQuickStep's sweeps inside the same
+ *     call, and dStepStatsB200.exact_status says so.
+ *   max_iters  > 0: up to max_iters SOR/PGS sweeps, stopping once the largest |delta lambda| of a sweep is below tol
+ *     (tol 0: always max_iters) -- converges to the same solution, slowly.
+ *   max_iters  < 0: dWorldStep == dWorldQuickStep.
+ * dWorldQuickStep is not affected. */
 void dWorldSetStepSolverB200(dWorldID, int max_iters, float tol);
 /* broadphase layout: -1 automatic (default), 0 uniform grid (sort + cell sweep), 1 all pairs per env (batched
  * worlds whose geoms were added env by env, or one world of <= 4096 geoms; falls back to the grid
@@ -157,7 +164,10 @@ typedef struct dStepStatsB200 {
     int colour_rounds;
     float cell_size;
     int grid_dims[3];
-    int solver_iters; /* sweeps the last solve ran (fewer than the limit when residual-terminated) */
+    int solver_iters; /* sweeps the last solve ran (fewer than the limit when residual-terminated; 0: exact solve) */
+    /* dWorldStep's exact solve: -1 not attempted (dWorldQuickStep, or sweeps requested), 0 the step's LCP was solved
+     * exactly, 1 world or island too large, 2 dContactApprox1 rows, 3 no convergence -- 1..3 fell back to the sweeps */
+    int exact_status, n_islands, max_island_rows, pivot_rounds;
 } dStepStatsB200;
 void dWorldGetStatsB200(dWorldID, dStepStatsB200 *); /* blocking */
 void dWorldEnableTimingB200(dWorldID, int on);

@@ -66,9 +66,9 @@ Engine *eng_create(int device) {
     OB_CUDA(cudaEventCreate(&e->ev_bp));
     OB_CUDA(cudaMalloc(&e->M.count, sizeof(int)));
     OB_CUDA(cudaMalloc(&e->M.colour_start, 72 * sizeof(int)));
-    OB_CUDA(cudaMalloc(&e->M.meta, 12 * sizeof(int)));
+    OB_CUDA(cudaMalloc(&e->M.meta, 16 * sizeof(int)));
     OB_CUDA(cudaMemset(e->M.count, 0, sizeof(int)));
-    OB_CUDA(cudaMemset(e->M.meta, 0, 12 * sizeof(int)));
+    OB_CUDA(cudaMemset(e->M.meta, 0, 16 * sizeof(int)));
     OB_CUDA(cudaMalloc(&e->bp.acc, 8 * sizeof(unsigned)));
     broadphase_acc_init(e->bp, e->st); // re-armed on the device after every use from here on
     OB_CUDA(cudaMalloc(&e->bp.gp, sizeof(GridParams)));
@@ -120,6 +120,8 @@ void eng_destroy(Engine *e) {
     ManifoldArrays &M = e->M;
     dev_free(M.rec); dev_free(M.colour); dev_free(M.skey); dev_free(M.sidx); dev_free(M.flag); dev_free(M.count);
     dev_free(M.colour_start); dev_free(M.meta);
+    dev_free(e->ex_label); dev_free(e->ex_desc); dev_free(e->ex_isl_row0); dev_free(e->ex_isl_mat); dev_free(e->ex_isl_label);
+    dev_free(e->ex_meta); dev_free(e->ex_A); dev_free(e->ex_C);
     SolverArrays &S = e->S;
     dev_free(S.q0); dev_free(S.q1); dev_free(S.q2); dev_free(S.q3); dev_free(S.q4); dev_free(S.q5); dev_free(S.lam); dev_free(S.mrec);
     sort_workspace_free(e->sort); scan_workspace_free(e->scan);

@@ -100,7 +100,10 @@ struct StepStats {
     int colour_rounds;
     float cell_size;
     int grid_dims[3];
-    int solver_iters; // sweeps the last solve ran (< iterations when residual-terminated)
+    int solver_iters; // sweeps the last solve ran (< iterations when residual-terminated; 0: exact solve)
+    // exact dWorldStep (solver_exact.cu): -1 not attempted, 0 solved exactly, 1 world/island too large, 2 rows it does not
+    // take (dContactApprox1), 3 pivoting did not converge -- 1..3: the step fell back to the sweeps
+    int exact_status, n_islands, max_island_rows, pivot_rounds;
 };
 enum StatFlags { SF_PAIR_OVERFLOW = 1, SF_MANIFOLD_OVERFLOW = 2, SF_CAND_OVERFLOW = 4 };
 
@@ -109,6 +112,7 @@ struct WorldParams {
     float erp = 0.2f, cfm = 1e-5f, sor_w = 1.3f;
     int iters = 20;
     float tol = 0.f; // > 0: residual-terminated sweeps (dWorldStep parity mode)
+    int exact = 0;   // this step: solve the LCP exactly if the world is small enough (dWorldStep)
     float max_vel = INFINITY, min_depth = 0.0f;
 };
 

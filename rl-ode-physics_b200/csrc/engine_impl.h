@@ -99,6 +99,13 @@ struct Engine {
     std::vector<int> h_g1, h_g2, h_first, h_count;
     std::vector<float> h_pd, h_ns;
 
+    // exact dWorldStep of small worlds (solver_exact.cu): island tables, row descriptors, island matrices
+    int *ex_label = nullptr, *ex_desc = nullptr, *ex_isl_row0 = nullptr, *ex_isl_label = nullptr, *ex_meta = nullptr;
+    size_t *ex_isl_mat = nullptr;
+    double *ex_A = nullptr, *ex_C = nullptr;
+    size_t ex_cap_mat = 0;
+    int ex_cap_rows = 0;
+
     StepStats *d_stats = nullptr;
     StepStats *h_stats = nullptr; // pinned
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};

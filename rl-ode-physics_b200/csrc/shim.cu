@@ -319,13 +319,19 @@ extern "C" int dWorldQuickStep(dWorldID w, dReal h) {
     w->device_contacts_pending = false;
     return 1;
 }
-// dWorldStep is libode's exact (Dantzig) stepper; here it is the same SOR/PGS solver, by default with the
-// QuickStep iteration count.  dWorldSetStepSolverB200 makes it run up to `max_iters` sweeps and stop when the
-// largest |delta lambda| of a sweep falls below `tol` (0: always max_iters): the LCP solution in the limit.
+// dWorldStep is libode's exact (Dantzig) stepper (what the reference calls, src/main.c:213).  Default: the step's LCP is
+// solved exactly on the device (solver_exact.cu) when the world is small enough, else QuickStep's sweeps;
+// dWorldSetStepSolverB200 selects residual-terminated sweeps (max_iters > 0) or plain QuickStep (max_iters < 0) instead.
 extern "C" int dWorldStep(dWorldID w, dReal h) {
     if (!w) return 0;
     WorldParams &p = eng_params(w->eng);
-    if (w->step_iters <= 0) return dWorldQuickStep(w, h);
+    if (w->step_iters < 0) return dWorldQuickStep(w, h);
+    if (w->step_iters == 0) {
+        p.exact = 1;
+        const int r = dWorldQuickStep(w, h);
+        p.exact = 0;
+        return r;
+    }
     const int iters = p.iters;
     p.iters = w->step_iters; p.tol = w->step_tol;
     const int r = dWorldQuickStep(w, h);

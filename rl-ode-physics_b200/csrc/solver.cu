@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256) k_stats_reset(StepStats *__restrict__ sta
     if (i == 0) {
         stats->n_rows = 0; stats->n_rows1 = 0; stats->n_rows2 = 0; stats->n_contacts = 0;
         stats->n_manifolds = 0; stats->n_colours = 0; stats->n_overflow = 0; stats->colour_rounds = 0;
+        stats->exact_status = -1; stats->n_islands = 0; stats->max_island_rows = 0; stats->pivot_rounds = 0;
     }
     for (int k = i; k < n_env_slots; k += gridDim.x * blockDim.x) { env_cnt[k] = 0; env_fill[k] = 0; }
 }
@@ -1056,6 +1057,9 @@ __global__ void __launch_bounds__(256) k_integrate(BodyArrays B, StepConfig cfg)
     if (i < B.n) integrate_body(i, B, cfg.h, __ldcg(&B.fc[2 * i]), __ldcg(&B.fc[2 * i + 1]));
 }
 
+void exact_solve_launch(Engine *e, const ManifoldArrays &M, const SolverArrays &S, const BodyArrays &B, const StepConfig &cfg,
+                        int *done_flag, cudaStream_t st);
+bool exact_solve_fits(int n_bodies);
 void env_solve2_launch(Engine *e, const EnvArrays &E, const BodyArrays &B, const ContactSource &src, const Surface &usurf,
                        const SolverArrays &S, const StepConfig &cfg, int fused, int rows_smem, cudaStream_t st);
 
@@ -1251,7 +1255,13 @@ void solver_step(Engine *e, float h, bool host_contacts, const Surface *uniform_
         if (cfg.tol > 0.f) OB_CUDA(cudaMemsetAsync(&M.meta[8], 0, 3 * sizeof(int), st)); // residual slots
         StepStats *d_stats = e->d_stats;
         const int *done_flag = nullptr;
-        if (nb <= TINY_BODIES && !(cfg.tol > 0.f) && e->tiny_solver) {
+        // dWorldStep on a world the size of the reference's: solve the step's LCP exactly (solver_exact.cu); when that
+        // succeeds it also integrates and raises the flag that makes the sweep kernels below return at once
+        const bool want_exact = e->params.exact && !(cfg.tol > 0.f) && max_manifolds > 0 && exact_solve_fits(nb);
+        if (want_exact) {
+            exact_solve_launch(e, M, S, B, cfg, &M.meta[12], st);
+            done_flag = &M.meta[12];
+        } else if (nb <= TINY_BODIES && !(cfg.tol > 0.f) && e->tiny_solver) {
             const size_t smem = (size_t)TINY_MANIFOLDS * (7 * 8 + 1) * 16 + (size_t)nb * 5 * 16;
             // per device (function attributes live in the context): once per engine, not once per process
             if (!e->tiny_attr_set) {

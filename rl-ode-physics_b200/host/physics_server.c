@@ -7,7 +7,9 @@
  * this repo's <ode/ode.h> and links libode_b200.so, i.e. it is the drop-in test of the boundary:
  * the only thing that changed for the host code is the library behind the ODE names.
  *
- * usage: physics_server <seed> <n_spawn> <n_kinematic> <ticks> <dt> <mode: compat|device|wire> <out.bin>
+ * usage: physics_server <seed> <n_spawn> <n_kinematic> <ticks> <dt> <mode: compat|device|wire> <out.bin> [step|quick]
+ * (step, the default: dWorldStep as the reference calls it -- the library solves the step's LCP exactly; quick: the
+ * same call made to run dWorldQuickStep's 20 sweeps, dWorldSetStepSolverB200(world, -1, 0))
  * (wire = device-resident tick + the MsgUpdateBodies image packed on the GPU, dWorldPackMsgUpdateBodiesB200)
  * Writes the MsgUpdateBodies image (inc/msgs.h:30-33) after the last tick to out.bin.
  */
@@ -15,6 +17,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "ode/ode.h"
 #include "ode_b200.h"
@@ -145,7 +148,7 @@ static int AddBodyMap(Body *bodies, BodyState *states, Vec3 pos, Vec3 rot, Vec3 
 
 int main(int argc, char **argv) {
     if (argc < 8) {
-        fprintf(stderr, "usage: %s seed n_spawn n_kinematic ticks dt compat|device out.bin\n", argv[0]);
+        fprintf(stderr, "usage: %s seed n_spawn n_kinematic ticks dt compat|device|wire out.bin [step|quick] [warm-up ticks]\n", argv[0]);
         return 2;
     }
     randState = (uint32_t)strtoul(argv[1], 0, 10);
@@ -159,6 +162,8 @@ int main(int argc, char **argv) {
     dWorldSetGravity(world, 0.0, -9.8, 0.0);
     space = dHashSpaceCreate(0);
     contactGroup = dJointGroupCreate(0);
+    if (argc > 8 && strcmp(argv[8], "quick") == 0) dWorldSetStepSolverB200(world, -1, 0.f); /* dWorldStep := dWorldQuickStep */
+    const int warm = argc > 9 ? atoi(argv[9]) : 0; /* untimed ticks before the timed ones (bench.py --workload C1) */
 
     static Body bodies[MAX_BODIES];
     static BodyState bodyStates[MAX_BODIES];
@@ -201,12 +206,19 @@ int main(int argc, char **argv) {
         AddBody(bodies, bodyStates, CMASK_OBJ, CMASK_OBJ | CMASK_MAP, state, 1);
     }
 
-    for (int t = 0; t < ticks; t++) {            /* src/main.c:211-216 */
+    struct timespec t0, t1;
+    for (int t = 0; t < warm + ticks; t++) {     /* src/main.c:211-216 */
+        if (t == warm) { dWorldWaitB200(world); clock_gettime(CLOCK_MONOTONIC, &t0); }
         if (device_mode) dSpaceCollideDeviceB200(space, 8);
         else dSpaceCollide(space, NULL, NearCallback);
         dWorldStep(world, dt);
         dJointGroupEmpty(contactGroup);
     }
+    dWorldWaitB200(world);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double ms_per_tick = ((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6) / (ticks > 0 ? ticks : 1);
+    dStepStatsB200 stats;
+    dWorldGetStatsB200(world, &stats);
 
     static MsgUpdateBodies updatedBodies;        /* src/main.c:239-240 */
     if (wire_mode) {
@@ -247,7 +259,8 @@ int main(int argc, char **argv) {
     if (!f) { perror("out"); return 1; }
     fwrite(&updatedBodies, sizeof(updatedBodies), 1, f);
     fclose(f);
-    printf("ticks=%d bytes=%zu\n", ticks, sizeof(updatedBodies));
+    printf("ticks=%d bytes=%zu ms_per_tick=%.6f exact_status=%d islands=%d max_island_rows=%d contacts=%d\n", ticks,
+           sizeof(updatedBodies), ms_per_tick, stats.exact_status, stats.n_islands, stats.max_island_rows, stats.n_contacts);
 
     for (int i = 0; i < MAX_BODIES; i++) {       /* src/main.c:259-267 */
         if (bodies[i].type == BODYTYPE_NULL) continue;

@@ -42,6 +42,9 @@ class Server:
         L.dWorldSetGravity(self.world, 0.0, -9.8, 0.0)
         self.space = C.c_void_p(L.dHashSpaceCreate(None))
         self.group = C.c_void_p(L.dJointGroupCreate(0))
+        # these tests compare with the oracle's 20-sweep QuickStep: make dWorldStep run the sweeps (its default, the exact
+        # solve, has its own tests in test_parity_gpu.py)
+        L.dWorldSetStepSolverB200(self.world, -1, 0.0)
         self.calls = [0]
         self.cb = _near_callback(L, self.world, self.group, self.calls)
         self.bodies, self.geoms = [], []

@@ -63,6 +63,10 @@ class CompatWorld:
             self.geoms.append(h)
         self.n_callbacks = 0
         self.n_joints = 0
+        # the comparisons in this file are about the callback path (same contacts, same rows as the device-resident
+        # path, which steps with dWorldQuickStep): make dWorldStep run QuickStep's sweeps here; its default -- the exact
+        # solve of the step's LCP -- is tested against the oracle in test_parity_gpu.py
+        L.dWorldSetStepSolverB200(self.world, -1, 0.0)
 
         def near(data, o1, o2):
             # src/main.c:674-693
@@ -137,12 +141,12 @@ def test_callback_path_equals_device_resident_path(name):
     ew.close(); ew2.close()
 
 
-def _run_server(mode, ticks, out):
+def _run_server(mode, ticks, out, stepper="quick"):
     exe = os.path.join(ROOT, "rl-ode-physics_b200", "host", "physics_server")
     if not os.path.exists(exe):
         subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
     dt = repr(float(np.float32(1.0 / 60.0)))
-    subprocess.check_call([exe, "1", "64", "4", str(ticks), dt, mode, out])
+    subprocess.check_call([exe, "1", "64", "4", str(ticks), dt, mode, out, stepper])
     raw = np.fromfile(out, dtype=np.uint8)
     assert raw.size == 43012                      # sizeof(MsgUpdateBodies) with float dReal
     msg = int(np.frombuffer(raw[:4].tobytes(), np.int32)[0])
@@ -161,6 +165,11 @@ def test_headless_reference_server_loop_drop_in():
         raw_c = np.fromfile(os.path.join(d, "c.bin"), dtype=np.uint8)
         _run_server("wire", ticks, os.path.join(d, "w.bin"))
         raw_w = np.fromfile(os.path.join(d, "w.bin"), dtype=np.uint8)
+        # the reference's own stepper: dWorldStep with its default, the exact solve (both contact paths again)
+        _, _, tr_xc, _ = _run_server("compat", ticks, os.path.join(d, "xc.bin"), "step")
+        _, _, tr_xd, _ = _run_server("device", ticks, os.path.join(d, "xd.bin"), "step")
+    assert np.array_equal(tr_xc, tr_xd)
+    assert not np.array_equal(tr_xc, tr_c) and np.abs(tr_xc[4:72, 12:15] - tr_c[4:72, 12:15]).max() < 2.0
     assert msg_c == 3 and msg_d == 3              # MSGTYPE_C_UPDATE_BODIES
     assert np.array_equal(types_c, types_d) and np.array_equal(tr_c, tr_d)
     # the GPU-packed wire image (dWorldPackMsgUpdateBodiesB200) equals the host-assembled one byte for byte,

@@ -477,17 +477,18 @@ def test_capacity_overflow_is_flagged_not_silent():
 
 def test_dworldstep_parity_mode_converges_to_the_exact_lcp():
     """the reference calls dWorldStep (src/main.c:213), libode's exact Dantzig stepper.
-    With dWorldSetStepSolverB200 the engine's dWorldStep runs residual-terminated sweeps; its distance from the
-    oracle's exact LCP restatement (order_mode 3) must shrink with the sweep budget, and the tolerance must end
-    the sweeps early.  Distances are velocities after one C1 tick (m/s, rad/s)."""
+    dWorldSetStepSolverB200(world, n > 0, tol) makes the engine's dWorldStep run residual-terminated sweeps; their
+    distance from the oracle's exact LCP restatement (order_mode 3) must shrink with the sweep budget, the tolerance
+    must end the sweeps early, and the DEFAULT dWorldStep -- the exact solve on the device (solver_exact.cu) -- must
+    land on the oracle's answer.  Distances are velocities after one C1 tick (m/s, rad/s)."""
     sc = _scene("c1_low")
     ow = util.oracle_world(sc)
     ow.collide_all(8, O.reference_surface())
     ow.quickstep(sc["h"], order_mode=3)
     so = ow.state()
     ref = np.concatenate([so["lvel"], so["avel"]], axis=1).astype(np.float64)
-    dist, used = {}, {}
-    for iters, tol in ((0, 0.0), (100, 0.0), (2000, 0.0), (20000, 1e-4)):
+    dist, used, status = {}, {}, {}
+    for iters, tol in ((-1, 0.0), (100, 0.0), (2000, 0.0), (20000, 1e-4), (0, 0.0)):
         ew = util.engine_world(sc)
         ew.set_step_solver(iters, tol)
         ew.collide()
@@ -495,14 +496,85 @@ def test_dworldstep_parity_mode_converges_to_the_exact_lcp():
         se = ew.state()
         v = np.concatenate([se["lvel"], se["avel"]], axis=1).astype(np.float64)
         dist[iters] = float(np.abs(v - ref).max())
-        used[iters] = ew.stats()["solver_iters"]
+        st = ew.stats()
+        used[iters], status[iters] = st["solver_iters"], st["exact_status"]
+        if iters == 0:
+            assert st["n_islands"] > 10 and 3 <= st["max_island_rows"] <= 384 and st["pivot_rounds"] >= 1
         ew.close()
-    print("dWorldStep parity mode: max |v - v_exact| by sweep budget:", dist, "sweeps used:", used)
-    assert used[0] == 20 and used[100] == 100 and used[2000] == 2000
+    print("dWorldStep: max |v - v_exact| by mode (-1 QuickStep, n sweeps, 0 exact):", dist, "sweeps used:", used)
+    assert used[-1] == 20 and used[100] == 100 and used[2000] == 2000 and status[-1] == -1 and status[100] == -1
     assert 20 < used[20000] < 20000                 # the tolerance ended the sweeps
-    assert dist[0] > 0.01                           # 20 QuickStep sweeps are visibly not the LCP solution
-    assert dist[100] < 0.2 * dist[0]
+    assert dist[-1] > 0.01                          # 20 QuickStep sweeps are visibly not the LCP solution
+    assert dist[100] < 0.2 * dist[-1]
     assert dist[2000] < 2e-3 and dist[20000] < 2e-3
+    assert status[0] == 0 and used[0] == 0 and dist[0] <= 1e-4     # default dWorldStep: the exact answer
+
+
+@pytest.mark.parametrize("h", [1.0 / 60.0, 1.0 / 120.0])
+def test_default_dworldstep_follows_the_exact_oracle_tick_by_tick(h):
+    """the reference's loop as it is written -- dSpaceCollide + dWorldStep(world, 1/120) (src/main.c:208-213) -- on its own
+    scene: every tick starts from the engine's state, the oracle solves that tick's LCP exactly (order_mode 3), and the
+    engine's dWorldStep must agree within 1e-4 on positions and 2e-4 m/s on velocities.  Ticks whose islands exceed
+    the exact solver's limits must say so (exact_status 1) and equal dWorldQuickStep."""
+    sc = scenes.server_scene(seed=1, h=h, y_range=(1.0, 9.0))
+    ow, ew = util.load_both(sc)
+    exact = fallback = 0
+    worst = 0.0
+    for step in range(150):
+        pre = ew.state()
+        for i in range(len(pre["pos"])):
+            ow.set_body_state(i, pos=pre["pos"][i], q=pre["quat"][i], lvel=pre["lvel"][i], avel=pre["avel"][i])
+        ew.collide(8)
+        ew.world_step(h)
+        st = ew.stats()
+        assert st["exact_status"] in (0, 1), st
+        ow.clear_contacts()
+        ow.collide_all(8, O.reference_surface())
+        if st["exact_status"] == 0:
+            exact += 1
+            ow.quickstep(h, order_mode=3)
+            es, os_ = ew.state(), ow.state()
+            for k in ("lvel", "avel"):
+                d = float(np.abs(es[k].astype(np.float64) - os_[k]).max())
+                worst = max(worst, d)
+                assert d <= 2e-4, (step, k, d)
+            assert util.rel_err(es["pos"], os_["pos"]).max() <= 1e-4 and util.rel_err(es["quat"], os_["quat"]).max() <= 1e-4
+        else:
+            fallback += 1
+        ow.clear_contacts()
+    print("default dWorldStep, h=1/%d: %d exact ticks (worst |dv| %.2e), %d fell back to the sweeps" % (round(1 / h), exact, worst, fallback))
+    assert exact >= 140
+    ew.close()
+
+
+def test_dworldstep_falls_back_to_the_sweeps_when_an_island_is_too_large():
+    """a dense pile is one island of thousands of rows: dWorldStep reports exact_status 1 and does what
+    dWorldQuickStep does, bit for bit; dContactApprox1 rows (bounds that follow another lambda) report 2."""
+    sc = _scene("pile_dense")
+    outs = []
+    for mode in ("step", "quick"):
+        ew = util.engine_world(sc)
+        for _ in range(5):
+            ew.collide()
+            if mode == "step":
+                ew.world_step(sc["h"])
+            else:
+                ew.step(sc["h"])
+        st = ew.stats()
+        assert st["exact_status"] == (1 if mode == "step" else -1), st
+        assert st["solver_iters"] == 20
+        outs.append(ew.state())
+        ew.close()
+    for k in ("pos", "quat", "lvel", "avel"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    so, se = _surface_case("approx1")
+    sc = _scene("c1_low")
+    ew = util.engine_world(sc)
+    ew.set_surface(se)
+    ew.collide()
+    ew.world_step(sc["h"])
+    assert ew.stats()["exact_status"] == 2 and ew.stats()["solver_iters"] == 20
+    ew.close()
 
 
 def test_boxes_rest_on_a_trimesh_floor():
