@@ -365,6 +365,45 @@ def secondary_c3(L, odeb200, local_rank, peak):
     return out
 
 
+def secondary_c5(L, odeb200, rank, local_rank, world, dev, sharding, torch, cols=64, settle=200, steps=20):
+    """BASELINE config 5 on the N GPUs of this run: one slab of `cols` x 1024 x 16 lattice columns per GPU (1 M bodies per
+    GPU), the C slab driver (dSlabTickB200: NCCL send/recv inside the library, event-ordered), dynamic halo + impulse
+    coupling + migration every 16 ticks.  The same ticks without the halo (ghosts frozen) give the exchange's share."""
+    from odeb200 import slabs
+    sc, info = slabs.dynamic_slab_scene(rank, world, nx_per_slab=cols, nz=1024, ny=16, seed=5, margin_cols=4)
+    ew = odeb200.World(gravity=sc["gravity"], device=local_rank)
+    ew.load_scene(sc)
+    h = sc["h"]
+    slab = slabs.CSlab(ew, info, slabs.nccl_unique_id(L, rank, world))
+    n = [0]
+
+    def tick():
+        if n[0] % 16 == 0 and n[0] > 0:
+            slab.migrate()
+        slab.tick(h)
+        n[0] += 1
+    for _ in range(settle):
+        tick()
+    n[0] = 1                                   # no migration inside the timed region's first tick
+    ms = sharding.all_reduce_max(timed_device_ticks(L, ew, tick, steps, sharding, torch), dev) / steps
+    ms_local = sharding.all_reduce_max(timed_device_ticks(L, ew, lambda: ew.tick(h), steps, sharding, torch), dev) / steps
+    inf = slab.get_info()
+    owned = sharding.all_reduce_sum(inf["n_owned"], dev)
+    sel = sharding.all_reduce_max(inf["halo_selected"], dev)
+    ovf = sharding.all_reduce_max(inf["halo_overflow"] + inf["mig_overflow"], dev)
+    mig = sharding.all_reduce_sum(inf["migrated_out"], dev)
+    sent = sharding.all_reduce_max(inf["halo_bytes_per_tick"], dev)
+    out = {"workload": "C5: slab-decomposed single world, %d x 1024 x 16 lattice columns per GPU, C slab driver (NCCL send/recv "
+                       "inside libode_b200.so, event-ordered), dynamic halo + impulse coupling + migration every 16 ticks" % cols,
+           "bodies_total": int(owned), "ms_per_step": ms, "value": owned / (ms * 1e-3), "unit": UNIT,
+           "ms_per_step_without_halo": ms_local, "halo_share": max(0.0, 1.0 - ms_local / ms),
+           "halo_bytes_sent_per_tick_per_gpu_max": int(sent), "halo_bodies_selected_per_face_max": int(sel),
+           "halo_or_migration_overflow_max": int(ovf), "bodies_migrated_total": int(mig)}
+    slab.close()
+    ew.close()
+    return out
+
+
 def main():
     args = parse_args()
     from odeb200 import sharding
@@ -411,16 +450,23 @@ def main():
     ew.load_scene(sc)
     h = sc["h"]
     if args.workload == "C5":
-        slab = slabs.DynamicSlabWorld(ew, halo, dev) if args.halo == "dynamic" else slabs.SlabWorld(ew, halo, dev)
-        exch = (lambda kind: slabs.exchange_nccl(slab, rank, world, kind)) if world > 1 else (lambda kind: None)
         tick_no = [0]
+        if args.halo == "dynamic":
+            # the C driver inside libode_b200.so: buffers, NCCL send/recv and the event ordering live in the library
+            slab = slabs.CSlab(ew, halo, slabs.nccl_unique_id(L, rank, world) if world > 1 else None)
 
-        def do_tick():
-            if args.halo == "dynamic":
-                slabs.tick_dynamic(slab, exch, h, tick_no[0], args.migrate_every)
-            else:
+            def do_tick():
+                if args.migrate_every > 0 and tick_no[0] % args.migrate_every == 0 and tick_no[0] > 0:
+                    slab.migrate()
+                slab.tick(h)
+                tick_no[0] += 1
+        else:
+            slab = slabs.SlabWorld(ew, halo, dev)
+            exch = (lambda kind: slabs.exchange_nccl(slab, rank, world, kind)) if world > 1 else (lambda kind: None)
+
+            def do_tick():
                 slabs.tick(slab, exch, h)
-            tick_no[0] += 1
+                tick_no[0] += 1
     else:
         def do_tick():
             ew.tick(h)
@@ -500,6 +546,13 @@ def main():
             strong["e2e"] = {"value": tot2 * args.steps / (dt2 * 1e-3), "ms_per_step": dt2 / args.steps}
         ew2.close()
 
+    # ---------------- BASELINE config 5 under the driver's eyes: the slab-decomposed single world on the same N GPUs
+    c5 = None
+    if world > 1 and args.workload == "C4" and not args.no_secondary:
+        ew.close()
+        ew = None
+        c5 = secondary_c5(L, odeb200, rank, local_rank, world, dev, sharding, torch)
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         ab = algorithmic_bytes(st, n_geoms)
@@ -560,6 +613,8 @@ def main():
             line["secondary"] = secondary
         if strong:
             line["strong_scaling"] = strong
+        if c5:
+            line.setdefault("secondary", {})["C5"] = c5
         print(json.dumps(line), flush=True)
     if ew is not None:
         ew.close()

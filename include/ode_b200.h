@@ -105,6 +105,41 @@ void dWorldSelectBodiesDeviceB200(dWorldID, int axis, float lo, float hi, const 
                                   int *d_count);
 void dWorldPackBodiesDeviceB200(dWorldID, const int *d_idx, int cap, const int *d_body_geom, float *d_out48);
 void dWorldUnpackBodiesDeviceB200(dWorldID, const int *d_ghost_body, const int *d_ghost_geom, int cap, const float *d_in48);
+/* the CUDA stream (cudaStream_t) every kernel and copy of this world is queued on */
+void *dWorldGetStreamB200(dWorldID);
+
+/* Slab decomposition of ONE large world over several GPUs (BASELINE config 5), driven from C:
+ * one process per GPU, each owning the bodies whose centre lies in its x-interval [face_left, face_right); a contact
+ * across a face belongs to the LOWER slab, which mirrors its upper neighbour's boundary bodies (x < face + margin)
+ * as dynamic ghosts in a pool of `pool` body/geom slots created by the application.  dSlabTickB200 = state halo down
+ * -> dSpaceCollideDeviceB200 + dWorldQuickStep -> impulse halo up, NCCL send/recv inside the library, ordered by CUDA
+ * events only (no host synchronisation).  dSlabMigrateB200 (every few ticks) moves the ownership of bodies that
+ * crossed a face by more than `hyst`.  The communicator is built from an NCCL unique id the application distributes
+ * (rank 0: dSlabGetUniqueIdB200, then MPI / sockets / a file).  Several slabs in one process (one GPU, tests) are
+ * connected with dSlabConnectLocalB200 and ticked together with dSlabTickLocalB200: same phases, device copies. */
+typedef struct dxSlabB200 *dSlabID;
+typedef struct dSlabLayoutB200 {
+    float face_left, face_right, margin, hyst;
+    int n_own;            /* bodies [0, n_own) are owned at set-up */
+    int n_static;         /* static geoms precede the body geoms: geom of body b = n_static + b */
+    int pool, pool_first_body, pool_first_geom; /* ghost slots (ignored on the last rank) */
+    int mig_cap;          /* bodies that may change owner per face per migration */
+} dSlabLayoutB200;
+typedef struct dSlabInfoB200 {
+    int n_owned, halo_selected, halo_overflow, mig_overflow;
+    long migrated_in, migrated_out, ticks, halo_bytes_per_tick;
+} dSlabInfoB200;
+int dSlabGetUniqueIdB200(char id128[128]); /* 0: NCCL not available */
+dSlabID dSlabCreateB200(dWorldID, dSpaceID, int rank, int n_ranks, const char *nccl_id128 /* NULL: local transport */,
+                        const dSlabLayoutB200 *);
+void dSlabDestroyB200(dSlabID);
+void dSlabTickB200(dSlabID, dReal h, int max_contacts);
+void dSlabMigrateB200(dSlabID);
+void dSlabConnectLocalB200(dSlabID lower, dSlabID upper);
+void dSlabTickLocalB200(dSlabID *slabs, int n, dReal h, int max_contacts);
+void dSlabMigrateLocalB200(dSlabID *slabs, int n);
+void dSlabGetInfoB200(dSlabID, dSlabInfoB200 *); /* blocking */
+
 /* CUDA-event timer on the world's stream: everything queued between start and stop */
 void dWorldTimerStartB200(dWorldID);
 void dWorldTimerStopB200(dWorldID);

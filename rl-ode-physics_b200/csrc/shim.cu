@@ -350,6 +350,7 @@ extern "C" void dWorldSetBroadphaseB200(dWorldID w, int mode) { eng_set_broadpha
 extern "C" void dWorldSetSolverModeB200(dWorldID w, int mode, int env_group) { eng_set_solver_mode(w->eng, mode, env_group); }
 extern "C" void dWorldSetContactUnitsB200(dWorldID w, int per_contact) { eng_set_contact_units(w->eng, per_contact); }
 extern "C" void dWorldWaitB200(dWorldID w) { eng_wait(w->eng); }
+extern "C" void *dWorldGetStreamB200(dWorldID w) { return (void *)eng_stream(w->eng); }
 extern "C" void dWorldPackStatesDeviceB200(dWorldID w, const int *d_idx, int n, float *d_out) { eng_pack_states_device(w->eng, d_idx, n, d_out); }
 extern "C" void dWorldPackImpulsesDeviceB200(dWorldID w, const int *d_idx, int n, float *d_out) { eng_pack_impulses_device(w->eng, d_idx, n, d_out); }
 extern "C" void dWorldAddImpulsesDeviceB200(dWorldID w, const int *d_idx, int n, const float *d_in) { eng_add_impulses_device(w->eng, d_idx, n, d_in); }

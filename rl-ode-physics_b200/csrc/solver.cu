@@ -490,8 +490,11 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // largest |delta lambda| of its sweep, the grid max goes through one of three rotating slots (meta[8..10]:
 // a slot is re-zeroed only after every CTA has passed the barrier that follows its last read), and all CTAs
 // take the same exit decision after the sweep's last barrier.
+#ifndef OB_SOLVE_CTAS
+#define OB_SOLVE_CTAS 2 // CTAs of 256 threads per SM the register budget is sized for
+#endif
 template <bool TOL>
-__global__ void __launch_bounds__(256, 2) k_solve(ManifoldArrays M, SolverArrays S, BodyArrays B, StepConfig cfg,
+__global__ void __launch_bounds__(256, OB_SOLVE_CTAS) k_solve(ManifoldArrays M, SolverArrays S, BodyArrays B, StepConfig cfg,
                                                   StepStats *__restrict__ stats, const int *__restrict__ done_flag) {
     if (done_flag && *done_flag) return; // the small-world solver already did the whole solve + tail
     const int n = *M.count;

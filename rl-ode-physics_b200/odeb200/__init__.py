@@ -55,6 +55,17 @@ class StepStats(C.Structure):
         return d
 
 
+class SlabLayout(C.Structure):
+    _fields_ = [("face_left", C.c_float), ("face_right", C.c_float), ("margin", C.c_float), ("hyst", C.c_float),
+                ("n_own", C.c_int), ("n_static", C.c_int), ("pool", C.c_int), ("pool_first_body", C.c_int),
+                ("pool_first_geom", C.c_int), ("mig_cap", C.c_int)]
+
+
+class SlabInfo(C.Structure):
+    _fields_ = [("n_owned", C.c_int), ("halo_selected", C.c_int), ("halo_overflow", C.c_int), ("mig_overflow", C.c_int),
+                ("migrated_in", C.c_long), ("migrated_out", C.c_long), ("ticks", C.c_long), ("halo_bytes_per_tick", C.c_long)]
+
+
 NearCallback = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p)
 
 # (name, restype, argtypes) for every exported entry point the binding uses
@@ -127,6 +138,12 @@ _SIGS = [
     ("dWorldSelectBodiesDeviceB200", None, [_vp, _i, _f, _f, _vp, _vp, _i, _vp]),
     ("dWorldPackBodiesDeviceB200", None, [_vp, _vp, _i, _vp, _vp]),
     ("dWorldUnpackBodiesDeviceB200", None, [_vp, _vp, _vp, _i, _vp]),
+    ("dWorldGetStreamB200", _vp, [_vp]),
+    ("dSlabGetUniqueIdB200", _i, [C.c_char_p]),
+    ("dSlabCreateB200", _vp, [_vp, _vp, _i, _i, C.c_char_p, C.POINTER(SlabLayout)]),
+    ("dSlabDestroyB200", None, [_vp]), ("dSlabTickB200", None, [_vp, _f, _i]), ("dSlabMigrateB200", None, [_vp]),
+    ("dSlabConnectLocalB200", None, [_vp, _vp]), ("dSlabTickLocalB200", None, [C.POINTER(_vp), _i, _f, _i]),
+    ("dSlabMigrateLocalB200", None, [C.POINTER(_vp), _i]), ("dSlabGetInfoB200", None, [_vp, C.POINTER(SlabInfo)]),
     ("dWorldTimerStartB200", None, [_vp]), ("dWorldTimerStopB200", None, [_vp]),
     ("dWorldTimerElapsedB200", C.c_float, [_vp]), ("dGetKernelLaunchCountB200", C.c_long, []),
     ("dWorldSetCapacityB200", None, [_vp, C.c_long, C.c_long]),

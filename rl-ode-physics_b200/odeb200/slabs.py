@@ -410,3 +410,83 @@ def tick_dynamic(slab, exchange, h, step, migrate_every=16, max_contacts=8):
         exchange("mig")
         slab.unpack("mig")
     tick(slab, exchange, h, max_contacts)
+
+
+# ------------------------------------------------------------------ the C driver (csrc/slab.cu)
+#
+# Everything above orchestrates the halo from Python (torch tensors as buffers, torch.distributed as transport) and
+# is kept as the reference the C driver is tested against.  The product path is the C driver: dSlabCreateB200 /
+# dSlabTickB200 / dSlabMigrateB200 behind include/ode_b200.h -- buffers, NCCL calls and the event ordering live inside
+# libode_b200.so, so a C application needs nothing but an NCCL unique id from its launcher.
+
+class CSlab:
+    """One rank's slab driven by the library (dSlab*B200).  `nccl_id`: 128 bytes from dSlabGetUniqueIdB200 of rank 0
+    (None: same-process slabs, connect them with CSlab.connect and tick them with CSlab.tick_local)."""
+
+    def __init__(self, world, info, nccl_id=None):
+        from . import SlabLayout
+        import ctypes as C
+        self.w, self.info = world, info
+        lay = SlabLayout(face_left=info["face_left"], face_right=info["face_right"], margin=info["margin"], hyst=info["hyst"],
+                         n_own=info["n_own"], n_static=info["n_static"], pool=info["pool"],
+                         pool_first_body=info["pool_first_body"], pool_first_geom=info["pool_first_geom"], mig_cap=info["mig_cap"])
+        world.L.dSpaceCollideDeviceB200  # (the library must be loaded)
+        world.wait()
+        self.h = C.c_void_p(world.L.dSlabCreateB200(world.w, world.space, info["rank"], info["n_slabs"], nccl_id, C.byref(lay)))
+
+    def tick(self, h, max_contacts=8):
+        self.w.L.dSlabTickB200(self.h, float(h), int(max_contacts))
+
+    def migrate(self):
+        self.w.L.dSlabMigrateB200(self.h)
+
+    def get_info(self):
+        from . import SlabInfo
+        import ctypes as C
+        i = SlabInfo()
+        self.w.L.dSlabGetInfoB200(self.h, C.byref(i))
+        return {k: getattr(i, k) for k, _ in SlabInfo._fields_}
+
+    def halo_bytes(self):
+        return self.get_info()["halo_bytes_per_tick"]
+
+    @property
+    def migrated_out(self):
+        return self.get_info()["migrated_out"]
+
+    def close(self):
+        if self.h:
+            self.w.L.dSlabDestroyB200(self.h)
+            self.h = None
+
+    @staticmethod
+    def connect(lower, upper):
+        lower.w.L.dSlabConnectLocalB200(lower.h, upper.h)
+
+    @staticmethod
+    def _array(slabs):
+        import ctypes as C
+        return (C.c_void_p * len(slabs))(*[s.h for s in slabs])
+
+    @staticmethod
+    def tick_local(slabs, h, max_contacts=8):
+        slabs[0].w.L.dSlabTickLocalB200(CSlab._array(slabs), len(slabs), float(h), int(max_contacts))
+
+    @staticmethod
+    def migrate_local(slabs):
+        slabs[0].w.L.dSlabMigrateLocalB200(CSlab._array(slabs), len(slabs))
+
+
+def nccl_unique_id(lib, rank, world):
+    """128-byte NCCL unique id created by rank 0's library and broadcast to the others (here through torch.distributed,
+    which the benchmark already uses for its barrier; a C application would use its own launcher's channel)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    buf = C.create_string_buffer(128)
+    if rank == 0 and not lib.dSlabGetUniqueIdB200(buf):
+        raise RuntimeError("NCCL is not available to libode_b200.so (libnccl.so.2 not found)")
+    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone().cuda()
+    if world > 1:
+        dist.broadcast(t, 0)
+    return bytes(t.cpu().numpy().tobytes())

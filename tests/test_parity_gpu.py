@@ -499,7 +499,7 @@ def test_dworldstep_parity_mode_converges_to_the_exact_lcp():
         st = ew.stats()
         used[iters], status[iters] = st["solver_iters"], st["exact_status"]
         if iters == 0:
-            assert st["n_islands"] > 10 and 3 <= st["max_island_rows"] <= 384 and st["pivot_rounds"] >= 1
+            assert st["n_islands"] >= 3 and 3 <= st["max_island_rows"] <= 384 and st["pivot_rounds"] >= 1
         ew.close()
     print("dWorldStep: max |v - v_exact| by mode (-1 QuickStep, n sweeps, 0 exact):", dist, "sweeps used:", used)
     assert used[-1] == 20 and used[100] == 100 and used[2000] == 2000 and status[-1] == -1 and status[100] == -1
