@@ -419,6 +419,7 @@ def main():
     torch.cuda.set_device(local_rank)
     prev_affinity = bind_to_gpu_numa_node(local_rank) if (world > 1 and not os.environ.get("ODE_B200_NO_BIND")) else None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # NCCL's version banner goes to stdout: keep the one-JSON-line contract
         sharding.init_process_group("nccl")
     dev = "cuda:%d" % local_rank
     L = odeb200.lib()

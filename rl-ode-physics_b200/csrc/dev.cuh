@@ -53,6 +53,12 @@ struct MeshInfo {
     const int *tris;    // 3*nt
     int nv, nt;
     float lo[3], hi[3];
+    // uniform grid over the mesh-local bounds, built once at dGeomTriMeshDataBuild*: triangle t is listed in every
+    // cell its box touches; cell (x, y, z) holds cell_tris[cell_start[c] .. cell_start[c + 1]), c = (z * gd[1] + y) * gd[0] + x
+    const int *cell_start;
+    const int *cell_tris;
+    int gd[3];
+    float gcell[3], ginv[3];
 };
 constexpr int MAX_MESHES = 8;
 struct MeshTable {

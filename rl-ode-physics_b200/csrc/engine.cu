@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 
 #include "solver_dev.cuh"
 
@@ -128,7 +129,7 @@ void eng_destroy(Engine *e) {
     dev_free(e->E.first_body); dev_free(e->E.n_body); dev_free(e->E.cnt); dev_free(e->E.start); dev_free(e->E.fill); dev_free(e->E.order); dev_free(e->E.rec); dev_free(e->E.perm); dev_free(e->E.col);
     dev_free(e->hc_pd); dev_free(e->hc_ns); dev_free(e->hc_surf); dev_free(e->hc_mrec);
     dev_free(e->dl_first); dev_free(e->dl_pd); dev_free(e->dl_ns);
-    for (auto &m : e->hmeshes) { dev_free(m.d_verts); dev_free(m.d_tris); }
+    for (auto &m : e->hmeshes) { dev_free(m.d_verts); dev_free(m.d_tris); dev_free(m.d_cell_start); dev_free(m.d_cell_tris); }
     dev_free(e->d_stats);
     dev_free(e->msg_body); dev_free(e->msg_geom); dev_free(e->msg_type); dev_free(e->msg_size); dev_free(e->msg_col); dev_free(e->msg_out);
     dev_free(e->d_f6[0]); dev_free(e->d_f6[1]);
@@ -215,6 +216,62 @@ int eng_add_mesh(Engine *e, const float *verts, int nv, const int *tris, int nt)
     MeshInfo &mi = e->meshes.m[id];
     mi.verts = m.d_verts; mi.tris = m.d_tris; mi.nv = nv; mi.nt = nt;
     for (int k = 0; k < 3; k++) { mi.lo[k] = m.lo[k]; mi.hi[k] = m.hi[k]; }
+    {
+        // Triangle grid: ~2 cells per triangle, cell edges proportional to the bounds (a flat mesh gets a flat grid).
+        // A collider visits only the cells its box touches instead of every triangle of the mesh.
+        double ext[3], vol = 1.0;
+        int flat = 0;
+        for (int k = 0; k < 3; k++) { ext[k] = std::max((double)m.hi[k] - (double)m.lo[k], 0.0); if (ext[k] <= 0) flat++; }
+        double emax = std::max(ext[0], std::max(ext[1], ext[2]));
+        if (emax <= 0) emax = 1.0;
+        for (int k = 0; k < 3; k++) vol *= std::max(ext[k], 1e-3 * emax);
+        const double target = std::max(8.0, 2.0 * nt);
+        const double cell = std::cbrt(vol / target);
+        long total = 1;
+        for (int k = 0; k < 3; k++) {
+            int d = (int)std::floor(ext[k] / cell) + 1;
+            d = std::min(std::max(d, 1), 256);
+            mi.gd[k] = d;
+            mi.gcell[k] = (float)(ext[k] > 0 ? ext[k] / d : 1.0);
+            mi.ginv[k] = 1.0f / mi.gcell[k];
+            total *= d;
+        }
+        auto cell_of = [&](float v, int k) {
+            int c = (int)floorf((v - m.lo[k]) * mi.ginv[k]);
+            return std::min(std::max(c, 0), mi.gd[k] - 1);
+        };
+        std::vector<int> start((size_t)total + 1, 0);
+        std::vector<int> range((size_t)nt * 6);
+        for (int t = 0; t < nt; t++) {
+            for (int k = 0; k < 3; k++) {
+                float lo = INFINITY, hi = -INFINITY;
+                for (int c = 0; c < 3; c++) {
+                    const float v = verts[3 * (size_t)tris[3 * (size_t)t + c] + k];
+                    lo = fminf(lo, v); hi = fmaxf(hi, v);
+                }
+                range[6 * (size_t)t + 2 * k] = cell_of(lo, k);
+                range[6 * (size_t)t + 2 * k + 1] = cell_of(hi, k);
+            }
+            const int *r = &range[6 * (size_t)t];
+            for (int z = r[4]; z <= r[5]; z++)
+                for (int y = r[2]; y <= r[3]; y++)
+                    for (int x = r[0]; x <= r[1]; x++) start[((size_t)z * mi.gd[1] + y) * mi.gd[0] + x + 1]++;
+        }
+        for (long c = 0; c < total; c++) start[c + 1] += start[c];
+        std::vector<int> list((size_t)std::max(start[total], 1));
+        std::vector<int> cur(start.begin(), start.end() - 1);
+        for (int t = 0; t < nt; t++) { // ascending triangle index inside every cell
+            const int *r = &range[6 * (size_t)t];
+            for (int z = r[4]; z <= r[5]; z++)
+                for (int y = r[2]; y <= r[3]; y++)
+                    for (int x = r[0]; x <= r[1]; x++) list[cur[((size_t)z * mi.gd[1] + y) * mi.gd[0] + x]++] = t;
+        }
+        OB_CUDA(cudaMalloc(&m.d_cell_start, start.size() * sizeof(int)));
+        OB_CUDA(cudaMalloc(&m.d_cell_tris, list.size() * sizeof(int)));
+        OB_CUDA(cudaMemcpy(m.d_cell_start, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice));
+        OB_CUDA(cudaMemcpy(m.d_cell_tris, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice));
+        mi.cell_start = m.d_cell_start; mi.cell_tris = m.d_cell_tris;
+    }
     e->meshes.n = id + 1;
     e->hmeshes.push_back(std::move(m));
     return id;

@@ -90,6 +90,7 @@ struct TriMesh {
     float lo[3], hi[3];       // local bounds
     std::vector<float> h_verts;
     std::vector<int> h_tris;
+    int *d_cell_start = nullptr, *d_cell_tris = nullptr; // triangle grid (device)
 };
 
 // per-step counters read back once per step (pinned)

@@ -512,10 +512,14 @@ __global__ void __launch_bounds__(256) k_np_none(const BroadCounters *__restrict
 //
 // One warp per (sphere, trimesh) pair; the mesh (vertices + indices) is staged once per CTA in
 // shared memory with a TMA bulk copy (cp.async.bulk global->shared completing on an mbarrier)
-// when it fits, which the reference's teapot.obj does (8884 triangles, 165 KB).  Lanes stride
-// over triangles; hits go to a per-warp candidate list; the <= 8 contacts are then chosen by the
+// when it fits, which the reference's teapot.obj does (8884 triangles, 165 KB).  The warp visits only the
+// cells of the mesh's triangle grid (engine.cu, eng_add_mesh) that the collider's box touches: one lane per
+// cell fetches the cell's triangle range, a warp scan flattens the ranges, and the lanes then take the listed
+// triangles 32 at a time (round 1 walked all 8884 triangles of the teapot for every pair).  A triangle listed in
+// several visited cells is taken in exactly one of them (the lowest cell, per axis, of the overlap between its own
+// cell range and the query's).  Hits go to a per-warp candidate list; the <= 8 contacts are then chosen by the
 // order-independent rule documented in DESIGN.md "sphere-trimesh" (depth desc, triangle index asc,
-// duplicates within 1e-3 r dropped).
+// duplicates within 1e-3 r dropped) -- so the contacts equal the brute-force walk's bit for bit.
 
 constexpr int TM_WARPS = 8;
 constexpr int TM_CAND = 64;
@@ -557,6 +561,68 @@ struct TriCand {
     int tri;
     float qx, qy, qz, nx, ny, nz;
 };
+
+__device__ __forceinline__ int mesh_cell_of(const MeshInfo &mesh, float v, int k) {
+    const int c = (int)floorf((v - mesh.lo[k]) * mesh.ginv[k]); // the host's arithmetic (eng_add_mesh), float for float
+    return min(max(c, 0), mesh.gd[k] - 1);
+}
+
+// Warp-cooperative walk over the triangles listed in the grid cells [q0, q1]: calls body(t, a, b, c) with, per lane,
+// one triangle (t >= 0) or nothing (t = -1), 32 triangles per call, every triangle whose box overlaps the cells' union
+// exactly once.  All lanes call body together (it may use warp votes).
+template <typename Body>
+__device__ __forceinline__ void for_each_grid_triangle(const MeshInfo &mesh, const float *verts, const int *tris,
+                                                       const int q0[3], const int q1[3], int lane, Body &&body) {
+    const int ncx = q1[0] - q0[0] + 1, ncy = q1[1] - q0[1] + 1, ncz = q1[2] - q0[2] + 1;
+    const int ncell = ncx * ncy * ncz;
+    for (int cb = 0; cb < ncell; cb += 32) {
+        const int ci = cb + lane;
+        const bool valid = ci < ncell;
+        const int cx = q0[0] + ci % ncx, cy = q0[1] + (ci / ncx) % ncy, cz = q0[2] + ci / (ncx * ncy);
+        int s0 = 0, cnt = 0;
+        if (valid) {
+            const int cid = (cz * mesh.gd[1] + cy) * mesh.gd[0] + cx;
+            s0 = mesh.cell_start[cid];
+            cnt = mesh.cell_start[cid + 1] - s0;
+        }
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        const int excl = inc - cnt;
+        for (int k0 = 0; k0 < total; k0 += 32) {
+            const int k = k0 + lane;
+            // owner = the last lane whose exclusive prefix is <= k
+            int j = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int cand = j + step;
+                const int e = __shfl_sync(0xffffffffu, excl, cand & 31);
+                if (cand < 32 && e <= k) j = cand;
+            }
+            const int os0 = __shfl_sync(0xffffffffu, s0, j), oex = __shfl_sync(0xffffffffu, excl, j);
+            const int ox = __shfl_sync(0xffffffffu, cx, j), oy = __shfl_sync(0xffffffffu, cy, j), oz = __shfl_sync(0xffffffffu, cz, j);
+            int t = -1;
+            V3 a = v3(0.f, 0.f, 0.f), b = a, c = a;
+            if (k < total) {
+                t = mesh.cell_tris[os0 + (k - oex)];
+                const int i0 = tris[3 * t], i1 = tris[3 * t + 1], i2 = tris[3 * t + 2];
+                a = v3(verts[3 * i0], verts[3 * i0 + 1], verts[3 * i0 + 2]);
+                b = v3(verts[3 * i1], verts[3 * i1 + 1], verts[3 * i1 + 2]);
+                c = v3(verts[3 * i2], verts[3 * i2 + 1], verts[3 * i2 + 2]);
+                // taken only in the lowest visited cell of the triangle's own cell range
+                const int tx = max(mesh_cell_of(mesh, fminf(a.x, fminf(b.x, c.x)), 0), q0[0]);
+                const int ty = max(mesh_cell_of(mesh, fminf(a.y, fminf(b.y, c.y)), 1), q0[1]);
+                const int tz = max(mesh_cell_of(mesh, fminf(a.z, fminf(b.z, c.z)), 2), q0[2]);
+                if (tx != ox || ty != oy || tz != oz) t = -1;
+            }
+            body(t, a, b, c);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(TM_WARPS * 32) k_np_sphere_trimesh(const BroadCounters *__restrict__ bc,
                                                                       const int2 *__restrict__ pairs, GeomArrays g,
@@ -632,16 +698,20 @@ __global__ void __launch_bounds__(TM_WARPS * 32) k_np_sphere_trimesh(const Broad
             const float hmin = fminf(h[0], fminf(h[1], h[2]));
             const float maxdepth = 2.0f * hmin;
             r = hmin;
-            for (int t0 = 0; t0 < mesh.nt; t0 += 32) {
-                const int t = t0 + lane;
+            int q0[3], q1[3];
+            {
+                const float cl[3] = {c.x, c.y, c.z}, ex[3] = {ext.x, ext.y, ext.z};
+                for (int k = 0; k < 3; k++) {
+                    const float sl = 1e-5f * (fabsf(cl[k]) + ex[k]) + 1e-6f; // a wider window only costs tests
+                    q0[k] = mesh_cell_of(mesh, cl[k] - ex[k] - sl, k);
+                    q1[k] = mesh_cell_of(mesh, cl[k] + ex[k] + sl, k);
+                }
+            }
+            for_each_grid_triangle(mesh, verts, tris, q0, q1, lane, [&](int t, V3 a, V3 b, V3 cc) {
                 bool live = false;
-                V3 a, b, cc, nr, n;
-                a = b = cc = nr = n = v3(0.f, 0.f, 0.f);
-                if (t < mesh.nt) {
-                    const int i0 = tris[3 * t], i1 = tris[3 * t + 1], i2 = tris[3 * t + 2];
-                    a = v3(verts[3 * i0], verts[3 * i0 + 1], verts[3 * i0 + 2]);
-                    b = v3(verts[3 * i1], verts[3 * i1 + 1], verts[3 * i1 + 2]);
-                    cc = v3(verts[3 * i2], verts[3 * i2 + 1], verts[3 * i2 + 2]);
+                V3 nr, n;
+                nr = n = v3(0.f, 0.f, 0.f);
+                if (t >= 0) {
                     bool skip = false;
                     skip |= (c.x - ext.x > fmaxf(a.x, fmaxf(b.x, cc.x))) || (c.x + ext.x < fminf(a.x, fminf(b.x, cc.x)));
                     skip |= (c.y - ext.y > fmaxf(a.y, fmaxf(b.y, cc.y))) || (c.y + ext.y < fminf(a.y, fminf(b.y, cc.y)));
@@ -656,7 +726,7 @@ __global__ void __launch_bounds__(TM_WARPS * 32) k_np_sphere_trimesh(const Broad
                         }
                     }
                 }
-                if (!__any_sync(0xffffffffu, live)) continue;
+                if (!__any_sync(0xffffffffu, live)) return;
                 for (int sub = 0; sub < 11; sub++) {
                     bool hit = false;
                     TriCand cd;
@@ -710,17 +780,21 @@ __global__ void __launch_bounds__(TM_WARPS * 32) k_np_sphere_trimesh(const Broad
                     }
                     ncand += __popc(hm);
                 }
+            });
+        } else {
+        int q0[3], q1[3];
+        {
+            const float cl[3] = {c.x, c.y, c.z};
+            for (int k = 0; k < 3; k++) {
+                const float sl = 1e-5f * (fabsf(cl[k]) + r) + 1e-6f;
+                q0[k] = mesh_cell_of(mesh, cl[k] - r - sl, k);
+                q1[k] = mesh_cell_of(mesh, cl[k] + r + sl, k);
             }
-        } else
-        for (int t0 = 0; t0 < mesh.nt; t0 += 32) {
-            const int t = t0 + lane;
+        }
+        for_each_grid_triangle(mesh, verts, tris, q0, q1, lane, [&](int t, V3 a, V3 b, V3 cc) {
             bool hit = false;
             TriCand cd;
-            if (t < mesh.nt) {
-                const int i0 = tris[3 * t], i1 = tris[3 * t + 1], i2 = tris[3 * t + 2];
-                const V3 a = v3(verts[3 * i0], verts[3 * i0 + 1], verts[3 * i0 + 2]);
-                const V3 b = v3(verts[3 * i1], verts[3 * i1 + 1], verts[3 * i1 + 2]);
-                const V3 cc = v3(verts[3 * i2], verts[3 * i2 + 1], verts[3 * i2 + 2]);
+            if (t >= 0) {
                 bool skip = false;
                 skip |= (c.x - r > fmaxf(a.x, fmaxf(b.x, cc.x))) || (c.x + r < fminf(a.x, fminf(b.x, cc.x)));
                 skip |= (c.y - r > fmaxf(a.y, fmaxf(b.y, cc.y))) || (c.y + r < fminf(a.y, fminf(b.y, cc.y)));
@@ -762,6 +836,7 @@ __global__ void __launch_bounds__(TM_WARPS * 32) k_np_sphere_trimesh(const Broad
                 if (slot < TM_CAND) mine[slot] = cd;
             }
             ncand += __popc(hm);
+        });
         }
         if (ncand > TM_CAND) {
             ncand = TM_CAND;
