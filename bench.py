@@ -607,7 +607,7 @@ def main():
                        "migrated_out_rank0": (getattr(slab, "migrated_out", 0) if slab else 0),
                        "l2": "inputs larger than L2: ~%.0f MB of body, contact and row arrays are touched per tick (126 MB L2)"
                              % ((sum(ab.values()) / 20 + 200 * n_bodies) / 1e6),
-                       "counts": {k: st[k] for k in ("n_pairs", "n_contacts", "n_manifolds", "n_rows1", "n_rows2", "n_colours")}},
+                       "counts": {k: st[k] for k in ("n_pairs", "n_contacts", "n_manifolds", "n_rows1", "n_rows2", "n_colours", "env_trips", "env_lanes")}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
         if secondary:

@@ -203,6 +203,8 @@ typedef struct dStepStatsB200 {
     /* dWorldStep's exact solve: -1 not attempted (dWorldQuickStep, or sweeps requested), 0 the step's LCP was solved
      * exactly, 1 world or island too large, 2 dContactApprox1 rows, 3 no convergence -- 1..3 fell back to the sweeps */
     int exact_status, n_islands, max_island_rows, pivot_rounds;
+    /* island solver of batched worlds: 32-lane trips and occupied lanes of one sweep, summed over the worlds */
+    int env_trips, env_lanes;
 } dStepStatsB200;
 void dWorldGetStatsB200(dWorldID, dStepStatsB200 *); /* blocking */
 void dWorldEnableTimingB200(dWorldID, int on);

@@ -105,6 +105,8 @@ struct StepStats {
     // exact dWorldStep (solver_exact.cu): -1 not attempted, 0 solved exactly, 1 world/island too large, 2 rows it does not
     // take (dContactApprox1), 3 pivoting did not converge -- 1..3: the step fell back to the sweeps
     int exact_status, n_islands, max_island_rows, pivot_rounds;
+    // lane-pair island solver: 32-lane trips and occupied lanes of ONE sweep, summed over the envs (lane fill = lanes / (32 trips))
+    int env_trips, env_lanes;
 };
 enum StatFlags { SF_PAIR_OVERFLOW = 1, SF_MANIFOLD_OVERFLOW = 2, SF_CAND_OVERFLOW = 4 };
 

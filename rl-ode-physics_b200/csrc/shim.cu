@@ -621,6 +621,11 @@ extern "C" void dGeomDestroy(dGeomID g) {
 extern "C" void dGeomSetBody(dGeomID g, dBodyID b) {
     if (b && b->w != g->space->w) fatal("dGeomSetBody: the body belongs to a different world than the geom's space");
     if (g->body && g->body != b) {
+        if (!b) { // detached: the geom keeps the pose it had on the body (ODE: dGeomSetBody(g, 0) leaves the geom in place)
+            const float *bp = dBodyGetPosition(g->body), *bR = dBodyGetRotation(g->body);
+            memcpy(&HG(g).pos[4 * g->idx], bp, 3 * sizeof(float));
+            memcpy(&HG(g).R[12 * g->idx], bR, 12 * sizeof(float));
+        }
         std::vector<dxGeom *> &v = g->body->geoms;
         v.erase(std::remove(v.begin(), v.end(), g), v.end());
     }

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) k_stats_reset(StepStats *__restrict__ sta
         stats->n_rows = 0; stats->n_rows1 = 0; stats->n_rows2 = 0; stats->n_contacts = 0;
         stats->n_manifolds = 0; stats->n_colours = 0; stats->n_overflow = 0; stats->colour_rounds = 0;
         stats->exact_status = -1; stats->n_islands = 0; stats->max_island_rows = 0; stats->pivot_rounds = 0;
+        stats->env_trips = 0; stats->env_lanes = 0;
     }
     for (int k = i; k < n_env_slots; k += gridDim.x * blockDim.x) { env_cnt[k] = 0; env_fill[k] = 0; }
 }

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(OB_ENV2_THREADS, (ROWS_SMEM ? OB_ENV2_WARPS_SM
     const float cfmh2 = ((usurf.mode & MODE_SLIP2) ? usurf.slip2 : cfg.cfm) * h1;
     const int the_m = surface_rows(usurf); // rows per contact: the same for every contact of the world
 
-    int rows1 = 0, rows2 = 0, ncont = 0, max_col = 0, max_rounds = 0;
+    int rows1 = 0, rows2 = 0, ncont = 0, max_col = 0, max_rounds = 0, ntrips = 0, nlanes = 0;
     int *next_item = &E.fill[E.n_envs];
     for (;;) {
         // persistent warps: the next env comes from a counter, largest envs first (k_env_order)
@@ -345,6 +345,12 @@ __global__ void __launch_bounds__(OB_ENV2_THREADS, (ROWS_SMEM ? OB_ENV2_WARPS_SM
         // ---- SOR/PGS sweeps.  Colour c: lanes [0, 2T) hold the halves of its T two-body contacts, lanes [2T, 2T + O)
         // its O one-body contacts; colours are separated by __syncwarp only (an env is an island).
         const int ovf0 = cs2[2 * OVERFLOW_COLOUR], ovf1 = cs2[2 * OVERFLOW_COLOUR + 1];
+        if (lane == 0) // diagnostics: 32-lane trips and occupied lanes of one sweep (dStepStatsB200.env_trips / env_lanes)
+            for (int c = 0; c < ncol; c++) {
+                const int nl = 2 * (cs2[2 * c + 1] - cs2[2 * c]) + (cs2[2 * c + 2] - cs2[2 * c + 1]);
+                ntrips += (nl + 31) >> 5;
+                nlanes += nl;
+            }
         for (int it = 0; it < cfg.iters; it++) {
             for (int c = 0; c < ncol; c++) {
                 const int p0 = cs2[2 * c], T = cs2[2 * c + 1] - p0, O = cs2[2 * c + 2] - cs2[2 * c + 1];
@@ -497,6 +503,7 @@ __global__ void __launch_bounds__(OB_ENV2_THREADS, (ROWS_SMEM ? OB_ENV2_WARPS_SM
         }
         atomicMax(&stats->n_colours, max_col);
         atomicMax(&stats->colour_rounds, max_rounds);
+        if (ntrips) { atomicAdd(&stats->env_trips, ntrips); atomicAdd(&stats->env_lanes, nlanes); }
         if (blockIdx.x == 0 && threadIdx.x == 0) stats->solver_iters = cfg.iters;
     }
     (void)WARPS;

@@ -45,7 +45,7 @@ class StepStats(C.Structure):
                 ("class_count", C.c_int * 7), ("n_rows", C.c_int), ("n_rows1", C.c_int), ("n_rows2", C.c_int),
                 ("colour_rounds", C.c_int), ("cell_size", C.c_float), ("grid_dims", C.c_int * 3),
                 ("solver_iters", C.c_int), ("exact_status", C.c_int), ("n_islands", C.c_int), ("max_island_rows", C.c_int),
-                ("pivot_rounds", C.c_int)]
+                ("pivot_rounds", C.c_int), ("env_trips", C.c_int), ("env_lanes", C.c_int)]
 
     def as_dict(self):
         d = {}

@@ -262,6 +262,25 @@ def test_destroyed_body_leaves_its_geom_in_place_incrementally():
     ew.close()
 
 
+def test_geom_detached_from_its_body_stays_where_the_body_was():
+    """dGeomSetBody(g, 0): ODE leaves the geom at the pose it had on the body; it becomes a static obstacle there."""
+    s = Server()
+    s.add_static_box((0, -0.5, 0), (40, 1, 40))
+    b, g = s.add_body((2.0, 0.3, 1.0), "box", (1.0, 0.6, 1.0))
+    for _ in range(60):
+        s.tick()
+    rest = s.pos(b)
+    assert abs(rest[1] - 0.3) < 0.02
+    s.L.dGeomSetBody(g, None)
+    gp = s.L.dGeomGetPosition(g)
+    assert np.array_equal(np.float32([gp[0], gp[1], gp[2]]), rest)          # not the origin, not the spawn pose
+    ball, _ = s.add_body((2.0, 3.0, 1.0), "sphere", (0.25,))
+    for _ in range(120):
+        s.tick()
+    assert abs(s.pos(ball)[1] - (rest[1] + 0.3 + 0.25)) < 0.03                # it landed on the detached box
+    s.close()
+
+
 def test_obj_loader_builds_the_same_trimesh_as_buildsingle(tmp_path):
     """SURVEY section 8 f4 (loader half): an OBJ with quads, `a/b/c` references, negative indices and noise lines
     must give the same collision mesh -- hence bit-identical contacts -- as dGeomTriMeshDataBuildSingle fed

@@ -335,3 +335,105 @@ def test_c_slab_driver_equals_the_python_orchestration_bit_for_bit():
         assert c.w.stats()["flags"] == 0
         c.close()
         c.w.close()
+
+
+def test_union_of_slab_pair_sets_equals_the_single_world_pair_set():
+    """The broadphase depends on the state only, so the decomposition can be checked EXACTLY: after the state halo, the
+    pairs slab 0 finds (own-own, own-ghost, own-static) united with the pairs slab 1 finds, mapped to global body
+    numbers, must be precisely the pair set of one undecomposed world holding the same bodies in the same states --
+    nothing lost at the cut, nothing found twice -- and the contacts of every cross-face pair must be bit-identical."""
+    import odeb200
+    kw = dict(nx_per_slab=6, nz=8, ny=3, seed=5, spacing=0.6, margin_cols=3, mig_cap=256)   # dense: neighbours overlap
+    built = _build_dynamic(2, **kw)
+    sl = [s for _, s in built]
+    scs = [sc for sc, _ in built]
+    h = scs[0]["h"]
+    for step in range(25):                       # let the pile collapse across the face (no migration: ids stay put)
+        _phase(sl, "state")
+        for s in sl:
+            s.w.tick(h)
+        _phase(sl, "imp")
+    _phase(sl, "state")                          # ghosts = the upper slab's current boundary bodies
+    n_own = [s.info["n_own"] for s in sl]
+    n_static = sl[0].info["n_static"]
+    states = [s.w.state() for s in sl]
+    # ghost slot k of slab 0 mirrors body send_idx[k] of slab 1
+    send_idx = sl[1].sides["left"]["send_state_idx"].cpu().numpy()
+    ghost_body = sl[0].sides["right"]["ghost_body"].cpu().numpy()
+    n_sel = int((send_idx >= 0).sum())
+    assert n_sel > 10
+
+    def gid(r, b):                               # global body number in the merged world
+        return b if r == 0 else n_own[0] + b
+
+    ghost_to_global = {int(ghost_body[k]): gid(1, int(send_idx[k])) for k in range(n_sel)}
+    pair_sets, cross_contacts = [], {}
+    for r, s in enumerate(sl):
+        s.w.collide(8)
+        pr, cnt, pd, nrm, side = s.w.contacts()
+        first = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+        gb = scs[r]["geoms"]["body"]
+        out = set()
+        for i, (a, b) in enumerate(pr.tolist()):
+            ends = []
+            for g in (a, b):
+                body = int(gb[g])
+                if body < 0:
+                    ends.append(("static", g))                       # the five planes: same geom numbers everywhere
+                elif body < n_own[r]:
+                    ends.append(("body", gid(r, body)))
+                else:
+                    assert r == 0 and body in ghost_to_global, "a pair with an unused ghost slot"
+                    ends.append(("body", ghost_to_global[body]))
+            if ends[0][0] == "static" and ends[1][0] == "static":
+                continue                                              # plane-plane pairs exist in every world
+            key = tuple(sorted(ends))
+            assert key not in out
+            out.add(key)
+            if r == 0 and any(int(gb[g]) >= n_own[0] for g in (a, b)):
+                cross_contacts[key] = (pd[first[i]:first[i] + cnt[i]].copy(), nrm[first[i]:first[i] + cnt[i]].copy())
+        pair_sets.append(out)
+    assert not (pair_sets[0] & pair_sets[1]), "a pair was found by both slabs"
+    assert len(cross_contacts) >= 3, "the test needs contacts across the face"
+    # the undecomposed world: the planes + both slabs' own bodies in their current states
+    bodies = {k: np.concatenate([scs[r]["bodies"][k][:n_own[r]] for r in range(2)]) for k in scs[0]["bodies"]}
+    for k in ("pos", "quat", "lvel", "avel"):
+        bodies[k] = np.concatenate([states[r][k][:n_own[r]] for r in range(2)])
+    geoms = {k: np.concatenate([scs[0]["geoms"][k][:n_static]] + [scs[r]["geoms"][k][n_static:n_static + n_own[r]] for r in range(2)])
+             for k in scs[0]["geoms"]}
+    geoms["body"] = np.concatenate([np.full(n_static, -1), np.arange(n_own[0] + n_own[1])]).astype(np.int32)
+    geoms["cat"][n_static:] = slabs.CAT_OBJ
+    geoms["col"][n_static:] = slabs.CAT_OBJ | slabs.CAT_MAP
+    one = odeb200.World(gravity=scs[0]["gravity"])
+    one.load_scene(scenes.from_arrays("one", bodies, geoms, h=h))
+    one.collide(8)
+    st1 = one.state()
+    for k in ("pos", "quat"):
+        assert np.array_equal(st1[k], bodies[k])
+    pr, cnt, pd, nrm, side = one.contacts()
+    first = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+    ref, ref_contacts = set(), {}
+    for i, (a, b) in enumerate(pr.tolist()):
+        ends = [("static", g) if g < n_static else ("body", g - n_static) for g in (a, b)]
+        if ends[0][0] == "static" and ends[1][0] == "static":
+            continue
+        key = tuple(sorted(ends))
+        ref.add(key)
+        ref_contacts[key] = (pd[first[i]:first[i] + cnt[i]], nrm[first[i]:first[i] + cnt[i]])
+    union = pair_sets[0] | pair_sets[1]
+    assert union == ref, (len(union), len(ref), sorted(union - ref)[:5], sorted(ref - union)[:5])
+    n_with_contacts = 0
+    for key, (cpd, cn) in cross_contacts.items():
+        rpd, rn = ref_contacts[key]
+        assert len(cpd) == len(rpd), key
+        if len(cpd):
+            n_with_contacts += 1
+            # the slab lists the ghost after its own bodies, the single world by global number: the same two geoms may be
+            # handed to the collider in the other order, which flips the normal's sign but nothing else
+            same = np.array_equal(cpd, rpd) and np.array_equal(cn, rn)
+            flipped = np.allclose(np.sort(cpd[:, 3]), np.sort(rpd[:, 3]), atol=1e-5) and np.allclose(np.abs(cn), np.abs(rn), atol=1e-5)
+            assert same or flipped, key
+    assert n_with_contacts >= 1
+    one.close()
+    for s in sl:
+        s.w.close()
