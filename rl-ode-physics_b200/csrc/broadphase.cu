@@ -160,6 +160,7 @@ __global__ void k_grid_params(unsigned *__restrict__ acc, GridParams *__restrict
     bc->first_big = n_geoms;
     bc->first_dead = n_geoms;
     bc->n_pairs = 0;
+    bc->n_bb = 0;
     acc_rearm(acc);
 }
 
@@ -572,6 +573,7 @@ __global__ void k_env_counters(BroadCounters *__restrict__ bc, GridParams *__res
     bc->first_dead = n_alive;
     bc->first_big = n_alive - n_shared;
     bc->n_pairs = 0;
+    bc->n_bb = 0;
     gp->cell = 0.f; gp->dx = gp->dy = gp->dz = 0; gp->n_envs = n_envs;
 }
 
@@ -606,6 +608,7 @@ __global__ void k_single_pair(GeomArrays g, int g1, int g2, int2 *__restrict__ p
     const int cls = (g.alive[g1] && g.alive[g2]) ? pair_class(ta, tb) : PC_NONE;
     pairs[0] = make_int2(ga, gb);
     bc->n_pairs = 1;
+    bc->n_bb = 0;
     bc->first_big = bc->first_dead = g.n;
     for (int c = 0; c <= PC_COUNT; c++) bc->class_start[c] = c <= cls ? 0 : 1;
     stats->n_pairs = 1;

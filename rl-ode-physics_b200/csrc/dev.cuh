@@ -73,6 +73,7 @@ struct GridParams {
 
 struct BroadCounters {
     int first_big, first_dead, n_pairs;
+    int n_bb; // box-box pairs that passed the separating-axis pass (two-pass narrowphase)
     int class_start[PC_COUNT + 1];
 };
 
@@ -93,6 +94,7 @@ struct BroadPhase {
     int2 *sweep_tmp = nullptr; // SWEEP_TCAP layers of n parked hits
     int *sweep_tot = nullptr;  // hits per sweep thread
     int2 *pairs = nullptr;
+    int *bb_list = nullptr; // box-box pairs without a separating axis (compacted by k_np_box_box_sat)
     SortWorkspace sort;
     ScanWorkspace scan;
 };

@@ -115,7 +115,7 @@ void eng_destroy(Engine *e) {
     dev_free(bp.blk);
     dev_free(bp.acc); dev_free(bp.gp); dev_free(bp.counters); dev_free(bp.keys); dev_free(bp.idx);
     dev_free(bp.s_min); dev_free(bp.s_max); dev_free(bp.s_flt); dev_free(bp.cell_start); dev_free(bp.cell_end);
-    dev_free(bp.cnt); dev_free(bp.pairs); dev_free(bp.sweep_tmp); dev_free(bp.sweep_tot);
+    dev_free(bp.cnt); dev_free(bp.pairs); dev_free(bp.bb_list); dev_free(bp.sweep_tmp); dev_free(bp.sweep_tot);
     sort_workspace_free(bp.sort); scan_workspace_free(bp.scan);
     dev_free(e->cs.pd); dev_free(e->cs.ns); dev_free(e->cs.nc);
     ManifoldArrays &M = e->M;
@@ -380,6 +380,7 @@ void engine_ensure_pair_capacity(Engine *e) {
     if (wantp > bp.cap_pairs) {
         const size_t n = (size_t)wantp;
         dev_realloc(bp.pairs, 0, n, st, false);
+        dev_realloc(bp.bb_list, 0, n, st, false);
         dev_realloc(e->cs.pd, 0, n * 8, st, false);
         dev_realloc(e->cs.ns, 0, n * 8, st, false);
         dev_realloc(e->cs.nc, 0, n, st, false);
@@ -770,7 +771,7 @@ static inline unsigned long long gk_bytes(unsigned long long h, const void *p, s
 static unsigned long long graph_key(Engine *e, bool step) {
     unsigned long long h = 0x243F6A8885A308D3ull;
     if (step) h = gk_ptr(h, e->B.snap); // alternates between the two snapshot buffers: one step graph per buffer
-    const void *ptrs[] = {e->B.pos, e->B.quat, e->B.fc, e->B.local, e->G.pos, e->G.amin, e->bp.pairs, e->bp.cnt, e->bp.blk,
+    const void *ptrs[] = {e->B.pos, e->B.quat, e->B.fc, e->B.local, e->G.pos, e->G.amin, e->bp.pairs, e->bp.bb_list, e->bp.cnt, e->bp.blk,
                           e->bp.sweep_tmp, e->bp.keys, e->bp.scan.sums[0], e->bp.scan.sums[1], e->scan.sums[0], e->scan.sums[1],
                           e->cs.pd, e->cs.nc, e->M.rec, e->M.flag, e->S.q0, e->S.mrec, e->E.rec, e->E.cnt, e->E.start, e->E.fill,
                           e->E.first_body, e->EB.first, e->EB.count, e->EB.shared, e->d_stats};

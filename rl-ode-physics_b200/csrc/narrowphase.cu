@@ -284,8 +284,10 @@ struct BoxBoxOut {
     int n;
 };
 
+// sat_only: stop after the 15-axis test and return 1 when no separating axis exists (the first pass of the two-pass
+// kernel below); the arithmetic up to that point is the full function's, so both passes take the same decision.
 __device__ int box_box(const float p1[3], const float R1[12], const float side1[3], const float p2[3],
-                       const float R2[12], const float side2[3], int maxc_in, BoxBoxOut &out) {
+                       const float R2[12], const float side2[3], int maxc_in, BoxBoxOut &out, bool sat_only = false) {
     const float fudge_factor = 1.05f;
     float p[3], pp[3], normalC[3] = {0, 0, 0};
     const float *normalR = nullptr;
@@ -340,6 +342,7 @@ __device__ int box_box(const float p1[3], const float R1[12], const float side1[
 #undef OB_TST2
 
     if (!code) return 0;
+    if (sat_only) return 1;
 
     if (normalR) { normal[0] = normalR[0]; normal[1] = normalR[4]; normal[2] = normalR[8]; }
     else { normal[0] = d11(R1, normalC); normal[1] = d11(R1 + 4, normalC); normal[2] = d11(R1 + 8, normalC); }
@@ -482,23 +485,59 @@ __device__ __forceinline__ void m3_to_arr(const M3 &R, float a[12]) {
     a[8] = R.r2.x; a[9] = R.r2.y; a[10] = R.r2.z; a[11] = 0;
 }
 
-__global__ void __launch_bounds__(128) k_np_box_box(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
-                                                     GeomArrays g, ContactSlots cs, int maxc) {
+// Two passes.  ncu had the one-pass kernel at 5.8 of 32 active lanes per instruction on the 1 M-body pile: two thirds of
+// the AABB-overlapping box pairs leave dBoxBox at a separating axis after a few dozen instructions while their warp
+// mates go on through rectangle clipping and cullPoints.  Pass 1 runs only the 15-axis test for every pair, writes
+// nc = 0 for the separated ones and compacts the others (warp ballot + one atomic per warp; the list's order does not
+// matter, every pair writes its own contact slots); pass 2 runs the whole of dBoxBox on the compacted list, so its
+// warps are full of pairs that all clip.  Same function, same arithmetic, same contacts.
+__device__ __forceinline__ void load_box_pair(const GeomArrays &g, int2 pr, float p1[3], float R1[12], float s1[3], float p2[3],
+                                              float R2[12], float s2[3]) {
+    const GeomPose b1 = load_geom(g, pr.x), b2 = load_geom(g, pr.y);
+    m3_to_arr(b1.R, R1);
+    m3_to_arr(b2.R, R2);
+    p1[0] = b1.p.x; p1[1] = b1.p.y; p1[2] = b1.p.z; p2[0] = b2.p.x; p2[1] = b2.p.y; p2[2] = b2.p.z;
+    s1[0] = b1.d.x; s1[1] = b1.d.y; s1[2] = b1.d.z; s2[0] = b2.d.x; s2[1] = b2.d.y; s2[2] = b2.d.z;
+}
+
+__global__ void __launch_bounds__(128) k_np_box_box_sat(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
+                                                         GeomArrays g, ContactSlots cs, int *__restrict__ list, int *__restrict__ n_list) {
     const int s = bc->class_start[PC_BOX_BOX], e = bc->class_start[PC_BOX_BOX + 1];
-    for (int pi = s + blockIdx.x * blockDim.x + threadIdx.x; pi < e; pi += gridDim.x * blockDim.x) {
-        const int2 pr = pairs[pi];
-        const GeomPose b1 = load_geom(g, pr.x), b2 = load_geom(g, pr.y);
-        float R1[12], R2[12];
-        m3_to_arr(b1.R, R1);
-        m3_to_arr(b2.R, R2);
-        const float p1[3] = {b1.p.x, b1.p.y, b1.p.z}, p2[3] = {b2.p.x, b2.p.y, b2.p.z};
-        const float s1[3] = {b1.d.x, b1.d.y, b1.d.z}, s2[3] = {b2.d.x, b2.d.y, b2.d.z};
+    const int lane = threadIdx.x & 31;
+    const int span = ((e - s) + 31) & ~31; // whole warps enter the loop together (ballot)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < span; i += gridDim.x * blockDim.x) {
+        const int pi = s + i;
+        bool hit = false;
+        if (pi < e) {
+            float p1[3], p2[3], s1[3], s2[3], R1[12], R2[12];
+            load_box_pair(g, pairs[pi], p1, R1, s1, p2, R2, s2);
+            BoxBoxOut out;
+            hit = box_box(p1, R1, s1, p2, R2, s2, 8, out, true) != 0;
+            if (!hit) cs.nc[pi] = 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(n_list, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (hit) list[base + __popc(m & ((1u << lane) - 1u))] = pi;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_np_box_box(const int2 *__restrict__ pairs, GeomArrays g, ContactSlots cs, int maxc,
+                                                     const int *__restrict__ list, const int *__restrict__ n_list) {
+    const int n = *n_list;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int pi = list[i];
+        float p1[3], p2[3], s1[3], s2[3], R1[12], R2[12];
+        load_box_pair(g, pairs[pi], p1, R1, s1, p2, R2, s2);
         BoxBoxOut out;
-        const int n = box_box(p1, R1, s1, p2, R2, s2, maxc > 8 ? 8 : maxc, out);
+        const int nc = box_box(p1, R1, s1, p2, R2, s2, maxc > 8 ? 8 : maxc, out);
         // dCollideBoxBox: contact normal = -dBoxBox normal
         const V3 nn = v3(-out.normal[0], -out.normal[1], -out.normal[2]);
-        for (int k = 0; k < n; k++) put_contact(cs, pi, k, v3(out.pos[k][0], out.pos[k][1], out.pos[k][2]), out.dep[k], nn, -1);
-        cs.nc[pi] = n;
+        for (int k = 0; k < nc; k++) put_contact(cs, pi, k, v3(out.pos[k][0], out.pos[k][1], out.pos[k][2]), out.dep[k], nn, -1);
+        cs.nc[pi] = nc;
     }
 }
 
@@ -915,8 +954,11 @@ void narrowphase_run(const BroadPhase &bp, GeomArrays g, MeshTable meshes, const
         for (int i = 0; i < 5; i++) OB_CUDA(cudaStreamWaitEvent(side[i], fork_ev, 0));
         s1 = side[0]; s2 = side[1]; s3 = side[2]; s4 = side[3]; s5 = side[4];
     }
-    k_np_box_box<<<grid, 128, 0, st>>>(bp.counters, bp.pairs, g, cs, max_contacts);
-    OB_CHECK_KERNEL("k_np_box_box", st);
+    // two-pass box-box: the compacted list lives in the sweep's (now idle) per-thread hit counters
+    k_np_box_box_sat<<<grid, 128, 0, s3>>>(bp.counters, bp.pairs, g, cs, bp.bb_list, &bp.counters->n_bb);
+    OB_CHECK_KERNEL("k_np_box_box_sat", s3);
+    k_np_box_box<<<grid, 128, 0, s3>>>(bp.pairs, g, cs, max_contacts, bp.bb_list, &bp.counters->n_bb);
+    OB_CHECK_KERNEL("k_np_box_box", s3);
     k_np_sphere_sphere<<<grid, 256, 0, s1>>>(bp.counters, bp.pairs, g, cs);
     OB_CHECK_KERNEL("k_np_sphere_sphere", s1);
     k_np_sphere_box<<<grid, 256, 0, s2>>>(bp.counters, bp.pairs, g, cs);

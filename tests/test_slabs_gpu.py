@@ -406,6 +406,15 @@ def test_union_of_slab_pair_sets_equals_the_single_world_pair_set():
     geoms["col"][n_static:] = slabs.CAT_OBJ | slabs.CAT_MAP
     one = odeb200.World(gravity=scs[0]["gravity"])
     one.load_scene(scenes.from_arrays("one", bodies, geoms, h=h))
+    # bit-exact states: the bulk loader re-normalises quaternions (dBodySetQuaternion semantics), the state scatter does not
+    import torch
+    nall = n_own[0] + n_own[1]
+    rec = np.zeros((nall, 16), np.float32)
+    rec[:, 0:3] = bodies["pos"]; rec[:, 4:8] = bodies["quat"]; rec[:, 8:11] = bodies["lvel"]; rec[:, 12:15] = bodies["avel"]
+    d_rec = torch.as_tensor(rec, device="cuda:0")
+    d_idx = torch.arange(nall, dtype=torch.int32, device="cuda:0")
+    one.collide(8)                               # (first sync of the world to the device)
+    one.L.dWorldUnpackStatesDeviceB200(one.w, d_idx.data_ptr(), nall, d_rec.data_ptr())
     one.collide(8)
     st1 = one.state()
     for k in ("pos", "quat"):
