@@ -81,6 +81,7 @@ constexpr int SWEEP_TCAP = 16; // hits a sweep thread can park in the count pass
 
 struct BroadPhase {
     int cap_geoms = 0, cap_cells = 0, key_bits = 0, cap_pairs = 0;
+    long cap_blk = 0; // ints in blk
     unsigned *acc = nullptr;
     GridParams *gp = nullptr;
     BroadCounters *counters = nullptr;
@@ -105,6 +106,8 @@ struct EnvBroad {
     int enabled = 0;
     int single = 0;      // one world: every geom belongs to the one range, env ids are ignored
     int n_shared = 0, n_alive = 0;
+    int sap = 1; // sort-and-sweep CTA per env when every env has <= 128 geoms (0: always the all-pairs sweep)
+    int n_envs = 0, max_count = 0; // number of env ranges and the largest one (<= 128: sort-and-sweep CTA per env)
     int *first = nullptr, *count = nullptr, *shared = nullptr;
 };
 
@@ -143,6 +146,7 @@ struct ManifoldArrays {
 // batched independent worlds: manifolds bucketed per env for the island solver (one lane group per env)
 struct EnvArrays {
     int n_envs;
+    int cap;         // capacity of rec / perm / col (solver units); more units than this: flagged, the step runs without contacts
     int max_bodies;  // largest number of bodies in one env (host-known)
     int contiguous;  // 1: every env's bodies are one contiguous index range (enables shared-memory staging)
     int *first_body; // first body of each env

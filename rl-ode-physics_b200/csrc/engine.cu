@@ -80,6 +80,7 @@ Engine *eng_create(int device) {
     if (const char *g = getenv("ODE_B200_COLOUR_SPREAD")) eng_set_colour_spread(e, atoi(g));
     if (const char *g = getenv("ODE_B200_CONTACT_UNITS")) e->contact_units = atoi(g);
     if (const char *g = getenv("ODE_B200_ENV_STAGE")) e->env_stage = atoi(g);
+    if (const char *g = getenv("ODE_B200_ENV_SAP")) e->EB.sap = atoi(g);
     if (const char *g = getenv("ODE_B200_ENV_PAIR")) e->env_pair = atoi(g);
     if (const char *g = getenv("ODE_B200_ENV_PAIR_ROWS")) e->env_pair_rows = atoi(g);
     if (const char *g = getenv("ODE_B200_L2_PERSIST")) e->l2_persist = atoi(g);
@@ -351,7 +352,8 @@ void engine_ensure_capacity(Engine *e) {
         dev_realloc(bp.s_min, 0, n, st, false); dev_realloc(bp.s_max, 0, n, st, false);
         dev_realloc(bp.s_flt, 0, n, st, false);
         dev_realloc(bp.cnt, 0, (size_t)PC_COUNT * n + 1, st, false);
-        dev_realloc(bp.blk, 0, (size_t)PC_COUNT * (n / 128 + 2) + 1, st, false);
+        bp.cap_blk = (long)PC_COUNT * (long)(n / 128 + 2 + (size_t)std::max(e->n_envs, 1) + 1) + 1;
+        dev_realloc(bp.blk, 0, (size_t)bp.cap_blk, st, false);
         dev_realloc(bp.sweep_tmp, 0, (size_t)SWEEP_TCAP * n, st, false);
         dev_realloc(bp.sweep_tot, 0, n, st, false);
         bp.cap_geoms = (int)n;
@@ -424,6 +426,7 @@ void engine_ensure_pair_capacity(Engine *e) {
         }
     }
     e->E.n_envs = e->n_envs;
+    e->E.cap = e->cap_env_rec;
 }
 
 template <typename T>
@@ -570,6 +573,8 @@ static void envg_upload_tables(Engine *e, cudaStream_t st) {
     eb.single = ne == 1 ? 1 : 0;
     eb.n_shared = (int)e->envg_shared.size();
     eb.n_alive = e->envg_alive;
+    eb.n_envs = ne;
+    eb.max_count = e->envg_max;
 }
 
 static void clear_dirty_bodies(Engine *e) {
@@ -727,7 +732,7 @@ void eng_sync_to_device(Engine *e) {
         e->patch_inflight = true;
         // (the per-env ranges are append-only; the alive count follows the patches)
         if (tables) envg_upload_tables(e, st);
-        else e->EB.n_alive = e->envg_alive;
+        else { e->EB.n_alive = e->envg_alive; e->EB.max_count = e->envg_max; }
         e->n_g_dev = g.n;
         clear_dirty_geoms(e);
     }
@@ -787,7 +792,7 @@ static unsigned long long graph_key(Engine *e, bool step) {
     }
     const int ints[] = {e->B.n, e->G.n, e->cap_b, e->cap_g, e->bp.cap_pairs, e->cs.stride, e->M.cap, e->S.cap, e->n_envs, e->max_contacts,
                         e->env_group, e->contact_units, e->solver_mode, e->env_stage, e->env_pair, e->env_pair_rows, e->env_fuse, e->colour_spread, e->broad_mode,
-                        e->tiny_solver, (int)e->keep_fc, e->EB.enabled, e->EB.single, e->EB.n_shared, e->EB.n_alive, e->E.contiguous,
+                        e->tiny_solver, (int)e->keep_fc, e->EB.enabled, e->EB.single, e->EB.n_shared, e->EB.n_alive, e->EB.max_count, e->EB.n_envs, e->EB.sap, e->E.contiguous,
                         e->E.max_bodies, e->meshes.n, (int)e->have_device_contacts, e->snap_fmt};
     h = gk_bytes(h, ints, sizeof(ints));
     h = gk_bytes(h, &e->params, sizeof(e->params));

@@ -673,6 +673,10 @@ __global__ void __launch_bounds__(256) k_env_bucket(const BroadCounters *__restr
                                                      EnvArrays E, StepStats *__restrict__ stats, int per_contact, int kstride,
                                                      int *__restrict__ m_count) {
     const int n = bc->n_pairs;
+    if (E.start[E.n_envs] > E.cap) { // more solver units than the arrays hold: flagged, never silent; the solve is skipped
+        if (blockIdx.x == 0 && threadIdx.x == 0) { atomicOr(&stats->flags, SF_MANIFOLD_OVERFLOW); stats->n_manifolds = 0; *m_count = 0; }
+        return;
+    }
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         const int2 pr = pairs[p];
         int b1 = g_body[pr.x], b2 = g_body[pr.y];
@@ -758,7 +762,8 @@ __global__ void __launch_bounds__(128, OB_ENV_CTAS) k_env_solve(EnvArrays E, Bod
         const int qi = item * W + lane / G;
         const bool have = qi < E.n_envs;
         const int env = have ? E.order[qi] : E.n_envs;
-        const int ms = have ? E.start[env] : 0, me = have ? E.start[env + 1] : 0;
+        const bool fits = E.start[E.n_envs] <= E.cap; // unit overflow (flagged by k_env_bucket): free flight
+        const int ms = (have && fits) ? E.start[env] : 0, me = (have && fits) ? E.start[env + 1] : 0;
         const int trips = (__reduce_max_sync(FULL, me - ms) + G - 1) / G; // warp-uniform
         const int fb = have ? E.first_body[env] : 0, nbod = have ? E.n_body[env] : 0;
         if (fused) { // per-body step preparation of this env (k_body_prep's work), fused in

@@ -92,10 +92,10 @@ __device__ __forceinline__ float row_delta(float rhs_s, float Adcfm, float s1, f
 } // namespace
 
 #ifndef OB_ENV2_THREADS
-#define OB_ENV2_THREADS 64
+#define OB_ENV2_THREADS 32 // one warp (= one env at a time) per CTA: measured 1.09 ms vs 1.12 (64) and 1.14 (128) on C4
 #endif
 #ifndef OB_ENV2_WARPS_SM
-#define OB_ENV2_WARPS_SM 20 // resident warps per SM the register budget of the global-rows variant is sized for
+#define OB_ENV2_WARPS_SM 16 // resident warps per SM the register budget is sized for: 126 registers, no spills (20 warps = 96 registers: +6 % time)
 #endif
 #ifndef OB_ENV2_WARPS_SM_ROWS
 #define OB_ENV2_WARPS_SM_ROWS 8 // ... of the shared-memory-rows variant (shared memory allows no more)
@@ -141,7 +141,8 @@ __global__ void __launch_bounds__(OB_ENV2_THREADS, (ROWS_SMEM ? OB_ENV2_WARPS_SM
         item = __shfl_sync(FULL, item, 0);
         if (item >= E.n_envs) break;
         const int env = E.order[item];
-        const int ms = E.start[env], me = E.start[env + 1];
+        const bool fits = E.start[E.n_envs] <= E.cap; // unit overflow (flagged by k_env_bucket): free flight
+        const int ms = fits ? E.start[env] : 0, me = fits ? E.start[env + 1] : 0;
         const int nun = me - ms;
         const int fb = E.first_body[env], nbod = E.n_body[env];
         rows.ms = ms;
@@ -351,64 +352,74 @@ __global__ void __launch_bounds__(OB_ENV2_THREADS, (ROWS_SMEM ? OB_ENV2_WARPS_SM
                 ntrips += (nl + 31) >> 5;
                 nlanes += nl;
             }
+        // one 32-lane trip: every lane updates one body's half of one contact (rows: normal, tangent 1, tangent 2)
+        auto solve_trip = [&](int pos, bool active, bool neg, const float4 A, const float4 Rh, const float4 C, const float4 D) {
+            float4 L = *rows.plane(5, pos);
+            const int flags = __float_as_int(A.w);
+            const bool two = flags & RF_TWO;
+            const int b = neg ? ((flags >> 12) & 0xfff) : (flags & 0xfff);
+            HalfBody hb;
+            {
+                const float4 a = sm_fc[b], w = sm_fc[mb + b];
+                hb.fl = v3(a); hb.fa = v3(w);
+                const float4 i0 = sm_inv[3 * b], i1 = sm_inv[3 * b + 1], i2 = sm_inv[3 * b + 2];
+                hb.iI = M3{v3(i0), v3(i1), v3(i2)};
+                hb.invM = i0.w;
+            }
+            const V3 n = v3(A), r = v3(Rh);
+            const float sgn = neg ? -1.0f : 1.0f;
+            V3 Ja;
+            // normal row
+            float s = half_dot(n, r, sgn * D.x, hb, Ja);
+            float so = __shfl_xor_sync(FULL, s, 1);
+            float delta = row_delta(C.x, D.x * cfmhN, neg ? so : s, neg ? s : so, two, 0.f, INFINITY, L.x);
+            half_apply(sgn * delta, n, Ja, hb);
+            if (the_m >= 2) {
+                V3 t1, t2;
+                plane_space_with_k(n, C.w, t1, t2);
+                const float mu = D.w;
+                float hi = mu, lo = -mu;
+                if (flags & RF_APPROX1) { hi = fabsf(mu * L.x); lo = -hi; }
+                s = half_dot(t1, r, sgn * D.y, hb, Ja);
+                so = __shfl_xor_sync(FULL, s, 1);
+                delta = row_delta(C.y, D.y * cfmh1, neg ? so : s, neg ? s : so, two, lo, hi, L.y);
+                half_apply(sgn * delta, t1, Ja, hb);
+                if (the_m >= 3) {
+                    const float mu2 = (flags & RF_MU2) ? (*rows.plane(2, pos)).w : mu;
+                    hi = mu2; lo = -mu2;
+                    if (flags & RF_APPROX2) { hi = fabsf(mu2 * L.x); lo = -hi; }
+                    s = half_dot(t2, r, sgn * D.z, hb, Ja);
+                    so = __shfl_xor_sync(FULL, s, 1);
+                    delta = row_delta(C.z, D.z * cfmh2, neg ? so : s, neg ? s : so, two, lo, hi, L.z);
+                    half_apply(sgn * delta, t2, Ja, hb);
+                }
+            }
+            if (active) {
+                sm_fc[b] = make_float4(hb.fl.x, hb.fl.y, hb.fl.z, 0.f);
+                sm_fc[mb + b] = make_float4(hb.fa.x, hb.fa.y, hb.fa.z, 0.f);
+                if (!neg) *rows.plane(5, pos) = L;
+            }
+        };
+        // lane -> (row slot, body half) of trip (c, gl0)
+        auto trip_lane = [&](int c, int gl0, int &pos, bool &active, bool &neg) {
+            const int p0 = cs2[2 * c], T = cs2[2 * c + 1] - p0, O = cs2[2 * c + 2] - cs2[2 * c + 1];
+            const int gl = gl0 + lane;
+            active = gl < 2 * T + O;
+            const bool pairlane = gl < 2 * T;
+            pos = active ? (pairlane ? p0 + (gl >> 1) : p0 + gl - T) : p0;
+            neg = pairlane && (gl & 1);
+        };
+        // (Fetching the next trip's immutable row planes a whole trip ahead -- a trip table in shared memory, 16 more
+        // registers -- was measured: C4 solve 1.09 -> 1.17 ms.  The loads of a trip already overlap the previous trip of
+        // the other resident warps; the extra live registers and the table look-ups cost more than the stall they hide.)
         for (int it = 0; it < cfg.iters; it++) {
             for (int c = 0; c < ncol; c++) {
-                const int p0 = cs2[2 * c], T = cs2[2 * c + 1] - p0, O = cs2[2 * c + 2] - cs2[2 * c + 1];
-                const int nl = 2 * T + O;
+                const int nl = 2 * (cs2[2 * c + 1] - cs2[2 * c]) + (cs2[2 * c + 2] - cs2[2 * c + 1]);
                 for (int gl0 = 0; gl0 < nl; gl0 += 32) {
-                    const int gl = gl0 + lane;
-                    const bool active = gl < nl;
-                    const bool pairlane = gl < 2 * T;
-                    const int pos = active ? (pairlane ? p0 + (gl >> 1) : p0 + gl - T) : p0;
-                    const bool neg = pairlane && (gl & 1);
-                    const float4 A = *rows.plane(0, pos);
-                    const float4 Rh = *rows.plane(neg ? 2 : 1, pos);
-                    const float4 C = *rows.plane(3, pos), D = *rows.plane(4, pos);
-                    float4 L = *rows.plane(5, pos);
-                    const int flags = __float_as_int(A.w);
-                    const bool two = flags & RF_TWO;
-                    const int b = neg ? ((flags >> 12) & 0xfff) : (flags & 0xfff);
-                    HalfBody hb;
-                    {
-                        const float4 a = sm_fc[b], w = sm_fc[mb + b];
-                        hb.fl = v3(a); hb.fa = v3(w);
-                        const float4 i0 = sm_inv[3 * b], i1 = sm_inv[3 * b + 1], i2 = sm_inv[3 * b + 2];
-                        hb.iI = M3{v3(i0), v3(i1), v3(i2)};
-                        hb.invM = i0.w;
-                    }
-                    const V3 n = v3(A), r = v3(Rh);
-                    const float sgn = neg ? -1.0f : 1.0f;
-                    V3 Ja;
-                    // normal row
-                    float s = half_dot(n, r, sgn * D.x, hb, Ja);
-                    float so = __shfl_xor_sync(FULL, s, 1);
-                    float delta = row_delta(C.x, D.x * cfmhN, neg ? so : s, neg ? s : so, two, 0.f, INFINITY, L.x);
-                    half_apply(sgn * delta, n, Ja, hb);
-                    if (the_m >= 2) {
-                        V3 t1, t2;
-                        plane_space_with_k(n, C.w, t1, t2);
-                        const float mu = D.w;
-                        float hi = mu, lo = -mu;
-                        if (flags & RF_APPROX1) { hi = fabsf(mu * L.x); lo = -hi; }
-                        s = half_dot(t1, r, sgn * D.y, hb, Ja);
-                        so = __shfl_xor_sync(FULL, s, 1);
-                        delta = row_delta(C.y, D.y * cfmh1, neg ? so : s, neg ? s : so, two, lo, hi, L.y);
-                        half_apply(sgn * delta, t1, Ja, hb);
-                        if (the_m >= 3) {
-                            const float mu2 = (flags & RF_MU2) ? (*rows.plane(2, pos)).w : mu;
-                            hi = mu2; lo = -mu2;
-                            if (flags & RF_APPROX2) { hi = fabsf(mu2 * L.x); lo = -hi; }
-                            s = half_dot(t2, r, sgn * D.z, hb, Ja);
-                            so = __shfl_xor_sync(FULL, s, 1);
-                            delta = row_delta(C.z, D.z * cfmh2, neg ? so : s, neg ? s : so, two, lo, hi, L.z);
-                            half_apply(sgn * delta, t2, Ja, hb);
-                        }
-                    }
-                    if (active) {
-                        sm_fc[b] = make_float4(hb.fl.x, hb.fl.y, hb.fl.z, 0.f);
-                        sm_fc[mb + b] = make_float4(hb.fa.x, hb.fa.y, hb.fa.z, 0.f);
-                        if (!neg) *rows.plane(5, pos) = L;
-                    }
+                    int pos;
+                    bool active, neg;
+                    trip_lane(c, gl0, pos, active, neg);
+                    solve_trip(pos, active, neg, *rows.plane(0, pos), *rows.plane(neg ? 2 : 1, pos), *rows.plane(3, pos), *rows.plane(4, pos));
                 }
                 __syncwarp();
             }

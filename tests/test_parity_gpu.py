@@ -475,6 +475,21 @@ def test_capacity_overflow_is_flagged_not_silent():
     ew.close()
 
 
+def test_unit_capacity_overflow_on_the_island_path_is_flagged_not_silent():
+    """batched worlds whose contacts outnumber the solver-unit arrays: the step says so (flag 2) and moves the bodies
+    without contact forces for that tick instead of writing past the arrays"""
+    sc = scenes.batched_worlds_scene(12, seed=4, spacing=0.7)
+    ew = util.engine_world(sc)
+    ew.set_capacity(0, 200)              # ~1200 contacts form in these 12 dense worlds
+    for _ in range(4):
+        ew.tick(sc["h"])
+    st = ew.stats()
+    assert st["flags"] & 2 and st["n_contacts"] == 0, st
+    s = ew.state()
+    assert np.isfinite(s["pos"]).all() and np.isfinite(s["lvel"]).all()
+    ew.close()
+
+
 def test_dworldstep_parity_mode_converges_to_the_exact_lcp():
     """the reference calls dWorldStep (src/main.c:213), libode's exact Dantzig stepper.
     dWorldSetStepSolverB200(world, n > 0, tol) makes the engine's dWorldStep run residual-terminated sweeps; their
