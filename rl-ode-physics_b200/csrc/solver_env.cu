@@ -89,11 +89,6 @@ __device__ __forceinline__ float row_delta(float rhs_s, float Adcfm, float s1, f
     return delta;
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 } // namespace
 
 #ifndef OB_ENV2_THREADS
@@ -101,9 +96,6 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #endif
 #ifndef OB_ENV2_WARPS_SM
 #define OB_ENV2_WARPS_SM 16 // resident warps per SM the register budget is sized for: 126 registers, no spills (20 warps = 96 registers: +6 % time)
-#endif
-#ifndef OB_ENV2_PREFETCH
-#define OB_ENV2_PREFETCH 1 // stage the next trip's immutable row planes in shared memory with cp.async (no registers in flight)
 #endif
 #ifndef OB_ENV2_WARPS_SM_ROWS
 #define OB_ENV2_WARPS_SM_ROWS 8 // ... of the shared-memory-rows variant (shared memory allows no more)
@@ -120,8 +112,7 @@ __global__ void __launch_bounds__(OB_ENV2_THREADS, (ROWS_SMEM ? OB_ENV2_WARPS_SM
     // per warp: body region (80 B per body: colouring scratch, then accumulators + world inverse inertias), bucket
     // starts + cursors, and with ROWS_SMEM the row planes
     const size_t region = (size_t)mb * 80;
-    constexpr bool PREFETCH = OB_ENV2_PREFETCH && !ROWS_SMEM;
-    const size_t per_warp = region + 2 * CS2 * sizeof(int) + (ROWS_SMEM ? (size_t)row_cap * 96 : (PREFETCH ? 4 * 32 * sizeof(float4) : 0));
+    const size_t per_warp = region + 2 * CS2 * sizeof(int) + (ROWS_SMEM ? (size_t)row_cap * 96 : 0);
     unsigned char *wbase = env_smem + (size_t)wid * per_warp;
     unsigned long long *masks = reinterpret_cast<unsigned long long *>(wbase);
     unsigned long long *prio = masks + mb;
@@ -134,9 +125,6 @@ __global__ void __launch_bounds__(OB_ENV2_THREADS, (ROWS_SMEM ? OB_ENV2_WARPS_SM
     rows.g = EnvRowPlanes{S.q0, S.q1, S.q2, S.q3, S.q4, S.lam};
     rows.sm = reinterpret_cast<float4 *>(wbase + region + 2 * CS2 * sizeof(int));
     rows.row_cap = row_cap;
-    float4 *pf = rows.sm;                          // PREFETCH: [plane A, R, C, D][lane] of the NEXT trip
-    int2 *tt = reinterpret_cast<int2 *>(cursor);   // PREFETCH: trip table of one sweep (the sort's cursors are dead by then)
-    constexpr int TT_MAX = CS2 / 2;
     // the three CFMs of the world's one surface (build_row: Adcfm = Ad * (cfm / h))
     const float h1 = 1.0f / cfg.h;
     const float cfmhN = ((usurf.mode & MODE_SOFT_CFM) ? usurf.soft_cfm : cfg.cfm) * h1;
@@ -423,63 +411,11 @@ __global__ void __launch_bounds__(OB_ENV2_THREADS, (ROWS_SMEM ? OB_ENV2_WARPS_SM
         };
         // (Fetching the next trip's immutable row planes a whole trip ahead -- a trip table in shared memory, 16 more
         // registers -- was measured: C4 solve 1.09 -> 1.17 ms.  The loads of a trip already overlap the previous trip of
-        // the other resident warps; the extra live registers and the table look-ups cost more than the stall they hide.)
-        // PREFETCH: the trips of one sweep as a table (lane -> row slot and body half without the bucket arithmetic), so
-        // that trip k can start the asynchronous copy of trip k+1's immutable planes (A, r, C, D: 64 B per lane) into
-        // shared memory before it computes.  cp.async keeps nothing in registers while the copy is in flight -- the
-        // register-held variant above lost to its own register pressure.  lambda is read directly (it changes per sweep).
-        int ntr = -1;
-        if (PREFETCH) {
-            if (lane == 0) {
-                int k = 0;
-                bool ok = true;
-                for (int c = 0; c < ncol && ok; c++) {
-                    const int p0 = cs2[2 * c], T = cs2[2 * c + 1] - p0, nl = 2 * T + (cs2[2 * c + 2] - cs2[2 * c + 1]);
-                    for (int gl0 = 0; gl0 < nl; gl0 += 32) {
-                        if (k >= TT_MAX || p0 + nl >= 65536) { ok = false; break; }
-                        const int npair = min(32, max(0, 2 * T - gl0)), nact = min(32, nl - gl0);
-                        tt[k++] = make_int2((p0 + (gl0 >> 1)) | (npair << 16) | (nact << 22) | ((gl0 + 32 >= nl ? 1 : 0) << 28), p0 + gl0 - T);
-                    }
-                }
-                ntr = ok ? k : -1;
-            }
-            ntr = __shfl_sync(FULL, ntr, 0);
-        }
-        auto table_lane = [&](int k, int &pos, bool &active, bool &neg, bool &last) {
-            const int2 t = tt[k];
-            const int npair = (t.x >> 16) & 63, nact = (t.x >> 22) & 63;
-            const bool pairlane = lane < npair;
-            active = lane < nact;
-            pos = pairlane ? (t.x & 0xffff) + (lane >> 1) : (active ? t.y + lane : (t.x & 0xffff));
-            neg = pairlane && (lane & 1);
-            last = (t.x >> 28) & 1;
-        };
-        auto prefetch_trip = [&](int pos, bool neg) {
-            cp_async16(pf + lane, rows.g.A + ms + pos);
-            cp_async16(pf + 32 + lane, (neg ? rows.g.R2 : rows.g.R1) + ms + pos);
-            cp_async16(pf + 64 + lane, rows.g.C + ms + pos);
-            cp_async16(pf + 96 + lane, rows.g.D + ms + pos);
-        };
-        int tpos = 0;
-        bool tactive = false, tneg = false, tlast = false;
-        if (PREFETCH && ntr > 0) {
-            table_lane(0, tpos, tactive, tneg, tlast);
-            prefetch_trip(tpos, tneg);
-        }
+        // the other resident warps; the extra live registers and the table look-ups cost more than the stall they hide.
+        // Staging the next trip's four immutable planes in shared memory with cp.async (no registers in flight; lambda one
+        // trip ahead in registers) was measured as well: 1.12 -> 1.20 ms.  ncu: long-scoreboard stalls fall from 1.6 to 1.0
+        // per issue but short-scoreboard ones rise by as much; the samples sit on the row's dependent chain, not on loads.)
         for (int it = 0; it < cfg.iters; it++) {
-            if (PREFETCH && ntr > 0) {
-                for (int k = 0; k < ntr; k++) {
-                    int npos;
-                    bool nactive, nneg, nlast;
-                    table_lane(k + 1 == ntr ? 0 : k + 1, npos, nactive, nneg, nlast);
-                    cp_async_wait_all();
-                    const float4 A = pf[lane], Rh = pf[32 + lane], C = pf[64 + lane], D = pf[96 + lane];
-                    prefetch_trip(npos, nneg); // each lane overwrites only the four slots it has just read
-                    solve_trip(tpos, tactive, tneg, A, Rh, C, D);
-                    if (tlast) __syncwarp();
-                    tpos = npos; tactive = nactive; tneg = nneg; tlast = nlast;
-                }
-            } else
             for (int c = 0; c < ncol; c++) {
                 const int nl = 2 * (cs2[2 * c + 1] - cs2[2 * c]) + (cs2[2 * c + 2] - cs2[2 * c + 1]);
                 for (int gl0 = 0; gl0 < nl; gl0 += 32) {
@@ -545,7 +481,6 @@ __global__ void __launch_bounds__(OB_ENV2_THREADS, (ROWS_SMEM ? OB_ENV2_WARPS_SM
                 __syncwarp();
             }
         }
-        if (PREFETCH && ntr > 0) cp_async_wait_all(); // the copy started by the last trip must not land in the next env's buffer
         // ---- solver tail: velocity update, dxStepBody, snapshot pack (or hand the accumulators to k_integrate)
         if (fused) {
             for (int i = lane; i < nbod; i += 32) {
@@ -595,7 +530,7 @@ void env_solve2_launch(Engine *e, const EnvArrays &E, const BodyArrays &B, const
                        const SolverArrays &S, const StepConfig &cfg, int fused, int rows_smem, cudaStream_t st) {
     const int mb = (E.max_bodies + 31) & ~31;
     constexpr int WARPS = OB_ENV2_THREADS / 32;
-    const size_t per_warp = (size_t)mb * 80 + 2 * CS2 * sizeof(int) + (rows_smem > 0 ? (size_t)rows_smem * 96 : (OB_ENV2_PREFETCH ? 4 * 32 * sizeof(float4) : 0));
+    const size_t per_warp = (size_t)mb * 80 + 2 * CS2 * sizeof(int) + (size_t)rows_smem * 96;
     const size_t smem = WARPS * per_warp;
     unsigned grid = (unsigned)((E.n_envs + WARPS - 1) / WARPS);
     int per_sm = 0;
