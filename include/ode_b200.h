@@ -107,6 +107,13 @@ void dWorldPackBodiesDeviceB200(dWorldID, const int *d_idx, int cap, const int *
 void dWorldUnpackBodiesDeviceB200(dWorldID, const int *d_ghost_body, const int *d_ghost_geom, int cap, const float *d_in48);
 /* the CUDA stream (cudaStream_t) every kernel and copy of this world is queued on */
 void *dWorldGetStreamB200(dWorldID);
+/* debugging aid: with ODE_B200_DEBUG_GUARD=1 in the environment every device allocation of the library carries a
+ * 256-byte guard band on both sides; this call synchronises, reads the bands back and returns how many allocations a
+ * kernel wrote outside of (naming them on stderr when verbose != 0).  Returns -1 when the guards are off. */
+int dCheckGuardsB200(int verbose);
+/* self-test of that mechanism: allocates a guarded scratch buffer of 1000 bytes, writes `overrun` bytes past its end
+ * (0 = stays inside), runs the check, frees the buffer; returns what dCheckGuardsB200 returned in between. */
+int dGuardSelfTestB200(int overrun);
 
 /* Slab decomposition of ONE large world over several GPUs (BASELINE config 5), driven from C:
  * one process per GPU, each owning the bodies whose centre lies in its x-interval [face_left, face_right); a contact

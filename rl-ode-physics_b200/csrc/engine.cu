@@ -17,17 +17,17 @@ static void apply_pending_forces(Engine *e);
 template <typename T>
 static void dev_realloc(T *&p, size_t old_n, size_t new_n, cudaStream_t st, bool keep = true) {
     T *q = nullptr;
-    OB_CUDA(cudaMalloc(&q, std::max<size_t>(new_n, 1) * sizeof(T)));
+    OB_CUDA(ob_malloc(&q, std::max<size_t>(new_n, 1) * sizeof(T)));
     if (p && keep && old_n) OB_CUDA(cudaMemcpyAsync(q, p, std::min(old_n, new_n) * sizeof(T), cudaMemcpyDeviceToDevice, st));
     if (p) {
         OB_CUDA(cudaStreamSynchronize(st));
-        OB_CUDA(cudaFree(p));
+        OB_CUDA(ob_free(p));
     }
     p = q;
 }
 template <typename T>
 static void dev_free(T *&p) {
-    if (p) cudaFree(p);
+    if (p) ob_free(p);
     p = nullptr;
 }
 
@@ -59,21 +59,21 @@ Engine *eng_create(int device) {
     OB_CUDA(cudaEventCreateWithFlags(&e->ev_f6, cudaEventDisableTiming));
     OB_CUDA(cudaEventCreateWithFlags(&e->ev_f6_consumed[0], cudaEventDisableTiming));
     OB_CUDA(cudaEventCreateWithFlags(&e->ev_f6_consumed[1], cudaEventDisableTiming));
-    OB_CUDA(cudaMalloc(&e->d_stats, sizeof(StepStats)));
+    OB_CUDA(ob_malloc(&e->d_stats, sizeof(StepStats)));
     OB_CUDA(cudaMemset(e->d_stats, 0, sizeof(StepStats)));
     OB_CUDA(cudaMallocHost(&e->h_stats, sizeof(StepStats)));
     memset(e->h_stats, 0, sizeof(StepStats));
     for (int i = 0; i < 5; i++) OB_CUDA(cudaEventCreate(&e->ev[i]));
     OB_CUDA(cudaEventCreate(&e->ev_bp));
-    OB_CUDA(cudaMalloc(&e->M.count, sizeof(int)));
-    OB_CUDA(cudaMalloc(&e->M.colour_start, 72 * sizeof(int)));
-    OB_CUDA(cudaMalloc(&e->M.meta, 16 * sizeof(int)));
+    OB_CUDA(ob_malloc(&e->M.count, sizeof(int)));
+    OB_CUDA(ob_malloc(&e->M.colour_start, 72 * sizeof(int)));
+    OB_CUDA(ob_malloc(&e->M.meta, 16 * sizeof(int)));
     OB_CUDA(cudaMemset(e->M.count, 0, sizeof(int)));
     OB_CUDA(cudaMemset(e->M.meta, 0, 16 * sizeof(int)));
-    OB_CUDA(cudaMalloc(&e->bp.acc, 8 * sizeof(unsigned)));
+    OB_CUDA(ob_malloc(&e->bp.acc, 8 * sizeof(unsigned)));
     broadphase_acc_init(e->bp, e->st); // re-armed on the device after every use from here on
-    OB_CUDA(cudaMalloc(&e->bp.gp, sizeof(GridParams)));
-    OB_CUDA(cudaMalloc(&e->bp.counters, sizeof(BroadCounters)));
+    OB_CUDA(ob_malloc(&e->bp.gp, sizeof(GridParams)));
+    OB_CUDA(ob_malloc(&e->bp.counters, sizeof(BroadCounters)));
     OB_CUDA(cudaMemset(e->bp.counters, 0, sizeof(BroadCounters)));
     e->meshes.n = 0;
     if (const char *g = getenv("ODE_B200_ENV_GROUP")) e->env_group = atoi(g);
@@ -111,7 +111,7 @@ void eng_destroy(Engine *e) {
     for (int i = 0; i < 2; i++) if (e->g_step[i].exec) cudaGraphExecDestroy(e->g_step[i].exec);
     dev_free(e->sel_flag);
     if (e->h_patch) cudaFreeHost(e->h_patch);
-    if (e->d_patch) cudaFree(e->d_patch);
+    if (e->d_patch) ob_free(e->d_patch);
     if (e->ev_patch) cudaEventDestroy(e->ev_patch);
     dev_free(bp.blk);
     dev_free(bp.acc); dev_free(bp.gp); dev_free(bp.counters); dev_free(bp.keys); dev_free(bp.idx);
@@ -207,8 +207,8 @@ int eng_add_mesh(Engine *e, const float *verts, int nv, const int *tris, int nt)
             m.hi[k] = fmaxf(m.hi[k], verts[3 * i + k]);
         }
     const size_t bv = ((size_t)nv * 3 * sizeof(float) + 15) / 16 * 16, bt = ((size_t)nt * 3 * sizeof(int) + 15) / 16 * 16;
-    OB_CUDA(cudaMalloc(&m.d_verts, bv));
-    OB_CUDA(cudaMalloc(&m.d_tris, bt));
+    OB_CUDA(ob_malloc(&m.d_verts, bv));
+    OB_CUDA(ob_malloc(&m.d_tris, bt));
     OB_CUDA(cudaMemset(m.d_verts, 0, bv));
     OB_CUDA(cudaMemset(m.d_tris, 0, bt));
     OB_CUDA(cudaMemcpy(m.d_verts, verts, (size_t)nv * 3 * sizeof(float), cudaMemcpyHostToDevice));
@@ -267,8 +267,8 @@ int eng_add_mesh(Engine *e, const float *verts, int nv, const int *tris, int nt)
                 for (int y = r[2]; y <= r[3]; y++)
                     for (int x = r[0]; x <= r[1]; x++) list[cur[((size_t)z * mi.gd[1] + y) * mi.gd[0] + x]++] = t;
         }
-        OB_CUDA(cudaMalloc(&m.d_cell_start, start.size() * sizeof(int)));
-        OB_CUDA(cudaMalloc(&m.d_cell_tris, list.size() * sizeof(int)));
+        OB_CUDA(ob_malloc(&m.d_cell_start, start.size() * sizeof(int)));
+        OB_CUDA(ob_malloc(&m.d_cell_tris, list.size() * sizeof(int)));
         OB_CUDA(cudaMemcpy(m.d_cell_start, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice));
         OB_CUDA(cudaMemcpy(m.d_cell_tris, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice));
         mi.cell_start = m.d_cell_start; mi.cell_tris = m.d_cell_tris;
@@ -371,8 +371,8 @@ void engine_ensure_pair_capacity(Engine *e) {
     if (!bp.cell_start) {
         bp.cap_cells = (1 << 24) - 2;
         bp.key_bits = 24;
-        OB_CUDA(cudaMalloc(&bp.cell_start, ((size_t)bp.cap_cells + 2) * sizeof(int)));
-        OB_CUDA(cudaMalloc(&bp.cell_end, ((size_t)bp.cap_cells + 2) * sizeof(int)));
+        OB_CUDA(ob_malloc(&bp.cell_start, ((size_t)bp.cap_cells + 2) * sizeof(int)));
+        OB_CUDA(ob_malloc(&bp.cell_end, ((size_t)bp.cap_cells + 2) * sizeof(int)));
         OB_CUDA(cudaMemsetAsync(bp.cell_start, 0, ((size_t)bp.cap_cells + 2) * sizeof(int), st));
         OB_CUDA(cudaMemsetAsync(bp.cell_end, 0, ((size_t)bp.cap_cells + 2) * sizeof(int), st));
     }
@@ -499,10 +499,10 @@ static void *patch_stage(Engine *e, size_t bytes) {
     }
     if (bytes > e->cap_patch) {
         if (e->h_patch) OB_CUDA(cudaFreeHost(e->h_patch));
-        if (e->d_patch) OB_CUDA(cudaFree(e->d_patch));
+        if (e->d_patch) OB_CUDA(ob_free(e->d_patch));
         e->cap_patch = bytes * 2 + 4096;
         OB_CUDA(cudaMallocHost(&e->h_patch, e->cap_patch));
-        OB_CUDA(cudaMalloc(&e->d_patch, e->cap_patch));
+        OB_CUDA(ob_malloc(&e->d_patch, e->cap_patch));
     }
     if (!e->ev_patch) OB_CUDA(cudaEventCreateWithFlags(&e->ev_patch, cudaEventDisableTiming));
     return e->h_patch;
@@ -1108,8 +1108,8 @@ void eng_set_forces(Engine *e, const float *f6, int n) {
         OB_CUDA(cudaStreamSynchronize(e->h2d_st));
         e->cap_f6 = n + n / 4 + 64;
         for (int i = 0; i < 2; i++) {
-            if (e->d_f6[i]) OB_CUDA(cudaFree(e->d_f6[i]));
-            OB_CUDA(cudaMalloc(&e->d_f6[i], (size_t)e->cap_f6 * 6 * sizeof(float)));
+            if (e->d_f6[i]) OB_CUDA(ob_free(e->d_f6[i]));
+            OB_CUDA(ob_malloc(&e->d_f6[i], (size_t)e->cap_f6 * 6 * sizeof(float)));
             e->f6_inflight[i] = false;
         }
     }
@@ -1374,9 +1374,9 @@ void eng_bind_msg_slots(Engine *e, int n_slots, const int *body, const int *geom
     e->msg_slots = n_slots;
     if (n_slots <= 0) return;
     const size_t n = (size_t)n_slots;
-    OB_CUDA(cudaMalloc(&e->msg_body, n * 4)); OB_CUDA(cudaMalloc(&e->msg_geom, n * 4)); OB_CUDA(cudaMalloc(&e->msg_type, n * 4));
-    OB_CUDA(cudaMalloc(&e->msg_size, n * 12)); OB_CUDA(cudaMalloc(&e->msg_col, n * 4));
-    OB_CUDA(cudaMalloc(&e->msg_out, 4 + n * 84));
+    OB_CUDA(ob_malloc(&e->msg_body, n * 4)); OB_CUDA(ob_malloc(&e->msg_geom, n * 4)); OB_CUDA(ob_malloc(&e->msg_type, n * 4));
+    OB_CUDA(ob_malloc(&e->msg_size, n * 12)); OB_CUDA(ob_malloc(&e->msg_col, n * 4));
+    OB_CUDA(ob_malloc(&e->msg_out, 4 + n * 84));
     OB_CUDA(cudaMemcpy(e->msg_body, body, n * 4, cudaMemcpyHostToDevice));
     OB_CUDA(cudaMemcpy(e->msg_geom, geom, n * 4, cudaMemcpyHostToDevice));
     OB_CUDA(cudaMemcpy(e->msg_type, type, n * 4, cudaMemcpyHostToDevice));

@@ -53,6 +53,20 @@ inline void ob_count_launch() { ++g_ob_launches; }
         }                                                                                          \
     } while (0)
 
+// Device memory of the library goes through ob_malloc / ob_free.  With ODE_B200_DEBUG_GUARD=1 every allocation gets a
+// 256-byte guard band on both sides, filled with a pattern; dCheckGuardsB200() (ode_b200.h) reads the bands back and
+// reports every allocation a kernel wrote outside of (the pool's compute-sanitizer is closed, so this is the library's
+// own overrun check; tests/test_guards_gpu.py runs the scenes of the parity tests under it).
+cudaError_t guard_malloc(void **p, size_t bytes, const char *file, int line);
+cudaError_t guard_free(void *p);
+int guard_check(int verbose); // number of allocations with a damaged band; -1 = guards are off
+template <typename T>
+inline cudaError_t ob_malloc_at(T **p, size_t bytes, const char *file, int line) {
+    return guard_malloc(reinterpret_cast<void **>(p), bytes, file, line);
+}
+#define ob_malloc(p, bytes) ob::ob_malloc_at(p, bytes, __FILE__, __LINE__)
+#define ob_free(p) ob::guard_free(p)
+
 enum GeomType { G_SPHERE = 0, G_BOX = 1, G_PLANE = 4, G_TRIMESH = 8 };
 enum BodyFlags { BF_KINEMATIC = 1, BF_NOGRAVITY = 2, BF_GYRO = 4 };
 

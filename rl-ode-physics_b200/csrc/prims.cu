@@ -1,7 +1,98 @@
 // prims.cu -- exclusive scan + stable radix sort (see prims.cuh).
 #include "prims.cuh"
 
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
+
 namespace ob {
+
+// ------------------------------------------------------------------------------ guarded device memory
+// (engine.h: ob_malloc / ob_free; ODE_B200_DEBUG_GUARD=1)
+
+namespace {
+constexpr size_t GUARD = 256; // cudaMalloc's own alignment, so guarded pointers stay as aligned as plain ones
+constexpr unsigned char GUARD_BYTE = 0xA5;
+struct GuardRec {
+    size_t bytes;
+    const char *file;
+    int line, device;
+};
+std::mutex g_guard_mu;
+std::unordered_map<void *, GuardRec> g_guard_recs;
+bool guards_on() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("ODE_B200_DEBUG_GUARD");
+        v = (s && s[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+} // namespace
+
+cudaError_t guard_malloc(void **p, size_t bytes, const char *file, int line) {
+    if (!guards_on()) return cudaMalloc(p, bytes);
+    const size_t body = (bytes + GUARD - 1) / GUARD * GUARD; // the tail band starts at the next 256-byte boundary ...
+    unsigned char *base = nullptr;
+    cudaError_t err = cudaMalloc(&base, body + 2 * GUARD);
+    if (err != cudaSuccess) return err;
+    // ... and the slack between the requested size and that boundary carries the pattern too
+    if ((err = cudaMemset(base, GUARD_BYTE, GUARD)) != cudaSuccess) return err;
+    if ((err = cudaMemset(base + GUARD + bytes, GUARD_BYTE, body - bytes + GUARD)) != cudaSuccess) return err;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_guard_mu);
+        g_guard_recs[base + GUARD] = GuardRec{bytes, file, line, dev};
+    }
+    *p = base + GUARD;
+    return cudaSuccess;
+}
+
+cudaError_t guard_free(void *p) {
+    if (!p || !guards_on()) return cudaFree(p);
+    {
+        std::lock_guard<std::mutex> lk(g_guard_mu);
+        g_guard_recs.erase(p);
+    }
+    return cudaFree(static_cast<unsigned char *>(p) - GUARD);
+}
+
+int guard_check(int verbose) {
+    if (!guards_on()) return -1;
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    int cur = 0, bad = 0;
+    cudaGetDevice(&cur);
+    std::vector<unsigned char> host;
+    for (const auto &kv : g_guard_recs) {
+        const GuardRec &r = kv.second;
+        unsigned char *user = static_cast<unsigned char *>(kv.first);
+        const size_t body = (r.bytes + GUARD - 1) / GUARD * GUARD, tail = body - r.bytes + GUARD;
+        cudaSetDevice(r.device);
+        cudaDeviceSynchronize();
+        host.resize(GUARD + tail);
+        if (cudaMemcpy(host.data(), user - GUARD, GUARD, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(host.data() + GUARD, user + r.bytes, tail, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            if (verbose) fprintf(stderr, "libode_b200: guard check could not read %s:%d\n", r.file, r.line);
+            bad++;
+            continue;
+        }
+        long first_before = -1, first_after = -1;
+        for (size_t i = 0; i < GUARD; i++)
+            if (host[i] != GUARD_BYTE) { first_before = (long)(GUARD - i); break; }
+        for (size_t i = 0; i < tail; i++)
+            if (host[GUARD + i] != GUARD_BYTE) { first_after = (long)i; break; }
+        if (first_before >= 0 || first_after >= 0) {
+            bad++;
+            if (verbose)
+                fprintf(stderr, "libode_b200: guard band damaged around the %zu-byte allocation of %s:%d (%ld bytes before it, %ld bytes past its end)\n",
+                        r.bytes, r.file, r.line, first_before, first_after);
+        }
+    }
+    cudaSetDevice(cur);
+    return bad;
+}
 
 // ------------------------------------------------------------------------------------------ scan
 
@@ -96,9 +187,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_single(const int *__restr
 
 static void ws_ensure(ScanWorkspace &ws, int level, size_t n) {
     if (ws.cap[level] >= n) return;
-    if (ws.sums[level]) OB_CUDA(cudaFree(ws.sums[level]));
+    if (ws.sums[level]) OB_CUDA(ob_free(ws.sums[level]));
     size_t cap = n + n / 2 + 64;
-    OB_CUDA(cudaMalloc(&ws.sums[level], cap * sizeof(int)));
+    OB_CUDA(ob_malloc(&ws.sums[level], cap * sizeof(int)));
     ws.cap[level] = cap;
 }
 
@@ -131,7 +222,7 @@ void scan_exclusive(const int *in, int *out, long n_max, const int *n_dev, int *
 
 void scan_workspace_free(ScanWorkspace &ws) {
     for (int i = 0; i < 3; i++) {
-        if (ws.sums[i]) cudaFree(ws.sums[i]);
+        if (ws.sums[i]) ob_free(ws.sums[i]);
         ws.sums[i] = nullptr;
         ws.cap[i] = 0;
     }
@@ -203,16 +294,16 @@ void sort_pairs(uint32_t *keys, int *vals, long n_max, const int *n_dev, int bit
     const int nchunks = (int)((n_max + SORT_CHUNK - 1) / SORT_CHUNK);
     size_t need = (size_t)256 * nchunks;
     if (ws.cap < need) {
-        if (ws.hist) OB_CUDA(cudaFree(ws.hist));
+        if (ws.hist) OB_CUDA(ob_free(ws.hist));
         ws.cap = need + need / 2;
-        OB_CUDA(cudaMalloc(&ws.hist, ws.cap * sizeof(int)));
+        OB_CUDA(ob_malloc(&ws.hist, ws.cap * sizeof(int)));
     }
     if (ws.cap_items < (size_t)n_max) {
-        if (ws.keys_tmp) OB_CUDA(cudaFree(ws.keys_tmp));
-        if (ws.vals_tmp) OB_CUDA(cudaFree(ws.vals_tmp));
+        if (ws.keys_tmp) OB_CUDA(ob_free(ws.keys_tmp));
+        if (ws.vals_tmp) OB_CUDA(ob_free(ws.vals_tmp));
         ws.cap_items = (size_t)n_max + (size_t)n_max / 2;
-        OB_CUDA(cudaMalloc(&ws.keys_tmp, ws.cap_items * sizeof(uint32_t)));
-        OB_CUDA(cudaMalloc(&ws.vals_tmp, ws.cap_items * sizeof(int)));
+        OB_CUDA(ob_malloc(&ws.keys_tmp, ws.cap_items * sizeof(uint32_t)));
+        OB_CUDA(ob_malloc(&ws.vals_tmp, ws.cap_items * sizeof(int)));
     }
     uint32_t *kin = keys, *kout = ws.keys_tmp;
     int *vin = vals, *vout = ws.vals_tmp;
@@ -234,9 +325,9 @@ void sort_pairs(uint32_t *keys, int *vals, long n_max, const int *n_dev, int bit
 }
 
 void sort_workspace_free(SortWorkspace &ws) {
-    if (ws.hist) cudaFree(ws.hist);
-    if (ws.keys_tmp) cudaFree(ws.keys_tmp);
-    if (ws.vals_tmp) cudaFree(ws.vals_tmp);
+    if (ws.hist) ob_free(ws.hist);
+    if (ws.keys_tmp) ob_free(ws.keys_tmp);
+    if (ws.vals_tmp) ob_free(ws.vals_tmp);
     ws.hist = nullptr; ws.keys_tmp = nullptr; ws.vals_tmp = nullptr;
     ws.cap = 0; ws.cap_items = 0;
     scan_workspace_free(ws.scan);

@@ -351,6 +351,16 @@ extern "C" void dWorldSetSolverModeB200(dWorldID w, int mode, int env_group) { e
 extern "C" void dWorldSetContactUnitsB200(dWorldID w, int per_contact) { eng_set_contact_units(w->eng, per_contact); }
 extern "C" void dWorldWaitB200(dWorldID w) { eng_wait(w->eng); }
 extern "C" void *dWorldGetStreamB200(dWorldID w) { return (void *)eng_stream(w->eng); }
+extern "C" int dCheckGuardsB200(int verbose) { return ob::guard_check(verbose); }
+extern "C" int dGuardSelfTestB200(int overrun) {
+    if (ob::guard_check(0) < 0) return -1; // guards off: there is no band to write into
+    unsigned char *p = nullptr;
+    OB_CUDA(ob_malloc(&p, 1000));
+    OB_CUDA(cudaMemset(p, 0, (size_t)(1000 + (overrun > 0 ? (overrun < 256 ? overrun : 256) : 0)))); // never leaves the band
+    const int bad = ob::guard_check(0);
+    ob_free(p);
+    return bad;
+}
 extern "C" void dWorldPackStatesDeviceB200(dWorldID w, const int *d_idx, int n, float *d_out) { eng_pack_states_device(w->eng, d_idx, n, d_out); }
 extern "C" void dWorldPackImpulsesDeviceB200(dWorldID w, const int *d_idx, int n, float *d_out) { eng_pack_impulses_device(w->eng, d_idx, n, d_out); }
 extern "C" void dWorldAddImpulsesDeviceB200(dWorldID w, const int *d_idx, int n, const float *d_in) { eng_add_impulses_device(w->eng, d_idx, n, d_in); }
@@ -1109,8 +1119,8 @@ extern "C" dBodyID dJointGetBody(dJointID j, int index) { return index == 0 ? j-
 extern "C" int dTestScanB200(const int *in, int *out, long n, int *total) {
     OB_CUDA(cudaSetDevice(default_device()));
     int *d = nullptr, *dt = nullptr;
-    OB_CUDA(cudaMalloc(&d, (size_t)(n > 0 ? n : 1) * sizeof(int)));
-    OB_CUDA(cudaMalloc(&dt, sizeof(int)));
+    OB_CUDA(ob_malloc(&d, (size_t)(n > 0 ? n : 1) * sizeof(int)));
+    OB_CUDA(ob_malloc(&dt, sizeof(int)));
     OB_CUDA(cudaMemcpy(d, in, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
     ScanWorkspace ws;
     scan_exclusive(d, d, n, nullptr, dt, ws, 0);
@@ -1118,8 +1128,8 @@ extern "C" int dTestScanB200(const int *in, int *out, long n, int *total) {
     OB_CUDA(cudaMemcpy(out, d, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
     OB_CUDA(cudaMemcpy(total, dt, sizeof(int), cudaMemcpyDeviceToHost));
     scan_workspace_free(ws);
-    cudaFree(d);
-    cudaFree(dt);
+    ob_free(d);
+    ob_free(dt);
     return 0;
 }
 
@@ -1127,8 +1137,8 @@ extern "C" int dTestSortB200(unsigned *keys, int *vals, long n, int bits) {
     OB_CUDA(cudaSetDevice(default_device()));
     uint32_t *dk = nullptr;
     int *dv = nullptr;
-    OB_CUDA(cudaMalloc(&dk, (size_t)(n > 0 ? n : 1) * sizeof(uint32_t)));
-    OB_CUDA(cudaMalloc(&dv, (size_t)(n > 0 ? n : 1) * sizeof(int)));
+    OB_CUDA(ob_malloc(&dk, (size_t)(n > 0 ? n : 1) * sizeof(uint32_t)));
+    OB_CUDA(ob_malloc(&dv, (size_t)(n > 0 ? n : 1) * sizeof(int)));
     OB_CUDA(cudaMemcpy(dk, keys, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice));
     OB_CUDA(cudaMemcpy(dv, vals, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
     SortWorkspace ws;
@@ -1137,7 +1147,7 @@ extern "C" int dTestSortB200(unsigned *keys, int *vals, long n, int bits) {
     OB_CUDA(cudaMemcpy(keys, dk, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     OB_CUDA(cudaMemcpy(vals, dv, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
     sort_workspace_free(ws);
-    cudaFree(dk);
-    cudaFree(dv);
+    ob_free(dk);
+    ob_free(dv);
     return 0;
 }

@@ -77,7 +77,7 @@ bool nccl_load() {
 template <typename T>
 T *dalloc(size_t n) {
     T *p = nullptr;
-    OB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    OB_CUDA(ob_malloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
     return p;
 }
 
@@ -171,10 +171,10 @@ extern "C" void dSlabDestroyB200(dSlabID s) {
     if (!s) return;
     cudaStreamSynchronize(s->st); cudaStreamSynchronize(s->comm_st);
     if (s->comm) g_nccl.CommDestroy(s->comm);
-    cudaFree(s->own_mask); cudaFree(s->body_geom); cudaFree(s->count);
-    cudaFree(s->send_state_idx); cudaFree(s->send_state_buf); cudaFree(s->recv_imp_buf);
-    cudaFree(s->ghost_body); cudaFree(s->ghost_geom); cudaFree(s->recv_state_buf); cudaFree(s->send_imp_buf);
-    for (int f = 0; f < 2; f++) { cudaFree(s->send_mig_idx[f]); cudaFree(s->send_mig_buf[f]); cudaFree(s->recv_mig_buf[f]); }
+    ob_free(s->own_mask); ob_free(s->body_geom); ob_free(s->count);
+    ob_free(s->send_state_idx); ob_free(s->send_state_buf); ob_free(s->recv_imp_buf);
+    ob_free(s->ghost_body); ob_free(s->ghost_geom); ob_free(s->recv_state_buf); ob_free(s->send_imp_buf);
+    for (int f = 0; f < 2; f++) { ob_free(s->send_mig_idx[f]); ob_free(s->send_mig_buf[f]); ob_free(s->recv_mig_buf[f]); }
     cudaEventDestroy(s->ev_pack); cudaEventDestroy(s->ev_comm); cudaStreamDestroy(s->comm_st);
     delete s;
 }

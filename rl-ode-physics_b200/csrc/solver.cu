@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(256, 2) k_barrier_bench(unsigned *bar, int ite
 
 float solver_barrier_bench(Engine *e, int iters) {
     unsigned *bar = nullptr;
-    OB_CUDA(cudaMalloc(&bar, sizeof(unsigned)));
+    OB_CUDA(ob_malloc(&bar, sizeof(unsigned)));
     OB_CUDA(cudaMemset(bar, 0, sizeof(unsigned)));
     int per_sm = 0;
     OB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)k_barrier_bench, 256, 0));
@@ -640,7 +640,7 @@ float solver_barrier_bench(Engine *e, int iters) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, a, b);
     cudaEventDestroy(a); cudaEventDestroy(b);
-    cudaFree(bar);
+    ob_free(bar);
     return ms * 1000.f / iters; // microseconds per barrier
 }
 

@@ -387,14 +387,14 @@ void exact_solve_launch(Engine *e, const ManifoldArrays &M, const SolverArrays &
                         int *done_flag, cudaStream_t st) {
     if (!e->ex_label) {
         const size_t cap_rows = (size_t)EX_MAX_UNITS * 8 * 3, cap_mat = (size_t)EX_MAX_ROWS * cap_rows / 8;
-        OB_CUDA(cudaMalloc(&e->ex_label, sizeof(int) * EX_MAX_BODIES));
-        OB_CUDA(cudaMalloc(&e->ex_desc, sizeof(int) * cap_rows));
-        OB_CUDA(cudaMalloc(&e->ex_isl_row0, sizeof(int) * (EX_MAX_BODIES + 1)));
-        OB_CUDA(cudaMalloc(&e->ex_isl_mat, sizeof(size_t) * (EX_MAX_BODIES + 1)));
-        OB_CUDA(cudaMalloc(&e->ex_isl_label, sizeof(int) * EX_MAX_BODIES));
-        OB_CUDA(cudaMalloc(&e->ex_meta, sizeof(int) * 8));
-        OB_CUDA(cudaMalloc(&e->ex_A, sizeof(double) * cap_mat));
-        OB_CUDA(cudaMalloc(&e->ex_C, sizeof(double) * cap_mat));
+        OB_CUDA(ob_malloc(&e->ex_label, sizeof(int) * EX_MAX_BODIES));
+        OB_CUDA(ob_malloc(&e->ex_desc, sizeof(int) * cap_rows));
+        OB_CUDA(ob_malloc(&e->ex_isl_row0, sizeof(int) * (EX_MAX_BODIES + 1)));
+        OB_CUDA(ob_malloc(&e->ex_isl_mat, sizeof(size_t) * (EX_MAX_BODIES + 1)));
+        OB_CUDA(ob_malloc(&e->ex_isl_label, sizeof(int) * EX_MAX_BODIES));
+        OB_CUDA(ob_malloc(&e->ex_meta, sizeof(int) * 8));
+        OB_CUDA(ob_malloc(&e->ex_A, sizeof(double) * cap_mat));
+        OB_CUDA(ob_malloc(&e->ex_C, sizeof(double) * cap_mat));
         e->ex_cap_mat = cap_mat;
         e->ex_cap_rows = (int)cap_rows;
         OB_CUDA(cudaFuncSetAttribute(k_exact_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exact_smem_bytes()));

@@ -139,6 +139,8 @@ _SIGS = [
     ("dWorldPackBodiesDeviceB200", None, [_vp, _vp, _i, _vp, _vp]),
     ("dWorldUnpackBodiesDeviceB200", None, [_vp, _vp, _vp, _i, _vp]),
     ("dWorldGetStreamB200", _vp, [_vp]),
+    ("dCheckGuardsB200", _i, [_i]),
+    ("dGuardSelfTestB200", _i, [_i]),
     ("dSlabGetUniqueIdB200", _i, [C.c_char_p]),
     ("dSlabCreateB200", _vp, [_vp, _vp, _i, _i, C.c_char_p, C.POINTER(SlabLayout)]),
     ("dSlabDestroyB200", None, [_vp]), ("dSlabTickB200", None, [_vp, _f, _i]), ("dSlabMigrateB200", None, [_vp]),

@@ -18,3 +18,14 @@ def oracle_lib():
     import oracle
     oracle.build()
     return oracle.lib()
+
+
+@pytest.fixture(autouse=True)
+def _guard_bands(request):
+    """With ODE_B200_DEBUG_GUARD=1 (tests/test_guards_gpu.py re-runs GPU tests that way) every device allocation of
+    the library carries guard bands; a test that made a kernel write outside an allocation fails here."""
+    yield
+    if os.environ.get("ODE_B200_DEBUG_GUARD") == "1" and request.node.get_closest_marker("gpu"):
+        import odeb200
+        bad = odeb200.lib().dCheckGuardsB200(1)
+        assert bad == 0, "%d device allocation(s) with a damaged guard band (named on stderr)" % bad
