@@ -284,6 +284,71 @@ def test_mass_and_inertia_parity():
     ew.close()
 
 
+def test_island_path_with_kinematic_heavy_and_gyroscopic_bodies():
+    """Batched worlds on the lane-pair island solver with everything a body can be: kinematic bodies ploughing through
+    the heap (their rows are one-body rows: a kinematic end never receives an impulse), masses over two decades, box
+    inertias with the gyroscopic term, bodies that ignore gravity.  Oracle of worlds 0, 3 and 7, stepped in the
+    engine's order, for 24 ticks (the heaps reach the plane): state within the tolerance (in fact bit-equal)."""
+    rs = np.random.RandomState(17)
+    nw, per = 8, 128
+    sc = scenes.batched_worlds_scene(nw, seed=40, spacing=0.7)
+    b, g = sc["bodies"], sc["geoms"]
+    body_geom = {int(bi): gi for gi, bi in enumerate(g["body"]) if bi >= 0}
+    for bi in range(nw * per):
+        gi = body_geom[bi]
+        k = bi % per
+        if k % 16 == 5:  # kinematic, moving sideways through the lattice
+            b["flags"][bi] = scenes.BODY_KINEMATIC
+            b["lvel"][bi] = (1.5 * (rs.rand() - 0.5), 0.0, 1.5 * (rs.rand() - 0.5))
+            b["avel"][bi] = (0.0, 2.0 * (rs.rand() - 0.5), 0.0)
+            continue
+        m = float(10.0 ** rs.uniform(-1.0, 1.0))
+        if g["type"][gi] == scenes.BOX:
+            lx, ly, lz = g["dims"][gi][:3]
+            I = np.diag([m / 12 * (ly * ly + lz * lz), m / 12 * (lx * lx + lz * lz), m / 12 * (lx * lx + ly * ly)])
+        else:
+            r = g["dims"][gi][0]
+            I = np.eye(3) * 0.4 * m * r * r
+        b["mass"][bi] = m
+        b["inertia"][bi] = I.reshape(9)
+        b["flags"][bi] = scenes.BODY_GYRO | (scenes.BODY_NOGRAVITY if k % 16 == 9 else 0)
+        b["avel"][bi] = 3.0 * (rs.rand(3) - 0.5)
+    ew = util.engine_world(sc)
+    subs = [(w,) + _world_of_batch(sc, w, per) for w in (0, 3, 7)]
+    for step in range(24):
+        ew.tick(sc["h"])
+        st = ew.stats()
+        assert st["flags"] == 0 and st["env_trips"] > 0  # the lane-pair island solver ran
+        order = ew.solver_order()
+        es = ew.state()
+        for w, sub, ow, gmap in subs:
+            util.oracle_tick_in_engine_order(ow, ew, sc["h"], geom_map=gmap, order=order)
+            os_ = ow.state()
+            sl = slice(w * per, (w + 1) * per)
+            for k in ("pos", "quat", "lvel", "avel"):
+                assert util.rel_err(es[k][sl], os_[k]).max() <= STATE_RTOL, (step, w, k)
+    assert st["n_rows1"] > 0 and st["n_rows2"] > 0
+    ew.close()
+
+
+def _world_of_batch(sc, w, per):
+    """(sub-scene, oracle world, engine geom id -> oracle geom id) of world w of a batched scene."""
+    b, g = sc["bodies"], sc["geoms"]
+    keep_g = np.where((g["env"] == w) | (g["env"] < 0))[0]
+    bodies = {k: v[w * per:(w + 1) * per].copy() for k, v in b.items()}
+    bodies["env"][:] = 0
+    geoms = {k: v[keep_g].copy() for k, v in g.items()}
+    geoms["body"] = np.where(geoms["body"] >= 0, geoms["body"] - w * per, -1).astype(np.int32)
+    geoms["env"] = np.where(geoms["env"] >= 0, 0, -1).astype(np.int32)
+    sub = scenes.from_arrays("world%d" % w, bodies, geoms, h=sc["h"])
+    ow = util.oracle_world(sub)
+    ow._types = [int(t) for t in sub["geoms"]["type"]]
+    ow._bodies = [int(x) for x in sub["geoms"]["body"]]
+    gmap = -np.ones(len(g["type"]), np.int64)
+    gmap[keep_g] = np.arange(len(keep_g))
+    return sub, ow, gmap
+
+
 @pytest.mark.parametrize("group", [8, 16, 32])
 def test_island_solver_equals_grid_barrier_solver(group):
     """Batched worlds take the island solver (one lane group per env, no grid barriers); it must give
