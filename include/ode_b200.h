@@ -151,6 +151,9 @@ void dSlabGetInfoB200(dSlabID, dSlabInfoB200 *); /* blocking */
 void dWorldTimerStartB200(dWorldID);
 void dWorldTimerStopB200(dWorldID);
 float dWorldTimerElapsedB200(dWorldID); /* ms, blocking */
+/* several worlds of one device ticking side by side (each world has its own stream, so their ticks overlap on the GPU):
+ * ms from start_world's start event to stop_world's stop event, blocking */
+float dWorldTimerElapsedBetweenB200(dWorldID start_world, dWorldID stop_world);
 /* number of CUDA kernels this library has launched in this process so far */
 long dGetKernelLaunchCountB200(void);
 

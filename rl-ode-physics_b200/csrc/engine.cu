@@ -1415,6 +1415,13 @@ float eng_timer_elapsed_ms(Engine *e) {
     return ms;
 }
 
+float eng_timer_elapsed_between_ms(Engine *start, Engine *stop) {
+    float ms = 0.f;
+    OB_CUDA(cudaEventSynchronize(stop->tev[1]));
+    OB_CUDA(cudaEventElapsedTime(&ms, start->tev[0], stop->tev[1]));
+    return ms;
+}
+
 void eng_wait(Engine *e) {
     OB_CUDA(cudaSetDevice(e->device));
     OB_CUDA(cudaStreamSynchronize(e->st));

@@ -232,6 +232,7 @@ int eng_export_solver_order(Engine *, int *pair_g1, int *pair_g2, int *pair_k, i
 void eng_timer_start(Engine *);
 void eng_timer_stop(Engine *);
 float eng_timer_elapsed_ms(Engine *);
+float eng_timer_elapsed_between_ms(Engine *start, Engine *stop); // start's start event -> stop's stop event (same device)
 long eng_launch_count();
 // wire image of the reference's MsgUpdateBodies: bind the slot table once, pack after any step
 void eng_bind_msg_slots(Engine *, int n_slots, const int *body, const int *geom, const int *type, const float *size3,

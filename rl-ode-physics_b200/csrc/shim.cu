@@ -378,6 +378,7 @@ extern "C" void dWorldUnpackStatesDeviceB200(dWorldID w, const int *d_idx, int n
 extern "C" void dWorldTimerStartB200(dWorldID w) { eng_timer_start(w->eng); }
 extern "C" void dWorldTimerStopB200(dWorldID w) { eng_timer_stop(w->eng); }
 extern "C" float dWorldTimerElapsedB200(dWorldID w) { return eng_timer_elapsed_ms(w->eng); }
+extern "C" float dWorldTimerElapsedBetweenB200(dWorldID a, dWorldID b) { return eng_timer_elapsed_between_ms(a->eng, b->eng); }
 extern "C" long dGetKernelLaunchCountB200(void) { return eng_launch_count(); }
 extern "C" void dWorldBindSnapshotSlotsB200(dWorldID w, int n_slots, const dBodyID *bodies, const dGeomID *geoms, const int *types,
                                             const float *size3, const unsigned *rgba) {

@@ -148,6 +148,7 @@ _SIGS = [
     ("dSlabMigrateLocalB200", None, [C.POINTER(_vp), _i]), ("dSlabGetInfoB200", None, [_vp, C.POINTER(SlabInfo)]),
     ("dWorldTimerStartB200", None, [_vp]), ("dWorldTimerStopB200", None, [_vp]),
     ("dWorldTimerElapsedB200", C.c_float, [_vp]), ("dGetKernelLaunchCountB200", C.c_long, []),
+    ("dWorldTimerElapsedBetweenB200", C.c_float, [_vp, _vp]),
     ("dWorldSetCapacityB200", None, [_vp, C.c_long, C.c_long]),
     ("dWorldSetBigExtentB200", None, [_vp, _f]),
     ("dWorldSetBroadphaseB200", None, [_vp, _i]),
