@@ -171,15 +171,25 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const int *__restri
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_single(const int *__restrict__ in, int *__restrict__ out,
                                                                long n_max, const int *__restrict__ n_dev,
                                                                int *__restrict__ total) {
+    // every thread owns SI consecutive elements per pass (scanned in registers), so a pass of the block covers 8192 elements
+    // with one block scan: the 14 k per-block class sums of a 2048-env broadphase take 2 passes instead of 28 (16 -> 4 us)
+    constexpr int SI = 16;
     __shared__ int sm[33];
     const long n = scan_len(n_max, n_dev);
     int carry = 0;
-    for (long b = 0; b < n; b += SCAN_THREADS) {
-        long i = b + threadIdx.x;
-        int v = (i < n) ? in[i] : 0;
+    for (long b = 0; b < n; b += (long)SCAN_THREADS * SI) {
+        const long i0 = b + (long)threadIdx.x * SI;
+        int v[SI];
+        int s = 0;
+#pragma unroll
+        for (int k = 0; k < SI; k++) v[k] = (i0 + k < n) ? in[i0 + k] : 0;
+#pragma unroll
+        for (int k = 0; k < SI; k++) { const int t = v[k]; v[k] = s; s += t; }
         int tot;
-        int ex = block_scan_excl(v, sm, &tot);
-        if (i < n) out[i] = carry + ex;
+        const int ex = block_scan_excl(s, sm, &tot);
+#pragma unroll
+        for (int k = 0; k < SI; k++)
+            if (i0 + k < n) out[i0 + k] = carry + ex + v[k];
         carry += tot;
     }
     if (total && threadIdx.x == 0) *total = carry;

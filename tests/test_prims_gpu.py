@@ -15,7 +15,7 @@ def _lib():
     return L
 
 
-@pytest.mark.parametrize("n", [1, 31, 512, 4096, 4097, 16384, 16385, 100003, 1 << 20, 5505060, (1 << 24) + 7])
+@pytest.mark.parametrize("n", [1, 31, 512, 4096, 4097, 8191, 8192, 8193, 14344, 16384, 16385, 100003, 1 << 20, 5505060, (1 << 24) + 7])
 def test_scan_matches_numpy(n):
     L = _lib()
     rs = np.random.RandomState(n % 1000)
