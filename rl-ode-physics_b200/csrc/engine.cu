@@ -2,6 +2,7 @@
 // orchestration (collide -> step) of libode_b200.  The tick mirrors the reference's
 // /root/reference/src/main.c:212-214: dSpaceCollide(+NearCallback), dWorldStep, dJointGroupEmpty.
 #include <string.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <cmath>
@@ -30,6 +31,23 @@ static void dev_free(T *&p) {
     if (p) ob_free(p);
     p = nullptr;
 }
+
+// address-space reservations of the StableVec host mirrors (engine.h)
+void *stable_reserve() {
+    void *p = mmap(nullptr, STABLE_RESERVE, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (p == MAP_FAILED) {
+        perror("libode_b200: mmap (host mirror reservation)");
+        abort();
+    }
+    return p;
+}
+void stable_commit(void *base, size_t old_bytes, size_t new_bytes) {
+    if (mprotect(static_cast<char *>(base) + old_bytes, new_bytes - old_bytes, PROT_READ | PROT_WRITE) != 0) {
+        perror("libode_b200: mprotect (host mirror growth)");
+        abort();
+    }
+}
+void stable_release(void *base) { munmap(base, STABLE_RESERVE); }
 
 Engine *eng_create(int device) {
     int count = 0;
@@ -508,7 +526,8 @@ static void *patch_stage(Engine *e, size_t bytes) {
     return e->h_patch;
 }
 
-static inline float4 ld4(const std::vector<float> &v, size_t i) { return make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]); }
+template <typename V>
+static inline float4 ld4(const V &v, size_t i) { return make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]); }
 
 // per-env body ranges: index of a body relative to the first body of its env makes the colouring priorities,
 // and with them the Gauss-Seidel order of a world, independent of which other worlds share the batch;

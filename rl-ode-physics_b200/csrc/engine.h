@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <initializer_list>
 #include <vector>
 
 namespace ob {
@@ -143,12 +144,82 @@ int eng_device(Engine *);
 cudaStream_t eng_stream(Engine *);
 
 // host mirrors (the shim reads/writes these, then marks dirty)
+// Growable host array whose elements NEVER move: dBodyGetPosition / Rotation / Quaternion / LinearVel / AngularVel and
+// dGeomGetPosition / Rotation hand out pointers into these mirrors, and libode guarantees such a pointer for the body's
+// lifetime (a later dBodyCreate must not invalidate it).  The array reserves address space once (mmap, PROT_NONE, no memory
+// committed) and commits pages as it grows, so data() is contiguous -- the bulk uploads / read-backs copy it in one piece.
+template <typename T>
+class StableVec {
+  public:
+    StableVec() = default;
+    StableVec(const StableVec &) = delete;
+    StableVec &operator=(const StableVec &) = delete;
+    ~StableVec();
+    size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    T *data() { return p_; }
+    const T *data() const { return p_; }
+    T &operator[](size_t i) { return p_[i]; }
+    const T &operator[](size_t i) const { return p_[i]; }
+    T *begin() { return p_; }
+    T *end() { return p_ + n_; }
+    void resize(size_t n, T v = T());
+    // append only (pos must be end()): the two forms the engine uses
+    void insert(T *pos, std::initializer_list<T> il) { append(pos, il.begin(), il.size()); }
+    void insert(T *pos, const T *first, const T *last) { append(pos, first, (size_t)(last - first)); }
+
+  private:
+    void append(T *pos, const T *src, size_t k);
+    void grow(size_t n); // make room for n elements
+    T *p_ = nullptr;
+    size_t n_ = 0, committed_ = 0; // elements in use; BYTES committed
+};
+void *stable_reserve();                                  // engine.cu
+void stable_commit(void *base, size_t old_bytes, size_t new_bytes);
+void stable_release(void *base);
+constexpr size_t STABLE_RESERVE = (size_t)8 << 30; // address space per array: 8 GiB = 178 M bodies' rotation matrices
+template <typename T>
+StableVec<T>::~StableVec() {
+    if (p_) stable_release(p_);
+}
+template <typename T>
+void StableVec<T>::grow(size_t n) {
+    const size_t need = n * sizeof(T);
+    if (need <= committed_) return;
+    if (need > STABLE_RESERVE) {
+        fprintf(stderr, "libode_b200: a host mirror outgrew its %zu-byte address reservation\n", STABLE_RESERVE);
+        abort();
+    }
+    if (!p_) p_ = static_cast<T *>(stable_reserve());
+    size_t want = committed_ ? committed_ * 2 : ((size_t)1 << 16);
+    while (want < need) want *= 2;
+    if (want > STABLE_RESERVE) want = STABLE_RESERVE;
+    stable_commit(p_, committed_, want);
+    committed_ = want;
+}
+template <typename T>
+void StableVec<T>::resize(size_t n, T v) {
+    grow(n);
+    for (size_t i = n_; i < n; i++) p_[i] = v;
+    n_ = n;
+}
+template <typename T>
+void StableVec<T>::append(T *pos, const T *src, size_t k) {
+    if (pos != end()) {
+        fprintf(stderr, "libode_b200: StableVec supports appending only\n");
+        abort();
+    }
+    grow(n_ + k);
+    for (size_t i = 0; i < k; i++) p_[n_ + i] = src[i];
+    n_ += k;
+}
+
 struct HostBodies {
-    std::vector<float> pos;   // 4 per body: x y z invMass
-    std::vector<float> quat;  // 4: w x y z
-    std::vector<float> R;     // 12 row-major 3x4
-    std::vector<float> lvel;  // 4: xyz, mass
-    std::vector<float> avel;  // 4: xyz, pad
+    StableVec<float> pos;   // 4 per body: x y z invMass      (the five arrays the dBodyGet* pointers point into)
+    StableVec<float> quat;  // 4: w x y z
+    StableVec<float> R;     // 12 row-major 3x4
+    StableVec<float> lvel;  // 4: xyz, mass
+    StableVec<float> avel;  // 4: xyz, pad
     std::vector<float> I;     // 12 body-frame inertia (3x4)
     std::vector<float> invI;  // 12 body-frame inverse inertia (3x4)
     std::vector<float> facc;  // 4
@@ -161,8 +232,8 @@ struct HostGeoms {
     std::vector<int> type;
     std::vector<float> dims;  // 4
     std::vector<int> body;    // -1 static
-    std::vector<float> pos;   // 4 (static pose; refreshed from body for getters)
-    std::vector<float> R;     // 12
+    StableVec<float> pos;   // 4 (static pose; refreshed from body for getters)   (dGeomGetPosition / Rotation)
+    StableVec<float> R;     // 12
     std::vector<uint32_t> cat, col;
     std::vector<int> env;     // -1 = every env
     std::vector<int> alive;   // 0 = destroyed (never collides)

@@ -452,3 +452,32 @@ def test_boxes_settle_on_the_reference_terrain_mesh_loaded_from_obj(tmp_path):
     y = finals[0][:, 1]
     assert y.min() > verts[:, 1].min() - 0.5 and y.max() < verts[:, 1].max() + 2.0      # on the terrain, not through it
     assert np.abs(finals[0][::2, 3:]).max() < 1.0                                         # the boxes came to rest (spheres may still roll)
+
+
+def test_getter_pointers_stay_valid_for_the_bodys_lifetime():
+    """libode guarantees the const dReal* of dBodyGetPosition & co for the body's lifetime.  The host
+    mirrors are address-stable arrays: a pointer taken before 70 000 more bodies are created (the mirrors grow by three
+    orders of magnitude) is still THE pointer afterwards, and reads the body's current state after a step."""
+    s = Server()
+    L = s.L
+    s.add_static_box((0, 0, 0), (100, 1, 100))
+    b0, g0 = s.add_body((0.25, 3.0, -0.5), "box", (0.4, 0.4, 0.4))
+    getters = [L.dBodyGetPosition, L.dBodyGetRotation, L.dBodyGetQuaternion, L.dBodyGetLinearVel, L.dBodyGetAngularVel]
+    before = [C.cast(f(b0), C.c_void_p).value for f in getters]
+    gp_before = C.cast(L.dGeomGetPosition(s.geoms[0]), C.c_void_p).value   # the static floor's own pose
+    p = L.dBodyGetPosition(b0)
+    assert (p[0], p[1], p[2]) == (0.25, 3.0, -0.5)
+    rs = np.random.RandomState(5)
+    for i in range(70000):
+        bi = C.c_void_p(L.dBodyCreate(s.world))
+        L.dBodySetPosition(bi, float(100 + 2 * (i % 300)), 50.0 + 2 * (i // 300), float(rs.rand()))
+        s.bodies.append(bi)
+    after = [C.cast(f(b0), C.c_void_p).value for f in getters]
+    assert before == after
+    assert C.cast(L.dGeomGetPosition(s.geoms[0]), C.c_void_p).value == gp_before
+    assert (p[0], p[1], p[2]) == (0.25, 3.0, -0.5)          # the old pointer still reads the body
+    s.tick()
+    q = L.dBodyGetPosition(b0)                               # refreshes the mirrors after the step
+    assert C.cast(q, C.c_void_p).value == before[0]
+    assert p[1] < 3.0 and p[1] == q[1]                       # ... and the OLD pointer sees the new state
+    s.close()
