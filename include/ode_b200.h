@@ -36,6 +36,11 @@ void dWorldSetMaxContactsB200(dWorldID, int max_contacts);
 /* batched independent worlds ("envs") inside one dWorldID: geoms of different envs never collide;
  * env -1 on a static geom means "present in every env". */
 void dWorldSetNumEnvsB200(dWorldID, int n_envs);
+/* slot re-use (default off): with on != 0, dBodyDestroy / dGeomDestroy remember the freed index and the next dBodyCreate /
+ * dCreateSphere / dCreateBox takes the lowest remembered one instead of growing the world's arrays -- for applications that
+ * spawn and destroy for ever (the reference's server: src/main.c:695-733 re-uses its own 512 slots the same way; the slab
+ * driver's migration).  Off, indices are handed out in creation order, which the parity tests rely on. */
+void dWorldSetSlotReuseB200(dWorldID, int on);
 void dBodySetEnvB200(dBodyID, int env);
 void dGeomSetEnvB200(dGeomID, int env);
 

@@ -208,6 +208,33 @@ int eng_add_geom(Engine *e) {
     return i;
 }
 
+// Slot re-use (dWorldSetSlotReuseB200): a destroyed body / geom slot is given back its creation defaults and sent to the
+// device as one whole-record patch, exactly like a fresh append.  The env of the slot is kept.
+void eng_reset_body(Engine *e, int i) {
+    HostBodies &b = e->hb;
+    static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    const float p4[4] = {0.f, 0.f, 0.f, 1.f}, q4[4] = {1.f, 0.f, 0.f, 0.f}, z4[4] = {0.f, 0.f, 0.f, 0.f};
+    memcpy(&b.pos[4 * (size_t)i], p4, sizeof(p4)); memcpy(&b.quat[4 * (size_t)i], q4, sizeof(q4));
+    memcpy(&b.lvel[4 * (size_t)i], p4, sizeof(p4)); memcpy(&b.avel[4 * (size_t)i], z4, sizeof(z4));
+    memcpy(&b.facc[4 * (size_t)i], z4, sizeof(z4)); memcpy(&b.tacc[4 * (size_t)i], z4, sizeof(z4));
+    memcpy(&b.R[12 * (size_t)i], ident, sizeof(ident)); memcpy(&b.I[12 * (size_t)i], ident, sizeof(ident));
+    memcpy(&b.invI[12 * (size_t)i], ident, sizeof(ident));
+    b.flags[i] = 0;
+    if (e->n_b_dev == 0) e->bodies_dirty = true;
+    else eng_mark_body_fields(e, i, FLD_ALL);
+}
+void eng_reset_geom(Engine *e, int i) {
+    HostGeoms &g = e->hg;
+    static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    const float z4[4] = {0.f, 0.f, 0.f, 0.f};
+    g.type[i] = G_SPHERE;
+    memcpy(&g.dims[4 * (size_t)i], z4, sizeof(z4)); memcpy(&g.pos[4 * (size_t)i], z4, sizeof(z4));
+    memcpy(&g.R[12 * (size_t)i], ident, sizeof(ident));
+    g.body[i] = -1; g.cat[i] = 0xffffffffu; g.col[i] = 0xffffffffu; g.alive[i] = 1;
+    if (e->n_g_dev == 0) e->geoms_dirty = true;
+    else eng_mark_geom(e, i);
+}
+
 int eng_add_mesh(Engine *e, const float *verts, int nv, const int *tris, int nt) {
     if ((int)e->hmeshes.size() >= MAX_MESHES) {
         fprintf(stderr, "libode_b200: at most %d trimesh data objects per world\n", MAX_MESHES);

@@ -243,6 +243,8 @@ HostBodies &eng_bodies(Engine *);
 HostGeoms &eng_geoms(Engine *);
 int eng_add_body(Engine *);  // default dBodyCreate state; returns index
 int eng_add_geom(Engine *);  // returns index
+void eng_reset_body(Engine *, int i); // slot re-use: creation defaults, whole record re-sent
+void eng_reset_geom(Engine *, int i);
 int eng_add_mesh(Engine *, const float *verts, int nv, const int *tris, int nt);
 void eng_mark_bodies_dirty(Engine *);  // host mirror changed -> upload before next device op
 void eng_mark_geoms_dirty(Engine *);

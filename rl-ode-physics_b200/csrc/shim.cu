@@ -72,6 +72,10 @@ struct dxWorld {
     int step_iters = 0;   // dWorldStep parity mode (dWorldSetStepSolverB200)
     float step_tol = 0.f;
     bool device_contacts_pending = false;
+    // dWorldSetSlotReuseB200: indices of destroyed bodies / sphere and box geoms, handed out again (lowest first) by the next
+    // dBodyCreate / dCreateSphere / dCreateBox instead of growing the arrays
+    bool reuse_slots = false;
+    std::vector<int> free_bodies, free_geoms;
     // callback context
     bool in_callback = false;
     int cb_g1 = -1, cb_g2 = -1, cb_first = 0, cb_count = 0;
@@ -344,6 +348,7 @@ extern "C" void dWorldSetSurfaceB200(dWorldID w, const dSurfaceParameters *s) { 
 extern "C" void dWorldGetSurfaceB200(dWorldID w, dSurfaceParameters *s) { *s = w->surface; }
 extern "C" void dWorldSetMaxContactsB200(dWorldID w, int n) { w->max_contacts = n < 1 ? 1 : (n > 8 ? 8 : n); }
 extern "C" void dWorldSetNumEnvsB200(dWorldID w, int n) { eng_set_num_envs(w->eng, n); }
+extern "C" void dWorldSetSlotReuseB200(dWorldID w, int on) { w->reuse_slots = on != 0; }
 extern "C" void dWorldSetCapacityB200(dWorldID w, long mp, long mm) { eng_set_capacity(w->eng, mp, mm); }
 extern "C" void dWorldSetBigExtentB200(dWorldID w, float e) { eng_set_big_extent(w->eng, e); }
 extern "C" void dWorldSetBroadphaseB200(dWorldID w, int mode) { eng_set_broadphase(w->eng, mode); }
@@ -413,7 +418,20 @@ extern "C" void dWorldGetStatsB200(dWorldID w, dStepStatsB200 *out) {
 
 // ------------------------------------------------------------------ bodies
 
+static int pop_lowest(std::vector<int> &v) {
+    auto it = std::min_element(v.begin(), v.end());
+    const int i = *it;
+    *it = v.back();
+    v.pop_back();
+    return i;
+}
 static dxBody *new_body(dxWorld *w) {
+    if (w->reuse_slots && !w->free_bodies.empty()) {
+        const int idx = pop_lowest(w->free_bodies);
+        eng_reset_body(w->eng, idx);
+        w->bodies[idx] = dxBody{w, idx, nullptr, true, {}};
+        return &w->bodies[idx];
+    }
     const int idx = eng_add_body(w->eng);
     w->bodies.push_back(dxBody{w, idx, nullptr, true, {}});
     return &w->bodies.back();
@@ -450,6 +468,7 @@ extern "C" void dBodyDestroy(dBodyID b) {
     for (int k = 0; k < 12; k++) hb.invI[12 * b->idx + k] = 0;
     eng_mark_body_fields(w->eng, b->idx, FLD_MASS | FLD_LVEL | FLD_AVEL);
     b->alive = false;
+    if (w->reuse_slots && hb.env[b->idx] == 0) w->free_bodies.push_back(b->idx);
 }
 
 #define HB(b) eng_bodies((b)->w->eng)
@@ -591,6 +610,21 @@ extern "C" dGeomID dSpaceGetGeomB200(dSpaceID s, int i) { return (i >= 0 && i < 
 static dxGeom *new_geom(dxSpace *s, int type, float d0, float d1, float d2, float d3) {
     if (!s) fatal("geoms must be created in a space (dSpaceID 0 is not supported)");
     dxWorld *w = space_world(s);
+    if (w->reuse_slots && !w->free_geoms.empty() && (type == G_SPHERE || type == G_BOX)) {
+        const int idx = pop_lowest(w->free_geoms);
+        eng_reset_geom(w->eng, idx);
+        HostGeoms &hg = eng_geoms(w->eng);
+        hg.type[idx] = type;
+        hg.dims[4 * idx] = d0; hg.dims[4 * idx + 1] = d1; hg.dims[4 * idx + 2] = d2; hg.dims[4 * idx + 3] = d3;
+        dxGeom *g = &w->geoms[idx];
+        if (g->space != s) {
+            std::vector<dxGeom *> &v = g->space->geoms;
+            v.erase(std::remove(v.begin(), v.end(), g), v.end());
+            s->geoms.push_back(g);
+        }
+        *g = dxGeom{s, idx, nullptr, nullptr, true, {0, 0, 0, 0, 0, 0}};
+        return g;
+    }
     const int idx = eng_add_geom(w->eng);
     HostGeoms &hg = eng_geoms(w->eng);
     hg.type[idx] = type;
@@ -628,6 +662,10 @@ extern "C" void dGeomDestroy(dGeomID g) {
     HG(g).alive[g->idx] = 0;
     eng_mark_geom(g->space->w->eng, g->idx);
     g->alive = false;
+    dxWorld *w = g->space->w;
+    const int t = HG(g).type[g->idx];
+    // (slots of env 0 only: a re-used slot keeps its env, and env 0 is where the handle API creates things)
+    if (w->reuse_slots && (t == G_SPHERE || t == G_BOX) && HG(g).env[g->idx] == 0) w->free_geoms.push_back(g->idx);
 }
 extern "C" void dGeomSetBody(dGeomID g, dBodyID b) {
     if (b && b->w != g->space->w) fatal("dGeomSetBody: the body belongs to a different world than the geom's space");

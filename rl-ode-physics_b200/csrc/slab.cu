@@ -121,6 +121,7 @@ extern "C" dSlabID dSlabCreateB200(dWorldID world, dSpaceID space, int rank, int
     dxSlabB200 *s = new dxSlabB200();
     s->world = world; s->space = space; s->rank = rank; s->n_ranks = n_ranks; s->L = *layout;
     s->has_left = rank > 0; s->has_right = rank < n_ranks - 1;
+    dWorldSetSlotReuseB200(world, 1); // arriving migrants take the body / geom slots of the ones that left
     s->st = (cudaStream_t)dWorldGetStreamB200(world);
     OB_CUDA(cudaGetDevice(&s->device));
     OB_CUDA(cudaStreamCreateWithFlags(&s->comm_st, cudaStreamNonBlocking));

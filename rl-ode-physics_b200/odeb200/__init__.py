@@ -116,6 +116,7 @@ _SIGS = [
     ("dWorldGetSurfaceB200", None, [_vp, C.POINTER(SurfaceParameters)]),
     ("dWorldSetMaxContactsB200", None, [_vp, _i]),
     ("dWorldSetNumEnvsB200", None, [_vp, _i]),
+    ("dWorldSetSlotReuseB200", None, [_vp, _i]),
     ("dWorldAddBodiesB200", _i, [_vp, _i, _fp, _fp, _fp, _fp, _fp, _fp, _ip, _ip]),
     ("dSpaceAddGeomsB200", _i, [_vp, _vp, _i, _ip, _fp, _ip, _fp, _fp, _up, _up, _ip]),
     ("dWorldAddTriMeshB200", _i, [_vp, _fp, _i, _ip, _i]),

@@ -282,6 +282,7 @@ class DynamicSlabWorld:
         self.body_geom[:n_bodies] = torch.arange(info["n_static"], info["n_static"] + n_bodies, dtype=torch.int32, device=device)
         self.n_owned = info["n_own"]
         self.count = torch.zeros(4, dtype=torch.int32, device=device)
+        world.L.dWorldSetSlotReuseB200(world.w, 1)   # migrants take the slots of bodies that left (as the C driver does)
         P, M = info["pool"], info["mig_cap"]
         f32 = dict(dtype=torch.float32, device=device)
         i32 = dict(dtype=torch.int32, device=device)
@@ -325,6 +326,18 @@ class DynamicSlabWorld:
                 L.dWorldPackBodiesDeviceB200(w, s["send_mig_idx"].data_ptr(), s["send_mig_idx"].numel(), self.body_geom.data_ptr(),
                                              s["send_mig_buf"].data_ptr())
         self.w.wait()
+        # overflow is reported, never silent: the selection kernels count every body in range, also those beyond capacity
+        if kind in ("state", "mig"):
+            cnt = self.count.cpu().numpy()
+            if kind == "state" and "left" in self.sides and cnt[0] > self.sides["left"]["send_state_idx"].numel():
+                raise RuntimeError("DynamicSlabWorld: %d bodies within the face margin, the ghost pool holds %d"
+                                   % (cnt[0], self.sides["left"]["send_state_idx"].numel()))
+            if kind == "mig":
+                for side, k in (("left", 1), ("right", 2)):
+                    if side in self.sides and cnt[k] > self.sides[side]["send_mig_idx"].numel():
+                        import warnings
+                        warnings.warn("DynamicSlabWorld: %d bodies crossed the %s face, the migration buffer holds %d; the rest "
+                                      "change owner at the next migration" % (cnt[k], side, self.sides[side]["send_mig_idx"].numel()))
 
     def unpack(self, kind="state"):
         L, w = self.w.L, self.w.w

@@ -481,3 +481,35 @@ def test_getter_pointers_stay_valid_for_the_bodys_lifetime():
     assert C.cast(q, C.c_void_p).value == before[0]
     assert p[1] < 3.0 and p[1] == q[1]                       # ... and the OLD pointer sees the new state
     s.close()
+
+
+def test_slot_reuse_gives_the_same_physics_without_growing_the_world():
+    """dWorldSetSlotReuseB200: a server that spawns and destroys for ever.  With re-use on, the world's arrays stop
+    growing (indices of destroyed bodies / geoms are handed out again, lowest first), and the live bodies move exactly
+    as in a world that appends: compared handle by handle over 40 ticks with a spawn + a destroy every other tick."""
+    rs = np.random.RandomState(11)
+    plan = [(rs.uniform(-1.5, 1.5), 2.0 + rs.uniform(0, 2), rs.uniform(-1.5, 1.5), rs.rand() < 0.5, rs.uniform(0.2, 0.5, 3))
+            for _ in range(40)]
+    runs = []
+    for reuse in (0, 1):
+        s = Server()
+        L = s.L
+        L.dWorldSetSlotReuseB200(s.world, reuse)
+        s.add_static_box((0, 0, 0), (100, 1, 100))
+        live, trace = [], []
+        for t in range(40):
+            x, y, z, sphere, d = plan[t]
+            if t % 2 == 0:
+                live.append(s.add_body((x, y, z), "sphere" if sphere else "box", (d[0],) if sphere else tuple(d)))
+            elif len(live) > 3:
+                b, g = live.pop(1)
+                L.dGeomDestroy(g)
+                L.dBodyDestroy(b)
+            s.tick()
+            trace.append(np.array([s.pos(b) for b, _ in live]))
+        runs.append((trace, L.dWorldGetNumBodiesB200(s.world), max(L.dBodyGetIndexB200(b) for b, _ in live)))
+        s.close()
+    (ta, na, _), (tb, nb, top) = runs
+    for a, b in zip(ta, tb):
+        assert np.array_equal(a, b)
+    assert na == 20 and nb < na and top < nb     # appended 20 slots vs re-used ones
