@@ -446,3 +446,39 @@ def test_union_of_slab_pair_sets_equals_the_single_world_pair_set():
     one.close()
     for s in sl:
         s.w.close()
+
+
+def test_c_host_drives_the_slab_decomposition():
+    """rl-ode-physics_b200/host/slab_server.c: a plain-C host builds two slabs of a lattice pile through the ODE handle
+    API and runs them through the C slab driver (local transport: one GPU): every body stays owned by exactly one slab,
+    nothing overflows, bodies cross the face in both directions of the bookkeeping (migrated out == migrated in), the
+    halo carries bodies, and the pile comes to rest on the plane."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "rl-ode-physics_b200", "host", "slab_server")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
+    cols, nz, ny, ticks = 12, 16, 6, 320
+    r = subprocess.run([exe, "local", "2", str(cols), str(nz), str(ny), str(ticks)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rows = []
+    for line in r.stdout.splitlines():
+        m = re.match(r"slab (\d+): (.*)", line)
+        if m:
+            toks = m.group(2).split()
+            d, i = {}, 0
+            while i < len(toks):
+                k = toks[i]
+                n = 3 if k == "momentum" else 1
+                d[k] = [float(x) for x in toks[i + 1:i + 1 + n]]
+                i += 1 + n
+            rows.append(d)
+    assert len(rows) == 2, r.stdout
+    assert sum(d["owned"][0] for d in rows) == 2 * cols * nz * ny
+    assert sum(d["migrated_in"][0] for d in rows) == sum(d["migrated_out"][0] for d in rows) > 0   # the kicked columns
+    for d in rows:
+        assert d["halo_overflow"][0] == 0 and d["mig_overflow"][0] == 0
+        assert d["ymin"][0] > -0.05 and d["vmax"][0] < 6.0, d
+    assert rows[1]["halo_selected"][0] > 0 and rows[1]["halo_bytes_per_tick"][0] > 0
