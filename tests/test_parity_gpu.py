@@ -146,6 +146,30 @@ def test_batched_worlds_are_independent_bit_exact():
             assert np.array_equal(sb[k][w * 128:(w + 1) * 128], s1[k]), (w, k)
 
 
+def test_world_batches_ticked_side_by_side_equal_one_batch():
+    """bench.py holds the worlds of a GPU in several dWorld objects whose ticks overlap on the GPU (one stream each).  The
+    worlds do not care how they are grouped: 24 worlds as 3 dWorlds of 8, ticked interleaved without waiting, end in the
+    very bits of one dWorld of 24."""
+    one = scenes.batched_worlds_scene(24, seed=4, spacing=0.7)
+    e1 = util.engine_world(one)
+    parts = []
+    for k in range(3):
+        sc = scenes.batched_worlds_scene(8, seed=4, spacing=0.7, first_world=8 * k)
+        parts.append(util.engine_world(sc))
+    for _ in range(30):
+        e1.tick(one["h"])
+        for p in parts:
+            p.tick(one["h"])      # queued on three streams; nobody waits
+    s1 = e1.state()
+    for k, p in enumerate(parts):
+        sp = p.state()
+        for f in ("pos", "quat", "lvel", "avel"):
+            assert np.array_equal(s1[f][k * 1024:(k + 1) * 1024], sp[f]), (k, f)
+        p.close()
+    assert e1.stats()["n_contacts"] > 500
+    e1.close()
+
+
 @pytest.mark.parametrize("name", ["batch8", "c1_low", "soup200"])
 def test_env_broadphase_equals_grid_broadphase(name):
     """The all-pairs-per-env sweep and the uniform-grid sweep must hand the narrowphase the same pair SET
