@@ -154,6 +154,9 @@ void eng_destroy(Engine *e) {
     dev_free(e->d_f6[0]); dev_free(e->d_f6[1]);
     if (e->tev[0]) { cudaEventDestroy(e->tev[0]); cudaEventDestroy(e->tev[1]); }
     if (e->h_stats) cudaFreeHost(e->h_stats);
+    if (e->x_host) cudaFreeHost(e->x_host);
+    if (e->hcs_host) cudaFreeHost(e->hcs_host);
+    dev_free(e->hcs_dev);
     for (int i = 0; i < 5; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     if (e->ev_bp) cudaEventDestroy(e->ev_bp);
     cudaStreamDestroy(e->st);
@@ -910,6 +913,54 @@ __global__ void __launch_bounds__(256) k_compact_contacts(const BroadCounters *_
     }
 }
 
+// compat mode, fast path: pairs, contact ranges and pair-major contacts written into the mapped host buffer
+struct ExportView {
+    int *hdr, *g1, *g2, *first, *count; // hdr: n_pairs, n_contacts, spare, spare
+    float4 *pd, *ns;
+};
+static ExportView export_view(unsigned char *base, int cap_pairs, int cap_contacts) {
+    ExportView v;
+    const size_t cp = ((size_t)cap_pairs + 4 + 3) & ~(size_t)3; // ints per array, 16-byte multiples
+    v.hdr = reinterpret_cast<int *>(base);
+    v.g1 = v.hdr + 4; v.g2 = v.g1 + cp; v.first = v.g2 + cp; v.count = v.first + cp;
+    v.pd = reinterpret_cast<float4 *>(v.count + cp);
+    v.ns = v.pd + cap_contacts;
+    return v;
+}
+static size_t export_bytes(int cap_pairs, int cap_contacts) {
+    const size_t cp = ((size_t)cap_pairs + 4 + 3) & ~(size_t)3;
+    return 16 + 4 * cp * sizeof(int) + 2 * (size_t)cap_contacts * sizeof(float4);
+}
+__global__ void __launch_bounds__(256) k_export_pairs(const BroadCounters *__restrict__ bc, const int2 *__restrict__ pairs,
+                                                      ContactSlots cs, const int *__restrict__ first, const int *__restrict__ total,
+                                                      ExportView x, int cap_pairs, int cap_contacts) {
+    const int np = bc->n_pairs, n = min(np, cap_pairs);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const int2 pr = pairs[p];
+        const int c = cs.nc[p], f = first[p];
+        x.g1[p] = pr.x; x.g2[p] = pr.y; x.first[p] = f; x.count[p] = c;
+        for (int k = 0; k < c; k++)
+            if (f + k < cap_contacts) {
+                x.pd[f + k] = cs.pd[(size_t)k * cs.stride + p];
+                x.ns[f + k] = cs.ns[(size_t)k * cs.stride + p];
+            }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        x.hdr[0] = np; x.hdr[1] = *total; x.hdr[2] = 0; x.hdr[3] = 0;
+        x.first[n] = *total;
+    }
+}
+constexpr int EXPORT_MAX_PAIRS = 1 << 16, EXPORT_MAX_CONTACTS = 1 << 17; // beyond: the copying path (bandwidth matters there)
+
+static void export_ensure(Engine *e, int pairs, int contacts) {
+    if (pairs <= e->x_cap_pairs && contacts <= e->x_cap_contacts) return;
+    if (e->x_host) { OB_CUDA(cudaStreamSynchronize(e->st)); OB_CUDA(cudaFreeHost(e->x_host)); }
+    e->x_cap_pairs = std::max(pairs, e->x_cap_pairs);
+    e->x_cap_contacts = std::max(contacts, e->x_cap_contacts);
+    OB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&e->x_host), export_bytes(e->x_cap_pairs, e->x_cap_contacts), cudaHostAllocMapped));
+    OB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&e->x_dev), e->x_host, 0));
+}
+
 // dCollide outside a space traversal: one pair through the same narrowphase kernels
 HostPairs eng_collide_pair(Engine *e, int g1, int g2, int max_contacts) {
     if (e->have_device_contacts) {
@@ -934,6 +985,39 @@ HostPairs eng_fetch_pairs(Engine *e) {
     OB_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = e->st;
     if (!e->have_device_contacts || e->G.n == 0) return hp;
+    // fast path: sized by what earlier traversals needed (+ headroom); a tick that outgrows the buffer takes the copying
+    // path below once.  Worlds beyond EXPORT_MAX_* always copy.
+    if (e->x_want_pairs > EXPORT_MAX_PAIRS || e->x_want_contacts > EXPORT_MAX_CONTACTS) {
+        if (e->x_host) { OB_CUDA(cudaStreamSynchronize(st)); OB_CUDA(cudaFreeHost(e->x_host)); e->x_host = nullptr; }
+        e->x_cap_pairs = e->x_cap_contacts = 0;
+    } else {
+        export_ensure(e, e->x_want_pairs, e->x_want_contacts);
+        const int capx = e->x_cap_pairs, capc = e->x_cap_contacts;
+        if (capx + 2 > e->cap_dl) {
+            dev_realloc(e->dl_first, 0, (size_t)capx + 1026, st, false);
+            e->cap_dl = capx + 1024;
+        }
+        int *d_total = e->dl_first + capx + 1;
+        scan_exclusive(e->cs.nc, e->dl_first, capx, &e->bp.counters->n_pairs, d_total, e->scan, st);
+        const ExportView xd = export_view(e->x_dev, capx, capc);
+        k_export_pairs<<<(unsigned)std::min((capx + 255) / 256, e->num_sms * 4), 256, 0, st>>>(e->bp.counters, e->bp.pairs, e->cs, e->dl_first,
+                                                                                              d_total, xd, capx, capc);
+        OB_CHECK_KERNEL("k_export_pairs", st);
+        OB_CUDA(cudaStreamSynchronize(st));
+        const ExportView xh = export_view(e->x_host, capx, capc);
+        const int np = xh.hdr[0], total = xh.hdr[1];
+        if (np <= capx && total <= capc) {
+            hp.n_pairs = np;
+            hp.g1 = xh.g1; hp.g2 = xh.g2; hp.first = xh.first; hp.count = xh.count;
+            hp.pos_depth = reinterpret_cast<const float *>(xh.pd); hp.normal_side = reinterpret_cast<const float *>(xh.ns);
+            if (np + np / 4 > capx) e->x_want_pairs = 2 * np + 64;             // keep a quarter of headroom
+            if (total + total / 4 > capc) e->x_want_contacts = 2 * total + 64;
+            return hp;
+        }
+        // outgrown (the scan above covered only capx pairs, so `total` is only valid when the pairs fitted)
+        if (np > capx) e->x_want_pairs = np + np / 2 + 64;
+        e->x_want_contacts = np > capx ? std::max(2 * capc, e->x_want_contacts) : total + total / 2 + 64;
+    }
     BroadCounters bc;
     OB_CUDA(cudaMemcpyAsync(&bc, e->bp.counters, sizeof(bc), cudaMemcpyDeviceToHost, st));
     OB_CUDA(cudaStreamSynchronize(st));
@@ -1013,6 +1097,17 @@ void eng_step_device_contacts(Engine *e, float h, const Surface &surf) {
     e->ev_valid = e->timing;
 }
 
+__global__ void __launch_bounds__(256) k_file_host_contacts(const float4 *__restrict__ pd, const float4 *__restrict__ ns,
+                                                            const Surface *__restrict__ surf, const int4 *__restrict__ mrec, int nc, int nm,
+                                                            float4 *__restrict__ o_pd, float4 *__restrict__ o_ns, Surface *__restrict__ o_surf,
+                                                            int4 *__restrict__ o_mrec, int *__restrict__ m_count, int *__restrict__ meta) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+    for (int i = gt; i < nc; i += gs) { o_pd[i] = pd[i]; o_ns[i] = ns[i]; o_surf[i] = surf[i]; }
+    for (int i = gt; i < nm; i += gs) o_mrec[i] = mrec[i];
+    if (gt == 0) *m_count = nm;
+    if (gt < 8) meta[gt] = 0;
+}
+
 void eng_step_host_contacts(Engine *e, float h, const HostContact *contacts, int n) {
     eng_sync_to_device(e);
     consume_force_mirrors(e);
@@ -1045,12 +1140,30 @@ void eng_step_host_contacts(Engine *e, float h, const HostContact *contacts, int
         dev_realloc(e->hc_surf, 0, cap, st, false);
         e->cap_hc = (int)cap;
     }
-    upload(e->hc_pd, e->st_pd.data(), (size_t)nc, st);
-    upload(e->hc_ns, e->st_ns.data(), (size_t)nc, st);
-    upload(e->hc_surf, e->st_surf.data(), (size_t)nc, st);
-    upload(e->M.rec, e->st_mrec.data(), (size_t)nm, st);
-    OB_CUDA(cudaMemcpyAsync(e->M.count, &nm, sizeof(int), cudaMemcpyHostToDevice, st));
-    OB_CUDA(cudaMemsetAsync(e->M.meta, 0, 8 * sizeof(int), st));
+    {
+        // one pinned blob [pd | ns | surfaces | manifold records], one copy, one kernel that files it (instead of five
+        // copies and a memset from pageable vectors)
+        const size_t o_ns = (size_t)nc * 16, o_surf = 2 * o_ns, o_mrec = o_surf + (((size_t)nc * sizeof(Surface) + 15) & ~(size_t)15);
+        const size_t bytes = o_mrec + (size_t)nm * 16;
+        if (bytes > e->hcs_cap) {
+            if (e->hcs_host) { OB_CUDA(cudaFreeHost(e->hcs_host)); dev_free(e->hcs_dev); }
+            e->hcs_cap = bytes + bytes / 2 + 4096;
+            OB_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&e->hcs_host), e->hcs_cap, cudaHostAllocDefault));
+            dev_realloc(e->hcs_dev, 0, e->hcs_cap, st, false);
+        }
+        if (nc) {
+            memcpy(e->hcs_host, e->st_pd.data(), o_ns);
+            memcpy(e->hcs_host + o_ns, e->st_ns.data(), o_ns);
+            memcpy(e->hcs_host + o_surf, e->st_surf.data(), (size_t)nc * sizeof(Surface));
+            memcpy(e->hcs_host + o_mrec, e->st_mrec.data(), (size_t)nm * 16);
+            OB_CUDA(cudaMemcpyAsync(e->hcs_dev, e->hcs_host, bytes, cudaMemcpyHostToDevice, st));
+        }
+        k_file_host_contacts<<<(unsigned)std::max(1, std::min((nc + 255) / 256, e->num_sms * 2)), 256, 0, st>>>(
+            reinterpret_cast<const float4 *>(e->hcs_dev), reinterpret_cast<const float4 *>(e->hcs_dev + o_ns),
+            reinterpret_cast<const Surface *>(e->hcs_dev + o_surf), reinterpret_cast<const int4 *>(e->hcs_dev + o_mrec), nc, nm, e->hc_pd,
+            e->hc_ns, e->hc_surf, e->M.rec, e->M.count, e->M.meta);
+        OB_CHECK_KERNEL("k_file_host_contacts", st);
+    }
     if (e->timing) {
         OB_CUDA(cudaEventRecord(e->ev[0], st));
         OB_CUDA(cudaEventRecord(e->ev[1], st));

@@ -91,6 +91,8 @@ struct Engine {
     std::vector<float4> st_pd, st_ns;
     std::vector<Surface> st_surf;
     std::vector<int4> st_mrec;
+    unsigned char *hcs_host = nullptr, *hcs_dev = nullptr; // one pinned staging blob + its device twin: the step's joints in ONE copy
+    size_t hcs_cap = 0;
 
     // compat-mode pair download
     int cap_dl = 0, cap_dlc = 0;
@@ -98,6 +100,11 @@ struct Engine {
     float4 *dl_pd = nullptr, *dl_ns = nullptr; // device: pair-major compacted contacts
     std::vector<int> h_g1, h_g2, h_first, h_count;
     std::vector<float> h_pd, h_ns;
+    // ... fast path for small and medium worlds: ONE kernel writes pairs, contact ranges and contacts straight into a
+    // mapped pinned host buffer (zero-copy), one synchronisation -- instead of three round trips with six small copies
+    unsigned char *x_host = nullptr, *x_dev = nullptr; // the same buffer: host address / device address
+    int x_cap_pairs = 0, x_cap_contacts = 0;
+    int x_want_pairs = 1024, x_want_contacts = 2048; // applied at the next traversal (the current one's pointers stay valid)
 
     // exact dWorldStep of small worlds (solver_exact.cu): island tables, row descriptors, island matrices
     int *ex_label = nullptr, *ex_desc = nullptr, *ex_isl_row0 = nullptr, *ex_isl_label = nullptr, *ex_meta = nullptr;
