@@ -28,7 +28,7 @@ def test_scan_matches_numpy(n):
     assert np.array_equal(out.astype(np.int64), ref)
 
 
-@pytest.mark.parametrize("n,bits", [(1, 8), (33, 8), (512, 10), (513, 16), (70000, 24), (262149, 24), (786437, 24),
+@pytest.mark.parametrize("n,bits", [(1, 8), (33, 8), (512, 10), (513, 16), (2000, 11), (4097, 24), (10006, 24), (32769, 24), (70000, 24), (262149, 24), (786437, 24),
                                     (1048581, 24), (3000001, 10)])
 def test_sort_is_stable_and_sorted(n, bits):
     L = _lib()
