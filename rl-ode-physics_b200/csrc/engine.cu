@@ -1566,9 +1566,12 @@ void eng_timer_start(Engine *e) {
     if (!e->tev[0]) { OB_CUDA(cudaEventCreate(&e->tev[0])); OB_CUDA(cudaEventCreate(&e->tev[1])); }
     OB_CUDA(cudaEventRecord(e->tev[0], e->st));
 }
-void eng_timer_stop(Engine *e) { OB_CUDA(cudaEventRecord(e->tev[1], e->st)); }
+void eng_timer_stop(Engine *e) {
+    if (e->tev[1]) OB_CUDA(cudaEventRecord(e->tev[1], e->st));
+}
 float eng_timer_elapsed_ms(Engine *e) {
     float ms = 0.f;
+    if (!e->tev[0]) return -1.f;
     OB_CUDA(cudaEventSynchronize(e->tev[1]));
     OB_CUDA(cudaEventElapsedTime(&ms, e->tev[0], e->tev[1]));
     return ms;
@@ -1576,6 +1579,7 @@ float eng_timer_elapsed_ms(Engine *e) {
 
 float eng_timer_elapsed_between_ms(Engine *start, Engine *stop) {
     float ms = 0.f;
+    if (!start->tev[0] || !stop->tev[1]) return -1.f; // a timer that was never started
     OB_CUDA(cudaEventSynchronize(stop->tev[1]));
     OB_CUDA(cudaEventElapsedTime(&ms, start->tev[0], stop->tev[1]));
     return ms;
