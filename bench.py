@@ -91,7 +91,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -115,7 +115,14 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines[getattr(self, "first", 0):]:
+        first = getattr(self, "first", 0)
+        lines, window = self.lines[first:], "timed region"
+        if len(lines) < 3:
+            # a query takes ~0.1 s and a short timed region sees one or none: add the samples taken just before it, during
+            # the warm-up ticks (the same kernels at the same rate), and say so
+            lines = self.lines[max(0, first - 4):]
+            window = "timed region + the warm-up ticks right before it (%d of the samples fall inside the timed region)" % len(self.lines[first:])
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -129,7 +136,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples: timed region shorter than the sampling period"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
-                "power_w_max": float(max(power)), "samples": len(sm)}
+                "power_w_max": float(max(power)), "samples": len(sm), "window": window}
 
 
 def measured_peaks():

@@ -21,6 +21,7 @@ extern "C" {
 /* CUDA device used by worlds created afterwards (default: env ODE_B200_DEVICE, LOCAL_RANK, or 0) */
 void dSetDeviceB200(int device);
 int dGetDeviceB200(void);
+int dWorldGetDeviceB200(dWorldID); /* the CUDA device this world lives on (fixed at dWorldCreate) */
 
 /* device-resident replacement of `dSpaceCollide(space, 0, NearCallback)` (src/main.c:212): runs
  * broadphase + narrowphase and keeps the contacts on the GPU for the next dWorldQuickStep/dWorldStep,

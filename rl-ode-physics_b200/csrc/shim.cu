@@ -251,6 +251,7 @@ extern "C" int dInitODE2(unsigned int) { return 1; }
 extern "C" void dCloseODE(void) {}
 extern "C" void dSetDeviceB200(int device) { g_device = device; }
 extern "C" int dGetDeviceB200(void) { return default_device(); }
+extern "C" int dWorldGetDeviceB200(dWorldID w) { return eng_device(w->eng); }
 
 extern "C" dWorldID dWorldCreate(void) {
     dxWorld *w = new dxWorld();

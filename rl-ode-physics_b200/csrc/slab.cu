@@ -123,7 +123,8 @@ extern "C" dSlabID dSlabCreateB200(dWorldID world, dSpaceID space, int rank, int
     s->has_left = rank > 0; s->has_right = rank < n_ranks - 1;
     dWorldSetSlotReuseB200(world, 1); // arriving migrants take the body / geom slots of the ones that left
     s->st = (cudaStream_t)dWorldGetStreamB200(world);
-    OB_CUDA(cudaGetDevice(&s->device));
+    s->device = dWorldGetDeviceB200(world); // not the calling thread's current device
+    OB_CUDA(cudaSetDevice(s->device));
     OB_CUDA(cudaStreamCreateWithFlags(&s->comm_st, cudaStreamNonBlocking));
     OB_CUDA(cudaEventCreateWithFlags(&s->ev_pack, cudaEventDisableTiming));
     OB_CUDA(cudaEventCreateWithFlags(&s->ev_comm, cudaEventDisableTiming));

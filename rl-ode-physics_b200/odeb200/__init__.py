@@ -141,6 +141,7 @@ _SIGS = [
     ("dWorldUnpackBodiesDeviceB200", None, [_vp, _vp, _vp, _i, _vp]),
     ("dWorldGetStreamB200", _vp, [_vp]),
     ("dCheckGuardsB200", _i, [_i]),
+    ("dWorldGetDeviceB200", _i, [_vp]),
     ("dGuardSelfTestB200", _i, [_i]),
     ("dSlabGetUniqueIdB200", _i, [C.c_char_p]),
     ("dSlabCreateB200", _vp, [_vp, _vp, _i, _i, C.c_char_p, C.POINTER(SlabLayout)]),
