@@ -116,12 +116,7 @@ class ClockSampler:
         sm, smax, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         first = getattr(self, "first", 0)
-        lines, window = self.lines[first:], "timed region"
-        if len(lines) < 3:
-            # a query takes ~0.1 s and a short timed region sees one or none: add the samples taken just before it, during
-            # the warm-up ticks (the same kernels at the same rate), and say so
-            lines = self.lines[max(0, first - 4):]
-            window = "timed region + the warm-up ticks right before it (%d of the samples fall inside the timed region)" % len(self.lines[first:])
+        lines, window = self.lines[first:], getattr(self, "window", "timed region")
         for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -539,9 +534,11 @@ def main():
                    "boundary-body states to the lower slab, contact impulses back to the owner" if args.coupling == "impulse"
                    else "boundary-body states both ways, kinematic ghosts"))
         n_bodies = sc["n_owned"]
-    # (overlap only pays with >= 2048 worlds per batch: measured at 8 GPUs, 1024 worlds per GPU run 2.63e9 in one batch and
-    # 2.54e9 in four)
-    n_batches = (args.batches if args.worlds_per_gpu >= 2048 * args.batches else 1) if args.workload == "C4" else 1
+    # (overlap pays down to ~1024 worlds per batch: measured, 4096 worlds per GPU run 1.38e9 in four batches and 1.25e9 in one
+    # at 2 GPUs; 1024 worlds per GPU run 2.54e9 in four batches of 256 and 2.66e9 in one at 8 GPUs)
+    def batches_for(n_worlds):
+        return max(1, min(args.batches, n_worlds // 1024))
+    n_batches = batches_for(args.worlds_per_gpu) if args.workload == "C4" else 1
     if n_batches > 1:
         # the same worlds as one big batch (seed 4 + global world index), held in n_batches dWorld objects
         grp = c4_world_group(odeb200, args.worlds_per_gpu, rank * args.worlds_per_gpu, n_batches, local_rank)
@@ -599,7 +596,7 @@ def main():
     launches0 = L.dGetKernelLaunchCountB200()
     elapsed_ms = timed_device_ticks(L, grp, do_tick, args.steps, sharding, torch)
     launches = L.dGetKernelLaunchCountB200() - launches0
-    clocks = sampler.stop()
+    t_timed_end = time.perf_counter()
     st = grp.stats()
     # per-kernel duration of the dominant kernel: CUDA events on the engine's stream around the solver launch, on
     # eight more live ticks right behind the timed ones (stage events are off inside the timed region: with them
@@ -641,12 +638,28 @@ def main():
                                                   "note": "dSnapshotExpandB200 rebuilds the 16-float transforms of tick t-1 on "
                                                           "the host's threads while tick t runs"}}
 
+    # ---------------- clocks: the sampler has been running since the start of the device-timed region.  An nvidia-smi query
+    # takes ~0.1 s, so short regions see one sample or none: keep the same ticks running (untimed, after every measured leg,
+    # so that no leg sees a later phase of the simulation) until ~0.8 s of load have been sampled, and say so
+    loaded = time.perf_counter() - t_timed_end + elapsed_ms * 1e-3
+    # (a tick COUNT agreed by all ranks, not a deadline: C5's ticks exchange halos, so every rank must run the same number)
+    n_extra = int(max(0.0, 0.8 - loaded) / max(elapsed_ms * 1e-3 / args.steps, 1e-5))
+    n_extra = int(sharding.all_reduce_max(float(n_extra), dev))
+    for i in range(n_extra):
+        do_tick()
+        if i % 10 == 9:
+            grp.wait()
+    grp.wait()
+    sampler.window = ("device-timed region (%.0f ms), the stage-timing and end-to-end legs, and the same ticks kept running after them: "
+                      "%.1f s of load" % (elapsed_ms, max(loaded, 0.8)))
+    clocks = sampler.stop()
+
     # ---------------- BASELINE config 4 as written: 8192 worlds in TOTAL, sharded over the GPUs (strong scaling)
     strong = None
     if world > 1 and args.workload == "C4" and not args.no_secondary:
         first, cnt = sharding.shard_range(args.worlds_per_gpu, rank, world)
         nb2 = cnt * 128
-        grp2 = c4_world_group(odeb200, cnt, first, args.batches if cnt >= 2048 * args.batches else 1, local_rank)
+        grp2 = c4_world_group(odeb200, cnt, first, batches_for(cnt), local_rank)
         tick2 = lambda: grp2.tick(h)  # noqa: E731
         for _ in range(settle + warmup):
             tick2()
