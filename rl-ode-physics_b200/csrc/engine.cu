@@ -33,13 +33,17 @@ static void dev_free(T *&p) {
 }
 
 // address-space reservations of the StableVec host mirrors (engine.h)
-void *stable_reserve() {
-    void *p = mmap(nullptr, STABLE_RESERVE, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-    if (p == MAP_FAILED) {
-        perror("libode_b200: mmap (host mirror reservation)");
-        abort();
+void *stable_reserve(size_t *bytes) {
+    // under an address-space limit (ulimit -v) the full reservation may be refused: take what can be had, down to 64 MiB
+    for (size_t want = *bytes; want >= ((size_t)64 << 20); want >>= 1) {
+        void *p = mmap(nullptr, want, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (p != MAP_FAILED) {
+            *bytes = want;
+            return p;
+        }
     }
-    return p;
+    perror("libode_b200: mmap (host mirror reservation)");
+    abort();
 }
 void stable_commit(void *base, size_t old_bytes, size_t new_bytes) {
     if (mprotect(static_cast<char *>(base) + old_bytes, new_bytes - old_bytes, PROT_READ | PROT_WRITE) != 0) {
@@ -47,7 +51,7 @@ void stable_commit(void *base, size_t old_bytes, size_t new_bytes) {
         abort();
     }
 }
-void stable_release(void *base) { munmap(base, STABLE_RESERVE); }
+void stable_release(void *base, size_t bytes) { munmap(base, bytes); }
 
 Engine *eng_create(int device) {
     int count = 0;

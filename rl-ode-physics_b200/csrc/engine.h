@@ -172,28 +172,33 @@ class StableVec {
     void append(T *pos, const T *src, size_t k);
     void grow(size_t n); // make room for n elements
     T *p_ = nullptr;
-    size_t n_ = 0, committed_ = 0; // elements in use; BYTES committed
+    size_t n_ = 0, committed_ = 0, reserved_ = 0; // elements in use; BYTES committed; BYTES of address space reserved
 };
-void *stable_reserve();                                  // engine.cu
+void *stable_reserve(size_t *bytes);                     // engine.cu; may reserve less than asked (address-space limits)
 void stable_commit(void *base, size_t old_bytes, size_t new_bytes);
-void stable_release(void *base);
-constexpr size_t STABLE_RESERVE = (size_t)8 << 30; // address space per array: 8 GiB = 178 M bodies' rotation matrices
+void stable_release(void *base, size_t bytes);
+// address space per array: 3 GiB = the rotation matrices (48 B) of 67 M bodies; 11 GiB per world with all seven mirrors, so
+// a process may hold thousands of worlds (the 47-bit address space has room for ~11 000)
+constexpr size_t STABLE_RESERVE = (size_t)3 << 30;
 template <typename T>
 StableVec<T>::~StableVec() {
-    if (p_) stable_release(p_);
+    if (p_) stable_release(p_, reserved_);
 }
 template <typename T>
 void StableVec<T>::grow(size_t n) {
     const size_t need = n * sizeof(T);
     if (need <= committed_) return;
-    if (need > STABLE_RESERVE) {
-        fprintf(stderr, "libode_b200: a host mirror outgrew its %zu-byte address reservation\n", STABLE_RESERVE);
+    if (!p_) {
+        reserved_ = STABLE_RESERVE;
+        p_ = static_cast<T *>(stable_reserve(&reserved_));
+    }
+    if (need > reserved_) {
+        fprintf(stderr, "libode_b200: a host mirror outgrew its %zu-byte address reservation\n", reserved_);
         abort();
     }
-    if (!p_) p_ = static_cast<T *>(stable_reserve());
     size_t want = committed_ ? committed_ * 2 : ((size_t)1 << 16);
     while (want < need) want *= 2;
-    if (want > STABLE_RESERVE) want = STABLE_RESERVE;
+    if (want > reserved_) want = reserved_;
     stable_commit(p_, committed_, want);
     committed_ = want;
 }

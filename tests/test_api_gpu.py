@@ -513,3 +513,27 @@ def test_slot_reuse_gives_the_same_physics_without_growing_the_world():
     for a, b in zip(ta, tb):
         assert np.array_equal(a, b)
     assert na == 20 and nb < na and top < nb     # appended 20 slots vs re-used ones
+
+
+def test_many_worlds_alive_at_once():
+    """The address-stable host mirrors reserve address space per world (up to 3 GiB per mirror in use): 300 worlds alive
+    at once, each with a body and a geom, must work and keep their getter pointers apart."""
+    L = odeb200.lib()
+    L.dInitODE()
+    worlds = []
+    for i in range(300):
+        w = C.c_void_p(L.dWorldCreate())
+        sp = C.c_void_p(L.dHashSpaceCreate(None))
+        b = C.c_void_p(L.dBodyCreate(w))
+        L.dBodySetPosition(b, float(i), 1.0, 0.0)
+        g = C.c_void_p(L.dCreateSphere(sp, 0.25))
+        L.dGeomSetBody(g, b)
+        worlds.append((w, sp, b, g))
+    ptrs = set()
+    for i, (w, sp, b, g) in enumerate(worlds):
+        p = L.dBodyGetPosition(b)
+        assert (p[0], p[1]) == (float(i), 1.0)
+        ptrs.add(C.cast(p, C.c_void_p).value)
+    assert len(ptrs) == 300
+    for w, sp, b, g in worlds:
+        L.dGeomDestroy(g); L.dBodyDestroy(b); L.dSpaceDestroy(sp); L.dWorldDestroy(w)
