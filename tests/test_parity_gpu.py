@@ -771,3 +771,53 @@ def test_fuzz_scenes_and_surfaces_against_the_oracle(seed0):
                 assert util.rel_err(es[k], os_[k]).max() <= STATE_RTOL, (seed, kind, case, step, k)
         assert ew.stats()["flags"] == 0
         ew.close()
+
+
+def _check_island_worlds(sc, nw, per, worlds, ticks, case=None, min_contacts_per_env=0):
+    ew = util.engine_world(sc)
+    so, rows = None, 3
+    if case:
+        so, se = _surface_case(case)
+        ew.set_surface(se)
+        rows = 1 if case == "mu0" else 3
+    subs = [(w,) + _world_of_batch(sc, w, per) for w in worlds]
+    st = None
+    for step in range(ticks):
+        ew.tick(sc["h"])
+        st = ew.stats()
+        assert st["flags"] == 0
+        order = ew.solver_order()
+        es = ew.state()
+        for w, sub, ow, gmap in subs:
+            util.oracle_tick_in_engine_order(ow, ew, sc["h"], surf=so, rows_per_contact=rows, geom_map=gmap, order=order)
+            os_ = ow.state()
+            sl = slice(w * per, (w + 1) * per)
+            for k in ("pos", "quat", "lvel", "avel"):
+                assert util.rel_err(es[k][sl], os_[k]).max() <= STATE_RTOL, (step, w, k)
+    assert st["n_contacts"] >= min_contacts_per_env * nw
+    ew.close()
+    return st
+
+
+@pytest.mark.parametrize("seed0", [300, 320])
+def test_fuzz_island_path_against_the_oracle(seed0):
+    """Twenty batches per parameter: 2-6 worlds of random lattice shape (1 to 160 bodies), spacing 0.4-1.2, the reference
+    surface or one of six others; first and last world against the oracle for four ticks on the island path."""
+    for seed in range(seed0, seed0 + 20):
+        rs = np.random.RandomState(seed)
+        nx, ny, nz = int(rs.randint(1, 9)), int(rs.randint(1, 6)), int(rs.randint(1, 5))
+        while nx * ny * nz > 160:
+            nx -= 1
+        nw = int(rs.randint(2, 7))
+        spacing = float(rs.uniform(0.4, 1.2))
+        sc = scenes.batched_worlds_scene(nw, seed=seed, nx=nx, ny=ny, nz=nz, spacing=spacing)
+        case = SURFACE_CASES[seed % len(SURFACE_CASES)] if rs.rand() < 0.5 else None
+        _check_island_worlds(sc, nw, nx * ny * nz, sorted({0, nw - 1}), 4, case)
+
+
+def test_island_path_with_more_units_than_the_shared_memory_cache_holds():
+    """48 heavily overlapping bodies per world: far more than four contacts per body slot, so the colouring's unit cache
+    lives in global memory instead of the warp's shared-memory region (solver_env.cu); still the oracle's bits."""
+    sc = scenes.batched_worlds_scene(3, seed=77, nx=4, ny=4, nz=3, spacing=0.35)
+    st = _check_island_worlds(sc, 3, 48, [0, 2], 3, min_contacts_per_env=4 * 64 + 1)
+    assert st["env_trips"] > 0
