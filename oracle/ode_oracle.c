@@ -1591,8 +1591,26 @@ int orc_quickstep(orc_world *w, float h, int order_mode, const int *perm) {
             double *A = (double *)calloc((size_t)m * (size_t)m, sizeof(double));
             double *bb = (double *)malloc(sizeof(double) * (size_t)m);
             double *x = (double *)calloc((size_t)m, sizeof(double));
+            /* M^-1 J^T in double from the float rows and the float inverse masses / world inverse inertias: with the
+             * float iMJ of the sweeps, A carries 1e-7 relative errors, which a resting box's nearly singular contact
+             * block (four coplanar contacts, cfm/h on the diagonal) amplifies to 1e-3 m/s in the answer -- found by
+             * fuzzing the engine's exact dWorldStep against this mode */
+            double *iMJd = (double *)calloc((size_t)m * 12, sizeof(double));
             for (int i = 0; i < m; i++) {
-                const float *im = iMJ + 12 * i;
+                double *im = iMJd + 12 * i;
+                const float *Ji = J + 12 * i;
+                for (int s1 = 0; s1 < 2; s1++) {
+                    int bi = jb[2 * i + s1];
+                    if (bi < 0) continue;
+                    const float *iI = invI + 12 * bi;
+                    for (int k = 0; k < 3; k++) im[6 * s1 + k] = (double)w->b[bi].invMass * (double)Ji[6 * s1 + k];
+                    for (int r = 0; r < 3; r++)
+                        im[6 * s1 + 3 + r] = (double)iI[4 * r] * (double)Ji[6 * s1 + 3] + (double)iI[4 * r + 1] * (double)Ji[6 * s1 + 4] +
+                                             (double)iI[4 * r + 2] * (double)Ji[6 * s1 + 5];
+                }
+            }
+            for (int i = 0; i < m; i++) {
+                const double *im = iMJd + 12 * i;
                 for (int j2 = 0; j2 < m; j2++) {
                     const float *Jj = J + 12 * j2;
                     double a = 0;
@@ -1601,7 +1619,7 @@ int orc_quickstep(orc_world *w, float h, int order_mode, const int *perm) {
                         if (bi < 0) continue;
                         for (int s2 = 0; s2 < 2; s2++)
                             if (jb[2 * j2 + s2] == bi)
-                                for (int k = 0; k < 6; k++) a += (double)im[6 * s1 + k] * (double)Jj[6 * s2 + k];
+                                for (int k = 0; k < 6; k++) a += im[6 * s1 + k] * (double)Jj[6 * s2 + k];
                     }
                     A[(size_t)i * m + j2] = a;
                 }
@@ -1610,14 +1628,16 @@ int orc_quickstep(orc_world *w, float h, int order_mode, const int *perm) {
                 if (findex[i] >= 0) { fprintf(stderr, "ode_oracle: exact mode does not take findex rows\n"); abort(); }
             }
             if (!solve_blcp(m, A, bb, lo, hi, x)) { fprintf(stderr, "ode_oracle: exact LCP did not terminate\n"); abort(); }
+            double *fcd = (double *)calloc(6 * (size_t)nb, sizeof(double));
             for (int i = 0; i < m; i++) {
                 lambda[i] = (float)x[i];
-                const float *im = iMJ + 12 * i;
+                const double *im = iMJd + 12 * i;
                 int b1 = jb[2 * i], b2 = jb[2 * i + 1];
-                for (int k = 0; k < 6; k++) fc[6 * b1 + k] += (float)(x[i] * (double)im[k]);
-                if (b2 >= 0) for (int k = 0; k < 6; k++) fc[6 * b2 + k] += (float)(x[i] * (double)im[6 + k]);
+                for (int k = 0; k < 6; k++) fcd[6 * b1 + k] += x[i] * im[k];
+                if (b2 >= 0) for (int k = 0; k < 6; k++) fcd[6 * b2 + k] += x[i] * im[6 + k];
             }
-            free(A); free(bb); free(x);
+            for (size_t k = 0; k < 6 * (size_t)nb; k++) fc[k] = (float)fcd[k];
+            free(A); free(bb); free(x); free(iMJd); free(fcd);
         }
         /* SOR_LCP */
         for (int i = 0; i < m && order_mode != 3; i++) {

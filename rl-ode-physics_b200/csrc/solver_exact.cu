@@ -157,10 +157,13 @@ __global__ void __launch_bounds__(EX_THREADS) k_exact_solve(SolverArrays S, Body
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
     const int row0 = X.isl_row0[isl], m = X.isl_row0[isl + 1] - row0;
     double *A = X.A + X.isl_mat[isl], *C = X.C + X.isl_mat[isl];
-    // shared: J, iMJ (12 floats each per row), b, x, w (double), lo, hi (float), bodies (2 ints), state, free list
-    float *J = reinterpret_cast<float *>(ex_smem);
-    float *iMJ = J + 12 * EX_MAX_ROWS;
-    double *bvec = reinterpret_cast<double *>(iMJ + 12 * EX_MAX_ROWS);
+    // shared: iMJ (12 doubles per row), J (12 floats per row), b, x, w (double), lo, hi (float), bodies (2 ints), state, free list.
+    // M^-1 J^T is formed in DOUBLE from the float J and the float inverse masses / world inverse inertias: with the float
+    // products of the sweeps, A carries 1e-7 relative errors, which the nearly singular contact block of a resting box
+    // (four coplanar contacts, only cfm/h on the diagonal) amplifies to 4e-4 m/s -- found by fuzzing against the oracle.
+    double *iMJ = reinterpret_cast<double *>(ex_smem);
+    float *J = reinterpret_cast<float *>(iMJ + 12 * EX_MAX_ROWS);
+    double *bvec = reinterpret_cast<double *>(J + 12 * EX_MAX_ROWS);
     double *x = bvec + EX_MAX_ROWS, *wv = x + EX_MAX_ROWS, *rr = wv + EX_MAX_ROWS;
     float *lo = reinterpret_cast<float *>(rr + EX_MAX_ROWS), *hi = lo + EX_MAX_ROWS, *cfmh = hi + EX_MAX_ROWS;
     int *jb = reinterpret_cast<int *>(cfmh + EX_MAX_ROWS); // 2 per row
@@ -191,18 +194,25 @@ __global__ void __launch_bounds__(EX_THREADS) k_exact_solve(SolverArrays S, Body
         }
         const bool two = rec.y >= 0;
         const V3 J1a = cross(c1, dir);
-        float *Jr = J + 12 * r, *im = iMJ + 12 * r;
+        float *Jr = J + 12 * r;
+        double *im = iMJ + 12 * r;
         Jr[0] = dir.x; Jr[1] = dir.y; Jr[2] = dir.z; Jr[3] = J1a.x; Jr[4] = J1a.y; Jr[5] = J1a.z;
-        const float4 i10 = B.inv[3 * rec.x], i11 = B.inv[3 * rec.x + 1], i12 = B.inv[3 * rec.x + 2];
-        const V3 a1 = mul(M3{v3(i10), v3(i11), v3(i12)}, J1a);
-        im[0] = i10.w * dir.x; im[1] = i10.w * dir.y; im[2] = i10.w * dir.z; im[3] = a1.x; im[4] = a1.y; im[5] = a1.z;
-        for (int q = 6; q < 12; q++) { Jr[q] = 0.f; im[q] = 0.f; }
+        for (int q = 6; q < 12; q++) { Jr[q] = 0.f; im[q] = 0.0; }
+        V3 J2a = v3(0.f, 0.f, 0.f);
         if (two) {
-            const V3 J2l = -dir, J2a = -cross(c2, dir);
+            const V3 J2l = -dir;
+            J2a = -cross(c2, dir);
             Jr[6] = J2l.x; Jr[7] = J2l.y; Jr[8] = J2l.z; Jr[9] = J2a.x; Jr[10] = J2a.y; Jr[11] = J2a.z;
-            const float4 i20 = B.inv[3 * rec.y], i21 = B.inv[3 * rec.y + 1], i22 = B.inv[3 * rec.y + 2];
-            const V3 a2 = mul(M3{v3(i20), v3(i21), v3(i22)}, J2a);
-            im[6] = i20.w * J2l.x; im[7] = i20.w * J2l.y; im[8] = i20.w * J2l.z; im[9] = a2.x; im[10] = a2.y; im[11] = a2.z;
+        }
+        for (int s1 = 0; s1 < (two ? 2 : 1); s1++) {
+            const int b = s1 ? rec.y : rec.x;
+            const float4 i0 = B.inv[3 * b], i1 = B.inv[3 * b + 1], i2 = B.inv[3 * b + 2];
+            const float *Jh = Jr + 6 * s1;
+            double *ih = im + 6 * s1;
+            for (int q = 0; q < 3; q++) ih[q] = (double)i0.w * (double)Jh[q];
+            ih[3] = (double)i0.x * Jh[3] + (double)i0.y * Jh[4] + (double)i0.z * Jh[5];
+            ih[4] = (double)i1.x * Jh[3] + (double)i1.y * Jh[4] + (double)i1.z * Jh[5];
+            ih[5] = (double)i2.x * Jh[3] + (double)i2.y * Jh[4] + (double)i2.z * Jh[5];
         }
         jb[2 * r] = rec.x; jb[2 * r + 1] = rec.y;
         bvec[r] = (double)rhs_s / (double)Ad;   // the sweeps store rhs * Ad (ODE's pre-scaled rows)
@@ -215,14 +225,15 @@ __global__ void __launch_bounds__(EX_THREADS) k_exact_solve(SolverArrays S, Body
     // A = J M^-1 J^T + cfm/h, accumulated in double from the float rows (oracle: order_mode 3)
     for (int e = tid; e < m * m; e += T) {
         const int i = e / m, j = e - i * m;
-        const float *im = iMJ + 12 * i, *Jj = J + 12 * j;
+        const double *im = iMJ + 12 * i;
+        const float *Jj = J + 12 * j;
         double a = 0.0;
         for (int s1 = 0; s1 < 2; s1++) {
             const int bi = jb[2 * i + s1];
             if (bi < 0) continue;
             for (int s2 = 0; s2 < 2; s2++)
                 if (jb[2 * j + s2] == bi)
-                    for (int k = 0; k < 6; k++) a += (double)im[6 * s1 + k] * (double)Jj[6 * s2 + k];
+                    for (int k = 0; k < 6; k++) a += im[6 * s1 + k] * (double)Jj[6 * s2 + k];
         }
         if (i == j) a += (double)cfmh[i];
         A[e] = a;
@@ -350,9 +361,9 @@ __global__ void __launch_bounds__(EX_THREADS) k_exact_solve(SolverArrays S, Body
         double acc[6] = {0, 0, 0, 0, 0, 0};
         for (int r = 0; r < m; r++) {
             if (jb[2 * r] == b)
-                for (int k = 0; k < 6; k++) acc[k] += x[r] * (double)iMJ[12 * r + k];
+                for (int k = 0; k < 6; k++) acc[k] += x[r] * iMJ[12 * r + k];
             if (jb[2 * r + 1] == b)
-                for (int k = 0; k < 6; k++) acc[k] += x[r] * (double)iMJ[12 * r + 6 + k];
+                for (int k = 0; k < 6; k++) acc[k] += x[r] * iMJ[12 * r + 6 + k];
         }
         B.fc[2 * b] = make_float4((float)acc[0], (float)acc[1], (float)acc[2], 0.f);
         B.fc[2 * b + 1] = make_float4((float)acc[3], (float)acc[4], (float)acc[5], 0.f);
@@ -379,7 +390,7 @@ __global__ void __launch_bounds__(256) k_exact_finish(BodyArrays B, ExactArrays 
 }
 
 static size_t exact_smem_bytes() {
-    return (size_t)EX_MAX_ROWS * (24 * sizeof(float) + 4 * sizeof(double) + 3 * sizeof(float) + 2 * sizeof(int) + sizeof(short) + 1) + 64;
+    return (size_t)EX_MAX_ROWS * (12 * sizeof(double) + 12 * sizeof(float) + 4 * sizeof(double) + 3 * sizeof(float) + 2 * sizeof(int) + sizeof(short) + 1) + 64;
 }
 
 // Try the exact solve of the rows k_rows just built.  *done_flag = 1 when it succeeded (integration included).

@@ -821,3 +821,45 @@ def test_island_path_with_more_units_than_the_shared_memory_cache_holds():
     sc = scenes.batched_worlds_scene(3, seed=77, nx=4, ny=4, nz=3, spacing=0.35)
     st = _check_island_worlds(sc, 3, 48, [0, 2], 3, min_contacts_per_env=4 * 64 + 1)
     assert st["env_trips"] > 0
+
+
+def test_fuzz_exact_dworldstep_against_the_oracles_exact_lcp():
+    """The default dWorldStep on 24 random small worlds (soups with rotated boxes, dense piles, server scenes; h = 1/60,
+    1/120, 1/240), 25 ticks each, every tick started from the engine's state: velocities within 5e-5 m/s of the oracle's
+    exact LCP solution.  (This fuzz found that both sides formed M^-1 J^T in float: a resting box's nearly singular
+    contact block amplified the 1e-7 errors of A to 4e-4 .. 4e-3 m/s.  Both now form it in double; worst over 1600
+    ticks: 7.6e-6.)"""
+    worst, exact = 0.0, 0
+    for seed in range(400, 424):
+        rs = np.random.RandomState(seed)
+        kind = seed % 3
+        h = [1 / 60.0, 1 / 120.0, 1 / 240.0][seed % 3]
+        if kind == 0:
+            sc = scenes.random_soup(int(rs.randint(10, 90)), seed=seed, extent=float(rs.uniform(2.5, 6.0)), rotated=bool(rs.rand() < 0.7))
+        elif kind == 1:
+            sc = scenes.pile_scene(int(rs.randint(2, 5)), int(rs.randint(2, 5)), int(rs.randint(1, 4)), seed=seed,
+                                   spacing=float(rs.uniform(0.7, 1.1)))
+        else:
+            sc = scenes.server_scene(seed=seed, h=h, y_range=(1.0, float(rs.uniform(2.0, 6.0))), n_dropped=int(rs.randint(8, 64)))
+        ow, ew = util.load_both(sc)
+        for step in range(25):
+            pre = ew.state()
+            for i in range(len(pre["pos"])):
+                ow.set_body_state(i, pos=pre["pos"][i], q=pre["quat"][i], lvel=pre["lvel"][i], avel=pre["avel"][i])
+            ew.collide(8)
+            ew.world_step(h)
+            st = ew.stats()
+            assert st["exact_status"] in (0, 1), (seed, step, st["exact_status"])
+            ow.clear_contacts()
+            ow.collide_all(8, O.reference_surface())
+            if st["exact_status"] == 0:
+                exact += 1
+                ow.quickstep(h, order_mode=3)
+                es, os_ = ew.state(), ow.state()
+                d = max(float(np.abs(es[k].astype(np.float64) - os_[k]).max()) for k in ("lvel", "avel"))
+                worst = max(worst, d)
+                assert d <= 5e-5, (seed, kind, step, d, st["n_islands"], st["max_island_rows"])
+            ow.clear_contacts()
+        ew.close()
+    print("exact dWorldStep fuzz: %d exact ticks, worst |dv| %.2e" % (exact, worst))
+    assert exact >= 500
