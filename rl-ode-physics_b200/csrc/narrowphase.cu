@@ -565,6 +565,55 @@ constexpr int TM_CAND = 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// The warp's candidate list keeps the TM_CAND candidates that come FIRST in the selection order (depth descending,
+// triangle index ascending).  While there is room, hits are appended (ballot + prefix); once the list is full every further
+// hit replaces the current last-in-order entry if it precedes it.  The greedy selection walks the candidates in that
+// order, so when it finds its <= 8 contacts inside the kept ones the result equals the unbounded list's (the oracle's);
+// only when it runs out of kept candidates first could a dropped one have mattered -- that case alone is flagged.
+template <typename Cand>
+__device__ __forceinline__ void cand_push(Cand *mine, int &ncand, bool &dropped, bool hit, const Cand &cd, int lane) {
+    const unsigned hm = __ballot_sync(0xffffffffu, hit);
+    if (!hm) return;
+    const int nh = __popc(hm);
+    if (ncand + nh <= TM_CAND) {
+        if (hit) mine[ncand + __popc(hm & ((1u << lane) - 1u))] = cd;
+        ncand += nh;
+        __syncwarp();
+        return;
+    }
+    for (unsigned rest = hm; rest; rest &= rest - 1) { // rare: one hit at a time
+        const int src = __ffs(rest) - 1;
+        const float d = __shfl_sync(0xffffffffu, cd.depth, src);
+        const int t = __shfl_sync(0xffffffffu, cd.tri, src);
+        if (ncand < TM_CAND) {
+            if (lane == src) mine[ncand] = cd;
+            ncand++;
+            __syncwarp();
+            continue;
+        }
+        // the kept entry that comes last in the order: smallest depth, largest triangle index among equals
+        float wd = INFINITY;
+        int wt = -1, wi = -1;
+        for (int i = lane; i < TM_CAND; i += 32) {
+            const float di = mine[i].depth;
+            const int ti = mine[i].tri;
+            if (di < wd || (di == wd && ti > wt)) { wd = di; wt = ti; wi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, wd, o);
+            const int ot = __shfl_xor_sync(0xffffffffu, wt, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+            if (od < wd || (od == wd && ot > wt)) { wd = od; wt = ot; wi = oi; }
+        }
+        dropped = true;
+        if (d > wd || (d == wd && t < wt)) {
+            if (lane == src) mine[wi] = cd;
+        }
+        __syncwarp();
+    }
+}
+
 __device__ __forceinline__ V3 closest_pt_triangle(V3 p, V3 a, V3 b, V3 c) {
     const V3 ab = b - a, ac = c - a, ap = p - a;
     const float d1 = dot(ab, ap), d2 = dot(ac, ap);
@@ -723,6 +772,7 @@ __global__ void __launch_bounds__(TM_WARPS * 32) k_np_sphere_trimesh(const Broad
         const bool is_box = g.type[pr.x] == G_BOX;   // warp-uniform: one pair per warp
         float r = g.dims[pr.x].x;                     // sphere radius, or (box) the smallest half side
         int ncand = 0;
+        bool dropped = false; // the candidate list was full and something was left out (cand_push)
         if (is_box) {
             // box vs trimesh: vertex/face rule of DESIGN.md "box-trimesh" (restated by the oracle).  Lane = triangle;
             // the 8 box vertices and the 3 triangle vertices are tried as sub-items in lockstep.
@@ -812,12 +862,7 @@ __global__ void __launch_bounds__(TM_WARPS * 32) k_np_sphere_trimesh(const Broad
                             }
                         }
                     }
-                    const unsigned hm = __ballot_sync(0xffffffffu, hit);
-                    if (hit) {
-                        const int slot = ncand + __popc(hm & lt);
-                        if (slot < TM_CAND) mine[slot] = cd;
-                    }
-                    ncand += __popc(hm);
+                    cand_push(mine, ncand, dropped, hit, cd, lane);
                 }
             });
         } else {
@@ -869,17 +914,8 @@ __global__ void __launch_bounds__(TM_WARPS * 32) k_np_sphere_trimesh(const Broad
                     }
                 }
             }
-            const unsigned hm = __ballot_sync(0xffffffffu, hit);
-            if (hit) {
-                const int slot = ncand + __popc(hm & lt);
-                if (slot < TM_CAND) mine[slot] = cd;
-            }
-            ncand += __popc(hm);
+            cand_push(mine, ncand, dropped, hit, cd, lane);
         });
-        }
-        if (ncand > TM_CAND) {
-            ncand = TM_CAND;
-            if (lane == 0) atomicOr(&stats->flags, SF_CAND_OVERFLOW);
         }
         __syncwarp();
         // greedy selection in (depth desc, tri asc) order with duplicate suppression
@@ -900,7 +936,12 @@ __global__ void __launch_bounds__(TM_WARPS * 32) k_np_sphere_trimesh(const Broad
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (od > bd || (od == bd && ot < bt)) { bd = od; bt = ot; bi = oi; }
             }
-            if (bi < 0) break;
+            if (bi < 0) {
+                // ran out of kept candidates below the contact limit although some were dropped: one of those might have
+                // been a contact -- flagged, never silent
+                if (dropped && lane == 0) atomicOr(&stats->flags, SF_CAND_OVERFLOW);
+                break;
+            }
             const TriCand w = mine[bi];
             __syncwarp();
             if (lane == 0) {
