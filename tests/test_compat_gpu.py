@@ -190,3 +190,22 @@ def test_headless_reference_server_loop_drop_in():
     assert np.array_equal(tr_c[1].reshape(4, 4)[:3, :3], rm[:, :3].T.T.T)
     assert np.array_equal(tr_c[1][12:], np.array([4, 3, 0, 1], np.float32))
     ew.close()
+
+
+@pytest.mark.parametrize("seed,n", [(701, 5), (702, 60), (703, 400), (704, 1500), (705, 2500)])
+def test_fuzz_callback_path_equals_device_path_while_the_world_grows(seed, n):
+    """Random soups of 5 .. 2500 bodies through the callback path and through the device-resident path: identical bits for
+    six ticks.  The larger ones outgrow the mapped read-back buffer of the callback path (sized for 1024 pairs at first),
+    so the copying fallback of the outgrown tick and the enlarged buffer of the following ticks are exercised too."""
+    sc = scenes.random_soup(n, seed=seed, extent=1.5 + 0.25 * n ** (1.0 / 3.0), with_static_box=(seed % 2 == 0))
+    cw = CompatWorld(sc)
+    ew = util.engine_world(sc)
+    for step in range(6):
+        cw.tick(sc["h"])
+        ew.tick(sc["h"])
+        a, b = cw.state(), ew.state()
+        for k in ("pos", "quat", "lvel", "avel", "R"):
+            assert np.array_equal(a[k], b[k]), (step, k)
+    assert n < 60 or cw.n_joints > n // 4
+    cw.close()
+    ew.close()
