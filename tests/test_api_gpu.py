@@ -537,3 +537,34 @@ def test_many_worlds_alive_at_once():
     assert len(ptrs) == 300
     for w, sp, b, g in worlds:
         L.dGeomDestroy(g); L.dBodyDestroy(b); L.dSpaceDestroy(sp); L.dWorldDestroy(w)
+
+
+def test_world_lifetimes_leak_no_device_memory():
+    """Forty worlds created, loaded, ticked, read back and destroyed one after the other (the handle path with its mapped
+    read-back and pinned staging buffers, and the bulk path): the device's free memory after cycle 40 is what it was
+    after cycle 5."""
+    import torch
+    torch.zeros(1, device="cuda")
+
+    def free():
+        torch.cuda.synchronize()
+        return torch.cuda.mem_get_info()[0]
+    sc = scenes.pile_scene(8, 8, 4, seed=5, spacing=0.6)
+    base = None
+    for i in range(40):
+        w = odeb200.World(gravity=sc["gravity"])
+        w.load_scene(sc)
+        for _ in range(3):
+            w.tick(sc["h"])
+        w.state()
+        w.close()
+        s = Server()
+        s.add_static_box((0, 0, 0), (100, 1, 100))
+        for k in range(6):
+            s.add_body((0.3 * k, 1.0 + 0.2 * k, 0.0), "box", (0.4, 0.4, 0.4))
+        for _ in range(3):
+            s.tick()
+        s.close()
+        if i == 4:
+            base = free()
+    assert free() >= base - (1 << 20), (base, free())
