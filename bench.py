@@ -239,7 +239,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def bind_to_gpu_numa_node(local_rank):
@@ -495,7 +495,27 @@ def secondary_c5(L, odeb200, rank, local_rank, world, dev, sharding, torch, cols
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit_line(line):
+    """the ONE line of the contract, on the process's real stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # stdout carries ONE JSON line and nothing else.  Libraries print there too (NCCL's "NCCL version ..." banner at
+    # NCCL_DEBUG >= VERSION, from torch's communicator and from the one the slab driver creates inside libode_b200.so), so
+    # file descriptor 1 points at stderr for the whole run and the line goes to a duplicate of the real stdout.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     from odeb200 import sharding
     rank, local_rank, world = sharding.dist_env()
@@ -510,7 +530,7 @@ def main():
     torch.cuda.set_device(local_rank)
     prev_affinity = bind_to_gpu_numa_node(local_rank) if (world > 1 and not os.environ.get("ODE_B200_NO_BIND")) else None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # NCCL's version banner goes to stdout: keep the one-JSON-line contract
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         sharding.init_process_group("nccl")
     dev = "cuda:%d" % local_rank
     L = odeb200.lib()
@@ -749,7 +769,7 @@ def main():
             line["strong_scaling"] = strong
         if c5:
             line.setdefault("secondary", {})["C5"] = c5
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if grp is not None:
         grp.close()
     if world > 1:
