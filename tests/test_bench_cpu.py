@@ -71,3 +71,14 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["config"]["workload"].startswith("C4: 8192 independent 128-body worlds")
+
+
+def test_stdout_carries_one_json_line_whatever_libraries_print():
+    """bench.py points file descriptor 1 at stderr for the run and writes its line to a duplicate of the real stdout: what
+    NCCL (its version banner) or anything else prints to stdout ends up on stderr."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; sys.stdout.flush(); bench._REAL_STDOUT = os.dup(1); os.dup2(2, 1); "
+            "os.write(1, b'NCCL version 2.28.9+cuda12.9\\n'); print('noise from python'); sys.stdout.flush(); bench.emit_line({'a': 1})" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"a": 1}\n'
+    assert "NCCL version" in r.stderr and "noise from python" in r.stderr
