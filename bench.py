@@ -724,6 +724,9 @@ def main():
                         "compulsory_bytes_per_launch": comp, "compulsory_frac": comp / t_solve / 1e9 / peak}
         if n_batches > 1:
             roofline["launches_per_step"] = n_batches
+            kb = (kernel_counters(args.workload) or {}).get("k_env_solve2_batch2048")
+            if kb:
+                roofline["ncu_one_batch_launch"] = kb   # the committed capture of ONE 2048-world launch (ncu below: 8192 worlds in one)
             roofline["kernel_ms_note"] = ("kernel_ms and stage_ms are sums over the %d batches, each timed with the GPU to itself "
                                           "(the per-launch durations); inside the timed region the batches overlap" % n_batches)
         roofline.update({"frac_of_8TBps_spec": roofline["achieved"] / 8000.0, "kernel_ms": t_solve * 1e3, "stage_ms": tm,
