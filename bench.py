@@ -618,6 +618,10 @@ def main():
     launches = L.dGetKernelLaunchCountB200() - launches0
     t_timed_end = time.perf_counter()
     st = grp.stats()
+    if st["flags"] != 0:
+        # a capacity overflow (pairs, solver units, trimesh candidates) means contacts were dropped: the engine flags it and
+        # carries on, but a throughput measured that way would be a number with work skipped
+        raise SystemExit("bench.py: the engine flagged a capacity overflow (dStepStatsB200.flags = %d) inside the timed region" % st["flags"])
     # per-kernel duration of the dominant kernel: CUDA events on the engine's stream around the solver launch, on
     # eight more live ticks right behind the timed ones (stage events are off inside the timed region: with them
     # the engine does not replay the tick as a CUDA graph)
@@ -763,7 +767,7 @@ def main():
                        "migrated_out_rank0": (getattr(slab, "migrated_out", 0) if slab else 0),
                        "l2": "inputs larger than L2: ~%.0f MB of body, contact and row arrays are touched per tick (126 MB L2)"
                              % ((sum(ab.values()) / 20 + 200 * n_bodies) / 1e6),
-                       "counts": {k: st[k] for k in ("n_pairs", "n_contacts", "n_manifolds", "n_rows1", "n_rows2", "n_colours", "env_trips", "env_lanes")}},
+                       "counts": {k: st[k] for k in ("n_pairs", "n_contacts", "n_manifolds", "n_rows1", "n_rows2", "n_colours", "env_trips", "env_lanes", "flags")}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
         if secondary:
