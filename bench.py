@@ -354,7 +354,7 @@ def timed_device_ticks(L, grp, do_tick, steps, sharding, torch):
     return max(float(L.dWorldTimerElapsedBetweenB200(grp.ws[0].w, w.w)) for w in grp.ws)
 
 
-def timed_e2e(L, grp, do_tick_of, steps, fmt, expand, sharding, torch, odeb200):
+def timed_e2e(L, grp, do_tick_of, steps, fmt, expand, sharding, torch, odeb200, wc_forces=True):
     """The same ticks through the C ABI with HOST buffers: per tick and per world the H2D copy of the per-body
     force/torque input (24 B/body, pinned) and the D2H copy of the step's snapshot (64 / 48 / 32 B per body by format),
     both inside the timed region; `expand` additionally rebuilds the reference's 16-float transforms on the host
@@ -364,10 +364,22 @@ def timed_e2e(L, grp, do_tick_of, steps, fmt, expand, sharding, torch, odeb200):
     K = len(grp.ws)
     for w in grp.ws:
         L.dWorldSetSnapshotFormatB200(w.w, fmt)
-    f6 = [torch.zeros((n, 6), dtype=torch.float32).pin_memory() for n in grp.nb]
+    # force / torque input: page-locked, write-combined (the host only writes it) -- dAllocPinnedB200; or torch's plain pinned
+    f6_raw = []
+    if wc_forces:
+        f6 = []
+        for n in grp.nb:
+            ptr = L.dAllocPinnedB200(n * 24, 1)
+            f6_raw.append(ptr)
+            C.memset(ptr, 0, n * 24)
+            f6.append(ptr)
+        fp_list = [C.cast(ptr, C.POINTER(C.c_float)) for ptr in f6]
+    else:
+        f6 = [torch.zeros((n, 6), dtype=torch.float32).pin_memory() for n in grp.nb]
+        fp_list = None
     snap = [[torch.empty((n, floats), dtype=torch.float32).pin_memory() for _ in range(2)] for n in grp.nb]
     full = [torch.empty((n, 16), dtype=torch.float32) if expand else None for n in grp.nb]
-    fp = [C.cast(t.data_ptr(), C.POINTER(C.c_float)) for t in f6]
+    fp = fp_list if fp_list is not None else [C.cast(t.data_ptr(), C.POINTER(C.c_float)) for t in f6]
     threads = max(1, (os.cpu_count() or 1) // max(1, sharding.dist_env()[2]))
 
     def step(i):
@@ -398,6 +410,8 @@ def timed_e2e(L, grp, do_tick_of, steps, fmt, expand, sharding, torch, odeb200):
         assert ok and (not expand or float(full[k][grp.nb[k] - 1, 15]) == 1.0)
     for w in grp.ws:
         L.dWorldSetSnapshotFormatB200(w.w, 0)
+    for ptr in f6_raw:
+        L.dFreePinnedB200(ptr)
     return dt_ms
 
 
@@ -655,7 +669,10 @@ def main():
             # the same loop with the full 64 B records, and with the compact records expanded to them on the host
             d0 = sharding.all_reduce_max(timed_e2e(L, grp, do_tick_of, args.steps, 0, False, sharding, torch, odeb200), dev)
             dx = sharding.all_reduce_max(timed_e2e(L, grp, do_tick_of, args.steps, fmt, True, sharding, torch, odeb200), dev)
+            dp = sharding.all_reduce_max(timed_e2e(L, grp, do_tick_of, args.steps, fmt, False, sharding, torch, odeb200, wc_forces=False), dev)
             e2e["variants"] = {
+                "forces_in_plain_pinned_memory": {"value": total_bodies * args.steps / (dp * 1e-3), "ms_per_step": dp / args.steps,
+                                                  "note": "the default leg uploads the forces from write-combined pinned memory (dAllocPinnedB200)"},
                 "format0_64B_per_body": {"value": total_bodies * args.steps / (d0 * 1e-3), "ms_per_step": d0 / args.steps,
                                          "d2h_bytes_per_step": int(n_bodies * 64 * world)},
                 "compact_then_expanded_on_host": {"value": total_bodies * args.steps / (dx * 1e-3), "ms_per_step": dx / args.steps,

@@ -21,7 +21,12 @@ extern "C" {
 /* CUDA device used by worlds created afterwards (default: env ODE_B200_DEVICE, LOCAL_RANK, or 0) */
 void dSetDeviceB200(int device);
 int dGetDeviceB200(void);
-int dWorldGetDeviceB200(dWorldID); /* the CUDA device this world lives on (fixed at dWorldCreate) */
+int dWorldGetDeviceB200(dWorldID);
+/* page-locked host memory for the buffers of dWorldSetForcesB200 / dWorldGetSnapshotB200 & co, so that a plain-C host needs no
+ * CUDA headers to get asynchronous copies at full PCIe rate.  write_combined != 0: for buffers the host only WRITES (force
+ * uploads) -- the GPU reads them without snooping the CPU caches; reading such memory from the CPU is slow. */
+void *dAllocPinnedB200(size_t bytes, int write_combined);
+void dFreePinnedB200(void *); /* the CUDA device this world lives on (fixed at dWorldCreate) */
 
 /* device-resident replacement of `dSpaceCollide(space, 0, NearCallback)` (src/main.c:212): runs
  * broadphase + narrowphase and keeps the contacts on the GPU for the next dWorldQuickStep/dWorldStep,

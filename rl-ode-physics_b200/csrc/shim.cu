@@ -252,6 +252,15 @@ extern "C" void dCloseODE(void) {}
 extern "C" void dSetDeviceB200(int device) { g_device = device; }
 extern "C" int dGetDeviceB200(void) { return default_device(); }
 extern "C" int dWorldGetDeviceB200(dWorldID w) { return eng_device(w->eng); }
+extern "C" void *dAllocPinnedB200(size_t bytes, int write_combined) {
+    void *p = nullptr;
+    OB_CUDA(cudaSetDevice(default_device()));
+    OB_CUDA(cudaHostAlloc(&p, bytes ? bytes : 1, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+    return p;
+}
+extern "C" void dFreePinnedB200(void *p) {
+    if (p) OB_CUDA(cudaFreeHost(p));
+}
 
 extern "C" dWorldID dWorldCreate(void) {
     dxWorld *w = new dxWorld();

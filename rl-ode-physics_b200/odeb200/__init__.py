@@ -142,6 +142,7 @@ _SIGS = [
     ("dWorldGetStreamB200", _vp, [_vp]),
     ("dCheckGuardsB200", _i, [_i]),
     ("dWorldGetDeviceB200", _i, [_vp]),
+    ("dAllocPinnedB200", _vp, [C.c_size_t, _i]), ("dFreePinnedB200", None, [_vp]),
     ("dGuardSelfTestB200", _i, [_i]),
     ("dSlabGetUniqueIdB200", _i, [C.c_char_p]),
     ("dSlabCreateB200", _vp, [_vp, _vp, _i, _i, C.c_char_p, C.POINTER(SlabLayout)]),
