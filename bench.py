@@ -670,6 +670,8 @@ def main():
             d0 = sharding.all_reduce_max(timed_e2e(L, grp, do_tick_of, args.steps, 0, False, sharding, torch, odeb200), dev)
             dx = sharding.all_reduce_max(timed_e2e(L, grp, do_tick_of, args.steps, fmt, True, sharding, torch, odeb200), dev)
             dp = sharding.all_reduce_max(timed_e2e(L, grp, do_tick_of, args.steps, fmt, False, sharding, torch, odeb200, wc_forces=False), dev)
+            e2e["variants_note"] = ("the variant legs run after the default leg, i.e. later in the simulation (the heaps carry more "
+                                    "contacts by then): compare them with each other, not with the default leg")
             e2e["variants"] = {
                 "forces_in_plain_pinned_memory": {"value": total_bodies * args.steps / (dp * 1e-3), "ms_per_step": dp / args.steps,
                                                   "note": "the default leg uploads the forces from write-combined pinned memory (dAllocPinnedB200)"},
